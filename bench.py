@@ -1,0 +1,496 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the geometric hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload all|ransac|warp]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+Prints ONE JSON line (rank 0).  BASELINE.json's metric has two halves, so the line has two records:
+
+* top level  -- RANSAC throughput in hypothesis x correspondences per second on BASELINE config 3
+  ("synthetic single-pair RANSAC: 20k correspondences, 50% outliers, 1M hypotheses", hypothesis-block
+  sharded over the ranks, one 16-byte NCCL max all-reduce per step);
+* "warp"     -- backward-warp throughput in Gpix/s on BASELINE config 4 ("4096 synthetic 1920x1080
+  RGB frames with random homographies", frame-sharded, no communication).
+
+A step = one pass of the hot path over the whole workload.  `value` is timed with CUDA events with
+the inputs resident in HBM; `e2e` is the same metric through the host-buffer entry points (pinned
+host memory -> device -> kernels -> host) with the copies inside the timed region.
+`--impl reference` times the CPU restatement of the reference (oracle/ref_numpy.py: same numpy /
+LAPACK calls as the reference, which itself is Python and cannot travel to the GPU box) on all host
+cores, on a bounded sample of the same workloads.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_PAIR = 25.0          # algorithmic FLOP per hypothesis x correspondence, fwd loss
+C3 = dict(M=20000, K=1_000_000, th=3.0, d=99.0, seed=1, idx_seed=0)
+C4 = dict(frames=4096, h=1080, w=1920, jitter=0.05)
+
+
+# ------------------------------------------------------------------------------------------------
+# workload generators
+# ------------------------------------------------------------------------------------------------
+def synth_pair(seed, M, outlier_frac=0.5, noise=0.5):
+    rs = np.random.RandomState(seed)
+    X = (rs.rand(2, M) * np.array([[1920.0], [1080.0]])).astype(np.float32)
+    Ht = np.array([[0.9, 0.05, 30], [-0.04, 1.1, -20], [1e-5, -2e-5, 1]])
+    q = Ht @ np.vstack([X.astype(np.float64), np.ones(M)])
+    Y = q[:2] / q[2] + rs.randn(2, M) * noise
+    out = rs.rand(M) < outlier_frac
+    Y[:, out] = rs.rand(2, int(out.sum())) * np.array([[1920.0], [1080.0]])
+    return X, Y.astype(np.float32)
+
+
+def frame_homographies(n, h, w, jitter, seed=0):
+    """Per-frame H from 4-corner jitter U(+-jitter of W/H), solved in float64 (plain 8x8 solve)."""
+    rs = np.random.RandomState(seed)
+    src = np.array([[0, 0], [w, 0], [w, h], [0, h]], np.float64)
+    Hs = np.empty((n, 3, 3))
+    for i in range(n):
+        dst = src + rs.uniform(-jitter, jitter, (4, 2)) * [w, h]
+        A = np.zeros((8, 8))
+        b = np.zeros(8)
+        for j, ((x, y), (X, Y)) in enumerate(zip(src, dst)):
+            A[2 * j] = [x, y, 1, 0, 0, 0, -x * X, -y * X]
+            A[2 * j + 1] = [0, 0, 0, x, y, 1, -x * Y, -y * Y]
+            b[2 * j], b[2 * j + 1] = X, Y
+        Hs[i] = np.append(np.linalg.solve(A, b), 1).reshape(3, 3)
+    return Hs
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=float(d["hbm_gbs"]), sm_max_mhz=float(d.get("sm_max_mhz", 1965.0)), source="measured")
+    return dict(hbm_gbs=6650.0, sm_max_mhz=1965.0, source="fallback")
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks / throttle sampling during the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "hw_power_brake": 0x80, "sync_boost": 0x10, "display_clocks": 0x100}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
+    def __enter__(self):
+        if self.nv:
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thr:
+            self._thr.join(1.0)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": []}
+        return {"sm_mhz": float(statistics.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def merge_clocks(a, b):
+    out = dict(a)
+    out["reasons"] = sorted(set(a.get("reasons", [])) | set(b.get("reasons", [])))
+    if a.get("sm_mhz") and b.get("sm_mhz"):
+        out["sm_mhz"] = min(a["sm_mhz"], b["sm_mhz"])
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arms
+# ------------------------------------------------------------------------------------------------
+def _cpu_ransac_block(args):
+    X, Y, idx, th = args
+    os.environ["OPENBLAS_NUM_THREADS"] = "1"
+    from oracle import ref_numpy as port
+    t = time.perf_counter()
+    port.score_block(X, Y, idx, th, "fwd")
+    return time.perf_counter() - t
+
+
+def _cpu_warp_block(args):
+    frames, Hs, h, w = args
+    from oracle import ref_numpy as port
+    t = time.perf_counter()
+    for f, H in zip(frames, Hs):
+        port.warp_scan(f, H, [h, w], True)[0].astype(np.uint8)
+    return time.perf_counter() - t
+
+
+def cpu_ransac(n_hyp, cores, pool=None):
+    """numpy port of RANSAC.run's loop body on a K = n_hyp sample of config 3; returns hyp*pts/s."""
+    import warnings
+    warnings.filterwarnings("ignore")
+    X, Y = synth_pair(C3["seed"], C3["M"])
+    idx = np.random.RandomState(C3["idx_seed"]).randint(0, C3["M"], (n_hyp, 4))
+    t0 = time.perf_counter()
+    if cores <= 1:
+        _cpu_ransac_block((X, Y, idx, C3["th"]))
+    else:
+        pool.map(_cpu_ransac_block, [(X, Y, blk, C3["th"]) for blk in np.array_split(idx, cores)])
+    dt = time.perf_counter() - t0
+    return n_hyp * C3["M"] / dt, dt
+
+
+def cpu_warp(n_frames, cores):
+    """numpy port of wrapPerspectiveScan + bilinear + astype(uint8) on n_frames 1080p frames; Gpix/s."""
+    h, w = C4["h"], C4["w"]
+    rs = np.random.RandomState(0)
+    frames = [rs.randint(0, 256, (h, w, 3)).astype(np.uint8) for _ in range(n_frames)]
+    Hs = frame_homographies(n_frames, h, w, C4["jitter"], seed=0)
+    t0 = time.perf_counter()
+    if cores <= 1:
+        _cpu_warp_block((frames, Hs, h, w))
+    else:
+        import multiprocessing as mp
+        parts = [(frames[i::cores], Hs[i::cores], h, w) for i in range(cores) if frames[i::cores]]
+        with mp.get_context("fork").Pool(len(parts)) as pool:
+            pool.map(_cpu_warp_block, parts)
+    dt = time.perf_counter() - t0
+    return n_frames * h * w / dt / 1e9, dt
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (numpy port) on all host cores; bounded samples."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    steps = max(1, args.steps)
+    n_hyp = cores * 2500                          # ~0.2 ms per hypothesis per core at M = 20k -> ~0.5 s per step
+    import multiprocessing as mp
+    os.environ["OPENBLAS_NUM_THREADS"] = "1"
+    pool = mp.get_context("fork").Pool(cores) if cores > 1 else None
+    for _ in range(min(args.warmup, 2)):
+        cpu_ransac(cores * 100, cores, pool)
+    vals, times = [], []
+    for _ in range(steps):
+        v, dt = cpu_ransac(n_hyp, cores, pool)
+        vals.append(v)
+        times.append(dt)
+    if pool is not None:
+        pool.close()
+    value = float(np.mean(vals))
+    line = {
+        "impl": "reference", "metric": "ransac_hyp_pts_per_s", "value": value, "unit": "hyp*pts/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": args.warmup, "ms_per_step": float(np.mean(times) * 1e3), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C3 single-pair RANSAC, fwd loss, M=20000 correspondences (50% outliers), th=3",
+                   "sample": f"{n_hyp} of 1000000 sample sets per step"},
+        "cpu_baseline": {"value": value, "unit": "hyp*pts/s", "cores": cores, "kind": "port",
+                         "sample": f"{n_hyp} of 1000000 sample sets x 20000 correspondences per step, numpy port of "
+                                   "ransac.py:176-184 (4-point SVD solve + scoring), one process per core"},
+        "e2e": {"value": value, "unit": "hyp*pts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    if args.workload in ("all", "warp"):
+        n_frames = max(cores, 8)
+        wv, wdt = cpu_warp(n_frames, cores)
+        line["warp"] = {"metric": "warp_gpix_per_s", "value": wv, "unit": "Gpix/s", "ms_per_step": wdt * 1e3,
+                        "config": {"workload": "C4 batched backward warp 1080p RGB bilinear (Scan grid)", "sample": f"{n_frames} of 4096 frames"},
+                        "cpu_baseline": {"value": wv, "unit": "Gpix/s", "cores": cores, "kind": "port",
+                                         "sample": f"{n_frames} frames, numpy port of homography.py:186-209,123-138"},
+                        "e2e": {"value": wv, "unit": "Gpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def timed_steps(torch, dist, world, fn, steps, warmup, flush=None):
+    """W warm-up steps, then K timed steps (CUDA events on the current stream; optional L2 flush
+    between steps, outside the events); barrier + synchronize on both sides; max over ranks.
+    Returns (total ms over the K steps as max over ranks)."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for a, b in ev:
+        if flush is not None:
+            flush()
+        a.record()
+        fn()
+        b.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
+def bench_ransac(torch, dist, rank, world, args, ctx, peaks, local_gpu):
+    from ransac_with_homography_b200 import device
+    from ransac_with_homography_b200.ransac import HomoModel, RANSAC
+    M, K, th, d = C3["M"], C3["K"], C3["th"], C3["d"]
+    X, Y = synth_pair(C3["seed"], M)
+    pts_h = np.empty((M, 4), np.float32)
+    pts_h[:, :2], pts_h[:, 2:] = X.T, Y.T
+    idx_h = np.random.RandomState(C3["idx_seed"]).randint(0, M, (K, 4)).astype(np.int32)
+    pts, idx = torch.from_numpy(pts_h).cuda(), torch.from_numpy(idx_h).cuda()
+    keys = torch.zeros(2, dtype=torch.int64, device="cuda")
+    result = torch.zeros(32, dtype=torch.float64, device="cuda")
+    mask = torch.zeros(M, dtype=torch.uint8, device="cuda")
+    l2 = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")        # > 126 MB L2
+    flush = lambda: l2.fill_(1)
+    group = None
+
+    def step():
+        device.ransac(pts, idx, th, d, 4, "fwd", group=group, keys=keys, result=result, mask=mask)
+
+    l0 = ctx.launch_count()
+    with ClockSampler(local_gpu) as cs:
+        ms = timed_steps(torch, dist, world, step, args.steps, args.warmup, flush)
+    launches = (ctx.launch_count() - l0) * args.steps // (args.steps + args.warmup)
+    value = K * M * args.steps / (ms / 1e3)
+    res = result.cpu().numpy()
+
+    # dominant kernel alone (K2 scoring of this rank's shard), CUDA events on the launching stream
+    lo, hi = device.shard_range(K, rank, world)
+    H, _, flags = device.dlt4(pts, idx[lo:hi].contiguous())
+    counts = torch.zeros(hi - lo, dtype=torch.int32, device="cuda")
+    kms = timed_steps(torch, dist, 1, lambda: device.score(pts, H, th, "fwd", flags=flags, counts=counts), args.steps, args.warmup, flush)
+    k_avg_s = kms / args.steps / 1e3
+    flops = FLOP_PER_PAIR * (hi - lo) * M
+    peak_tflops = 148 * 128 * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12
+    clocks = cs.summary()
+    roof = {"bound": "fp32", "kernel": "score (K2)", "achieved": flops / k_avg_s / 1e12, "peak": peak_tflops, "unit": "TFLOP/s",
+            "frac": flops / k_avg_s / 1e12 / peak_tflops, "traffic": None,
+            "peak_source": f"148 SM x 128 FP32 lanes x 2 x sm_max_mhz ({peaks['sm_max_mhz']:.0f} MHz, MEASURED_PEAKS.json: {peaks['source']})",
+            "algorithmic_flop_per_hyp_pt": FLOP_PER_PAIR, "kernel_ms": k_avg_s * 1e3,
+            "kernel_share_of_step": (k_avg_s * 1e3) / (ms / args.steps)}
+
+    # end to end: host buffers in, host results out, copies inside the timed region
+    h2d = pts_h.nbytes + idx_h.nbytes
+    d2h = 32 * 8 + M
+    if world == 1:
+        model = HomoModel(th=th, d=d, n=4)
+        runner = RANSAC(model, k=K)
+        import io
+        from contextlib import redirect_stdout
+
+        def e2e_step():
+            with redirect_stdout(io.StringIO()):
+                runner.run([X, Y], method="fwd", idx=idx_h)
+        d2h += K * 4                       # RANSAC.run also returns the per-hypothesis counts on request
+        for _ in range(max(1, min(args.warmup, 2))):
+            e2e_step()
+        t0 = time.perf_counter()
+        n_e2e = max(2, min(args.steps, 5))
+        for _ in range(n_e2e):
+            e2e_step()
+        e2e_s = (time.perf_counter() - t0) / n_e2e
+        e2e_how = "ransac.RANSAC.run([X, Y], 'fwd', idx=...) on numpy arrays (b200geo_ransac_host)"
+    else:
+        pin_p, pin_i = torch.from_numpy(pts_h).pin_memory(), torch.from_numpy(idx_h).pin_memory()
+        out_h = torch.empty(32, dtype=torch.float64).pin_memory()
+        mask_h = torch.empty(M, dtype=torch.uint8).pin_memory()
+
+        def e2e_step():
+            p = pin_p.cuda(non_blocking=True)
+            i = pin_i.cuda(non_blocking=True)
+            r, m = device.ransac(p, i, th, d, 4, "fwd", group=group, keys=keys, result=result, mask=mask)
+            out_h.copy_(r, non_blocking=True)
+            mask_h.copy_(m, non_blocking=True)
+            torch.cuda.synchronize()
+        n_e2e = max(2, min(args.steps, 5))
+        ems = timed_steps(torch, dist, world, e2e_step, n_e2e, 1)
+        e2e_s = ems / n_e2e / 1e3
+        e2e_how = "pinned host -> device.ransac (sharded, NCCL max) -> pinned host, per rank"
+    e2e = {"value": K * M / e2e_s, "unit": "hyp*pts/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+           "ms_per_step": e2e_s * 1e3, "how": e2e_how}
+    rec = {"metric": "ransac_hyp_pts_per_s", "value": value, "unit": "hyp*pts/s", "ms_per_step": ms / args.steps,
+           "config": {"workload": "C3 synthetic single-pair RANSAC: M=20000 correspondences (50% outliers), K=1000000 sample sets, "
+                                  "fwd loss, th=3, d=99 (no early exit); solve + score + select + mask + refit per step",
+                      "sharding": f"hypothesis blocks over {world} rank(s), one 16-byte all-reduce(MAX) per step",
+                      "l2": "256 MB buffer written between timed steps (inputs are 16.3 MB and L2-resident by nature)"},
+           "roofline": roof, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+           "result": {"winner": int(res[0]), "inliers": int(res[1])}}
+    return rec
+
+
+def bench_warp(torch, dist, rank, world, args, ctx, peaks, local_gpu):
+    from ransac_with_homography_b200 import device
+    h, w = C4["h"], C4["w"]
+    total = C4["frames"]
+    lo, hi = device.shard_range(total, rank, world)
+    n = hi - lo
+    free, _ = torch.cuda.mem_get_info()
+    per_frame = h * w * 3
+    if 2 * n * per_frame > 0.85 * free:
+        raise RuntimeError("not enough device memory for the frame shard")
+    src = torch.empty((n, h, w, 3), dtype=torch.uint8, device="cuda")
+    g = torch.Generator(device="cuda")
+    for i in range(0, n, 64):                                   # generated on the device, seed = first frame id
+        g.manual_seed(lo + i)
+        m = min(64, n - i)
+        src[i:i + m] = torch.randint(0, 256, (m, h, w, 3), dtype=torch.uint8, device="cuda", generator=g)
+    dst = torch.empty_like(src)
+    Hs = frame_homographies(total, h, w, C4["jitter"], seed=0)[lo:hi]
+    jobs = device.scan_jobs(Hs, (h, w), (h, w))
+    jobs_dev = device.upload_jobs(jobs, "cuda")
+
+    def step():
+        device.warp_resident(src, dst, jobs_dev, n, w, h, 3, "bilinear")
+
+    l0 = ctx.launch_count()
+    with ClockSampler(local_gpu) as cs:
+        ms = timed_steps(torch, dist, world, step, args.steps, args.warmup, None)
+    launches = (ctx.launch_count() - l0) * args.steps // (args.steps + args.warmup)
+    pix = total * h * w
+    value = pix * args.steps / (ms / 1e3) / 1e9
+    bytes_per_launch = 2.0 * n * per_frame                      # each source byte once + each output byte once
+    k_avg_s = ms / args.steps / 1e3
+    roof = {"bound": "hbm", "kernel": "warp (K4, bilinear u8 RGB)", "achieved": bytes_per_launch / k_avg_s / 1e9, "peak": peaks["hbm_gbs"],
+            "unit": "GB/s", "frac": bytes_per_launch / k_avg_s / 1e9 / peaks["hbm_gbs"], "traffic": None,
+            "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peaks['source']})", "algorithmic_bytes_per_pixel": 6.0,
+            "kernel_ms": k_avg_s * 1e3, "kernel_share_of_step": 1.0}
+
+    # end to end on a bounded batch: pinned host frames -> device -> warp -> pinned host
+    nb = min(64, n)
+    pin_in = torch.empty((nb, h, w, 3), dtype=torch.uint8).pin_memory()
+    pin_in.copy_(src[:nb])
+    pin_out = torch.empty((nb, h, w, 3), dtype=torch.uint8).pin_memory()
+    d_in, d_out = torch.empty_like(src[:nb]), torch.empty_like(src[:nb])
+    jb = device.scan_jobs(Hs[:nb], (h, w), (h, w))
+
+    def e2e_step():
+        d_in.copy_(pin_in, non_blocking=True)
+        device.warp(d_in, d_out, jb, 3, "bilinear")
+        pin_out.copy_(d_out, non_blocking=True)
+        torch.cuda.synchronize()
+    n_e2e = max(2, min(args.steps, 5))
+    ems = timed_steps(torch, dist, world, e2e_step, n_e2e, 1)
+    e2e_v = world * nb * h * w * n_e2e / (ems / 1e3) / 1e9
+    rec = {"metric": "warp_gpix_per_s", "value": value, "unit": "Gpix/s", "ms_per_step": ms / args.steps, "dtype": "u8 pixels, f64 coordinates",
+           "config": {"workload": "C4 batched backward warp: 4096 synthetic 1920x1080 RGB uint8 frames, per-frame random homography "
+                                  "(corner jitter +-5%), bilinear, fixed 1080x1920 output (wrapPerspectiveScan grid), one launch per step",
+                      "sharding": f"frames over {world} rank(s), no communication",
+                      "l2": "inputs (25.5 GB per 4096 frames) are larger than L2"},
+           "roofline": roof,
+           "e2e": {"value": e2e_v, "unit": "Gpix/s", "h2d_bytes_per_step": int(nb * per_frame), "d2h_bytes_per_step": int(nb * per_frame),
+                   "ms_per_step": ems / n_e2e, "how": f"{nb} frames per rank per step: pinned host -> device.warp -> pinned host"},
+           "gpu_launches": int(launches), "clocks": cs.summary()}
+    del src, dst
+    torch.cuda.empty_cache()
+    return rec
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product has no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from ransac_with_homography_b200 import _cabi
+    ctx = _cabi.context(local)
+    peaks = measured_peaks()
+    line = None
+    warp_rec = None
+    if args.workload in ("all", "ransac"):
+        line = bench_ransac(torch, dist, rank, world, args, ctx, peaks, local)
+    if args.workload in ("all", "warp"):
+        warp_rec = bench_warp(torch, dist, rank, world, args, ctx, peaks, local)
+    if line is None:
+        line, warp_rec = warp_rec, None
+    line.update({"n_gpus": world, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "strong",
+                 "vs_baseline": None, "data": "synthetic"})
+    line.setdefault("dtype", "f32")
+    if warp_rec is not None:
+        line["warp"] = warp_rec
+        line["clocks"] = merge_clocks(line["clocks"], warp_rec["clocks"])
+        line["gpu_launches"] = line["gpu_launches"] + warp_rec["gpu_launches"]
+    # CPU baseline: rank 0, N = 1 only, bounded sample, single process (the reference is single-threaded)
+    if rank == 0 and world == 1 and not args.no_cpu:
+        if line["metric"].startswith("ransac"):
+            v, dt = cpu_ransac(50000, 1)
+            line["cpu_baseline"] = {"value": v, "unit": "hyp*pts/s", "cores": 1, "kind": "port", "seconds": dt,
+                                    "sample": "50000 of 1000000 sample sets x 20000 correspondences, numpy port of ransac.py:176-184 "
+                                              "(oracle/ref_numpy.py), single process as the reference runs"}
+        tgt = line.get("warp") if "warp" in line else (line if line["metric"].startswith("warp") else None)
+        if tgt is not None:
+            v, dt = cpu_warp(16, 1)
+            tgt["cpu_baseline"] = {"value": v, "unit": "Gpix/s", "cores": 1, "kind": "port", "seconds": dt,
+                                   "sample": "16 of 4096 frames 1080p bilinear, numpy port of homography.py:186-209,123-138"}
+    if rank == 0:
+        order = ["metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                 "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"]
+        out = {k: line[k] for k in order if k in line}
+        out.update({k: v for k, v in line.items() if k not in out})
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="all", choices=["all", "ransac", "warp"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,201 @@
+/*
+ * b200geo.h -- C ABI of libb200geo.so: the B200 (sm_100a) implementation of the geometric hot path
+ * of choice17/ransac_with_homography (RANSAC homography estimation + backward perspective warp).
+ *
+ * The reference is pure Python/numpy and has no FFI; these entry points are what a binding for the
+ * hot path replaces.  Each declaration cites the reference interface it stands in for
+ * (file:line in the reference repository).  The binding a maintainer would add is a ctypes stub:
+ * see INTEGRATION.md and ransac_with_homography_b200/_cabi.py.
+ *
+ * Conventions
+ *   - every function returns 0 (B200GEO_OK) or a negative error code; b200geo_last_error() gives the
+ *     text of the last failure on the calling thread.  No exceptions cross the boundary.
+ *   - "_host" entry points take HOST pointers, perform the host<->device copies themselves and
+ *     return when the results are in the caller's buffers (synchronous).
+ *   - "_dev" entry points take DEVICE pointers on the context's GPU and are ordered on `stream`
+ *     (a cudaStream_t passed as void*; NULL = the legacy default stream).  They do not synchronise.
+ *   - a correspondence set is M rows of 4 float32: (x, y, x', y') -- the columns of the reference's
+ *     X (2,M) and Y (2,M) arrays (ransac.py:165) interleaved; 16 bytes per match, 16-byte aligned.
+ *   - homographies are 9 row-major values.  A sample-index set is K rows of 4 int32.
+ *   - a context belongs to one GPU; calls on one context must not overlap (thread-compatible).
+ *   - there is no CPU fallback: without a CUDA device b200geo_create fails.
+ */
+#ifndef B200GEO_H
+#define B200GEO_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200GEO_ABI_VERSION 1
+
+/* error codes */
+#define B200GEO_OK 0
+#define B200GEO_ERR_CUDA (-1)      /* a CUDA runtime call failed (text in last_error) */
+#define B200GEO_ERR_ARG (-2)       /* invalid argument */
+#define B200GEO_ERR_NODEVICE (-3)  /* no usable sm_100 device */
+#define B200GEO_ERR_SINGULAR (-4)  /* degenerate system: the reference raises LinAlgError here */
+#define B200GEO_ERR_NOMODEL (-5)   /* every hypothesis scored 0 inliers (reference: np.where(None) fails, ransac.py:206) */
+
+/* HomoModel.computeLoss method (ransac.py:84-98) */
+#define B200GEO_FWD 0
+#define B200GEO_BACKWARD 1
+#define B200GEO_REPROJ 2
+
+/* samplers (homography.py:140  convertfunc) */
+#define B200GEO_NN 0
+#define B200GEO_BILINEAR 1
+
+/* pixel types */
+#define B200GEO_U8 0
+#define B200GEO_F32 1
+#define B200GEO_F64 2
+
+typedef struct b200geo_ctx b200geo_ctx;
+
+int b200geo_abi_version(void);
+const char *b200geo_last_error(void);
+
+/* One context per (process, GPU).  Owns the scratch buffers the entry points need. */
+int b200geo_create(int device, b200geo_ctx **out);
+int b200geo_destroy(b200geo_ctx *ctx);
+/* sm_count, clock (kHz), total memory; any pointer may be NULL */
+int b200geo_device_info(b200geo_ctx *ctx, int *sm_count, int *cc, int *clock_khz, size_t *mem_bytes);
+/* number of kernels this context has launched since creation (bench.py's gpu_launches) */
+int64_t b200geo_launch_count(b200geo_ctx *ctx);
+/* blocks until all work of this context on `stream` is done */
+int b200geo_sync(b200geo_ctx *ctx, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (1) 4-point solve -- replaces calcHomography(u, v) on 4 points (homography.py:71-88, matrix of
+ *     :4-14) as called once per RANSAC iteration by HomoModel.fit (ransac.py:52, 180), and the
+ *     4-point calcHomographyLinear(u, v) of the Scanner (homography.py:90-105, 220).
+ *     One homography per sample set: H[k] maps pts[idx[k][j]].(x,y) -> .(x',y'), h22 = 1.
+ *     flags[k] != 0: degenerate sample (repeated index or singular system); H[k] is then NaN.
+ *     Hinv (optional, may be NULL): inverse of H[k] (np.linalg.inv, ransac.py:74) as float32.
+ * ---------------------------------------------------------------------------------------------- */
+int b200geo_dlt4_dev(b200geo_ctx *ctx, const float *pts, int M, const int32_t *idx, int K,
+                     float *H, float *Hinv, uint8_t *flags, void *stream);
+int b200geo_dlt4_host(b200geo_ctx *ctx, const float *pts, int M, const int32_t *idx, int K,
+                      float *H, float *Hinv, uint8_t *flags);
+/* float64 4-point solve of ONE system given as 4 source and 4 destination points
+ * (calcHomographyLinear(u, v), homography.py:90-105; u, v are 4 rows of (x, y)).  H: 9 doubles. */
+int b200geo_homography4_host(b200geo_ctx *ctx, const double *u, const double *v, double *H);
+
+/* ------------------------------------------------------------------------------------------------
+ * (2a) scoring -- replaces computeLoss + threshold + count, ransac.py:182-184 (HomoModel.fwd /
+ *      reproj / dist, ransac.py:55-98), for K hypotheses at once.
+ *      counts[k] = #{ j : loss(H[k], pts[j]) < th }.  Hinv is required unless method == FWD.
+ *      flags (optional): hypotheses with flags[k] != 0 get count 0.
+ *      Results are bit-identical to the reference's float32 numpy chain for the same H.
+ * ---------------------------------------------------------------------------------------------- */
+int b200geo_score_dev(b200geo_ctx *ctx, const float *pts, int M, const float *H, const float *Hinv,
+                      const uint8_t *flags, int K, float th, int method, int32_t *counts, void *stream);
+int b200geo_score_host(b200geo_ctx *ctx, const float *pts, int M, const float *H, const float *Hinv,
+                       int K, float th, int method, int32_t *counts);
+/* per-point loss of ONE hypothesis (HomoModel.computeLoss, ransac.py:84-98); err: M float32 */
+int b200geo_loss_host(b200geo_ctx *ctx, const float *pts, int M, const float *H, const float *Hinv,
+                      int method, float *err);
+
+/* HomoModel.fwd / HomoModel.reproj as standalone calls (ransac.py:55-76): P is 3 x M row-major
+ * float32 (third row 1 for 2-row input), Hm the 3x3 to apply (val, or inv(val) for reproj);
+ * out (3 x M) = (Hm @ P) / (row 2 + 1e-10). */
+int b200geo_project_host(b200geo_ctx *ctx, const float *Hm, const float *P, int M, float *out);
+/* HomoModel.dist (ransac.py:78-82): out[j] = sqrt(sum_r (a[r][j] - b[r][j])^2); a, b rows x M. */
+int b200geo_dist_host(b200geo_ctx *ctx, const float *a, const float *b, int rows, int M, float *out);
+
+/* ------------------------------------------------------------------------------------------------
+ * (2b) RANSAC search -- replaces the iteration loop of RANSAC.run (ransac.py:176-202) over the
+ *      explicit sample sets idx[k_begin .. k_end): solve, score, and reduce to two 64-bit keys
+ *        keys[0] = max_k  (count_k << 32) | (0xFFFFFFFF - k)          (best count, lowest index)
+ *        keys[1] = max_k  [count_k >= thr] * (0x100000000 - k)        (first k meeting M*d/100+n; 0 = none)
+ *      Both reduce across GPUs with one MAX all-reduce of two int64 (hypothesis-block sharding).
+ *      keys must be zeroed by the caller before the first shard is accumulated (or pass
+ *      zero_keys = 1).  counts (optional): K_total int32, entry k written for k in the range.
+ * ---------------------------------------------------------------------------------------------- */
+int b200geo_ransac_search_dev(b200geo_ctx *ctx, const float *pts, int M, const int32_t *idx,
+                              int k_begin, int k_end, float th, double thr, int method,
+                              unsigned long long *keys, int zero_keys, int32_t *counts, void *stream);
+
+/* (2c) finish -- replaces ransac.py:203-211: decode the winner from keys, recompute its H, its
+ *      inlier mask (err < th) and the least-squares refit over the inliers (calcHomographyLinear
+ *      collective, homography.py:48-69, 90-105 -- solved in float64 on the device).
+ *      result (device, 32 doubles):  [0] winner k (-1: none)  [1] inlier count  [2] status
+ *      (0 ok, B200GEO_ERR_*)  [3..11] H of the winning sample (float32 values)  [12..20] refit H.
+ *      mask: M uint8. */
+int b200geo_ransac_finish_dev(b200geo_ctx *ctx, const float *pts, int M, const int32_t *idx,
+                              const unsigned long long *keys, float th, int method,
+                              double *result, uint8_t *mask, void *stream);
+
+/* Whole RANSAC.run (ransac.py:159-213) on host buffers: H2D, search, finish, D2H.
+ *   thr = M*d/100 + n as the reference computes it (ransac.py:169,186).
+ *   out_H_best: 9 float32 (winning 4-point hypothesis), out_H: 9 float64 (refit, the reference's
+ *   return value), out_mask: M uint8, out_winner / out_count: scalars, out_counts (optional): K.
+ *   Returns B200GEO_ERR_NOMODEL / B200GEO_ERR_SINGULAR where the reference raises. */
+int b200geo_ransac_host(b200geo_ctx *ctx, const float *pts, int M, const int32_t *idx, int K,
+                        float th, double thr, int method, float *out_H_best, double *out_H,
+                        uint8_t *out_mask, int32_t *out_winner, int32_t *out_count, int32_t *out_counts);
+
+/* Batched form (config "batched stitch pipeline"): B independent pairs, each with its own
+ * correspondence set (M rows) and K sample sets; one launch sequence, no host round trips.
+ * pts: B*M*4, idx: B*K*4, results: B*32 doubles (layout of b200geo_ransac_finish_dev), masks: B*M. */
+int b200geo_ransac_batched_dev(b200geo_ctx *ctx, const float *pts, int M, const int32_t *idx, int K,
+                               int B, float th, double thr, int method, double *results,
+                               uint8_t *masks, void *stream);
+
+/* Least-squares refit alone: calcHomographyLinear(u, v, collective=True) (homography.py:90-105)
+ * over the rows with mask[j] != 0 (mask NULL = all rows).  H: 9 doubles. */
+int b200geo_refit_host(b200geo_ctx *ctx, const float *pts, int M, const uint8_t *mask, double *H);
+
+/* ------------------------------------------------------------------------------------------------
+ * (3) backward warp -- replaces wrapPerspective / wrapPerspectiveScan + the samplers
+ *     nearestNeighbor / bilinear (homography.py:108-209) and the astype(uint8) of
+ *     transformImage / transformImageH (homography.py:225, 241).
+ *
+ *     A job describes one image: the output sample grid  gx[c] = x0 + c*dx (last column = x_last),
+ *     gy[r] likewise -- exactly np.linspace's values (homography.py:166-167, 197-198) --, the
+ *     float64 inverse homography, the bounds the sampler tests against (image h,w for the bbox
+ *     form; `res` for the Scan form, homography.py:208), the true image size, and where the
+ *     image and its output live.  Source pixel (0,0) reads as 0 (homography.py:112-116).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct b200geo_warp_job {
+    double invH[9];          /* np.linalg.inv(H), float64 (homography.py:172, 203) */
+    double x0, dx, x_last;   /* output grid columns */
+    double y0, dy, y_last;   /* output grid rows */
+    int32_t ow, oh;          /* output size (max_w, max_h) */
+    int32_t bw, bh;          /* bounds given to the sampler (w, h) */
+    int32_t iw, ih;          /* true source size */
+    int32_t reserved0, reserved1;
+    int64_t src_offset;      /* byte offset of this image from the `src` base pointer */
+    int64_t src_pitch;       /* bytes per source row */
+    int64_t dst_offset;      /* byte offset of this output from the `dst` base pointer */
+    int64_t dst_pitch;       /* bytes per output row */
+} b200geo_warp_job;
+
+/* n_jobs images in one launch.  channels: 3 or 4.  src_type: B200GEO_U8 | B200GEO_F32.
+ * dst_type: B200GEO_U8 (value truncated toward zero, astype(np.uint8)), B200GEO_F32 or B200GEO_F64.
+ * jobs: HOST array (copied to the device by the call). */
+int b200geo_warp_dev(b200geo_ctx *ctx, const void *src, void *dst, const b200geo_warp_job *jobs,
+                     int n_jobs, int channels, int src_type, int dst_type, int sampler, void *stream);
+/* jobs already resident on the device (no host work at all; used by the batched pipelines) */
+int b200geo_warp_jobs_dev(b200geo_ctx *ctx, const void *src, void *dst, const b200geo_warp_job *jobs_dev,
+                          int n_jobs, int max_ow, int max_oh, int channels, int src_type, int dst_type,
+                          int sampler, void *stream);
+/* single image on host buffers: H2D, warp, D2H */
+int b200geo_warp_host(b200geo_ctx *ctx, const void *src, void *dst, const b200geo_warp_job *job,
+                      int channels, int src_type, int dst_type, int sampler);
+
+/* The samplers called on explicit coordinates: nearestNeighbor / bilinear(z_t, img, h, w, mh, mw)
+ * (homography.py:108-138).  zx, zy: N float64 each (rows 0 and 1 of z_t); bh, bw: the bounds the
+ * sampler tests against; dst: N*channels values of dst_type.  Host buffers. */
+int b200geo_sample_host(b200geo_ctx *ctx, const void *src, int ih, int iw, int channels, int src_type,
+                        const double *zx, const double *zy, long long N, int bh, int bw, int sampler,
+                        int dst_type, void *dst);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200GEO_H */

@@ -1,0 +1,584 @@
+// b200geo.cu -- the C ABI of libb200geo.so (declared in include/b200geo.h).
+// Host-side launch logic only; the kernels live in solve.cuh / score.cuh / select_refit.cuh / warp.cuh.
+#include "common.cuh"
+#include "score.cuh"
+#include "select_refit.cuh"
+#include "solve.cuh"
+#include "warp.cuh"
+
+#include <new>
+#include <vector>
+
+using namespace b200geo;
+
+#ifndef B200GEO_SOLVE_T
+#define B200GEO_SOLVE_T double
+#endif
+typedef B200GEO_SOLVE_T solve_t;
+
+extern "C" {
+
+int b200geo_abi_version(void) { return B200GEO_ABI_VERSION; }
+const char *b200geo_last_error(void) { return g_err; }
+
+int b200geo_create(int device, b200geo_ctx **out)
+{
+    if (!out) return fail(B200GEO_ERR_ARG, "out is NULL%s%s");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(B200GEO_ERR_NODEVICE, "no CUDA device: %s%s", e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= n) return fail(B200GEO_ERR_ARG, "device index out of range%s%s");
+    cudaDeviceProp p;
+    B2G_CUDA(cudaGetDeviceProperties(&p, device));
+    if (p.major < 10)
+        return fail(B200GEO_ERR_NODEVICE, "device %s is not sm_100 class; this library is built for sm_100a only%s", p.name);
+    b200geo_ctx *ctx = new (std::nothrow) b200geo_ctx();
+    if (!ctx) return fail(B200GEO_ERR_ARG, "out of host memory%s%s");
+    memset(ctx, 0, sizeof *ctx);
+    ctx->device = device;
+    ctx->sm_count = p.multiProcessorCount;
+    ctx->cc = p.major * 10 + p.minor;
+    int khz = 0;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
+    ctx->clock_khz = khz;
+    ctx->mem_bytes = p.totalGlobalMem;
+    *out = ctx;
+    return B200GEO_OK;
+}
+
+int b200geo_destroy(b200geo_ctx *ctx)
+{
+    if (!ctx) return B200GEO_OK;
+    {
+        DeviceGuard g(ctx->device);
+        for (int i = 0; i < S_NUM; ++i)
+            if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
+        if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    }
+    delete ctx;
+    return B200GEO_OK;
+}
+
+int b200geo_device_info(b200geo_ctx *ctx, int *sm_count, int *cc, int *clock_khz, size_t *mem_bytes)
+{
+    B2G_ARG(ctx != nullptr);
+    if (sm_count) *sm_count = ctx->sm_count;
+    if (cc) *cc = ctx->cc;
+    if (clock_khz) *clock_khz = ctx->clock_khz;
+    if (mem_bytes) *mem_bytes = ctx->mem_bytes;
+    return B200GEO_OK;
+}
+
+int64_t b200geo_launch_count(b200geo_ctx *ctx) { return ctx ? ctx->launches : -1; }
+
+int b200geo_sync(b200geo_ctx *ctx, void *stream)
+{
+    B2G_ENTER(ctx);
+    B2G_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return B200GEO_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// internal launch helpers (device pointers, stream ordered)
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+int launch_dlt4(b200geo_ctx *ctx, const float *pts, int M, const int32_t *idx, int k_begin, int k_end, int K_stride,
+                int B, float *H, float *Hinv, uint8_t *flags, cudaStream_t st)
+{
+    int nk = k_end - k_begin;
+    if (nk <= 0 || B <= 0) return B200GEO_OK;
+    dim3 grid((nk + 127) / 128, B);
+    dlt4_kernel<solve_t><<<grid, 128, 0, st>>>((const float4 *)pts, M, (const int4 *)idx, k_begin, k_end, K_stride, H, Hinv, flags);
+    B2G_CHECK_LAUNCH(ctx);
+    return B200GEO_OK;
+}
+
+int launch_score(b200geo_ctx *ctx, const float *pts, int M, const float *H, const float *Hinv, const uint8_t *flags,
+                 int k_begin, int k_end, int K_stride, int B, float th, int method, int32_t *counts, cudaStream_t st)
+{
+    int nk = k_end - k_begin;
+    if (nk <= 0 || B <= 0) return B200GEO_OK;
+    int gx = (nk + SCORE_THREADS - 1) / SCORE_THREADS;
+    // split the correspondence range when there are too few hypothesis blocks to fill the GPU
+    int splits = 1;
+    long long blocks = (long long)gx * B;
+    long long want = 2LL * ctx->sm_count;
+    if (blocks < want && M > SCORE_TILE) {
+        splits = (int)((want + blocks - 1) / blocks);
+        int max_splits = (M + SCORE_TILE - 1) / SCORE_TILE;
+        if (splits > max_splits) splits = max_splits;
+    }
+    int per = (M + splits - 1) / splits;
+    per = ((per + SCORE_TILE - 1) / SCORE_TILE) * SCORE_TILE;
+    splits = M > 0 ? (M + per - 1) / per : 1;
+    if (splits < 1) splits = 1;
+    if (splits > 1) {
+        // zero only the range being written, per batch row
+        for (int b = 0; b < B; ++b)
+            B2G_CUDA(cudaMemsetAsync(counts + (size_t)b * K_stride + k_begin, 0, sizeof(int32_t) * (size_t)nk, st));
+    }
+    dim3 grid(gx, splits, B);
+    const float4 *p4 = (const float4 *)pts;
+    switch (method) {
+    case B200GEO_FWD:
+        score_exact_kernel<B200GEO_FWD><<<grid, SCORE_THREADS, 0, st>>>(p4, M, H, Hinv, flags, k_begin, k_end, K_stride, th, per, counts);
+        break;
+    case B200GEO_BACKWARD:
+        score_exact_kernel<B200GEO_BACKWARD><<<grid, SCORE_THREADS, 0, st>>>(p4, M, H, Hinv, flags, k_begin, k_end, K_stride, th, per, counts);
+        break;
+    default:
+        score_exact_kernel<B200GEO_REPROJ><<<grid, SCORE_THREADS, 0, st>>>(p4, M, H, Hinv, flags, k_begin, k_end, K_stride, th, per, counts);
+        break;
+    }
+    B2G_CHECK_LAUNCH(ctx);
+    return B200GEO_OK;
+}
+
+int launch_select(b200geo_ctx *ctx, const int32_t *counts, int k_begin, int k_end, int K_stride, int B, double thr,
+                  unsigned long long *keys, cudaStream_t st)
+{
+    int nk = k_end - k_begin;
+    if (nk <= 0 || B <= 0) return B200GEO_OK;
+    int gx = (nk + 256 * 8 - 1) / (256 * 8);
+    if (gx > 4 * ctx->sm_count) gx = 4 * ctx->sm_count;
+    if (gx < 1) gx = 1;
+    select_kernel<<<dim3(gx, B), 256, 0, st>>>(counts, k_begin, k_end, K_stride, thr, keys);
+    B2G_CHECK_LAUNCH(ctx);
+    return B200GEO_OK;
+}
+
+// solve + score + select over idx[k_begin, k_end) for B independent pairs
+int search(b200geo_ctx *ctx, const float *pts, int M, const int32_t *idx, int k_begin, int k_end, int K_stride, int B,
+           float th, double thr, int method, unsigned long long *keys, int32_t *counts, cudaStream_t st)
+{
+    size_t nH = (size_t)B * K_stride;
+    float *H = nullptr, *Hinv = nullptr;
+    uint8_t *flags = nullptr;
+    int rc;
+    if ((rc = scratch(ctx, S_H, nH * 9 * sizeof(float), (void **)&H))) return rc;
+    if (method != B200GEO_FWD && (rc = scratch(ctx, S_HINV, nH * 9 * sizeof(float), (void **)&Hinv))) return rc;
+    if ((rc = scratch(ctx, S_FLAGS, nH, (void **)&flags))) return rc;
+    if (!counts && (rc = scratch(ctx, S_COUNTS, nH * sizeof(int32_t), (void **)&counts))) return rc;
+    if ((rc = launch_dlt4(ctx, pts, M, idx, k_begin, k_end, K_stride, B, H, Hinv, flags, st))) return rc;
+    if ((rc = launch_score(ctx, pts, M, H, Hinv, flags, k_begin, k_end, K_stride, B, th, method, counts, st))) return rc;
+    return launch_select(ctx, counts, k_begin, k_end, K_stride, B, thr, keys, st);
+}
+
+int launch_finish(b200geo_ctx *ctx, const float *pts, int M, const int32_t *idx, int K_stride, int B,
+                  const unsigned long long *keys, float th, int method, double *result, uint8_t *mask, cudaStream_t st)
+{
+    finish_kernel<solve_t><<<B, REFIT_THREADS, 0, st>>>((const float4 *)pts, M, (const int4 *)idx, K_stride, keys, th, method, result, mask);
+    B2G_CHECK_LAUNCH(ctx);
+    return B200GEO_OK;
+}
+
+template <typename SrcT, int C>
+int launch_warp_t(b200geo_ctx *ctx, const void *src, void *dst, const b200geo_warp_job *jobs_dev, int n_jobs, int max_ow,
+                  int max_oh, int dst_type, int sampler, cudaStream_t st)
+{
+    dim3 block(64, 4);
+    dim3 grid((max_ow + 63) / 64, (max_oh + 3) / 4, n_jobs);
+    const uint8_t *s = (const uint8_t *)src;
+    uint8_t *d = (uint8_t *)dst;
+#define B2G_WARP_CASE(DT, BL) warp_generic_kernel<SrcT, DT, C, BL><<<grid, block, 0, st>>>(s, d, jobs_dev)
+    if (sampler == B200GEO_BILINEAR) {
+        if (dst_type == B200GEO_U8) B2G_WARP_CASE(uint8_t, 1);
+        else if (dst_type == B200GEO_F32) B2G_WARP_CASE(float, 1);
+        else B2G_WARP_CASE(double, 1);
+    } else {
+        if (dst_type == B200GEO_U8) B2G_WARP_CASE(uint8_t, 0);
+        else if (dst_type == B200GEO_F32) B2G_WARP_CASE(float, 0);
+        else B2G_WARP_CASE(double, 0);
+    }
+#undef B2G_WARP_CASE
+    B2G_CHECK_LAUNCH(ctx);
+    return B200GEO_OK;
+}
+
+int launch_warp(b200geo_ctx *ctx, const void *src, void *dst, const b200geo_warp_job *jobs_dev, int n_jobs, int max_ow,
+                int max_oh, int channels, int src_type, int dst_type, int sampler, cudaStream_t st)
+{
+    if (n_jobs <= 0 || max_ow <= 0 || max_oh <= 0) return B200GEO_OK;
+    if (n_jobs > 65535) return fail(B200GEO_ERR_ARG, "at most 65535 warp jobs per call%s%s");
+    if (src_type == B200GEO_U8 && channels == 3) return launch_warp_t<uint8_t, 3>(ctx, src, dst, jobs_dev, n_jobs, max_ow, max_oh, dst_type, sampler, st);
+    if (src_type == B200GEO_U8 && channels == 4) return launch_warp_t<uint8_t, 4>(ctx, src, dst, jobs_dev, n_jobs, max_ow, max_oh, dst_type, sampler, st);
+    if (src_type == B200GEO_F32 && channels == 3) return launch_warp_t<float, 3>(ctx, src, dst, jobs_dev, n_jobs, max_ow, max_oh, dst_type, sampler, st);
+    if (src_type == B200GEO_F32 && channels == 4) return launch_warp_t<float, 4>(ctx, src, dst, jobs_dev, n_jobs, max_ow, max_oh, dst_type, sampler, st);
+    return fail(B200GEO_ERR_ARG, "unsupported source type / channel count%s%s");
+}
+
+size_t type_size(int t) { return t == B200GEO_U8 ? 1 : (t == B200GEO_F32 ? 4 : 8); }
+
+template <typename SrcT, int C>
+int launch_sample_t(b200geo_ctx *ctx, const void *src, int ih, int iw, int bh, int bw, const double *zx, const double *zy,
+                    long long N, int sampler, int dst_type, void *dst, cudaStream_t st)
+{
+    long long want = (N + 255) / 256;
+    int blocks = (int)(want < 1 ? 1 : (want > 16LL * ctx->sm_count ? 16LL * ctx->sm_count : want));
+    const SrcT *s = (const SrcT *)src;
+    size_t pitch = (size_t)iw * C;
+#define B2G_SAMPLE_CASE(DT, BL) sample_kernel<SrcT, DT, C, BL><<<blocks, 256, 0, st>>>(s, pitch, iw, ih, bw, bh, zx, zy, N, (DT *)dst)
+    if (sampler == B200GEO_BILINEAR) {
+        if (dst_type == B200GEO_U8) B2G_SAMPLE_CASE(uint8_t, 1);
+        else if (dst_type == B200GEO_F32) B2G_SAMPLE_CASE(float, 1);
+        else B2G_SAMPLE_CASE(double, 1);
+    } else {
+        if (dst_type == B200GEO_U8) B2G_SAMPLE_CASE(uint8_t, 0);
+        else if (dst_type == B200GEO_F32) B2G_SAMPLE_CASE(float, 0);
+        else B2G_SAMPLE_CASE(double, 0);
+    }
+#undef B2G_SAMPLE_CASE
+    B2G_CHECK_LAUNCH(ctx);
+    return B200GEO_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// exported entry points
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int b200geo_dlt4_dev(b200geo_ctx *ctx, const float *pts, int M, const int32_t *idx, int K, float *H, float *Hinv,
+                     uint8_t *flags, void *stream)
+{
+    B2G_ENTER(ctx);
+    B2G_ARG(pts && idx && H && M > 0 && K >= 0);
+    return launch_dlt4(ctx, pts, M, idx, 0, K, K, 1, H, Hinv, flags, (cudaStream_t)stream);
+}
+
+int b200geo_dlt4_host(b200geo_ctx *ctx, const float *pts, int M, const int32_t *idx, int K, float *H, float *Hinv,
+                      uint8_t *flags)
+{
+    B2G_ENTER(ctx);
+    B2G_ARG(pts && idx && H && M > 0 && K >= 0);
+    if (K == 0) return B200GEO_OK;
+    float *dp, *dH, *dHi = nullptr;
+    int32_t *di;
+    uint8_t *df;
+    int rc;
+    if ((rc = scratch(ctx, S_PTS, (size_t)M * 16, (void **)&dp))) return rc;
+    if ((rc = scratch(ctx, S_IDX, (size_t)K * 16, (void **)&di))) return rc;
+    if ((rc = scratch(ctx, S_H, (size_t)K * 36, (void **)&dH))) return rc;
+    if (Hinv && (rc = scratch(ctx, S_HINV, (size_t)K * 36, (void **)&dHi))) return rc;
+    if ((rc = scratch(ctx, S_FLAGS, (size_t)K, (void **)&df))) return rc;
+    B2G_CUDA(cudaMemcpyAsync(dp, pts, (size_t)M * 16, cudaMemcpyHostToDevice, 0));
+    B2G_CUDA(cudaMemcpyAsync(di, idx, (size_t)K * 16, cudaMemcpyHostToDevice, 0));
+    if ((rc = launch_dlt4(ctx, dp, M, di, 0, K, K, 1, dH, dHi, df, 0))) return rc;
+    B2G_CUDA(cudaMemcpyAsync(H, dH, (size_t)K * 36, cudaMemcpyDeviceToHost, 0));
+    if (Hinv) B2G_CUDA(cudaMemcpyAsync(Hinv, dHi, (size_t)K * 36, cudaMemcpyDeviceToHost, 0));
+    if (flags) B2G_CUDA(cudaMemcpyAsync(flags, df, (size_t)K, cudaMemcpyDeviceToHost, 0));
+    B2G_CUDA(cudaStreamSynchronize(0));
+    return B200GEO_OK;
+}
+
+int b200geo_homography4_host(b200geo_ctx *ctx, const double *u, const double *v, double *H)
+{
+    B2G_ENTER(ctx);
+    B2G_ARG(u && v && H);
+    double *d;
+    int rc;
+    if ((rc = scratch(ctx, S_MISC, 16 * 8 + 9 * 8 + 8, (void **)&d))) return rc;
+    B2G_CUDA(cudaMemcpyAsync(d, u, 64, cudaMemcpyHostToDevice, 0));
+    B2G_CUDA(cudaMemcpyAsync(d + 8, v, 64, cudaMemcpyHostToDevice, 0));
+    homography4_kernel<<<1, 32, 0, 0>>>(d, d + 16, (int *)(d + 25));
+    B2G_CHECK_LAUNCH(ctx);
+    double host[10];
+    B2G_CUDA(cudaMemcpy(host, d + 16, sizeof host, cudaMemcpyDeviceToHost));
+    int status;
+    memcpy(&status, &host[9], sizeof status);
+    memcpy(H, host, 72);
+    if (status) return fail(B200GEO_ERR_SINGULAR, "singular 4-point system (the reference raises LinAlgError)%s%s");
+    return B200GEO_OK;
+}
+
+int b200geo_score_dev(b200geo_ctx *ctx, const float *pts, int M, const float *H, const float *Hinv, const uint8_t *flags,
+                      int K, float th, int method, int32_t *counts, void *stream)
+{
+    B2G_ENTER(ctx);
+    B2G_ARG(pts && H && counts && M >= 0 && K >= 0);
+    B2G_ARG(method == B200GEO_FWD || method == B200GEO_BACKWARD || method == B200GEO_REPROJ);
+    B2G_ARG(method == B200GEO_FWD || Hinv != nullptr);
+    return launch_score(ctx, pts, M, H, Hinv, flags, 0, K, K, 1, th, method, counts, (cudaStream_t)stream);
+}
+
+int b200geo_score_host(b200geo_ctx *ctx, const float *pts, int M, const float *H, const float *Hinv, int K, float th,
+                       int method, int32_t *counts)
+{
+    B2G_ENTER(ctx);
+    B2G_ARG(pts && H && counts && M >= 0 && K >= 0);
+    B2G_ARG(method == B200GEO_FWD || method == B200GEO_BACKWARD || method == B200GEO_REPROJ);
+    B2G_ARG(method == B200GEO_FWD || Hinv != nullptr);
+    if (K == 0) return B200GEO_OK;
+    float *dp, *dH, *dHi = nullptr;
+    int32_t *dc;
+    int rc;
+    if ((rc = scratch(ctx, S_PTS, (size_t)M * 16, (void **)&dp))) return rc;
+    if ((rc = scratch(ctx, S_H, (size_t)K * 36, (void **)&dH))) return rc;
+    if (Hinv && (rc = scratch(ctx, S_HINV, (size_t)K * 36, (void **)&dHi))) return rc;
+    if ((rc = scratch(ctx, S_COUNTS, (size_t)K * 4, (void **)&dc))) return rc;
+    if (M) B2G_CUDA(cudaMemcpyAsync(dp, pts, (size_t)M * 16, cudaMemcpyHostToDevice, 0));
+    B2G_CUDA(cudaMemcpyAsync(dH, H, (size_t)K * 36, cudaMemcpyHostToDevice, 0));
+    if (Hinv) B2G_CUDA(cudaMemcpyAsync(dHi, Hinv, (size_t)K * 36, cudaMemcpyHostToDevice, 0));
+    if ((rc = launch_score(ctx, dp, M, dH, dHi, nullptr, 0, K, K, 1, th, method, dc, 0))) return rc;
+    B2G_CUDA(cudaMemcpyAsync(counts, dc, (size_t)K * 4, cudaMemcpyDeviceToHost, 0));
+    B2G_CUDA(cudaStreamSynchronize(0));
+    return B200GEO_OK;
+}
+
+int b200geo_loss_host(b200geo_ctx *ctx, const float *pts, int M, const float *H, const float *Hinv, int method, float *err)
+{
+    B2G_ENTER(ctx);
+    B2G_ARG(pts && H && err && M >= 0);
+    B2G_ARG(method == B200GEO_FWD || Hinv != nullptr);
+    if (M == 0) return B200GEO_OK;
+    float *dp, *dH, *de;
+    int rc;
+    if ((rc = scratch(ctx, S_PTS, (size_t)M * 16, (void **)&dp))) return rc;
+    if ((rc = scratch(ctx, S_H, 72, (void **)&dH))) return rc;
+    if ((rc = scratch(ctx, S_MISC, (size_t)M * 4, (void **)&de))) return rc;
+    B2G_CUDA(cudaMemcpyAsync(dp, pts, (size_t)M * 16, cudaMemcpyHostToDevice, 0));
+    B2G_CUDA(cudaMemcpyAsync(dH, H, 36, cudaMemcpyHostToDevice, 0));
+    if (Hinv) B2G_CUDA(cudaMemcpyAsync(dH + 9, Hinv, 36, cudaMemcpyHostToDevice, 0));
+    int blocks = (M + 255) / 256;
+    if (blocks > 8 * ctx->sm_count) blocks = 8 * ctx->sm_count;
+    loss_kernel<<<blocks, 256, 0, 0>>>((const float4 *)dp, M, dH, Hinv ? dH + 9 : nullptr, method, de);
+    B2G_CHECK_LAUNCH(ctx);
+    B2G_CUDA(cudaMemcpy(err, de, (size_t)M * 4, cudaMemcpyDeviceToHost));
+    return B200GEO_OK;
+}
+
+int b200geo_project_host(b200geo_ctx *ctx, const float *Hm, const float *P, int M, float *out)
+{
+    B2G_ENTER(ctx);
+    B2G_ARG(Hm && P && out && M >= 0);
+    if (M == 0) return B200GEO_OK;
+    float *dp, *dh, *dout;
+    int rc;
+    if ((rc = scratch(ctx, S_PTS, (size_t)M * 12, (void **)&dp))) return rc;
+    if ((rc = scratch(ctx, S_H, 36, (void **)&dh))) return rc;
+    if ((rc = scratch(ctx, S_MISC, (size_t)M * 12, (void **)&dout))) return rc;
+    B2G_CUDA(cudaMemcpyAsync(dp, P, (size_t)M * 12, cudaMemcpyHostToDevice, 0));
+    B2G_CUDA(cudaMemcpyAsync(dh, Hm, 36, cudaMemcpyHostToDevice, 0));
+    int blocks = (M + 255) / 256;
+    if (blocks > 8 * ctx->sm_count) blocks = 8 * ctx->sm_count;
+    project_kernel<<<blocks, 256, 0, 0>>>(dp, M, dh, dout);
+    B2G_CHECK_LAUNCH(ctx);
+    B2G_CUDA(cudaMemcpy(out, dout, (size_t)M * 12, cudaMemcpyDeviceToHost));
+    return B200GEO_OK;
+}
+
+int b200geo_dist_host(b200geo_ctx *ctx, const float *a, const float *b, int rows, int M, float *out)
+{
+    B2G_ENTER(ctx);
+    B2G_ARG(a && b && out && rows > 0 && M >= 0);
+    if (M == 0) return B200GEO_OK;
+    float *da, *dout;
+    int rc;
+    size_t n = (size_t)rows * M;
+    if ((rc = scratch(ctx, S_PTS, n * 8, (void **)&da))) return rc;
+    if ((rc = scratch(ctx, S_MISC, (size_t)M * 4, (void **)&dout))) return rc;
+    B2G_CUDA(cudaMemcpyAsync(da, a, n * 4, cudaMemcpyHostToDevice, 0));
+    B2G_CUDA(cudaMemcpyAsync(da + n, b, n * 4, cudaMemcpyHostToDevice, 0));
+    int blocks = (M + 255) / 256;
+    if (blocks > 8 * ctx->sm_count) blocks = 8 * ctx->sm_count;
+    dist_kernel<<<blocks, 256, 0, 0>>>(da, da + n, rows, M, dout);
+    B2G_CHECK_LAUNCH(ctx);
+    B2G_CUDA(cudaMemcpy(out, dout, (size_t)M * 4, cudaMemcpyDeviceToHost));
+    return B200GEO_OK;
+}
+
+int b200geo_ransac_search_dev(b200geo_ctx *ctx, const float *pts, int M, const int32_t *idx, int k_begin, int k_end,
+                              float th, double thr, int method, unsigned long long *keys, int zero_keys, int32_t *counts,
+                              void *stream)
+{
+    B2G_ENTER(ctx);
+    B2G_ARG(pts && idx && keys && M > 0 && k_begin >= 0 && k_end >= k_begin);
+    B2G_ARG(method == B200GEO_FWD || method == B200GEO_BACKWARD || method == B200GEO_REPROJ);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (zero_keys) B2G_CUDA(cudaMemsetAsync(keys, 0, 16, st));
+    // scratch H / flags are indexed by absolute k: stride = k_end
+    return search(ctx, pts, M, idx, k_begin, k_end, k_end, 1, th, thr, method, keys, counts, st);
+}
+
+int b200geo_ransac_finish_dev(b200geo_ctx *ctx, const float *pts, int M, const int32_t *idx, const unsigned long long *keys,
+                              float th, int method, double *result, uint8_t *mask, void *stream)
+{
+    B2G_ENTER(ctx);
+    B2G_ARG(pts && idx && keys && result && mask && M > 0);
+    return launch_finish(ctx, pts, M, idx, 0, 1, keys, th, method, result, mask, (cudaStream_t)stream);
+}
+
+int b200geo_ransac_host(b200geo_ctx *ctx, const float *pts, int M, const int32_t *idx, int K, float th, double thr,
+                        int method, float *out_H_best, double *out_H, uint8_t *out_mask, int32_t *out_winner,
+                        int32_t *out_count, int32_t *out_counts)
+{
+    B2G_ENTER(ctx);
+    B2G_ARG(pts && idx && M > 0 && K > 0);
+    B2G_ARG(method == B200GEO_FWD || method == B200GEO_BACKWARD || method == B200GEO_REPROJ);
+    float *dp;
+    int32_t *di, *dc;
+    unsigned long long *dk;
+    double *dr;
+    uint8_t *dm;
+    int rc;
+    if ((rc = scratch(ctx, S_PTS, (size_t)M * 16, (void **)&dp))) return rc;
+    if ((rc = scratch(ctx, S_IDX, (size_t)K * 16, (void **)&di))) return rc;
+    if ((rc = scratch(ctx, S_COUNTS, (size_t)K * 4, (void **)&dc))) return rc;
+    if ((rc = scratch(ctx, S_KEYS, 16, (void **)&dk))) return rc;
+    if ((rc = scratch(ctx, S_RESULT, 32 * 8, (void **)&dr))) return rc;
+    if ((rc = scratch(ctx, S_MASK, (size_t)M, (void **)&dm))) return rc;
+    B2G_CUDA(cudaMemcpyAsync(dp, pts, (size_t)M * 16, cudaMemcpyHostToDevice, 0));
+    B2G_CUDA(cudaMemcpyAsync(di, idx, (size_t)K * 16, cudaMemcpyHostToDevice, 0));
+    B2G_CUDA(cudaMemsetAsync(dk, 0, 16, 0));
+    if ((rc = search(ctx, dp, M, di, 0, K, K, 1, th, thr, method, dk, dc, 0))) return rc;
+    if ((rc = launch_finish(ctx, dp, M, di, K, 1, dk, th, method, dr, dm, 0))) return rc;
+    double res[32];
+    B2G_CUDA(cudaMemcpyAsync(res, dr, sizeof res, cudaMemcpyDeviceToHost, 0));
+    if (out_mask) B2G_CUDA(cudaMemcpyAsync(out_mask, dm, (size_t)M, cudaMemcpyDeviceToHost, 0));
+    if (out_counts) B2G_CUDA(cudaMemcpyAsync(out_counts, dc, (size_t)K * 4, cudaMemcpyDeviceToHost, 0));
+    B2G_CUDA(cudaStreamSynchronize(0));
+    if (out_winner) *out_winner = (int32_t)res[0];
+    if (out_count) *out_count = (int32_t)res[1];
+    if (out_H_best) for (int j = 0; j < 9; ++j) out_H_best[j] = (float)res[3 + j];
+    if (out_H) for (int j = 0; j < 9; ++j) out_H[j] = res[12 + j];
+    int status = (int)res[2];
+    if (status == B200GEO_ERR_NOMODEL) return fail(status, "no hypothesis has any inlier (the reference fails in np.where(None), ransac.py:206)%s%s");
+    if (status == B200GEO_ERR_SINGULAR) return fail(status, "singular refit system (the reference raises LinAlgError)%s%s");
+    return status;
+}
+
+int b200geo_ransac_batched_dev(b200geo_ctx *ctx, const float *pts, int M, const int32_t *idx, int K, int B, float th,
+                               double thr, int method, double *results, uint8_t *masks, void *stream)
+{
+    B2G_ENTER(ctx);
+    B2G_ARG(pts && idx && results && masks && M > 0 && K > 0 && B > 0 && B <= 65535);
+    B2G_ARG(method == B200GEO_FWD || method == B200GEO_BACKWARD || method == B200GEO_REPROJ);
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long *dk;
+    int rc;
+    if ((rc = scratch(ctx, S_KEYS, (size_t)B * 16, (void **)&dk))) return rc;
+    B2G_CUDA(cudaMemsetAsync(dk, 0, (size_t)B * 16, st));
+    if ((rc = search(ctx, pts, M, idx, 0, K, K, B, th, thr, method, dk, nullptr, st))) return rc;
+    return launch_finish(ctx, pts, M, idx, K, B, dk, th, method, results, masks, st);
+}
+
+int b200geo_refit_host(b200geo_ctx *ctx, const float *pts, int M, const uint8_t *mask, double *H)
+{
+    B2G_ENTER(ctx);
+    B2G_ARG(pts && H && M > 0);
+    float *dp;
+    uint8_t *dm = nullptr;
+    double *dr;
+    int rc;
+    if ((rc = scratch(ctx, S_PTS, (size_t)M * 16, (void **)&dp))) return rc;
+    if (mask && (rc = scratch(ctx, S_MASK, (size_t)M, (void **)&dm))) return rc;
+    if ((rc = scratch(ctx, S_RESULT, 32 * 8, (void **)&dr))) return rc;
+    B2G_CUDA(cudaMemcpyAsync(dp, pts, (size_t)M * 16, cudaMemcpyHostToDevice, 0));
+    if (mask) B2G_CUDA(cudaMemcpyAsync(dm, mask, (size_t)M, cudaMemcpyHostToDevice, 0));
+    refit_kernel<<<1, REFIT_THREADS, 0, 0>>>((const float4 *)dp, M, dm, dr);
+    B2G_CHECK_LAUNCH(ctx);
+    double res[10];
+    B2G_CUDA(cudaMemcpy(res, dr, sizeof res, cudaMemcpyDeviceToHost));
+    for (int j = 0; j < 9; ++j) H[j] = res[1 + j];
+    if ((int)res[0] != 0) return fail(B200GEO_ERR_SINGULAR, "singular least-squares system (the reference raises LinAlgError)%s%s");
+    return B200GEO_OK;
+}
+
+int b200geo_warp_jobs_dev(b200geo_ctx *ctx, const void *src, void *dst, const b200geo_warp_job *jobs_dev, int n_jobs,
+                          int max_ow, int max_oh, int channels, int src_type, int dst_type, int sampler, void *stream)
+{
+    B2G_ENTER(ctx);
+    B2G_ARG(src && dst && jobs_dev && n_jobs >= 0);
+    B2G_ARG(sampler == B200GEO_NN || sampler == B200GEO_BILINEAR);
+    B2G_ARG(dst_type == B200GEO_U8 || dst_type == B200GEO_F32 || dst_type == B200GEO_F64);
+    return launch_warp(ctx, src, dst, jobs_dev, n_jobs, max_ow, max_oh, channels, src_type, dst_type, sampler, (cudaStream_t)stream);
+}
+
+int b200geo_warp_dev(b200geo_ctx *ctx, const void *src, void *dst, const b200geo_warp_job *jobs, int n_jobs, int channels,
+                     int src_type, int dst_type, int sampler, void *stream)
+{
+    B2G_ENTER(ctx);
+    B2G_ARG(src && dst && jobs && n_jobs >= 0);
+    B2G_ARG(sampler == B200GEO_NN || sampler == B200GEO_BILINEAR);
+    B2G_ARG(dst_type == B200GEO_U8 || dst_type == B200GEO_F32 || dst_type == B200GEO_F64);
+    if (n_jobs == 0) return B200GEO_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    b200geo_warp_job *dj;
+    void *hp;
+    int rc;
+    size_t bytes = sizeof(b200geo_warp_job) * (size_t)n_jobs;
+    if ((rc = scratch(ctx, S_JOBS, bytes, (void **)&dj))) return rc;
+    if ((rc = pinned(ctx, bytes, &hp))) return rc;
+    // the pinned block is reused by the next call: wait for earlier copies out of it
+    B2G_CUDA(cudaStreamSynchronize(st));
+    memcpy(hp, jobs, bytes);
+    int max_ow = 0, max_oh = 0;
+    for (int i = 0; i < n_jobs; ++i) {
+        if (jobs[i].ow > max_ow) max_ow = jobs[i].ow;
+        if (jobs[i].oh > max_oh) max_oh = jobs[i].oh;
+    }
+    B2G_CUDA(cudaMemcpyAsync(dj, hp, bytes, cudaMemcpyHostToDevice, st));
+    return launch_warp(ctx, src, dst, dj, n_jobs, max_ow, max_oh, channels, src_type, dst_type, sampler, st);
+}
+
+int b200geo_warp_host(b200geo_ctx *ctx, const void *src, void *dst, const b200geo_warp_job *job, int channels,
+                      int src_type, int dst_type, int sampler)
+{
+    B2G_ENTER(ctx);
+    B2G_ARG(src && dst && job);
+    B2G_ARG(job->ow > 0 && job->oh > 0 && job->iw > 0 && job->ih > 0);
+    size_t sbytes = (size_t)job->src_pitch * (size_t)job->ih;
+    size_t dbytes = (size_t)job->dst_pitch * (size_t)job->oh;
+    B2G_ARG((size_t)job->src_pitch >= (size_t)job->iw * channels * type_size(src_type));
+    B2G_ARG((size_t)job->dst_pitch >= (size_t)job->ow * channels * type_size(dst_type));
+    void *ds, *dd;
+    int rc;
+    if ((rc = scratch(ctx, S_SRC, sbytes, &ds))) return rc;
+    if ((rc = scratch(ctx, S_DST, dbytes, &dd))) return rc;
+    b200geo_warp_job j = *job;
+    j.src_offset = 0;
+    j.dst_offset = 0;
+    B2G_CUDA(cudaMemcpyAsync(ds, (const uint8_t *)src + job->src_offset, sbytes, cudaMemcpyHostToDevice, 0));
+    if ((rc = b200geo_warp_dev(ctx, ds, dd, &j, 1, channels, src_type, dst_type, sampler, nullptr))) return rc;
+    B2G_CUDA(cudaMemcpyAsync((uint8_t *)dst + job->dst_offset, dd, dbytes, cudaMemcpyDeviceToHost, 0));
+    B2G_CUDA(cudaStreamSynchronize(0));
+    return B200GEO_OK;
+}
+
+int b200geo_sample_host(b200geo_ctx *ctx, const void *src, int ih, int iw, int channels, int src_type, const double *zx,
+                        const double *zy, long long N, int bh, int bw, int sampler, int dst_type, void *dst)
+{
+    B2G_ENTER(ctx);
+    B2G_ARG(src && zx && zy && dst && ih > 0 && iw > 0 && N >= 0);
+    B2G_ARG(sampler == B200GEO_NN || sampler == B200GEO_BILINEAR);
+    B2G_ARG(dst_type == B200GEO_U8 || dst_type == B200GEO_F32 || dst_type == B200GEO_F64);
+    B2G_ARG((channels == 3 || channels == 4) && (src_type == B200GEO_U8 || src_type == B200GEO_F32));
+    if (N == 0) return B200GEO_OK;
+    size_t sbytes = (size_t)ih * iw * channels * type_size(src_type);
+    size_t dbytes = (size_t)N * channels * type_size(dst_type);
+    void *ds, *dd;
+    double *dz;
+    int rc;
+    if ((rc = scratch(ctx, S_SRC, sbytes, &ds))) return rc;
+    if ((rc = scratch(ctx, S_DST, dbytes, &dd))) return rc;
+    if ((rc = scratch(ctx, S_MISC, (size_t)N * 16, (void **)&dz))) return rc;
+    B2G_CUDA(cudaMemcpyAsync(ds, src, sbytes, cudaMemcpyHostToDevice, 0));
+    B2G_CUDA(cudaMemcpyAsync(dz, zx, (size_t)N * 8, cudaMemcpyHostToDevice, 0));
+    B2G_CUDA(cudaMemcpyAsync(dz + N, zy, (size_t)N * 8, cudaMemcpyHostToDevice, 0));
+    if (src_type == B200GEO_U8 && channels == 3) rc = launch_sample_t<uint8_t, 3>(ctx, ds, ih, iw, bh, bw, dz, dz + N, N, sampler, dst_type, dd, 0);
+    else if (src_type == B200GEO_U8) rc = launch_sample_t<uint8_t, 4>(ctx, ds, ih, iw, bh, bw, dz, dz + N, N, sampler, dst_type, dd, 0);
+    else if (channels == 3) rc = launch_sample_t<float, 3>(ctx, ds, ih, iw, bh, bw, dz, dz + N, N, sampler, dst_type, dd, 0);
+    else rc = launch_sample_t<float, 4>(ctx, ds, ih, iw, bh, bw, dz, dz + N, N, sampler, dst_type, dd, 0);
+    if (rc) return rc;
+    B2G_CUDA(cudaMemcpyAsync(dst, dd, dbytes, cudaMemcpyDeviceToHost, 0));
+    B2G_CUDA(cudaStreamSynchronize(0));
+    return B200GEO_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,115 @@
+// common.cuh -- context, scratch memory and error plumbing shared by the kernels' host wrappers.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/b200geo.h"
+
+static_assert(sizeof(b200geo_warp_job) == 184, "b200geo_warp_job layout is part of the ABI");
+
+namespace b200geo {
+
+static thread_local char g_err[512] = "";
+
+inline int fail(int code, const char *fmt, const char *a = "", const char *b = "")
+{
+    snprintf(g_err, sizeof g_err, fmt, a, b);
+    return code;
+}
+
+#define B2G_CUDA(call)                                                                          \
+    do {                                                                                        \
+        cudaError_t e__ = (call);                                                               \
+        if (e__ != cudaSuccess) return ::b200geo::fail(B200GEO_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e__)); \
+    } while (0)
+
+#define B2G_CHECK_LAUNCH(ctx)                                                                   \
+    do {                                                                                        \
+        (ctx)->launches++;                                                                      \
+        cudaError_t e__ = cudaGetLastError();                                                   \
+        if (e__ != cudaSuccess) return ::b200geo::fail(B200GEO_ERR_CUDA, "kernel launch: %s%s", cudaGetErrorString(e__)); \
+    } while (0)
+
+#define B2G_ARG(cond)                                                                           \
+    do {                                                                                        \
+        if (!(cond)) return ::b200geo::fail(B200GEO_ERR_ARG, "invalid argument: %s%s", #cond);    \
+    } while (0)
+
+enum ScratchSlot {
+    S_PTS = 0, S_IDX, S_H, S_HINV, S_FLAGS, S_COUNTS, S_KEYS, S_RESULT, S_MASK, S_JOBS, S_SRC, S_DST, S_MISC,
+    S_NUM
+};
+
+}  // namespace b200geo
+
+struct b200geo_ctx {
+    int device;
+    int sm_count;
+    int cc;
+    int clock_khz;
+    size_t mem_bytes;
+    int64_t launches;
+    void *scratch[b200geo::S_NUM];
+    size_t scratch_cap[b200geo::S_NUM];
+    void *pinned;          // small pinned staging block for scalar results
+    size_t pinned_cap;
+};
+
+namespace b200geo {
+
+// grow-on-demand device scratch; contents are NOT preserved across a growth
+inline int scratch(b200geo_ctx *ctx, int slot, size_t bytes, void **out)
+{
+    if (bytes == 0) bytes = 16;
+    if (ctx->scratch_cap[slot] < bytes) {
+        if (ctx->scratch[slot]) {
+            B2G_CUDA(cudaFree(ctx->scratch[slot]));
+            ctx->scratch[slot] = nullptr;
+            ctx->scratch_cap[slot] = 0;
+        }
+        size_t cap = bytes + bytes / 4;
+        cap = (cap + 255) & ~(size_t)255;
+        B2G_CUDA(cudaMalloc(&ctx->scratch[slot], cap));
+        ctx->scratch_cap[slot] = cap;
+    }
+    *out = ctx->scratch[slot];
+    return B200GEO_OK;
+}
+
+inline int pinned(b200geo_ctx *ctx, size_t bytes, void **out)
+{
+    if (ctx->pinned_cap < bytes) {
+        if (ctx->pinned) B2G_CUDA(cudaFreeHost(ctx->pinned));
+        ctx->pinned = nullptr;
+        ctx->pinned_cap = 0;
+        B2G_CUDA(cudaMallocHost(&ctx->pinned, bytes));
+        ctx->pinned_cap = bytes;
+    }
+    *out = ctx->pinned;
+    return B200GEO_OK;
+}
+
+struct DeviceGuard {
+    int prev;
+    bool ok;
+    explicit DeviceGuard(int dev) : prev(-1), ok(true)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard()
+    {
+        int cur = -1;
+        if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+    }
+};
+
+#define B2G_ENTER(ctx)                                                                          \
+    B2G_ARG((ctx) != nullptr);                                                                  \
+    ::b200geo::DeviceGuard guard__((ctx)->device);                                              \
+    if (!guard__.ok) return ::b200geo::fail(B200GEO_ERR_CUDA, "cudaSetDevice failed%s%s")
+
+}  // namespace b200geo

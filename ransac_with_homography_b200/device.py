@@ -1,0 +1,221 @@
+"""Device-resident / batched / multi-GPU interface to the hot path.
+
+PyTorch is used here for plumbing only: device memory (tensors), streams and
+``torch.distributed`` (NCCL).  All arithmetic goes through the ``_dev`` entry points of the C ABI
+(include/b200geo.h) on the current torch CUDA stream; nothing here synchronises with the host
+unless it says so.
+
+Multi-GPU (one process per GPU):
+  * single-pair RANSAC shards the K sample sets by hypothesis block; every rank reduces its block
+    to two packed 64-bit keys and ONE ``all_reduce(MAX)`` of those 16 bytes picks the global winner
+    (``ransac``).  The winner's H, inlier mask and refit are then recomputed on every rank from
+    the shared index set -- no broadcast.
+  * batched warps and batched pairs are sharded by frame / pair with no communication.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _cabi
+
+
+def _ctx(t: torch.Tensor) -> _cabi.Context:
+    assert t.is_cuda, "device tensors required (no CPU fallback)"
+    return _cabi.context(t.device.index if t.device.index is not None else torch.cuda.current_device())
+
+
+def _stream(t: torch.Tensor):
+    return _cabi._vp(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _p(t: torch.Tensor | None):
+    return None if t is None else _cabi._vp(t.data_ptr())
+
+
+def _chk_pts(pts: torch.Tensor):
+    assert pts.dtype == torch.float32 and pts.is_contiguous() and pts.shape[-1] == 4, "pts: (..., M, 4) float32 rows (x, y, x', y')"
+
+
+def dlt4(pts: torch.Tensor, idx: torch.Tensor, want_inv: bool = False):
+    """K1.  pts (M,4) float32, idx (K,4) int32 -> H (K,3,3) float32, Hinv or None, flags (K,) uint8."""
+    _chk_pts(pts)
+    assert idx.dtype == torch.int32 and idx.is_contiguous() and idx.shape[-1] == 4
+    ctx = _ctx(pts)
+    K = idx.shape[0]
+    H = torch.empty((K, 3, 3), dtype=torch.float32, device=pts.device)
+    Hinv = torch.empty_like(H) if want_inv else None
+    flags = torch.empty((K,), dtype=torch.uint8, device=pts.device)
+    _cabi.check(ctx.lib.b200geo_dlt4_dev(ctx.handle, _p(pts), pts.shape[0], _p(idx), K, _p(H), _p(Hinv), _p(flags), _stream(pts)))
+    return H, Hinv, flags
+
+
+def score(pts: torch.Tensor, H: torch.Tensor, th: float, method: str = "fwd", Hinv: torch.Tensor | None = None,
+          flags: torch.Tensor | None = None, counts: torch.Tensor | None = None) -> torch.Tensor:
+    """K2.  Inlier count of every hypothesis H[k] over pts; int32 (K,)."""
+    _chk_pts(pts)
+    assert H.dtype == torch.float32 and H.is_contiguous()
+    ctx = _ctx(pts)
+    K = H.numel() // 9
+    if counts is None:
+        counts = torch.empty((K,), dtype=torch.int32, device=pts.device)
+    _cabi.check(ctx.lib.b200geo_score_dev(ctx.handle, _p(pts), pts.shape[0], _p(H), _p(Hinv), _p(flags), K,
+                                          float(np.float32(th)), _cabi.METHODS[method], _p(counts), _stream(pts)))
+    return counts
+
+
+def ransac_search(pts, idx, k_begin, k_end, th, thr, method="fwd", keys=None, counts=None, zero_keys=True):
+    """Solve + score + select over idx[k_begin:k_end]; returns the (2,) int64 key tensor."""
+    _chk_pts(pts)
+    assert idx.dtype == torch.int32 and idx.is_contiguous()
+    ctx = _ctx(pts)
+    if keys is None:
+        keys = torch.empty((2,), dtype=torch.int64, device=pts.device)
+    _cabi.check(ctx.lib.b200geo_ransac_search_dev(ctx.handle, _p(pts), pts.shape[0], _p(idx), int(k_begin), int(k_end),
+                                                  float(np.float32(th)), float(thr), _cabi.METHODS[method], _p(keys),
+                                                  int(bool(zero_keys)), _p(counts), _stream(pts)))
+    return keys
+
+
+def ransac_finish(pts, idx, keys, th, method="fwd", result=None, mask=None):
+    """K3 from reduced keys: result (32,) float64 [winner, count, status, H_sample(9), H_refit(9)], mask (M,) uint8."""
+    ctx = _ctx(pts)
+    if result is None:
+        result = torch.empty((32,), dtype=torch.float64, device=pts.device)
+    if mask is None:
+        mask = torch.empty((pts.shape[0],), dtype=torch.uint8, device=pts.device)
+    _cabi.check(ctx.lib.b200geo_ransac_finish_dev(ctx.handle, _p(pts), pts.shape[0], _p(idx), _p(keys),
+                                                  float(np.float32(th)), _cabi.METHODS[method], _p(result), _p(mask),
+                                                  _stream(pts)))
+    return result, mask
+
+
+def shard_range(K: int, rank: int, world: int):
+    """Contiguous hypothesis block of `rank` (blocks differ by at most one sample set)."""
+    base, rem = divmod(K, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def ransac(pts, idx, th, d, n=4, method="fwd", group=None, keys=None, result=None, mask=None, counts=None):
+    """RANSAC.run over K explicit sample sets, hypothesis-block sharded over the ranks of `group`
+    (all ranks hold the same pts and idx).  Returns (result, mask) on every rank; see ransac_finish.
+    With torch.distributed uninitialised (or world size 1) no collective is issued."""
+    import torch.distributed as dist
+    M, K = pts.shape[0], idx.shape[0]
+    thr = M * d / 100 + n
+    world, rank = 1, 0
+    if dist.is_available() and dist.is_initialized():
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+    lo, hi = shard_range(K, rank, world)
+    keys = ransac_search(pts, idx, lo, hi, th, thr, method, keys=keys, counts=counts)
+    if world > 1:
+        dist.all_reduce(keys, op=dist.ReduceOp.MAX, group=group)     # 16 bytes over NVLink
+    return ransac_finish(pts, idx, keys, th, method, result=result, mask=mask)
+
+
+def ransac_batched(pts, idx, th, d, n=4, method="fwd", results=None, masks=None):
+    """B independent pairs: pts (B,M,4), idx (B,K,4) -> results (B,32) float64, masks (B,M) uint8."""
+    _chk_pts(pts)
+    assert pts.dim() == 3 and idx.dim() == 3 and idx.dtype == torch.int32 and idx.is_contiguous()
+    B, M, _ = pts.shape
+    K = idx.shape[1]
+    ctx = _ctx(pts)
+    if results is None:
+        results = torch.empty((B, 32), dtype=torch.float64, device=pts.device)
+    if masks is None:
+        masks = torch.empty((B, M), dtype=torch.uint8, device=pts.device)
+    _cabi.check(ctx.lib.b200geo_ransac_batched_dev(ctx.handle, _p(pts), M, _p(idx), K, B, float(np.float32(th)),
+                                                   float(M * d / 100 + n), _cabi.METHODS[method], _p(results), _p(masks),
+                                                   _stream(pts)))
+    return results, masks
+
+
+# ------------------------------------------------------------------------------------------------
+# batched warps
+# ------------------------------------------------------------------------------------------------
+def scan_jobs(H: np.ndarray, src_hw, res_hw, channels=3, src_itemsize=1, dst_itemsize=1) -> np.ndarray:
+    """Jobs for wrapPerspectiveScan semantics (reference homography.py:186-209) on a batch of
+    equally sized frames stored back to back: H (B,3,3) float64; output res = (h, w) per frame."""
+    H = np.asarray(H, np.float64).reshape(-1, 3, 3)
+    B = H.shape[0]
+    ih, iw = src_hw
+    oh, ow = res_hw
+    jobs = np.zeros(B, _cabi.WARP_JOB_DTYPE)
+    jobs["invH"] = np.linalg.inv(H).reshape(B, 9)
+    jobs["x0"], jobs["dx"], jobs["x_last"] = 0.0, (ow / (ow - 1) if ow > 1 else 0.0), (float(ow) if ow > 1 else 0.0)
+    jobs["y0"], jobs["dy"], jobs["y_last"] = 0.0, (oh / (oh - 1) if oh > 1 else 0.0), (float(oh) if oh > 1 else 0.0)
+    jobs["ow"], jobs["oh"] = ow, oh
+    jobs["bw"], jobs["bh"] = ow, oh            # the reference passes `res` as the sampler's bounds
+    jobs["iw"], jobs["ih"] = iw, ih
+    sp, dp = iw * channels * src_itemsize, ow * channels * dst_itemsize
+    jobs["src_pitch"], jobs["dst_pitch"] = sp, dp
+    jobs["src_offset"] = np.arange(B, dtype=np.int64) * (sp * ih)
+    jobs["dst_offset"] = np.arange(B, dtype=np.int64) * (dp * oh)
+    return jobs
+
+
+def bbox_jobs(H: np.ndarray, src_hw, channels=3, src_itemsize=1, dst_itemsize=1, canvas_hw=None):
+    """Jobs for wrapPerspective semantics (reference homography.py:142-179): per-frame bounding box
+    of the warped corners.  Outputs are packed back to back unless canvas_hw is given (each output
+    then occupies a canvas_hw slot and is clipped to it).  Returns (jobs, (min_x, min_y, w, h) per frame)."""
+    H = np.asarray(H, np.float64).reshape(-1, 3, 3)
+    B = H.shape[0]
+    ih, iw = src_hw
+    bnd = np.array([[0, iw - 1, iw - 1, 0], [0, 0, ih - 1, ih - 1], [1.0, 1, 1, 1]])
+    q = H @ bnd
+    q = q / q[:, 2:3, :]
+    trunc = lambda a: np.trunc(a).astype(np.int64)   # int(): toward zero
+    min_x, max_x = trunc(q[:, 0].min(1)), trunc(q[:, 0].max(1))
+    min_y, max_y = trunc(q[:, 1].min(1)), trunc(q[:, 1].max(1))
+    ow, oh = max_x - min_x + 1, max_y - min_y + 1
+    if canvas_hw is not None:
+        ow, oh = np.minimum(ow, canvas_hw[1]), np.minimum(oh, canvas_hw[0])
+    jobs = np.zeros(B, _cabi.WARP_JOB_DTYPE)
+    jobs["invH"] = np.linalg.inv(H).reshape(B, 9)
+    jobs["x0"], jobs["dx"], jobs["x_last"] = min_x, 1.0, min_x + ow - 1
+    jobs["y0"], jobs["dy"], jobs["y_last"] = min_y, 1.0, min_y + oh - 1
+    jobs["ow"], jobs["oh"] = ow, oh
+    jobs["bw"], jobs["bh"] = iw, ih
+    jobs["iw"], jobs["ih"] = iw, ih
+    sp = iw * channels * src_itemsize
+    jobs["src_pitch"] = sp
+    jobs["src_offset"] = np.arange(B, dtype=np.int64) * (sp * ih)
+    if canvas_hw is not None:
+        dp = canvas_hw[1] * channels * dst_itemsize
+        jobs["dst_pitch"] = dp
+        jobs["dst_offset"] = np.arange(B, dtype=np.int64) * (dp * canvas_hw[0])
+    else:
+        dpitch = ow * channels * dst_itemsize
+        jobs["dst_pitch"] = dpitch
+        sizes = dpitch * oh
+        jobs["dst_offset"] = np.concatenate([[0], np.cumsum(sizes)[:-1]])
+    return jobs, np.stack([min_x, min_y, ow, oh], axis=1)
+
+
+_TORCH_TYPE = {torch.uint8: _cabi.U8, torch.float32: _cabi.F32, torch.float64: _cabi.F64}
+
+
+def warp(src: torch.Tensor, dst: torch.Tensor, jobs: np.ndarray, channels: int = 3, sampler: str = "bilinear"):
+    """K4 over a batch: src / dst are device buffers the jobs' offsets index into."""
+    assert src.is_cuda and dst.is_cuda and jobs.dtype == _cabi.WARP_JOB_DTYPE
+    ctx = _ctx(src)
+    jobs = np.ascontiguousarray(jobs)
+    _cabi.check(ctx.lib.b200geo_warp_dev(ctx.handle, _p(src), _p(dst), _cabi._vp(jobs.ctypes.data), jobs.shape[0],
+                                         channels, _TORCH_TYPE[src.dtype], _TORCH_TYPE[dst.dtype],
+                                         _cabi.SAMPLERS[sampler], _stream(src)))
+    return dst
+
+
+def upload_jobs(jobs: np.ndarray, device) -> torch.Tensor:
+    """Copy a job array to the device once (for repeated launches with b200geo_warp_jobs_dev)."""
+    return torch.from_numpy(np.ascontiguousarray(jobs).view(np.uint8).copy()).to(device)
+
+
+def warp_resident(src, dst, jobs_dev: torch.Tensor, n_jobs: int, max_ow: int, max_oh: int, channels=3, sampler="bilinear"):
+    """K4 with the job array already on the device: no host work per launch."""
+    ctx = _ctx(src)
+    _cabi.check(ctx.lib.b200geo_warp_jobs_dev(ctx.handle, _p(src), _p(dst), _p(jobs_dev), int(n_jobs), int(max_ow),
+                                              int(max_oh), channels, _TORCH_TYPE[src.dtype], _TORCH_TYPE[dst.dtype],
+                                              _cabi.SAMPLERS[sampler], _stream(src)))
+    return dst

@@ -1,0 +1,246 @@
+"""Drop-in for the reference's ``ransac`` module (reference: ransac.py): ``Model``, ``HomoModel``,
+``RANSAC`` and ``stitching`` with the reference's signatures, defaults, return types and side
+effects; hypothesis generation, scoring, selection, inlier mask and refit run on the GPU through
+the C ABI (include/b200geo.h).  No CPU fallback.
+
+Parallel form of the loop (reference ransac.py:176-202): the k sample sets are drawn up front from
+the same global ``np.random`` stream the reference consumes (``randint(0, M, (k, n))`` is
+stream-identical to k sequential ``randint(0, M, n)`` calls), all k hypotheses are solved and
+scored at once, and the winner is the first iteration meeting ``M*d/100 + n`` if any (the
+reference's ``break``), else the lowest-index maximum (the reference's strict ``>``).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _cabi
+from .homography import calcHomographyLinear, calcHomography, stitchPanorama, cylindericlMap  # noqa: F401
+
+LVL = 0
+
+
+def DEBUG(*args):
+    if LVL >= 1:
+        print("[DEBUG]", *args)
+
+
+def _rows(X, Y):
+    """[X (2|3, M), Y (2|3, M)] -> (M, 4) float32 rows (x, y, x', y') for the C ABI."""
+    X, Y = np.asarray(X), np.asarray(Y)
+    out = np.empty((X.shape[1], 4), dtype=np.float32)
+    out[:, 0:2] = X[:2].T
+    out[:, 2:4] = Y[:2].T
+    return out
+
+
+class Model(object):
+    __slots__ = ('val', 'th', 'd', 'n')
+
+    def fit(self, X, Y):
+        raise NotImplementedError
+
+    def fwd(self, X):
+        raise NotImplementedError
+
+    def dist(self, predY, trueY):
+        raise NotImplementedError
+
+
+class HomoModel(Model):
+    """Homography model: threshold th (px), required inlier percentage d, sample size n
+    (reference ransac.py:22-98)."""
+
+    def __init__(self, th=5, d=50, n=4):
+        self.th = th
+        self.d = d
+        self.n = n
+        self.val = np.empty((3, 3), dtype=np.float32)
+
+    def fit(self, X, Y, collective=False):
+        """X, Y: (2|3, 4) -> 4-point solve (float32); (2|3, m>4) with collective=True -> least
+        squares over all columns (float64).  Reference ransac.py:30-53."""
+        nx, mx = X.shape
+        ny, my = Y.shape
+        assert ((mx == my) and (mx == self.n)) or ((mx == my) and (mx > self.n) and collective), "invalid data size should be %d" % self.n
+        assert (nx == ny) and nx in [2, 3], "invalid input dimension for row numbers"
+        if collective:
+            self.val = calcHomographyLinear(X.T[:, :2], Y.T[:, :2], True)
+        else:
+            self.val = calcHomography(X.T[:, :2], Y.T[:, :2], False)
+        return self.val
+
+    def fwd(self, X):
+        """val @ [X;1] / (w + 1e-10), float32 (3, M) (reference ransac.py:55-64)."""
+        nx, mx = X.shape
+        assert nx in [2, 3], "invalid input dimension for row numbers"
+        return _project(self.val, X)
+
+    def reproj(self, Y):
+        """inv(val) @ [Y;1] / (w + 1e-10) (reference ransac.py:66-76)."""
+        ny, my = Y.shape
+        assert ny in [2, 3], "invalid input dimension for row numbers"
+        return _project(np.linalg.inv(self.val), Y)
+
+    def dist(self, predY, trueY):
+        """sqrt(sum((pred - true)^2, axis=0)), float32 (reference ransac.py:78-82)."""
+        a = np.ascontiguousarray(predY, dtype=np.float32)
+        b = np.ascontiguousarray(trueY, dtype=np.float32)
+        assert a.shape == b.shape and a.ndim == 2
+        out = np.empty(a.shape[1], dtype=np.float32)
+        ctx = _cabi.context()
+        _cabi.check(ctx.lib.b200geo_dist_host(ctx.handle, _cabi.ptr(a), _cabi.ptr(b), a.shape[0], a.shape[1], _cabi.ptr(out)))
+        return out
+
+    def computeLoss(self, X, Y, method="reproj"):
+        """Per-point loss of the current model, float32 (M,), on the GPU (reference ransac.py:84-98)."""
+        if method not in _cabi.METHODS:
+            exit("Invalid method!")
+        ctx = _cabi.context()
+        rows = _rows(X, Y)
+        H = np.ascontiguousarray(self.val, dtype=np.float32)
+        Hinv = None
+        if method != "fwd":
+            Hinv = np.ascontiguousarray(np.linalg.inv(np.asarray(self.val, dtype=np.float32)), dtype=np.float32)
+        err = np.empty(rows.shape[0], dtype=np.float32)
+        _cabi.check(ctx.lib.b200geo_loss_host(ctx.handle, _cabi.ptr(rows), rows.shape[0], _cabi.ptr(H),
+                                              _cabi.ptr(Hinv), _cabi.METHODS[method], _cabi.ptr(err)))
+        return err
+
+
+def _project(Hm, P):
+    """(Hm @ [P;1]) / (row 2 + 1e-10) on the GPU: the homogeneous product and divide of
+    HomoModel.fwd / reproj (reference ransac.py:58-64), float32 (3, M)."""
+    P = np.asarray(P)
+    m = P.shape[1]
+    x = np.ones((3, m), dtype=np.float32)
+    x[:P.shape[0], :] = P
+    Hm = np.ascontiguousarray(Hm, dtype=np.float32)
+    out = np.empty((3, m), dtype=np.float32)
+    ctx = _cabi.context()
+    _cabi.check(ctx.lib.b200geo_project_host(ctx.handle, _cabi.ptr(Hm), _cabi.ptr(x), m, _cabi.ptr(out)))
+    return out
+
+
+class RANSAC(object):
+    """reference ransac.py:137-213"""
+
+    __slots__ = ('model', 'th', 'd', 'n', 'k')
+
+    def __init__(self, model, k=1000):
+        self.model = model
+        self.th = model.th
+        self.d = model.d
+        self.n = model.n
+        self.k = k
+
+    def computeLoss(self, X, Y, method="reproj"):
+        return self.model.computeLoss(X, Y, method)
+
+    def run(self, data, method="reproj", *, idx=None, return_details=False):
+        """RANSAC over data = [X (2|3, M), Y (2|3, M)].
+
+        Returns ``(H, inliers, count)`` like the reference: H (3,3) float64 refit on the inliers of
+        the winning hypothesis (also stored in ``model.val``), ``inliers`` the tuple
+        ``(int64 indices,)`` that ``np.where`` returns, ``count`` an ``np.int64``.
+
+        Keyword-only extensions: ``idx`` (k, 4) explicit sample sets instead of drawing from
+        ``np.random``; ``return_details`` appends a dict (winner, per-hypothesis counts, H of the
+        winning sample)."""
+        X, Y = data
+        nx, mx = X.shape
+        ny, my = Y.shape
+        assert mx == my, "data observation not consistent!"
+        if method not in _cabi.METHODS:
+            exit("Invalid method!")
+        assert self.n == 4, "the homography model samples 4 correspondences"
+        d = mx * self.d / 100
+        k = int(self.k)
+        if idx is None:
+            idx = np.random.randint(0, mx, (k, self.n))      # same stream as k draws of n (ransac.py:177)
+        idx = np.ascontiguousarray(idx, dtype=np.int32).reshape(-1, 4)
+        k = idx.shape[0]
+        rows = _rows(X, Y)
+        ctx = _cabi.context()
+        H_best = np.empty(9, np.float32)
+        H = np.empty(9, np.float64)
+        mask = np.empty(mx, np.uint8)
+        winner = np.zeros(1, np.int32)
+        count = np.zeros(1, np.int32)
+        counts = np.empty(k, np.int32)
+        rc = ctx.lib.b200geo_ransac_host(ctx.handle, _cabi.ptr(rows), mx, _cabi.ptr(idx), k, float(np.float32(self.th)),
+                                         float(d + self.n), _cabi.METHODS[method], _cabi.ptr(H_best), _cabi.ptr(H),
+                                         _cabi.ptr(mask), _cabi.ptr(winner), _cabi.ptr(count), _cabi.ptr(counts))
+        if rc == _cabi.ERR_NOMODEL:
+            # the reference reaches np.where(None) here (ransac.py:206)
+            raise ValueError("RANSAC: no hypothesis has any inlier (" + _cabi.last_error() + ")")
+        _cabi.check(rc)
+        w = int(winner[0])
+        totalfitLen = np.int64(count[0])
+        # the reference's warning tests the LAST evaluated iteration's count (ransac.py:203-204)
+        last = w if counts[w] >= (d + self.n) else k - 1
+        if counts[last] < (d + self.n):
+            print("Warning:: fitting model does not exceed required threshold %d vs %d" % (totalfitLen, d + self.n))
+        inliers = np.where(mask.astype(bool))
+        DEBUG("Fitting final model using all inliers")
+        finalModel = H.reshape(3, 3)
+        self.model.val = finalModel
+        if return_details:
+            return finalModel, inliers, totalfitLen, dict(winner=w, counts=counts, H_sample=H_best.reshape(3, 3))
+        return finalModel, inliers, totalfitLen
+
+
+def example0(FILE="matchespoints.npy"):
+    """reference ransac.py:220-232 (the fixture is a pickled dict: allow_pickle is required on numpy >= 1.16.3)"""
+    a = np.load(FILE, allow_pickle=True).tolist()
+    ptsA, ptsB = a['ptsA'].T, a['ptsB'].T
+    model = HomoModel(th=5, d=70, n=4)
+    ransac = RANSAC(model, k=1000)
+    H, inliers, _len = ransac.run([ptsA, ptsB], method="fwd")
+    print(H, _len, '\n')
+    print(0)
+
+
+def stitching(trainImg, queryImg,
+              ransacMet="fwd",
+              th=5,
+              d=70,
+              n=4,
+              k=1000,
+              blending=False,
+              blendrate=0.2,
+              mode=None,
+              override=0,
+              cylinderT=1):
+    """Stitch trainImg into queryImg's frame (reference ransac.py:235-283; called from app.py:364).
+    ORB detection and brute-force Hamming matching stay on OpenCV as in the reference (third-party,
+    SURVEY.md section 8f-2); RANSAC and the backward warp run on the GPU."""
+    import cv2
+    if override == 0:
+        trainImg_gray = cv2.cvtColor(trainImg, cv2.COLOR_RGB2GRAY)
+        queryImg_gray = cv2.cvtColor(queryImg, cv2.COLOR_RGB2GRAY)
+
+        descriptor = cv2.ORB_create()
+        (kpsA, featuresA) = descriptor.detectAndCompute(trainImg_gray, None)
+        (kpsB, featuresB) = descriptor.detectAndCompute(queryImg_gray, None)
+
+        bf = cv2.BFMatcher(cv2.NORM_HAMMING, crossCheck=True)
+        matches = sorted(bf.match(featuresA, featuresB), key=lambda m: m.distance)
+
+        kpsA = np.float32([kp.pt for kp in kpsA])
+        kpsB = np.float32([kp.pt for kp in kpsB])
+        ptsA = np.float32([kpsA[m.queryIdx] for m in matches])
+        ptsB = np.float32([kpsB[m.trainIdx] for m in matches])
+
+        if mode is None:
+            model = HomoModel(th=th, d=d, n=4)
+            ransac = RANSAC(model, k=k)
+            H, inliers, _len = ransac.run([ptsA.T, ptsB.T], method=ransacMet)
+        else:
+            reprojThresh = 4
+            (H, status) = cv2.findHomography(ptsA, ptsB, cv2.RANSAC, reprojThresh)
+
+        imgn = stitchPanorama(queryImg, trainImg, H=H, blending=blending, blendrate=blendrate)
+    else:
+        stitcher = cv2.Stitcher_create()
+        (status, imgn) = stitcher.stitch([trainImg, queryImg])
+    return imgn

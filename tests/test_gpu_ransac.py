@@ -1,0 +1,330 @@
+"""GPU parity tests for the RANSAC half of the hot path (K1 solve, K2 score, K2b select, K3 mask +
+refit), through the C ABI.  Oracle = oracle/ (CPU restatement pinned by the golden vectors).
+
+Tolerances (BASELINE.json north_star): inlier counts / chosen hypothesis bit-exact given the same
+H; homography within 1e-4 relative; everything integer is compared exactly."""
+import numpy as np
+import pytest
+
+import oracle
+from conftest import FIXTURE_CASES, case_method, synth_pair
+
+pytestmark = pytest.mark.gpu
+
+H_RTOL = 1e-4          # north_star: "the homography matches within 1e-4 relative error"
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from ransac_with_homography_b200 import _cabi
+    return _cabi.context(0)
+
+
+def _score(ctx, pts, H, th, method="fwd", Hinv=None):
+    from ransac_with_homography_b200 import _cabi
+    pts = np.ascontiguousarray(pts, np.float32)
+    H = np.ascontiguousarray(H, np.float32).reshape(-1, 9)
+    Hi = None if Hinv is None else np.ascontiguousarray(Hinv, np.float32).reshape(-1, 9)
+    counts = np.empty(H.shape[0], np.int32)
+    _cabi.check(ctx.lib.b200geo_score_host(ctx.handle, _cabi.ptr(pts), pts.shape[0], _cabi.ptr(H), _cabi.ptr(Hi),
+                                           H.shape[0], float(np.float32(th)), _cabi.METHODS[method], _cabi.ptr(counts)))
+    return counts
+
+
+def _dlt4(ctx, pts, idx, want_inv=False):
+    from ransac_with_homography_b200 import _cabi
+    pts = np.ascontiguousarray(pts, np.float32)
+    idx = np.ascontiguousarray(idx, np.int32)
+    K = idx.shape[0]
+    H = np.empty((K, 9), np.float32)
+    Hi = np.empty((K, 9), np.float32) if want_inv else None
+    flags = np.empty(K, np.uint8)
+    _cabi.check(ctx.lib.b200geo_dlt4_host(ctx.handle, _cabi.ptr(pts), pts.shape[0], _cabi.ptr(idx), K, _cabi.ptr(H),
+                                          _cabi.ptr(Hi), _cabi.ptr(flags)))
+    return H.reshape(K, 3, 3), (None if Hi is None else Hi.reshape(K, 3, 3)), flags.astype(bool)
+
+
+# ---------------------------------------------------------------- T1: scoring, bit level
+@pytest.mark.parametrize("name", FIXTURE_CASES)
+def test_score_counts_equal_reference_on_fixture(ctx, golden, name):
+    """Reference per-hypothesis H (golden) -> K2 counts == the reference's counts, exactly."""
+    A, B = golden.points()
+    c = golden.case("ransac_fixture", name)
+    m = case_method(name)
+    pts = oracle.pack_points(A.T, B.T)
+    ok = c["finite"]
+    got = _score(ctx, pts, c["H"], float(c["th"]), m, c["Hinv"] if m != "fwd" else None)
+    assert np.array_equal(got[ok], c["counts"][ok])
+
+
+@pytest.mark.parametrize("name", ["m37", "m2000", "m20000"])
+@pytest.mark.parametrize("method", ["fwd", "reproj"])
+def test_score_counts_equal_reference_on_synthetic(ctx, golden, name, method):
+    z = golden.file("ransac_synth")
+    pts = oracle.pack_points(z[f"{name}__X"], z[f"{name}__Y"])
+    ok = z[f"{name}_{method}__finite"]
+    got = _score(ctx, pts, z[f"{name}_{method}__H"], float(z[f"{name}__th"]), method,
+                 z[f"{name}_{method}__Hinv"] if method != "fwd" else None)
+    assert np.array_equal(got[ok], z[f"{name}_{method}__counts"][ok])
+
+
+@pytest.mark.parametrize("M,K", [(1, 5), (31, 33), (2047, 300), (2049, 257), (5000, 1), (20000, 1500)])
+@pytest.mark.parametrize("method", ["fwd", "backward", "reproj"])
+def test_score_counts_equal_oracle_random(ctx, M, K, method):
+    """Ragged sizes around the tile / block boundaries; H from the GPU solver + perturbed copies
+    so that many points sit near the threshold."""
+    X, Y = synth_pair(7 + M, M)
+    pts = oracle.pack_points(X, Y)
+    rs = np.random.RandomState(M + K)
+    idx = rs.randint(0, M, (K, 4)).astype(np.int32)
+    H, Hinv, flags = _dlt4(ctx, pts, idx, True)
+    good = ~flags & np.isfinite(H).all((1, 2)) & np.isfinite(Hinv).all((1, 2))
+    H, Hinv = H[good], Hinv[good]
+    if len(H) == 0:
+        pytest.skip("all samples degenerate")
+    for th in (0.5, 3.0):
+        want = oracle.score_counts(pts, H, th, Hinv, method)
+        got = _score(ctx, pts, H, th, method, Hinv)
+        assert np.array_equal(got, want)
+
+
+def test_score_threshold_band_is_exact(ctx):
+    """Points constructed to land within a few ulp of the threshold on both sides."""
+    rs = np.random.RandomState(5)
+    M = 4096
+    x = (rs.rand(M) * 1900).astype(np.float32)
+    y = (rs.rand(M) * 1000).astype(np.float32)
+    H = np.array([[0.93, 0.04, 12.5], [-0.03, 1.07, -8.25], [2e-5, -1e-5, 1]], np.float32)
+    th = 3.0
+    q = H.astype(np.float64) @ np.vstack([x, y, np.ones(M)])
+    px, py = q[0] / q[2], q[1] / q[2]
+    ang = rs.rand(M) * 2 * np.pi
+    r = th + (rs.randint(-40, 41, M) * 2.4e-7 * th)          # +-40 ulp(th) around the threshold
+    pts = np.stack([x, y, (px + r * np.cos(ang)).astype(np.float32), (py + r * np.sin(ang)).astype(np.float32)], 1)
+    e = oracle.errors(pts, H, None, "fwd")
+    assert 0.2 < np.mean(e < th) < 0.8                       # the set really straddles the threshold
+    Hs = np.stack([H, H * np.float32(1.0)], 0)
+    got = _score(ctx, pts, Hs, th)
+    assert got[0] == int(np.sum(e < np.float32(th))) == got[1]
+
+
+def test_loss_bit_exact(ctx, golden):
+    from ransac_with_homography_b200.ransac import HomoModel
+    A, B = golden.points()
+    c = golden.case("ransac_fixture", "R_s0")
+    pts = oracle.pack_points(A.T, B.T)
+    for k in (0, 3, 17):
+        if not c["finite"][k]:
+            continue
+        m = HomoModel(th=5)
+        m.val = c["H"][k]
+        for method in ("fwd", "backward", "reproj"):
+            want = oracle.errors(pts, c["H"][k], np.linalg.inv(c["H"][k]), method)
+            got = m.computeLoss(A.T, B.T, method)
+            assert got.dtype == np.float32 and np.array_equal(got.view(np.uint32), want.view(np.uint32))
+        f = m.fwd(A.T)
+        assert f.shape == (3, 185) and f.dtype == np.float32
+        d = m.dist(f[:2], B.T)
+        assert np.array_equal(d.view(np.uint32), oracle.errors(pts, c["H"][k], None, "fwd").view(np.uint32))
+
+
+# ---------------------------------------------------------------- T2: 4-point solve
+def test_dlt4_vs_float64_truth(ctx, golden):
+    A, B = golden.points()
+    c = golden.case("ransac_fixture", "B_s0")
+    pts = oracle.pack_points(A.T, B.T)
+    H, Hinv, flags = _dlt4(ctx, pts, c["idx"], True)
+    T, tflags = oracle.dlt4_f64(pts, c["idx"])
+    assert np.array_equal(flags, tflags)                       # degenerate = repeated index
+    assert np.isnan(H[flags]).all()
+    g = ~flags
+    rel = np.linalg.norm((H[g] - T[g]).reshape(-1, 9), axis=1) / np.linalg.norm(T[g].reshape(-1, 9), axis=1)
+    assert rel.max() < H_RTOL and np.median(rel) < 2e-7
+    # ours must be at least as close to the truth as the reference's float32 SVD is
+    gr = g & c["finite"]
+    ref_rel = np.linalg.norm((c["H"][gr] - T[gr]).reshape(-1, 9), axis=1) / np.linalg.norm(T[gr].reshape(-1, 9), axis=1)
+    our_rel = np.linalg.norm((H[gr] - T[gr]).reshape(-1, 9), axis=1) / np.linalg.norm(T[gr].reshape(-1, 9), axis=1)
+    for q in (0.5, 0.9, 0.99):
+        assert np.quantile(our_rel, q) <= np.quantile(ref_rel, q)
+    # inverse: H @ Hinv ~ I
+    prod = np.einsum("kij,kjl->kil", H[g].astype(np.float64), Hinv[g].astype(np.float64))
+    scale = np.linalg.norm(H[g].reshape(-1, 9), axis=1) * np.linalg.norm(Hinv[g].reshape(-1, 9), axis=1)
+    assert (np.abs(prod - np.eye(3)).reshape(-1, 9).max(1) / scale).max() < 1e-6
+
+
+def test_dlt4_synthetic_and_collinear(ctx):
+    X, Y = synth_pair(1, 20000)
+    pts = oracle.pack_points(X, Y)
+    idx = np.random.RandomState(0).randint(0, 20000, (4096, 4)).astype(np.int32)
+    H, _, flags = _dlt4(ctx, pts, idx)
+    T, tflags = oracle.dlt4_f64(pts, idx)
+    assert np.array_equal(flags, tflags)
+    g = ~flags
+    rel = np.linalg.norm((H[g] - T[g]).reshape(-1, 9), axis=1) / np.linalg.norm(T[g].reshape(-1, 9), axis=1)
+    assert np.quantile(rel, 0.99) < 1e-6 and rel.max() < H_RTOL
+    # exactly collinear source points: singular system -> flagged, NaN (the reference's Linear path raises)
+    p = np.array([[0, 0, 1, 1], [1, 1, 2, 3], [2, 2, 5, 4], [3, 3, 7, 9]], np.float32)
+    Hc, _, fc = _dlt4(ctx, p, np.array([[0, 1, 2, 3]], np.int32))
+    assert fc[0] or not np.isfinite(Hc).all() or np.abs(Hc).max() > 1e6
+
+
+def test_calc_homography_api(golden):
+    from ransac_with_homography_b200 import homography as hg
+    s = golden.file("solves")
+    H = hg.calcHomographyLinear(s["u"], s["v"])
+    assert H.shape == (3, 3) and H.dtype == np.float64 and H[2, 2] == 1.0
+    q = H @ np.vstack([s["u"].T, np.ones(4)])
+    assert np.abs(q[:2] / q[2] - s["v"].T).max() < 1e-9      # regression.ipynb:22938-22952: <= 0.02 px
+    np.testing.assert_allclose(H, s["H_linear"], rtol=2e-3, atol=2e-3)   # reference float32 normal eq.
+    Hs = hg.calcHomography(s["u"].astype(np.float32), s["v"].astype(np.float32))
+    assert Hs.dtype == np.float32 and Hs.shape == (3, 3)
+    np.testing.assert_allclose(Hs, s["H_svd"], rtol=H_RTOL, atol=1e-4)
+    H2 = hg.calcHomographyLinear(s["u2"], s["v2"])
+    np.testing.assert_allclose(H2, s["H2_linear"], rtol=2e-3, atol=2e-3)
+    with pytest.raises(np.linalg.LinAlgError):
+        hg.calcHomographyLinear(np.array([[0, 0], [1, 1], [2, 2], [3, 3.0]]), np.array([[0, 0], [1, 0], [1, 1], [0, 1.0]]))
+
+
+# ---------------------------------------------------------------- T3/T4: whole run
+@pytest.mark.parametrize("name", FIXTURE_CASES)
+def test_ransac_run_against_oracle_and_reference(ctx, golden, name):
+    from ransac_with_homography_b200.ransac import HomoModel, RANSAC
+    A, B = golden.points()
+    c = golden.case("ransac_fixture", name)
+    m = case_method(name)
+    th, d, k = float(c["th"]), float(c["d"]), int(c["k"])
+    model = HomoModel(th=th, d=d, n=4)
+    H, inl, cnt, det = RANSAC(model, k=k).run([A.T, B.T], method=m, idx=c["idx"], return_details=True)
+    # return contract (ransac.py:213)
+    assert H.shape == (3, 3) and H.dtype == np.float64 and model.val is H
+    assert isinstance(inl, tuple) and len(inl) == 1 and inl[0].dtype == np.int64 and isinstance(cnt, np.int64)
+    pts = oracle.pack_points(A.T, B.T)
+    # (a) internal consistency with the oracle, exact: counts from OUR H, selection rule, mask
+    ctx_H, ctx_Hi, flags = _dlt4(ctx, pts, c["idx"], True)
+    live = ~flags
+    want = np.zeros(k, np.int32)
+    want[live] = oracle.score_counts(pts, ctx_H[live], th, ctx_Hi[live] if m != "fwd" else None, m)
+    assert np.array_equal(det["counts"], want)
+    win, best, _ = oracle.select(want, 185, d)
+    assert det["winner"] == win and int(cnt) == best
+    mask = oracle.inlier_mask(pts, det["H_sample"], th, ctx_Hi[win] if m != "fwd" else None, m)
+    assert np.array_equal(inl[0], np.where(mask)[0])
+    # (b) refit == float64 least squares over those inliers
+    T = oracle.refit_f64(pts, mask)
+    assert np.linalg.norm(H - T) / np.linalg.norm(T) < H_RTOL
+    # (c) against the reference's own run: its per-hypothesis H come from a float32 SVD, so counts
+    # differ on a small fraction of hypotheses; census, not equality
+    ok = c["finite"] & live
+    diff = det["counts"][ok] != c["counts"][ok]
+    assert diff.mean() < 0.03
+    assert np.abs(det["counts"][ok].astype(int) - c["counts"][ok]).max() <= 6
+    assert abs(int(cnt) - int(c["run_count"])) <= 2
+    jac = len(np.intersect1d(inl[0], c["run_inliers"])) / len(np.union1d(inl[0], c["run_inliers"]))
+    assert jac > 0.9
+
+
+def test_ransac_run_global_rng_and_warning(golden, capsys):
+    """Drawing from np.random inside run() consumes the same stream as the reference."""
+    from ransac_with_homography_b200.ransac import HomoModel, RANSAC
+    A, B = golden.points()
+    c = golden.case("ransac_fixture", "A_s2")
+    np.random.seed(2)
+    H, inl, cnt, det = RANSAC(HomoModel(th=5, d=70, n=4), k=1000).run([A.T, B.T], method="fwd", return_details=True)
+    H2, inl2, cnt2, det2 = RANSAC(HomoModel(th=5, d=70, n=4), k=1000).run([A.T, B.T], method="fwd", idx=c["idx"], return_details=True)
+    assert np.array_equal(det["counts"], det2["counts"]) and cnt == cnt2 and np.array_equal(H, H2)
+    out = capsys.readouterr().out
+    assert "Warning:: fitting model does not exceed required threshold" in out      # 120 < 133.5 (ransac.py:203-204)
+
+
+def test_ransac_no_model_raises():
+    from ransac_with_homography_b200.ransac import HomoModel, RANSAC
+    rs = np.random.RandomState(0)
+    X = (rs.rand(2, 50) * 1000).astype(np.float32)
+    Y = (rs.rand(2, 50) * 1000).astype(np.float32)
+    idx = np.zeros((8, 4), np.int32)            # every sample degenerate -> all counts 0
+    with pytest.raises(ValueError):
+        RANSAC(HomoModel(th=1e-3, d=50), k=8).run([X, Y], method="fwd", idx=idx)
+
+
+def test_refit_matches_lstsq_and_handles_exact_data(ctx):
+    from ransac_with_homography_b200 import homography as hg
+    rs = np.random.RandomState(11)
+    Ht = np.array([[1.02, -0.03, 55.0], [0.04, 0.97, -31.0], [3e-5, -2e-5, 1]])
+    for n, noise in ((4, 0.0), (5, 0.0), (60, 0.7), (5000, 0.5)):
+        u = rs.rand(n, 2) * [1920, 1080]
+        q = Ht @ np.vstack([u.T, np.ones(n)])
+        v = (q[:2] / q[2]).T + rs.randn(n, 2) * noise
+        pts = np.concatenate([u, v], 1).astype(np.float32)
+        H = hg.calcHomographyLinear(pts[:, :2], pts[:, 2:], True)
+        T = oracle.refit_f64(pts, np.ones(n, bool))
+        assert np.linalg.norm(H - T) / np.linalg.norm(T) < (1e-6 if noise == 0 else H_RTOL)
+    with pytest.raises(np.linalg.LinAlgError):
+        hg.calcHomographyLinear(np.zeros((3, 2)), np.ones((3, 2)), True)
+
+
+# ---------------------------------------------------------------- device-resident / batched / large
+def test_device_api_matches_host_api(golden):
+    import torch
+    from ransac_with_homography_b200 import device
+    from ransac_with_homography_b200.ransac import HomoModel, RANSAC
+    X, Y = synth_pair(3, 2000)
+    pts = oracle.pack_points(X, Y)
+    idx = np.random.RandomState(9).randint(0, 2000, (8192, 4)).astype(np.int32)
+    H, inl, cnt, det = RANSAC(HomoModel(th=4, d=95, n=4), k=8192).run([X, Y], method="fwd", idx=idx, return_details=True)
+    tp, ti = torch.from_numpy(pts).cuda(), torch.from_numpy(idx).cuda()
+    counts = torch.zeros(8192, dtype=torch.int32, device="cuda")
+    res, mask = device.ransac(tp, ti, 4, 95, counts=counts)
+    res = res.cpu().numpy()
+    assert int(res[0]) == det["winner"] and int(res[1]) == int(cnt) and int(res[2]) == 0
+    assert np.array_equal(counts.cpu().numpy(), det["counts"])
+    assert np.array_equal(res[12:21].reshape(3, 3), H)
+    assert np.array_equal(np.where(mask.cpu().numpy())[0], inl[0])
+    # sharded search (as ranks would run it) + max of keys == unsharded
+    keys = [device.ransac_search(tp, ti, a, b, 4, 2000 * 95 / 100 + 4).clone() for a, b in
+            (device.shard_range(8192, r, 4) for r in range(4))]
+    red = torch.stack(keys).max(0).values
+    res2, _ = device.ransac_finish(tp, ti, red, 4)
+    assert np.array_equal(res2.cpu().numpy()[:21], res[:21])
+    # batched: 3 pairs == 3 single runs
+    Xs = [synth_pair(20 + b, 2000) for b in range(3)]
+    P = np.stack([oracle.pack_points(x, y) for x, y in Xs])
+    I = np.stack([np.random.RandomState(b).randint(0, 2000, (1024, 4)).astype(np.int32) for b in range(3)])
+    R, Mk = device.ransac_batched(torch.from_numpy(P).cuda(), torch.from_numpy(I).cuda(), 4, 95)
+    for b in range(3):
+        Hb, inlb, cntb, detb = RANSAC(HomoModel(th=4, d=95, n=4), k=1024).run(list(Xs[b]), method="fwd", idx=I[b], return_details=True)
+        r = R[b].cpu().numpy()
+        assert int(r[0]) == detb["winner"] and int(r[1]) == int(cntb) and np.array_equal(r[12:21].reshape(3, 3), Hb)
+        assert np.array_equal(np.where(Mk[b].cpu().numpy())[0], inlb[0])
+
+
+def test_full_size_single_pair_properties():
+    """BASELINE config 3 at full size (20k correspondences, 1M sample sets): the oracle cannot score
+    2e10 pairs in seconds, so check (a) a random sample of 512 hypotheses bit-exactly, (b) the
+    selection keys against numpy on the full count vector, (c) the known structure of the answer."""
+    import torch
+    from ransac_with_homography_b200 import device
+    M, K = 20000, 1_000_000
+    X, Y = synth_pair(1, M)
+    pts = oracle.pack_points(X, Y)
+    idx = np.random.RandomState(0).randint(0, M, (K, 4)).astype(np.int32)
+    tp, ti = torch.from_numpy(pts).cuda(), torch.from_numpy(idx).cuda()
+    counts = torch.zeros(K, dtype=torch.int32, device="cuda")
+    res, mask = device.ransac(tp, ti, 3.0, 99, counts=counts)
+    cn = counts.cpu().numpy()
+    r = res.cpu().numpy()
+    pick = np.random.RandomState(1).choice(K, 512, replace=False)
+    Hs, _, fl = device.dlt4(tp, torch.from_numpy(idx[pick]).cuda())
+    Hs, fl = Hs.cpu().numpy(), fl.cpu().numpy().astype(bool)
+    want = np.zeros(512, np.int32)
+    want[~fl] = oracle.score_counts(pts, Hs[~fl], 3.0)
+    assert np.array_equal(cn[pick], want)
+    win, best, _ = oracle.select(cn, M, 99)
+    assert int(r[0]) == win and int(r[1]) == best == cn.max()
+    assert 9900 < best < 10300                                    # ~50% inliers of 20k (~10100)
+    assert int(mask.sum()) == best
+    Ht = np.array([[0.9, 0.05, 30], [-0.04, 1.1, -20], [1e-5, -2e-5, 1]])
+    assert np.linalg.norm(r[12:21].reshape(3, 3) - Ht) / np.linalg.norm(Ht) < 1e-3
+    # early exit variant: d = 45 -> first hypothesis reaching 9004 inliers wins
+    res2, _ = device.ransac(tp, ti, 3.0, 45)
+    first = int(np.argmax(cn >= M * 45 / 100 + 4))
+    assert int(res2.cpu().numpy()[0]) == first

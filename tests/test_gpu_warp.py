@@ -1,0 +1,208 @@
+"""GPU parity tests for the backward warp (K4) through the C ABI and the drop-in Python API.
+Golden vectors = outputs of the live reference; tolerance per BASELINE.json north_star:
+warped pixels within +-1 on uint8 (the float64 kernel is expected to be exact)."""
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+WARP_H = ["stitch", "rot", "shrink", "shift"]
+U8_TOL = 1     # north_star: "warped pixels match within +-1 on uint8"
+
+
+def _maxdiff(a, b):
+    return int(np.abs(a.astype(np.int16) - b.astype(np.int16)).max()) if a.size else 0
+
+
+@pytest.mark.parametrize("name", WARP_H)
+@pytest.mark.parametrize("conv", ["nn", "bilinear"])
+def test_wrap_perspective_matches_reference(golden, name, conv):
+    from ransac_with_homography_b200 import homography as hg
+    w = golden.file("warps")
+    img = w["img"].copy()
+    out, mx, my = hg.wrapPerspective(img, w[f"H_{name}"], conv)
+    assert [mx, my] == w[f"bbox_{name}_{conv}_off"].tolist()
+    assert (img[0, 0] == 0).all()                         # side effect of the reference's samplers
+    assert out.dtype == (np.uint8 if conv == "nn" else np.float64)
+    got = out.astype(np.uint8)
+    ref = w[f"bbox_{name}_{conv}"]
+    assert got.shape == ref.shape
+    assert _maxdiff(got, ref) <= (0 if conv == "nn" else U8_TOL)
+    assert np.mean(got != ref) < 1e-4
+    if conv == "bilinear":
+        o64, _, _ = oracle.wrapPerspective(w["img"], w[f"H_{name}"], conv)
+        np.testing.assert_allclose(out, o64, rtol=0, atol=1e-9)
+
+
+@pytest.mark.parametrize("name", WARP_H)
+def test_transform_image_h_matches_reference(golden, name):
+    from ransac_with_homography_b200 import homography as hg
+    w = golden.file("warps")
+    out, mx, my = hg.transformImageH(w["img"].copy(), w[f"H_{name}"])
+    assert out.dtype == np.uint8 and [mx, my] == w[f"bbox_{name}_bilinear_off"].tolist()
+    assert _maxdiff(out, w[f"tih_{name}"]) <= U8_TOL and np.mean(out != w[f"tih_{name}"]) < 1e-4
+
+
+def test_rgba_float_warp_matches_reference(golden):
+    from ransac_with_homography_b200 import homography as hg
+    w = golden.file("warps")
+    rgba = np.zeros(w["img"].shape[:2] + (4,), np.float32)
+    rgba[:, :, :3] = w["img"]
+    rgba[:, :, 3] = 0.2 + 1e-10
+    out, mx, my = hg.transformImageH(rgba, w["H_stitch"])
+    assert out.dtype == np.float64 and out.shape == w["bbox_stitch_rgba"].shape
+    np.testing.assert_allclose(out, w["bbox_stitch_rgba"], rtol=0, atol=1e-9)
+
+
+@pytest.mark.parametrize("tag", ["s1", "s2"])
+@pytest.mark.parametrize("conv", ["nn", "bilinear"])
+def test_scanner_matches_reference(golden, tag, conv):
+    from ransac_with_homography_b200 import homography as hg
+    w = golden.file("warps")
+    u, v = w[f"scan_{tag}_u"], w[f"scan_{tag}_v"]
+    res = [int(v[1, 2]), int(v[0, 2])]
+    # same H to both sides: the Scan-form warp
+    out, mx, my = hg.wrapPerspectiveScan(w["img"].copy(), w[f"scan_{tag}_H"], res, conv)
+    assert (mx, my) == (0, 0)
+    got = out.astype(np.uint8)
+    assert _maxdiff(got, w[f"scan_{tag}_{conv}"]) <= (0 if conv == "nn" else U8_TOL)
+    assert np.mean(got != w[f"scan_{tag}_{conv}"]) < 1e-4
+    # whole Scanner call (our own float64 4-point solve; the reference's is float32 normal equations,
+    # ~8e-3 px of source displacement): +-1 except at nn rounding boundaries / strong edges
+    ti = hg.transformImage(w["img"].copy(), u, v, box=res, method=conv)
+    ref = w[f"scan_{tag}_{conv}_ti"]
+    assert ti.dtype == np.uint8 and ti.shape == ref.shape
+    frac = np.mean(np.abs(ti.astype(np.int16) - ref.astype(np.int16)) > U8_TOL)
+    assert frac < (0.02 if conv == "nn" else 0.002)
+
+
+def test_transform_image_without_box(golden):
+    from ransac_with_homography_b200 import homography as hg
+    w = golden.file("warps")
+    ti = hg.transformImage(w["img"].copy(), w["scan_s1_u"], w["scan_s1_v"])
+    ref = w["scan_s1_ti_nobox"]
+    assert ti.shape == ref.shape and ti.dtype == np.uint8
+    assert np.mean(np.abs(ti.astype(np.int16) - ref.astype(np.int16)) > U8_TOL) < 0.002
+
+
+@pytest.mark.parametrize("name", ["pp", "nn_", "np_", "pn_"])
+def test_stitch_panorama_matches_reference(golden, name, capsys):
+    from ransac_with_homography_b200 import homography as hg
+    w = golden.file("warps")
+    H = w[f"pano_{name}_H"]
+    paste = hg.stitchPanorama(w["img2"].copy(), w["img"].copy(), H)
+    assert paste.dtype == np.uint8 and paste.shape == w[f"pano_{name}_paste"].shape
+    assert _maxdiff(paste, w[f"pano_{name}_paste"]) <= U8_TOL
+    blend = hg.stitchPanorama(w["img2"].copy(), w["img"].copy(), H, blending="Rate", blendrate=0.2)
+    assert blend.shape == w[f"pano_{name}_blend"].shape
+    assert _maxdiff(blend, w[f"pano_{name}_blend"]) <= U8_TOL
+    capsys.readouterr()
+
+
+def test_samplers_on_explicit_coordinates(golden):
+    from ransac_with_homography_b200 import homography as hg
+    w = golden.file("warps")
+    img = w["img"]
+    h, wd = img.shape[:2]
+    rs = np.random.RandomState(2)
+    n = 37 * 41
+    z = np.vstack([rs.rand(n) * (wd + 20) - 10, rs.rand(n) * (h + 20) - 10, np.ones(n)])
+    z[0, :5] = [0.0, wd - 1.0, -0.4, wd - 0.6, -1.49]       # edge rows of SURVEY A.5
+    z[1, :5] = [0.0, 3.0, 2.0, 2.0, 7.0]
+    for name, fn in (("nn", hg.nearestNeighbor), ("bilinear", hg.bilinear)):
+        got = fn(z.copy(), img.copy(), h, wd, 37, 41)
+        inv = np.eye(3)
+        want = oracle.warp(img, inv, z[0], np.array([0.0]), (h, wd), name)   # placeholder shape, replaced below
+        # oracle over explicit coordinates: one row per point via a 1 x n grid is not expressible, so
+        # evaluate point by point through a degenerate grid
+        want = np.stack([oracle.warp(img, inv, z[0, i:i + 1], z[1, i:i + 1], (h, wd), name)[0, 0] for i in range(n)])
+        want = want.reshape(37, 41, 3)
+        if name == "nn":
+            assert got.dtype == np.uint8 and np.array_equal(got, want.astype(np.uint8))
+        else:
+            assert got.dtype == np.float64
+            np.testing.assert_allclose(got, want, rtol=0, atol=1e-9)
+
+
+def test_edge_semantics():
+    """A.5/A.6 quirks: pixel (0,0) reads 0; nn truncation x in (-1.5,-0.5] -> column 0 only from -0.5;
+    taps beyond the image read 0 where the reference would raise; Scan bounds are `res`."""
+    from ransac_with_homography_b200 import homography as hg
+    img = (np.arange(6 * 8 * 3).reshape(6, 8, 3) % 251 + 3).astype(np.uint8)
+    T = np.array([[1.0, 0, 0], [0, 1, 0], [0, 0, 1]])
+    out, mx, my = hg.wrapPerspective(img.copy(), T, "nn")
+    want = img.copy()
+    want[0, 0] = 0
+    assert (mx, my) == (0, 0) and np.array_equal(out, want)
+    # identity + bilinear: x == w-1 exactly -> the reference raises IndexError; here the zero-weight tap reads 0
+    outb, _, _ = hg.wrapPerspective(img.copy(), T, "bilinear")
+    assert np.array_equal(outb.astype(np.uint8), want)
+    o, _, _ = oracle.wrapPerspective(img, T, "bilinear")
+    assert np.array_equal(outb, o)
+    # Scan form with res larger than the image: coordinates between image and res read 0
+    S = np.array([[1.0, 0, 0], [0, 1, 0], [0, 0, 1]])
+    outs, _, _ = hg.wrapPerspectiveScan(img.copy(), S, [9, 12], "bilinear")
+    os_, _, _ = oracle.wrapPerspectiveScan(img, S, [9, 12], "bilinear")
+    assert outs.shape == (9, 12, 3) and np.array_equal(outs, os_)
+    # singular-ish map: w crosses zero inside the grid -> inf / NaN coordinates are masked
+    P = np.array([[1.0, 0, 0], [0, 1, 0], [-0.3, 0, 1]])
+    outp, _, _ = hg.wrapPerspectiveScan(img.copy(), P, [6, 8], "nn")
+    op, _, _ = oracle.wrapPerspectiveScan(img, P, [6, 8], "nn")
+    assert np.array_equal(outp, op.astype(np.uint8))
+
+
+def test_batched_device_warp_and_round_trip():
+    """Batched, device-resident K4 (config 4 shape at reduced size) vs the oracle, plus a
+    size-independent property at full 1080p: an integer nn shift followed by its inverse
+    reproduces the interior of the frame exactly."""
+    import torch
+    from ransac_with_homography_b200 import device
+    rs = np.random.RandomState(4)
+    B, h, w = 5, 90, 160
+    frames = rs.randint(0, 256, (B, h, w, 3)).astype(np.uint8)
+    Hs = []
+    for b in range(B):
+        src = np.array([[0, 0], [w, 0], [w, h], [0, h]], np.float64)
+        dst = src + rs.uniform(-0.05, 0.05, (4, 2)) * [w, h]
+        pts = np.concatenate([src, dst], 1).astype(np.float32)
+        Hs.append(oracle.dlt4_f64(pts, np.array([[0, 1, 2, 3]], np.int32))[0][0])
+    Hs = np.stack(Hs)
+    src_t = torch.from_numpy(frames).cuda()
+    for sampler in ("nn", "bilinear"):
+        jobs = device.scan_jobs(Hs, (h, w), (h, w))
+        dst_t = torch.zeros((B, h, w, 3), dtype=torch.uint8, device="cuda")
+        device.warp(src_t, dst_t, jobs, 3, sampler)
+        got = dst_t.cpu().numpy()
+        for b in range(B):
+            want = oracle.to_u8(oracle.wrapPerspectiveScan(frames[b], Hs[b], [h, w], sampler)[0])
+            assert _maxdiff(got[b], want) <= (0 if sampler == "nn" else U8_TOL)
+            assert np.mean(got[b] != want) < 1e-4
+        # bbox form, packed outputs
+        jb, boxes = device.bbox_jobs(Hs, (h, w))
+        total = int((jb["dst_pitch"] * jb["oh"]).sum())
+        out_t = torch.zeros(total, dtype=torch.uint8, device="cuda")
+        device.warp(src_t, out_t, jb, 3, sampler)
+        flat = out_t.cpu().numpy()
+        for b in range(B):
+            o, mx, my = oracle.wrapPerspective(frames[b], Hs[b], sampler)
+            assert boxes[b].tolist() == [mx, my, o.shape[1], o.shape[0]]
+            g = flat[jb["dst_offset"][b]: jb["dst_offset"][b] + o.size].reshape(o.shape)
+            assert _maxdiff(g, oracle.to_u8(o)) <= (0 if sampler == "nn" else U8_TOL)
+    # full-size property: 1080p frame, integer shift by (+37, -21) and back, nn
+    big = torch.randint(0, 256, (1, 1080, 1920, 3), dtype=torch.uint8, device="cuda")
+    S = np.array([[[1.0, 0, 37], [0, 1, -21], [0, 0, 1]]])
+    j1 = device.scan_jobs(S, (1080, 1920), (1080, 1920))
+    # Scan grids sample at c*w/(w-1); use the bbox form (integer grid) for an exact round trip
+    j1, box1 = device.bbox_jobs(S, (1080, 1920))
+    mid = torch.zeros((int(box1[0][3]), int(box1[0][2]), 3), dtype=torch.uint8, device="cuda")
+    device.warp(big, mid, j1, 3, "nn")
+    j2, box2 = device.bbox_jobs(np.linalg.inv(S), tuple(mid.shape[:2]))
+    back = torch.zeros((int(box2[0][3]), int(box2[0][2]), 3), dtype=torch.uint8, device="cuda")
+    device.warp(mid, back, j2, 3, "nn")
+    a = big[0].cpu().numpy()
+    bk = back.cpu().numpy()
+    assert box1[0][:2].tolist() == [37, -21] and box2[0][:2].tolist() == [-37, 21]
+    # mid[r, c] = big[r, c] (offset folded into min_x/min_y); interior must survive the round trip
+    assert np.array_equal(bk[2:1000, 2:1800], a[2:1000, 2:1800])
