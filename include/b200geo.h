@@ -66,6 +66,13 @@ int b200geo_destroy(b200geo_ctx *ctx);
 int b200geo_device_info(b200geo_ctx *ctx, int *sm_count, int *cc, int *clock_khz, size_t *mem_bytes);
 /* number of kernels this context has launched since creation (bench.py's gpu_launches) */
 int64_t b200geo_launch_count(b200geo_ctx *ctx);
+/* Number of (hypothesis, correspondence) pairs whose inlier decision fell inside the rounding shell
+ * around the threshold and was therefore taken by the reference-order chain (the "reported" band
+ * hits); cumulative since creation or the last reset.  Synchronises the device. */
+int b200geo_stats(b200geo_ctx *ctx, unsigned long long *exact_path_pairs, int reset);
+/* options */
+#define B200GEO_OPT_FORCE_EXACT 1   /* value != 0: score every pair with the reference-order chain */
+int b200geo_set_option(b200geo_ctx *ctx, int option, int value);
 /* blocks until all work of this context on `stream` is done */
 int b200geo_sync(b200geo_ctx *ctx, void *stream);
 

@@ -60,6 +60,8 @@ SIGNATURES = {
     "b200geo_device_info": (_i, [_vp, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_sz)]),
     "b200geo_launch_count": (C.c_int64, [_vp]),
     "b200geo_sync": (_i, [_vp, _vp]),
+    "b200geo_stats": (_i, [_vp, C.POINTER(C.c_ulonglong), _i]),
+    "b200geo_set_option": (_i, [_vp, _i, _i]),
     "b200geo_dlt4_dev": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp]),
     "b200geo_dlt4_host": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp]),
     "b200geo_homography4_host": (_i, [_vp, _vp, _vp, _vp]),
@@ -139,6 +141,15 @@ class Context:
 
     def launch_count(self) -> int:
         return int(self.lib.b200geo_launch_count(self.handle))
+
+    def exact_path_pairs(self, reset: bool = False) -> int:
+        """Pairs scored by the reference-order chain because they fell inside the threshold shell."""
+        v = C.c_ulonglong(0)
+        check(self.lib.b200geo_stats(self.handle, C.byref(v), int(reset)))
+        return int(v.value)
+
+    def force_exact(self, on: bool) -> None:
+        check(self.lib.b200geo_set_option(self.handle, 1, int(on)))
 
     def sync(self, stream=None) -> None:
         check(self.lib.b200geo_sync(self.handle, _vp(stream or 0)))

@@ -73,6 +73,26 @@ int b200geo_device_info(b200geo_ctx *ctx, int *sm_count, int *cc, int *clock_khz
 
 int64_t b200geo_launch_count(b200geo_ctx *ctx) { return ctx ? ctx->launches : -1; }
 
+int b200geo_stats(b200geo_ctx *ctx, unsigned long long *exact_path_pairs, int reset)
+{
+    B2G_ENTER(ctx);
+    unsigned long long v[2] = {0, 0};
+    if (ctx->scratch_cap[S_STATS]) {
+        B2G_CUDA(cudaDeviceSynchronize());
+        B2G_CUDA(cudaMemcpy(v, ctx->scratch[S_STATS], 16, cudaMemcpyDeviceToHost));
+        if (reset) B2G_CUDA(cudaMemset(ctx->scratch[S_STATS], 0, 16));
+    }
+    if (exact_path_pairs) *exact_path_pairs = v[0];
+    return B200GEO_OK;
+}
+
+int b200geo_set_option(b200geo_ctx *ctx, int option, int value)
+{
+    B2G_ARG(ctx != nullptr);
+    if (option == B200GEO_OPT_FORCE_EXACT) { ctx->force_exact = value; return B200GEO_OK; }
+    return fail(B200GEO_ERR_ARG, "unknown option%s%s");
+}
+
 int b200geo_sync(b200geo_ctx *ctx, void *stream)
 {
     B2G_ENTER(ctx);
@@ -98,11 +118,11 @@ int launch_dlt4(b200geo_ctx *ctx, const float *pts, int M, const int32_t *idx, i
     return B200GEO_OK;
 }
 
-int launch_score(b200geo_ctx *ctx, const float *pts, int M, const float *H, const float *Hinv, const uint8_t *flags,
-                 int k_begin, int k_end, int K_stride, int B, float th, int method, int32_t *counts, cudaStream_t st)
+// exact kernel: any method, any threshold
+int launch_score_exact(b200geo_ctx *ctx, const float *pts, int M, const float *H, const float *Hinv, const uint8_t *flags,
+                       int k_begin, int k_end, int K_stride, int B, float th, int method, int32_t *counts, cudaStream_t st)
 {
     int nk = k_end - k_begin;
-    if (nk <= 0 || B <= 0) return B200GEO_OK;
     int gx = (nk + SCORE_THREADS - 1) / SCORE_THREADS;
     // split the correspondence range when there are too few hypothesis blocks to fill the GPU
     int splits = 1;
@@ -118,7 +138,6 @@ int launch_score(b200geo_ctx *ctx, const float *pts, int M, const float *H, cons
     splits = M > 0 ? (M + per - 1) / per : 1;
     if (splits < 1) splits = 1;
     if (splits > 1) {
-        // zero only the range being written, per batch row
         for (int b = 0; b < B; ++b)
             B2G_CUDA(cudaMemsetAsync(counts + (size_t)b * K_stride + k_begin, 0, sizeof(int32_t) * (size_t)nk, st));
     }
@@ -135,6 +154,55 @@ int launch_score(b200geo_ctx *ctx, const float *pts, int M, const float *H, cons
         score_exact_kernel<B200GEO_REPROJ><<<grid, SCORE_THREADS, 0, st>>>(p4, M, H, Hinv, flags, k_begin, k_end, K_stride, th, per, counts);
         break;
     }
+    B2G_CHECK_LAUNCH(ctx);
+    return B200GEO_OK;
+}
+
+// K2.  fwd / backward with a positive finite threshold take the division-free FFMA2 kernel (exact
+// chain only inside the ambiguity shell); everything else takes the exact kernel.
+int launch_score(b200geo_ctx *ctx, const float *pts, int M, const float *H, const float *Hinv, const uint8_t *flags,
+                 int k_begin, int k_end, int K_stride, int B, float th, int method, int32_t *counts, cudaStream_t st)
+{
+    int nk = k_end - k_begin;
+    if (nk <= 0 || B <= 0) return B200GEO_OK;
+    const bool fast_ok = (method == B200GEO_FWD || method == B200GEO_BACKWARD) && th > 0.f && th < 1.0e15f && M > 0 &&
+                         !ctx->force_exact;
+    if (!fast_ok) return launch_score_exact(ctx, pts, M, H, Hinv, flags, k_begin, k_end, K_stride, B, th, method, counts, st);
+
+    float *cmax;
+    unsigned long long *stats;
+    int rc;
+    if ((rc = scratch(ctx, S_CMAX, sizeof(float) * (size_t)B, (void **)&cmax))) return rc;
+    if (ctx->scratch_cap[S_STATS] == 0) {
+        if ((rc = scratch(ctx, S_STATS, 16, (void **)&stats))) return rc;
+        B2G_CUDA(cudaMemsetAsync(stats, 0, 16, st));
+    }
+    stats = (unsigned long long *)ctx->scratch[S_STATS];
+    cmax_kernel<<<B, 256, 0, st>>>((const float4 *)pts, M, cmax);
+    B2G_CHECK_LAUNCH(ctx);
+
+    const int per_cta = FAST_THREADS * FAST_T;
+    int gx = (nk + per_cta - 1) / per_cta;
+    long long blocks = (long long)gx * B;
+    long long want = 16LL * 2 * ctx->sm_count;                      // >= 16 waves at 2 CTAs per SM
+    int max_splits = (M + FAST_TILE - 1) / FAST_TILE;
+    int splits = 1;
+    if (blocks < want) {
+        splits = (int)((want + blocks - 1) / blocks);
+        if (splits > max_splits) splits = max_splits;
+    }
+    int per = (M + splits - 1) / splits;
+    per = ((per + FAST_TILE - 1) / FAST_TILE) * FAST_TILE;
+    splits = (M + per - 1) / per;
+    if (splits > 1) {
+        for (int b = 0; b < B; ++b)
+            B2G_CUDA(cudaMemsetAsync(counts + (size_t)b * K_stride + k_begin, 0, sizeof(int32_t) * (size_t)nk, st));
+    }
+    dim3 grid(gx, splits, B);
+    if (method == B200GEO_FWD)
+        score_fast_kernel<B200GEO_FWD><<<grid, FAST_THREADS, 0, st>>>((const float4 *)pts, M, H, flags, k_begin, k_end, K_stride, th, cmax, per, counts, stats);
+    else
+        score_fast_kernel<B200GEO_BACKWARD><<<grid, FAST_THREADS, 0, st>>>((const float4 *)pts, M, Hinv, flags, k_begin, k_end, K_stride, th, cmax, per, counts, stats);
     B2G_CHECK_LAUNCH(ctx);
     return B200GEO_OK;
 }

@@ -39,7 +39,7 @@ inline int fail(int code, const char *fmt, const char *a = "", const char *b = "
     } while (0)
 
 enum ScratchSlot {
-    S_PTS = 0, S_IDX, S_H, S_HINV, S_FLAGS, S_COUNTS, S_KEYS, S_RESULT, S_MASK, S_JOBS, S_SRC, S_DST, S_MISC,
+    S_PTS = 0, S_IDX, S_H, S_HINV, S_FLAGS, S_COUNTS, S_KEYS, S_RESULT, S_MASK, S_JOBS, S_SRC, S_DST, S_MISC, S_CMAX, S_STATS,
     S_NUM
 };
 
@@ -52,6 +52,7 @@ struct b200geo_ctx {
     int clock_khz;
     size_t mem_bytes;
     int64_t launches;
+    int force_exact;       // B200GEO_OPT_FORCE_EXACT: score with the reference-order chain only
     void *scratch[b200geo::S_NUM];
     size_t scratch_cap[b200geo::S_NUM];
     void *pinned;          // small pinned staging block for scalar results

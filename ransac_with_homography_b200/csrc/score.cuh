@@ -88,6 +88,223 @@ score_exact_kernel(const float4 *__restrict__ pts, int M, const float *__restric
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Fast scoring kernel (fwd / backward loss).
+//
+// The reference's chain costs ~60 SASS instructions per (hypothesis, correspondence) because of
+// the two IEEE divisions and the IEEE square root.  Whether  e < th  holds is, for all but a thin
+// shell of correspondences around the threshold circle, decided by a division-free test:
+//     e < th   <=>   a^2 + b^2 - (th*w)^2 < 0 ,   a = r0 - x'*w ,  b = r1 - y'*w
+// evaluated as 11 FMA-pipe operations:
+//     w' = T*w           = fma(T*h6, x, fma(T*h7, y, T*h8))
+//     a  = r0 - x'*w     = fma(h0, x, fma(h1, y, fma(-x'/T, w', h2)))        (b likewise)
+//     q  = fma(a, a, fma(b, b, -(w'*w')))
+// All rounding errors of this form AND of the reference's chain are absolute in the "times w"
+// domain, so one per-hypothesis constant `band` (derived in DESIGN.md, from the magnitudes of the
+// rows of H and the largest coordinate) bounds them: |q| > band  =>  sign(q) IS the reference's
+// decision.  Correspondences with |q| <= band (a ~1e-2 px shell) are re-evaluated with the exact
+// chain, so the counts are bit-identical to the reference's for the same H.
+//
+// Blackwell specifics: the 11 operations are issued as packed FFMA2/FMUL2 (fma.rn.f32x2), one
+// instruction for TWO hypotheses, which halves the issue slots and leaves the kernel bound by the
+// FMA pipe itself; the sign bit of q is accumulated with one LEA.HI, min |q| with one FMNMX.
+// Correspondences are staged in shared memory already duplicated as (x,x) (y,y) (-x'/T,-x'/T)
+// (-y'/T,-y'/T) so that every operand of an FFMA2 is a ready 64-bit register pair.
+// ------------------------------------------------------------------------------------------------
+constexpr int FAST_THREADS = 256;
+constexpr int FAST_T = 4;          // hypotheses per thread (two FFMA2 lanes-pairs)
+constexpr int FAST_TILE = 1024;    // correspondences per tile: 32 bytes each -> 32 KB
+constexpr int FAST_CHUNK = 8;      // correspondences between two ambiguity checks
+
+__device__ __forceinline__ float2 neg2(float2 v) { return make_float2(-v.x, -v.y); }
+
+// the division-free quantity for one hypothesis pair and one correspondence
+__device__ __forceinline__ float2 fast_q2(const float2 (&hp)[9], float4 pa, float4 pb)
+{
+    const float2 xx = make_float2(pa.x, pa.y), yy = make_float2(pa.z, pa.w);
+    const float2 nX = make_float2(pb.x, pb.y), nY = make_float2(pb.z, pb.w);
+    const float2 w = __ffma2_rn(hp[6], xx, __ffma2_rn(hp[7], yy, hp[8]));
+    const float2 a = __ffma2_rn(hp[0], xx, __ffma2_rn(hp[1], yy, __ffma2_rn(nX, w, hp[2])));
+    const float2 b = __ffma2_rn(hp[3], xx, __ffma2_rn(hp[4], yy, __ffma2_rn(nY, w, hp[5])));
+    const float2 t = __fmul2_rn(w, w);
+    return __ffma2_rn(a, a, __ffma2_rn(b, b, neg2(t)));
+}
+
+// scalar twin of fast_q2 (bit-identical per lane: both are IEEE fma / mul, round to nearest)
+__device__ __forceinline__ float fast_q1(const float (&h)[9], float x, float y, float nX, float nY)
+{
+    const float w = __fmaf_rn(h[6], x, __fmaf_rn(h[7], y, h[8]));
+    const float a = __fmaf_rn(h[0], x, __fmaf_rn(h[1], y, __fmaf_rn(nX, w, h[2])));
+    const float b = __fmaf_rn(h[3], x, __fmaf_rn(h[4], y, __fmaf_rn(nY, w, h[5])));
+    const float t = __fmul_rn(w, w);
+    return __fmaf_rn(a, a, __fmaf_rn(b, b, -t));
+}
+
+// per-hypothesis half-width of the ambiguous shell in q (see DESIGN.md "scoring: error bound")
+__device__ __forceinline__ float fast_band(const float (&h)[9], float C, float T)
+{
+    const float u = 5.9604645e-8f;   // 2^-24
+    const float S0 = (fabsf(h[0]) + fabsf(h[1])) * C + fabsf(h[2]);
+    const float S1 = (fabsf(h[3]) + fabsf(h[4])) * C + fabsf(h[5]);
+    const float S2 = (fabsf(h[6]) + fabsf(h[7])) * C + fabsf(h[8]);
+    const float P = C + 2.f * T;
+    const float D = 7.f * u * (S0 + S1) + u * S2 * (8.f * P + 16.f * C + 7.f * T) + 2.f * P * 1e-10f;
+    return 1.5f * (fmaxf(3.03f * T * S2 * D, 3.f * D * D) + 3.f * u * T * T * S2 * S2);
+}
+
+// largest |coordinate| of each correspondence set (NaN -> inf); grid (B), block 256
+__global__ void __launch_bounds__(256) cmax_kernel(const float4 *__restrict__ pts, int M, float *__restrict__ cmax)
+{
+    pts += (size_t)blockIdx.x * M;
+    float m = 0.f;
+    for (int i = threadIdx.x; i < M; i += blockDim.x) {
+        float4 p = __ldg(pts + i);
+        float v = fmaxf(fmaxf(fabsf(p.x), fabsf(p.y)), fmaxf(fabsf(p.z), fabsf(p.w)));
+        if (p.x != p.x || p.y != p.y || p.z != p.z || p.w != p.w) v = __int_as_float(0x7f800000);
+        m = fmaxf(m, v);
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s));
+    __shared__ float sm[8];
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) m = fmaxf(m, sm[w]);
+        cmax[blockIdx.x] = m;
+    }
+}
+
+// Grid: (ceil(nk / (FAST_THREADS*FAST_T)), point_splits, B).  METHOD is FWD or BACKWARD; for
+// BACKWARD `H` must point at the inverse matrices and the tile is filled with the roles of the
+// two point sets exchanged.  T = (float)th > 0 and finite.
+template <int METHOD>
+__global__ void __launch_bounds__(FAST_THREADS, 2)
+score_fast_kernel(const float4 *__restrict__ pts, int M, const float *__restrict__ H, const uint8_t *__restrict__ flags,
+                  int k_begin, int k_end, int K_stride, float T, const float *__restrict__ cmax, int pts_per_split,
+                  int32_t *__restrict__ counts, unsigned long long *__restrict__ stat_ambiguous)
+{
+    __shared__ float4 tile[2 * FAST_TILE];
+    const int b = blockIdx.z;
+    pts += (size_t)b * M;
+    const float C = cmax[b];
+    const float invT = 1.0f / T;       // only to scale x', y' in the tile; its rounding is inside `band`
+
+    // this thread's FAST_T hypotheses: k = base + t*FAST_THREADS + tid  (t = 0..3), paired (0,1) (2,3)
+    const int base = k_begin + blockIdx.x * (FAST_THREADS * FAST_T) + threadIdx.x;
+    float hs[FAST_T][9];
+    float band[FAST_T];
+    bool live[FAST_T], dead[FAST_T];
+#pragma unroll
+    for (int t = 0; t < FAST_T; ++t) {
+        const int k = base + t * FAST_THREADS;
+        live[t] = k < k_end;
+        const size_t o = (size_t)b * K_stride + (live[t] ? k : k_begin);
+        bool bad = flags ? (flags[o] != 0) : false;
+#pragma unroll
+        for (int j = 0; j < 9; ++j) {
+            hs[t][j] = __ldg(H + o * 9 + j);
+            bad = bad || !(fabsf(hs[t][j]) <= 3.0e38f);                 // NaN / inf
+        }
+        dead[t] = bad || !live[t];
+        if (dead[t]) {
+            // scored as the identity (cheap, never ambiguous in a way that matters) and discarded
+#pragma unroll
+            for (int j = 0; j < 9; ++j) hs[t][j] = (j == 0 || j == 4 || j == 8) ? 1.f : 0.f;
+        }
+        band[t] = fast_band(hs[t], C, T);
+        hs[t][6] = __fmul_rn(T, hs[t][6]);
+        hs[t][7] = __fmul_rn(T, hs[t][7]);
+        hs[t][8] = __fmul_rn(T, hs[t][8]);
+    }
+    float2 hp[FAST_T / 2][9];
+#pragma unroll
+    for (int g = 0; g < FAST_T / 2; ++g)
+#pragma unroll
+        for (int j = 0; j < 9; ++j) hp[g][j] = make_float2(hs[2 * g][j], hs[2 * g + 1][j]);
+
+    unsigned cnt[FAST_T];
+    float mq[FAST_T];
+#pragma unroll
+    for (int t = 0; t < FAST_T; ++t) { cnt[t] = 0u; mq[t] = 3.0e38f; }
+    unsigned n_amb = 0;
+
+    const int j_begin = blockIdx.y * pts_per_split;
+    const int j_end = min(M, j_begin + pts_per_split);
+    for (int t0 = j_begin; t0 < j_end; t0 += FAST_TILE) {
+        const int n = min(FAST_TILE, j_end - t0);
+        const int n_pad = (n + FAST_CHUNK - 1) / FAST_CHUNK * FAST_CHUNK;
+        __syncthreads();
+        for (int i = threadIdx.x; i < n_pad; i += FAST_THREADS) {
+            float4 p;
+            if (i < n) {
+                p = __ldg(pts + t0 + i);
+                if (METHOD == B200GEO_BACKWARD) p = make_float4(p.z, p.w, p.x, p.y);
+            } else {
+                // padding: a correspondence no hypothesis can count (q = +huge), never ambiguous
+                p = make_float4(0.f, 0.f, 1.0e18f, 1.0e18f);
+            }
+            const float nX = -__fmul_rn(p.z, invT), nY = -__fmul_rn(p.w, invT);
+            tile[2 * i] = make_float4(p.x, p.x, p.y, p.y);
+            tile[2 * i + 1] = make_float4(nX, nX, nY, nY);
+        }
+        __syncthreads();
+        for (int i = 0; i < n_pad; i += FAST_CHUNK) {
+#pragma unroll
+            for (int u = 0; u < FAST_CHUNK; ++u) {
+                const float4 pa = tile[2 * (i + u)], pb = tile[2 * (i + u) + 1];
+#pragma unroll
+                for (int g = 0; g < FAST_T / 2; ++g) {
+                    const float2 q = fast_q2(hp[g], pa, pb);
+                    cnt[2 * g] += __float_as_uint(q.x) >> 31;
+                    cnt[2 * g + 1] += __float_as_uint(q.y) >> 31;
+                    mq[2 * g] = fminf(mq[2 * g], fabsf(q.x));
+                    mq[2 * g + 1] = fminf(mq[2 * g + 1], fabsf(q.y));
+                }
+            }
+            bool amb = false;
+#pragma unroll
+            for (int t = 0; t < FAST_T; ++t) amb = amb || !(mq[t] > band[t]);
+            if (amb) {
+                // rare: some |q| in this chunk is inside the shell (or NaN): redo the chunk exactly
+#pragma unroll
+                for (int t = 0; t < FAST_T; ++t) {
+                    if (mq[t] > band[t]) continue;
+                    mq[t] = 3.0e38f;
+                    if (dead[t]) continue;
+                    float hx[9], hq[9];
+                    const size_t o = (size_t)b * K_stride + base + t * FAST_THREADS;
+#pragma unroll
+                    for (int j = 0; j < 9; ++j) {
+                        hx[j] = __ldg(H + o * 9 + j);
+                        hq[j] = (t & 1) ? hp[t / 2][j].y : hp[t / 2][j].x;
+                    }
+                    for (int u = 0; u < FAST_CHUNK; ++u) {
+                        const int jj = t0 + i + u;
+                        if (jj >= j_end) break;
+                        const float4 pa = tile[2 * (i + u)], pb = tile[2 * (i + u) + 1];
+                        const float q = fast_q1(hq, pa.x, pa.z, pb.x, pb.z);
+                        if (fabsf(q) > band[t]) continue;
+                        float4 p = __ldg(pts + jj);
+                        if (METHOD == B200GEO_BACKWARD) p = make_float4(p.z, p.w, p.x, p.y);
+                        const int exact_in = exact_err(hx, p.x, p.y, p.z, p.w) < T ? 1 : 0;
+                        cnt[t] += (unsigned)(exact_in - (int)(__float_as_uint(q) >> 31));
+                        ++n_amb;
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < FAST_T; ++t) {
+        if (!live[t]) continue;
+        const size_t o = (size_t)b * K_stride + base + t * FAST_THREADS;
+        const int c = dead[t] ? 0 : (int)cnt[t];
+        if (gridDim.y > 1) { if (c) atomicAdd(counts + o, c); }
+        else counts[o] = c;
+    }
+    if (stat_ambiguous && n_amb) atomicAdd(stat_ambiguous, (unsigned long long)n_amb);
+}
+
 // per-point loss of one hypothesis (HomoModel.computeLoss, ransac.py:84-98)
 __global__ void loss_kernel(const float4 *__restrict__ pts, int M, const float *__restrict__ H,
                             const float *__restrict__ Hinv, int method, float *__restrict__ err)

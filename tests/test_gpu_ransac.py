@@ -328,3 +328,42 @@ def test_full_size_single_pair_properties():
     res2, _ = device.ransac(tp, ti, 3.0, 45)
     first = int(np.argmax(cn >= M * 45 / 100 + 4))
     assert int(res2.cpu().numpy()[0]) == first
+
+
+def test_fast_path_equals_reference_order_chain(ctx):
+    """The division-free FFMA2 kernel against the same library forced onto the reference-order
+    chain, on 4k hypotheses x 20k correspondences with a dense shell of points at the threshold;
+    the pairs that fell inside the rounding shell are reported (north_star: 'reported')."""
+    rs = np.random.RandomState(21)
+    M = 20000
+    X, Y = synth_pair(5, M, outlier_frac=0.3)
+    Ht = np.array([[0.9, 0.05, 30], [-0.04, 1.1, -20], [1e-5, -2e-5, 1]])
+    q = Ht @ np.vstack([X.astype(np.float64), np.ones(M)])
+    ang = rs.rand(M) * 2 * np.pi
+    shell = rs.rand(M) < 0.2                       # 20% of the points within 1e-5 px of th under Ht
+    r = 3.0 * (1 + (rs.rand(M) - 0.5) * 1e-5)
+    Y64 = Y.astype(np.float64)
+    Y64[0, shell] = (q[0] / q[2] + r * np.cos(ang))[shell]
+    Y64[1, shell] = (q[1] / q[2] + r * np.sin(ang))[shell]
+    pts = oracle.pack_points(X, Y64.astype(np.float32))
+    idx = rs.randint(0, M, (4096, 4)).astype(np.int32)
+    H, Hinv, flags = _dlt4(ctx, pts, idx, True)
+    H[:64] = Ht.astype(np.float32)                 # and the generating model itself
+    Hinv[:64] = np.linalg.inv(Ht).astype(np.float32)
+    good = np.isfinite(H).all((1, 2)) & np.isfinite(Hinv).all((1, 2))
+    H, Hinv = H[good], Hinv[good]
+    for method in ("fwd", "backward"):
+        ctx.exact_path_pairs(reset=True)
+        fast = _score(ctx, pts, H, 3.0, method, Hinv)
+        n_shell = ctx.exact_path_pairs(reset=True)
+        ctx.force_exact(True)
+        try:
+            exact = _score(ctx, pts, H, 3.0, method, Hinv)
+        finally:
+            ctx.force_exact(False)
+        assert np.array_equal(fast, exact)
+        assert ctx.exact_path_pairs() == 0 or method == "backward"
+        if method == "fwd":
+            assert n_shell >= 64 * 0.15 * M        # the constructed shell really exercised the exact path
+            sub = np.arange(0, len(H), 37)
+            assert np.array_equal(fast[sub], oracle.score_counts(pts, H[sub], 3.0))
