@@ -198,11 +198,27 @@ int launch_score(b200geo_ctx *ctx, const float *pts, int M, const float *H, cons
         for (int b = 0; b < B; ++b)
             B2G_CUDA(cudaMemsetAsync(counts + (size_t)b * K_stride + k_begin, 0, sizeof(int32_t) * (size_t)nk, st));
     }
+    // deferred exact work: capacity for a 1/64 trigger rate per (hypothesis, chunk), 1M .. 64M entries
+    unsigned long long want_cap = (unsigned long long)nk * B * (unsigned long long)((M + FAST_CHUNK - 1) / FAST_CHUNK) / 64;
+    if (want_cap < (1ull << 20)) want_cap = 1ull << 20;
+    if (want_cap > (1ull << 26)) want_cap = 1ull << 26;
+    FastDeferred *wl;
+    unsigned *wl_count = (unsigned *)(stats + 1);
+    if ((rc = scratch(ctx, S_WORKLIST, want_cap * sizeof(FastDeferred), (void **)&wl))) return rc;
+    unsigned wl_cap = (unsigned)(ctx->scratch_cap[S_WORKLIST] / sizeof(FastDeferred));
+    B2G_CUDA(cudaMemsetAsync(wl_count, 0, sizeof(unsigned), st));
     dim3 grid(gx, splits, B);
-    if (method == B200GEO_FWD)
-        score_fast_kernel<B200GEO_FWD><<<grid, FAST_THREADS, 0, st>>>((const float4 *)pts, M, H, flags, k_begin, k_end, K_stride, th, cmax, per, counts, stats);
-    else
-        score_fast_kernel<B200GEO_BACKWARD><<<grid, FAST_THREADS, 0, st>>>((const float4 *)pts, M, Hinv, flags, k_begin, k_end, K_stride, th, cmax, per, counts, stats);
+    const float4 *p4 = (const float4 *)pts;
+    int fix_blocks = 8 * ctx->sm_count;
+    if (method == B200GEO_FWD) {
+        score_fast_kernel<B200GEO_FWD><<<grid, FAST_THREADS, 0, st>>>(p4, M, H, flags, k_begin, k_end, K_stride, th, cmax, per, counts, stats, wl, wl_count, wl_cap);
+        B2G_CHECK_LAUNCH(ctx);
+        score_fixup_kernel<B200GEO_FWD><<<fix_blocks, 256, 0, st>>>(p4, M, H, K_stride, th, cmax, wl, wl_count, wl_cap, counts, stats);
+    } else {
+        score_fast_kernel<B200GEO_BACKWARD><<<grid, FAST_THREADS, 0, st>>>(p4, M, Hinv, flags, k_begin, k_end, K_stride, th, cmax, per, counts, stats, wl, wl_count, wl_cap);
+        B2G_CHECK_LAUNCH(ctx);
+        score_fixup_kernel<B200GEO_BACKWARD><<<fix_blocks, 256, 0, st>>>(p4, M, Hinv, K_stride, th, cmax, wl, wl_count, wl_cap, counts, stats);
+    }
     B2G_CHECK_LAUNCH(ctx);
     return B200GEO_OK;
 }

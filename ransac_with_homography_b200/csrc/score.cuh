@@ -140,17 +140,27 @@ __device__ __forceinline__ float fast_q1(const float (&h)[9], float x, float y, 
     return __fmaf_rn(a, a, __fmaf_rn(b, b, -t));
 }
 
-// per-hypothesis half-width of the ambiguous shell in q (see DESIGN.md "scoring: error bound")
+// Per-hypothesis half-width of the ambiguous shell in q (derivation: DESIGN.md "scoring: error
+// bound").  E bounds, in the "times |w|" domain, the sum of every rounding error of the
+// reference's chain and of fast_q for a correspondence whose true error is within 2*th:
+//   reference: r_i (3 roundings each), w (+1e-10), two divisions, two subtractions, the sqrt chain
+//   fast path: T*h6.. coefficient roundings, x'/T scaling, the 3+3+2 fused operations
+// with |x|,|y|,|x'|,|y'| <= C and |w| <= S2.  Then  | |q| | > band  =>  sign(q) is the
+// reference's decision, because  band >= E*(2*T*S2 + E) + (rounding of q itself).
 __device__ __forceinline__ float fast_band(const float (&h)[9], float C, float T)
 {
     const float u = 5.9604645e-8f;   // 2^-24
-    const float S0 = (fabsf(h[0]) + fabsf(h[1])) * C + fabsf(h[2]);
-    const float S1 = (fabsf(h[3]) + fabsf(h[4])) * C + fabsf(h[5]);
     const float S2 = (fabsf(h[6]) + fabsf(h[7])) * C + fabsf(h[8]);
     const float P = C + 2.f * T;
-    const float D = 7.f * u * (S0 + S1) + u * S2 * (8.f * P + 16.f * C + 7.f * T) + 2.f * P * 1e-10f;
-    return 1.5f * (fmaxf(3.03f * T * S2 * D, 3.f * D * D) + 3.f * u * T * T * S2 * S2);
+    const float E = u * (2.f * (fabsf(h[0]) + fabsf(h[3])) * C + 2.f * (fabsf(h[2]) + fabsf(h[5])) +
+                         P * (12.f * S2 + 2.f * fabsf(h[6]) * C + 2.f * fabsf(h[8])) + 12.f * C * S2 + 18.f * T * S2) +
+                    2.f * P * 1e-10f;
+    return 1.25f * (E * (2.0001f * T * S2 + E) + 3.f * u * T * T * S2 * S2);
 }
+
+// One deferred unit of exact work: hypothesis slot (b*K_stride + k) and the first correspondence of
+// the FAST_CHUNK-sized chunk in which some |q| fell inside the shell.
+struct FastDeferred { unsigned slot, j0; };
 
 // largest |coordinate| of each correspondence set (NaN -> inf); grid (B), block 256
 __global__ void __launch_bounds__(256) cmax_kernel(const float4 *__restrict__ pts, int M, float *__restrict__ cmax)
@@ -181,7 +191,8 @@ template <int METHOD>
 __global__ void __launch_bounds__(FAST_THREADS, 2)
 score_fast_kernel(const float4 *__restrict__ pts, int M, const float *__restrict__ H, const uint8_t *__restrict__ flags,
                   int k_begin, int k_end, int K_stride, float T, const float *__restrict__ cmax, int pts_per_split,
-                  int32_t *__restrict__ counts, unsigned long long *__restrict__ stat_ambiguous)
+                  int32_t *__restrict__ counts, unsigned long long *__restrict__ stat_ambiguous,
+                  FastDeferred *__restrict__ wl, unsigned *__restrict__ wl_count, unsigned wl_cap)
 {
     __shared__ float4 tile[2 * FAST_TILE];
     const int b = blockIdx.z;
@@ -265,14 +276,23 @@ score_fast_kernel(const float4 *__restrict__ pts, int M, const float *__restrict
 #pragma unroll
             for (int t = 0; t < FAST_T; ++t) amb = amb || !(mq[t] > band[t]);
             if (amb) {
-                // rare: some |q| in this chunk is inside the shell (or NaN): redo the chunk exactly
+                // Some |q| of this chunk is inside the shell (or NaN).  The exact re-evaluation is
+                // DEFERRED to score_fixup_kernel through a global work list, so that one lane's
+                // rare event does not stall the other 31; only if the list is full is the chunk
+                // redone here.
 #pragma unroll
                 for (int t = 0; t < FAST_T; ++t) {
                     if (mq[t] > band[t]) continue;
                     mq[t] = 3.0e38f;
                     if (dead[t]) continue;
-                    float hx[9], hq[9];
                     const size_t o = (size_t)b * K_stride + base + t * FAST_THREADS;
+                    const unsigned w = atomicAdd(wl_count, 1u);
+                    if (w < wl_cap) {
+                        wl[w].slot = (unsigned)o;
+                        wl[w].j0 = (unsigned)(t0 + i);
+                        continue;
+                    }
+                    float hx[9], hq[9];
 #pragma unroll
                     for (int j = 0; j < 9; ++j) {
                         hx[j] = __ldg(H + o * 9 + j);
@@ -303,6 +323,44 @@ score_fast_kernel(const float4 *__restrict__ pts, int M, const float *__restrict
         else counts[o] = c;
     }
     if (stat_ambiguous && n_amb) atomicAdd(stat_ambiguous, (unsigned long long)n_amb);
+}
+
+// Exact re-evaluation of the deferred chunks: one thread per (deferred chunk, correspondence).
+// Recomputes q with the scalar twin of fast_q2 (bit-identical), and for |q| <= band replaces the
+// fast decision by the reference-order chain's:  counts[slot] += exact - fast.
+template <int METHOD>
+__global__ void __launch_bounds__(256)
+score_fixup_kernel(const float4 *__restrict__ pts, int M, const float *__restrict__ H, int K_stride, float T,
+                   const float *__restrict__ cmax, const FastDeferred *__restrict__ wl, const unsigned *__restrict__ wl_count,
+                   unsigned wl_cap, int32_t *__restrict__ counts, unsigned long long *__restrict__ stat_ambiguous)
+{
+    const unsigned n = min(*wl_count, wl_cap);
+    const unsigned long long total = (unsigned long long)n * FAST_CHUNK;
+    const float invT = 1.0f / T;
+    unsigned local = 0;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < total;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const FastDeferred e = wl[i / FAST_CHUNK];
+        const unsigned j = e.j0 + (unsigned)(i % FAST_CHUNK);
+        if (j >= (unsigned)M) continue;
+        const unsigned b = e.slot / (unsigned)K_stride;
+        float hx[9], hq[9];
+#pragma unroll
+        for (int c = 0; c < 9; ++c) hx[c] = hq[c] = __ldg(H + (size_t)e.slot * 9 + c);
+        const float band = fast_band(hx, cmax[b], T);
+        hq[6] = __fmul_rn(T, hq[6]);
+        hq[7] = __fmul_rn(T, hq[7]);
+        hq[8] = __fmul_rn(T, hq[8]);
+        float4 p = __ldg(pts + (size_t)b * M + j);
+        if (METHOD == B200GEO_BACKWARD) p = make_float4(p.z, p.w, p.x, p.y);
+        const float q = fast_q1(hq, p.x, p.y, -__fmul_rn(p.z, invT), -__fmul_rn(p.w, invT));
+        if (fabsf(q) > band) continue;
+        const int exact_in = exact_err(hx, p.x, p.y, p.z, p.w) < T ? 1 : 0;
+        const int d = exact_in - (int)(__float_as_uint(q) >> 31);
+        if (d) atomicAdd(counts + e.slot, d);
+        ++local;
+    }
+    if (stat_ambiguous && local) atomicAdd(stat_ambiguous, (unsigned long long)local);
 }
 
 // per-point loss of one hypothesis (HomoModel.computeLoss, ransac.py:84-98)
