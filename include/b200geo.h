@@ -72,7 +72,13 @@ int64_t b200geo_launch_count(b200geo_ctx *ctx);
 int b200geo_stats(b200geo_ctx *ctx, unsigned long long *exact_path_pairs, int reset);
 /* options */
 #define B200GEO_OPT_FORCE_EXACT 1   /* value != 0: score every pair with the reference-order chain */
+#define B200GEO_OPT_WARP_EXACT 2    /* value != 0: warp uint8 RGB with the float64 kernel (bit-exact bilinear) */
+#define B200GEO_OPT_WARP_VARIANT 3  /* fast uint8 warp: 0 = persistent TMA-pipelined kernel (default), 1 = one CTA per tile */
 int b200geo_set_option(b200geo_ctx *ctx, int option, int value);
+/* Number of output pixels the fast uint8 warp kernel evaluated with the float64 reference-order
+ * path (inside the coordinate-error band around a mask / rounding boundary, or in tiles where
+ * the float32 bound does not hold); cumulative.  Synchronises the device. */
+int b200geo_warp_stats(b200geo_ctx *ctx, unsigned long long *exact_pixels, int reset);
 /* blocks until all work of this context on `stream` is done */
 int b200geo_sync(b200geo_ctx *ctx, void *stream);
 
@@ -191,6 +197,19 @@ int b200geo_warp_dev(b200geo_ctx *ctx, const void *src, void *dst, const b200geo
 int b200geo_warp_jobs_dev(b200geo_ctx *ctx, const void *src, void *dst, const b200geo_warp_job *jobs_dev,
                           int n_jobs, int max_ow, int max_oh, int channels, int src_type, int dst_type,
                           int sampler, void *stream);
+/* Same, with a description of the source buffer: every job's image lies inside one 2-D byte array
+ * starting at `src` (16-byte aligned) of `rows` rows, `pitch` bytes apart (pitch % 16 == 0); a job
+ * whose src_pitch equals `pitch` and whose src_offset is a multiple of it is then fetched with one
+ * 2-D TMA tensor copy per output tile instead of one bulk copy per source row.  Frames stored back
+ * to back (the batched configs) are such an array with rows = n_frames * height.  Results do not
+ * depend on the layout hint; layout == NULL is b200geo_warp_jobs_dev. */
+typedef struct b200geo_src_layout {
+    int64_t pitch;   /* bytes between rows */
+    int64_t rows;    /* number of rows readable from src */
+} b200geo_src_layout;
+int b200geo_warp_batch_dev(b200geo_ctx *ctx, const void *src, void *dst, const b200geo_warp_job *jobs_dev,
+                           int n_jobs, int max_ow, int max_oh, int channels, int src_type, int dst_type,
+                           int sampler, const b200geo_src_layout *layout, void *stream);
 /* single image on host buffers: H2D, warp, D2H */
 int b200geo_warp_host(b200geo_ctx *ctx, const void *src, void *dst, const b200geo_warp_job *job,
                       int channels, int src_type, int dst_type, int sampler);

@@ -13,7 +13,7 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200geo.so")
+LIB_PATH = os.environ.get("B200GEO_LIB") or os.path.join(_HERE, "libb200geo.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 OK, ERR_CUDA, ERR_ARG, ERR_NODEVICE, ERR_SINGULAR, ERR_NOMODEL = 0, -1, -2, -3, -4, -5
@@ -49,6 +49,11 @@ WARP_JOB_DTYPE = np.dtype([("invH", np.float64, 9), ("x0", np.float64), ("dx", n
                            ("dst_offset", np.int64), ("dst_pitch", np.int64)])
 assert WARP_JOB_DTYPE.itemsize == C.sizeof(WarpJob) == 184
 
+class SrcLayout(C.Structure):
+    """struct b200geo_src_layout (include/b200geo.h)"""
+    _fields_ = [("pitch", C.c_int64), ("rows", C.c_int64)]
+
+
 _vp, _i, _f, _d, _sz = C.c_void_p, C.c_int, C.c_float, C.c_double, C.c_size_t
 
 # name -> (restype, argtypes); every symbol include/b200geo.h declares
@@ -62,6 +67,7 @@ SIGNATURES = {
     "b200geo_sync": (_i, [_vp, _vp]),
     "b200geo_stats": (_i, [_vp, C.POINTER(C.c_ulonglong), _i]),
     "b200geo_set_option": (_i, [_vp, _i, _i]),
+    "b200geo_warp_stats": (_i, [_vp, C.POINTER(C.c_ulonglong), _i]),
     "b200geo_dlt4_dev": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp]),
     "b200geo_dlt4_host": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp]),
     "b200geo_homography4_host": (_i, [_vp, _vp, _vp, _vp]),
@@ -77,6 +83,7 @@ SIGNATURES = {
     "b200geo_refit_host": (_i, [_vp, _vp, _i, _vp, _vp]),
     "b200geo_warp_dev": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "b200geo_warp_jobs_dev": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "b200geo_warp_batch_dev": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "b200geo_warp_host": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i]),
     "b200geo_sample_host": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, C.c_longlong, _i, _i, _i, _i, _vp]),
 }
@@ -150,6 +157,20 @@ class Context:
 
     def force_exact(self, on: bool) -> None:
         check(self.lib.b200geo_set_option(self.handle, 1, int(on)))
+
+    def warp_exact(self, on: bool) -> None:
+        """Warp uint8 RGB images with the float64 kernel only (bit-exact bilinear) instead of the fast path."""
+        check(self.lib.b200geo_set_option(self.handle, 2, int(on)))
+
+    def warp_variant(self, v: int) -> None:
+        """0 = persistent TMA-pipelined fast warp kernel (default), 1 = one CTA per tile."""
+        check(self.lib.b200geo_set_option(self.handle, 3, int(v)))
+
+    def warp_exact_pixels(self, reset: bool = False) -> int:
+        """Output pixels the fast warp kernel evaluated in float64 (band / slow tiles)."""
+        v = C.c_ulonglong(0)
+        check(self.lib.b200geo_warp_stats(self.handle, C.byref(v), int(reset)))
+        return int(v.value)
 
     def sync(self, stream=None) -> None:
         check(self.lib.b200geo_sync(self.handle, _vp(stream or 0)))

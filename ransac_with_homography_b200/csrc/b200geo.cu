@@ -5,8 +5,10 @@
 #include "select_refit.cuh"
 #include "solve.cuh"
 #include "warp.cuh"
+#include "warp_fast.cuh"
 
 #include <new>
+#include <stdlib.h>
 #include <vector>
 
 using namespace b200geo;
@@ -76,13 +78,26 @@ int64_t b200geo_launch_count(b200geo_ctx *ctx) { return ctx ? ctx->launches : -1
 int b200geo_stats(b200geo_ctx *ctx, unsigned long long *exact_path_pairs, int reset)
 {
     B2G_ENTER(ctx);
-    unsigned long long v[2] = {0, 0};
+    unsigned long long v = 0;
     if (ctx->scratch_cap[S_STATS]) {
         B2G_CUDA(cudaDeviceSynchronize());
-        B2G_CUDA(cudaMemcpy(v, ctx->scratch[S_STATS], 16, cudaMemcpyDeviceToHost));
-        if (reset) B2G_CUDA(cudaMemset(ctx->scratch[S_STATS], 0, 16));
+        B2G_CUDA(cudaMemcpy(&v, ctx->scratch[S_STATS], 8, cudaMemcpyDeviceToHost));
+        if (reset) B2G_CUDA(cudaMemset(ctx->scratch[S_STATS], 0, 8));
     }
-    if (exact_path_pairs) *exact_path_pairs = v[0];
+    if (exact_path_pairs) *exact_path_pairs = v;
+    return B200GEO_OK;
+}
+
+int b200geo_warp_stats(b200geo_ctx *ctx, unsigned long long *exact_pixels, int reset)
+{
+    B2G_ENTER(ctx);
+    unsigned long long v = 0;
+    if (ctx->scratch_cap[S_STATS]) {
+        B2G_CUDA(cudaDeviceSynchronize());
+        B2G_CUDA(cudaMemcpy(&v, (char *)ctx->scratch[S_STATS] + 16, 8, cudaMemcpyDeviceToHost));
+        if (reset) B2G_CUDA(cudaMemset((char *)ctx->scratch[S_STATS] + 16, 0, 8));
+    }
+    if (exact_pixels) *exact_pixels = v;
     return B200GEO_OK;
 }
 
@@ -90,6 +105,8 @@ int b200geo_set_option(b200geo_ctx *ctx, int option, int value)
 {
     B2G_ARG(ctx != nullptr);
     if (option == B200GEO_OPT_FORCE_EXACT) { ctx->force_exact = value; return B200GEO_OK; }
+    if (option == B200GEO_OPT_WARP_EXACT) { ctx->warp_exact = value; return B200GEO_OK; }
+    if (option == B200GEO_OPT_WARP_VARIANT) { ctx->warp_variant = value; return B200GEO_OK; }
     return fail(B200GEO_ERR_ARG, "unknown option%s%s");
 }
 
@@ -106,6 +123,20 @@ int b200geo_sync(b200geo_ctx *ctx, void *stream)
 // internal launch helpers (device pointers, stream ordered)
 // ------------------------------------------------------------------------------------------------
 namespace {
+
+// 64-byte statistics block: [0] score pairs taken by the exact chain, [1] deferred-work counter,
+// [2] warp pixels evaluated in float64 by the fast warp kernel
+int ensure_stats(b200geo_ctx *ctx, cudaStream_t st, unsigned long long **out)
+{
+    if (ctx->scratch_cap[S_STATS] == 0) {
+        void *p;
+        int rc;
+        if ((rc = scratch(ctx, S_STATS, 64, &p))) return rc;
+        B2G_CUDA(cudaMemsetAsync(p, 0, 64, st));
+    }
+    *out = (unsigned long long *)ctx->scratch[S_STATS];
+    return B200GEO_OK;
+}
 
 int launch_dlt4(b200geo_ctx *ctx, const float *pts, int M, const int32_t *idx, int k_begin, int k_end, int K_stride,
                 int B, float *H, float *Hinv, uint8_t *flags, cudaStream_t st)
@@ -173,11 +204,7 @@ int launch_score(b200geo_ctx *ctx, const float *pts, int M, const float *H, cons
     unsigned long long *stats;
     int rc;
     if ((rc = scratch(ctx, S_CMAX, sizeof(float) * (size_t)B, (void **)&cmax))) return rc;
-    if (ctx->scratch_cap[S_STATS] == 0) {
-        if ((rc = scratch(ctx, S_STATS, 16, (void **)&stats))) return rc;
-        B2G_CUDA(cudaMemsetAsync(stats, 0, 16, st));
-    }
-    stats = (unsigned long long *)ctx->scratch[S_STATS];
+    if ((rc = ensure_stats(ctx, st, &stats))) return rc;
     cmax_kernel<<<B, 256, 0, st>>>((const float4 *)pts, M, cmax);
     B2G_CHECK_LAUNCH(ctx);
 
@@ -284,11 +311,88 @@ int launch_warp_t(b200geo_ctx *ctx, const void *src, void *dst, const b200geo_wa
     return B200GEO_OK;
 }
 
+// 2-D tensor map over the source byte array (uint8, rows x pitch), box WF_TMA_BOX_W x WF_TMA_BOX_H.
+// Returns 1 and fills ctx->tmap when the layout is usable, 0 otherwise (never an error: the
+// kernels fall back to per-row bulk copies).
+int prepare_tmap(b200geo_ctx *ctx, const void *src, const b200geo_src_layout *layout)
+{
+    if (!layout || layout->pitch <= 0 || layout->rows <= 0) return 0;
+    if ((layout->pitch & 15) || ((size_t)src & 15) || layout->pitch < WF_TMA_BOX_W || layout->rows < 1) return 0;
+    if (!ctx->tmap_probed) {
+        ctx->tmap_probed = 1;
+        cudaDriverEntryPointQueryResult q;
+        void *fn = nullptr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            ctx->tmap_encode = fn;
+        cudaGetLastError();
+    }
+    if (!ctx->tmap_encode) return 0;
+    if (ctx->tmap_src == src && ctx->tmap_pitch == layout->pitch && ctx->tmap_rows == layout->rows) return 1;
+    typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    const cuuint64_t gdim[2] = {(cuuint64_t)layout->pitch, (cuuint64_t)layout->rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)layout->pitch};
+    const cuuint32_t box[2] = {(cuuint32_t)WF_TMA_BOX_W, (cuuint32_t)WF_TMA_BOX_H};
+    const cuuint32_t estride[2] = {1, 1};
+    CUresult r = ((encode_fn)ctx->tmap_encode)(&ctx->tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(src), gdim, gstride, box,
+                                               estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { ctx->tmap_src = nullptr; return 0; }
+    ctx->tmap_src = src; ctx->tmap_pitch = layout->pitch; ctx->tmap_rows = layout->rows;
+    return 1;
+}
+
 int launch_warp(b200geo_ctx *ctx, const void *src, void *dst, const b200geo_warp_job *jobs_dev, int n_jobs, int max_ow,
-                int max_oh, int channels, int src_type, int dst_type, int sampler, cudaStream_t st)
+                int max_oh, int channels, int src_type, int dst_type, int sampler, cudaStream_t st,
+                const b200geo_src_layout *layout = nullptr)
 {
     if (n_jobs <= 0 || max_ow <= 0 || max_oh <= 0) return B200GEO_OK;
     if (n_jobs > 65535) return fail(B200GEO_ERR_ARG, "at most 65535 warp jobs per call%s%s");
+    if (src_type == B200GEO_U8 && dst_type == B200GEO_U8 && channels == 3 && !ctx->warp_exact) {
+        // fast path: tile-staged, float32 tile-relative coordinates, integer blend (warp_fast.cuh)
+        unsigned long long *stats;
+        int rc;
+        if ((rc = ensure_stats(ctx, st, &stats))) return rc;
+        const int tiles_x = (max_ow + WF_TW - 1) / WF_TW, tiles_y = (max_oh + WF_TH - 1) / WF_TH;
+        if (tiles_y > 65535) return fail(B200GEO_ERR_ARG, "output too tall for one launch%s%s");
+        WfDesc *descs;
+        if ((rc = scratch(ctx, S_TILES, sizeof(WfDesc) * (size_t)tiles_x * tiles_y * n_jobs, (void **)&descs))) return rc;
+        dim3 sgrid((tiles_x + 31) / 32, (tiles_y + 7) / 8, n_jobs), sblock(32, 8);
+        const uint8_t *s8 = (const uint8_t *)src;
+        uint8_t *d8 = (uint8_t *)dst;
+        const int use_tmap = ctx->warp_variant == 0 ? prepare_tmap(ctx, src, layout) : 0;
+        if (getenv("B200GEO_DEBUG"))
+            fprintf(stderr, "[b200geo] warp: jobs %d tiles %dx%d sampler %d layout %p use_tmap %d (encode %p)\n", n_jobs, tiles_x, tiles_y,
+                    sampler, (const void *)layout, use_tmap, ctx->tmap_encode);
+        const long long tma_pitch = use_tmap ? layout->pitch : 0;
+        if (sampler == B200GEO_BILINEAR) warp_setup_kernel<1><<<sgrid, sblock, 0, st>>>(jobs_dev, s8, tma_pitch, tiles_x, tiles_y, descs);
+        else warp_setup_kernel<0><<<sgrid, sblock, 0, st>>>(jobs_dev, s8, tma_pitch, tiles_x, tiles_y, descs);
+        B2G_CHECK_LAUNCH(ctx);
+        if (ctx->warp_variant == 1) {
+            // one CTA per tile (kept for comparison)
+            dim3 grid(tiles_x, tiles_y, n_jobs);
+            if (sampler == B200GEO_BILINEAR) warp_fast_kernel<1><<<grid, WF_THREADS, 0, st>>>(s8, d8, jobs_dev, descs, stats + 2);
+            else warp_fast_kernel<0><<<grid, WF_THREADS, 0, st>>>(s8, d8, jobs_dev, descs, stats + 2);
+        } else {
+            // persistent CTAs, TMA bulk copies one tile ahead
+            const long long n_tiles = (long long)tiles_x * tiles_y * n_jobs;
+            if (n_tiles > 0x7fffffffLL) return fail(B200GEO_ERR_ARG, "too many warp tiles for one launch%s%s");
+            if (!ctx->warp_pipe_ready) {
+                B2G_CUDA(cudaFuncSetAttribute(warp_pipe_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WpSmem)));
+                B2G_CUDA(cudaFuncSetAttribute(warp_pipe_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WpSmem)));
+                ctx->warp_pipe_ready = 1;
+            }
+            long long ctas = (long long)ctx->sm_count * WP_OCC;
+            if (ctas > n_tiles) ctas = n_tiles;
+            if (sampler == B200GEO_BILINEAR)
+                warp_pipe_kernel<1><<<(unsigned)ctas, WP_THREADS, sizeof(WpSmem), st>>>(s8, d8, jobs_dev, descs, (int)n_tiles, tiles_x, tiles_y, stats + 2, ctx->tmap, use_tmap);
+            else
+                warp_pipe_kernel<0><<<(unsigned)ctas, WP_THREADS, sizeof(WpSmem), st>>>(s8, d8, jobs_dev, descs, (int)n_tiles, tiles_x, tiles_y, stats + 2, ctx->tmap, use_tmap);
+        }
+        B2G_CHECK_LAUNCH(ctx);
+        return B200GEO_OK;
+    }
     if (src_type == B200GEO_U8 && channels == 3) return launch_warp_t<uint8_t, 3>(ctx, src, dst, jobs_dev, n_jobs, max_ow, max_oh, dst_type, sampler, st);
     if (src_type == B200GEO_U8 && channels == 4) return launch_warp_t<uint8_t, 4>(ctx, src, dst, jobs_dev, n_jobs, max_ow, max_oh, dst_type, sampler, st);
     if (src_type == B200GEO_F32 && channels == 3) return launch_warp_t<float, 3>(ctx, src, dst, jobs_dev, n_jobs, max_ow, max_oh, dst_type, sampler, st);
@@ -584,6 +688,17 @@ int b200geo_warp_jobs_dev(b200geo_ctx *ctx, const void *src, void *dst, const b2
     return launch_warp(ctx, src, dst, jobs_dev, n_jobs, max_ow, max_oh, channels, src_type, dst_type, sampler, (cudaStream_t)stream);
 }
 
+int b200geo_warp_batch_dev(b200geo_ctx *ctx, const void *src, void *dst, const b200geo_warp_job *jobs_dev, int n_jobs,
+                           int max_ow, int max_oh, int channels, int src_type, int dst_type, int sampler,
+                           const b200geo_src_layout *layout, void *stream)
+{
+    B2G_ENTER(ctx);
+    B2G_ARG(src && dst && jobs_dev && n_jobs >= 0);
+    B2G_ARG(sampler == B200GEO_NN || sampler == B200GEO_BILINEAR);
+    B2G_ARG(dst_type == B200GEO_U8 || dst_type == B200GEO_F32 || dst_type == B200GEO_F64);
+    return launch_warp(ctx, src, dst, jobs_dev, n_jobs, max_ow, max_oh, channels, src_type, dst_type, sampler, (cudaStream_t)stream, layout);
+}
+
 int b200geo_warp_dev(b200geo_ctx *ctx, const void *src, void *dst, const b200geo_warp_job *jobs, int n_jobs, int channels,
                      int src_type, int dst_type, int sampler, void *stream)
 {
@@ -603,12 +718,17 @@ int b200geo_warp_dev(b200geo_ctx *ctx, const void *src, void *dst, const b200geo
     B2G_CUDA(cudaStreamSynchronize(st));
     memcpy(hp, jobs, bytes);
     int max_ow = 0, max_oh = 0;
+    // the jobs are visible here: describe the source as one 2-D byte array when they share a pitch
+    b200geo_src_layout lay = {jobs[0].src_pitch, 0};
+    bool uniform = true;
     for (int i = 0; i < n_jobs; ++i) {
         if (jobs[i].ow > max_ow) max_ow = jobs[i].ow;
         if (jobs[i].oh > max_oh) max_oh = jobs[i].oh;
+        if (jobs[i].src_pitch != lay.pitch || lay.pitch <= 0 || jobs[i].src_offset < 0 || jobs[i].src_offset % lay.pitch) uniform = false;
+        else if (jobs[i].src_offset / lay.pitch + jobs[i].ih > lay.rows) lay.rows = jobs[i].src_offset / lay.pitch + jobs[i].ih;
     }
     B2G_CUDA(cudaMemcpyAsync(dj, hp, bytes, cudaMemcpyHostToDevice, st));
-    return launch_warp(ctx, src, dst, dj, n_jobs, max_ow, max_oh, channels, src_type, dst_type, sampler, st);
+    return launch_warp(ctx, src, dst, dj, n_jobs, max_ow, max_oh, channels, src_type, dst_type, sampler, st, uniform ? &lay : nullptr);
 }
 
 int b200geo_warp_host(b200geo_ctx *ctx, const void *src, void *dst, const b200geo_warp_job *job, int channels,

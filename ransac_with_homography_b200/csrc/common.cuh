@@ -1,6 +1,7 @@
 // common.cuh -- context, scratch memory and error plumbing shared by the kernels' host wrappers.
 #pragma once
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -39,7 +40,7 @@ inline int fail(int code, const char *fmt, const char *a = "", const char *b = "
     } while (0)
 
 enum ScratchSlot {
-    S_PTS = 0, S_IDX, S_H, S_HINV, S_FLAGS, S_COUNTS, S_KEYS, S_RESULT, S_MASK, S_JOBS, S_SRC, S_DST, S_MISC, S_CMAX, S_STATS, S_WORKLIST,
+    S_PTS = 0, S_IDX, S_H, S_HINV, S_FLAGS, S_COUNTS, S_KEYS, S_RESULT, S_MASK, S_JOBS, S_SRC, S_DST, S_MISC, S_CMAX, S_STATS, S_WORKLIST, S_TILES,
     S_NUM
 };
 
@@ -53,6 +54,14 @@ struct b200geo_ctx {
     size_t mem_bytes;
     int64_t launches;
     int force_exact;       // B200GEO_OPT_FORCE_EXACT: score with the reference-order chain only
+    int warp_exact;        // B200GEO_OPT_WARP_EXACT: warp uint8 images with the float64 kernel only
+    int warp_variant;      // B200GEO_OPT_WARP_VARIANT: 0 = persistent TMA-pipelined kernel, 1 = one CTA per tile
+    int warp_pipe_ready;   // dynamic shared memory attribute of warp_pipe_kernel set
+    void *tmap_encode;     // cuTensorMapEncodeTiled (driver entry point), or NULL
+    int tmap_probed;
+    CUtensorMap tmap;      // cached 2-D tensor map of the last source layout
+    const void *tmap_src;
+    long long tmap_pitch, tmap_rows;
     void *scratch[b200geo::S_NUM];
     size_t scratch_cap[b200geo::S_NUM];
     void *pinned;          // small pinned staging block for scalar results

@@ -1,0 +1,843 @@
+// warp_fast.cuh -- K4 fast path: backward warp of uint8 RGB images to uint8 RGB, bilinear or nn.
+//
+// Same element semantics as warp.cuh (reference homography.py:108-209 + astype(uint8) of :225/:241),
+// organised for throughput.  The output is cut into 64 x 32 tiles; two kernels:
+//
+// warp_setup_kernel (one THREAD per tile, float64): re-expresses the projective map of the tile
+//   around the tile's centre pixel and an integer anchor (xc, yc) next to the centre's source
+//   position,
+//       rel_x = x - xc = (nx0 + ax*di + bx*dj) / (1 + gw*di + hw*dj)        (di, dj = pixel - centre)
+//   rounds the nine coefficients to float32 once, bounds the float32 evaluation error of rel
+//   (`band`), maps the four tile corners and classifies the tile: ZERO (wholly masked), INTERIOR
+//   (wholly unmasked), BORDER (per-pixel mask) or SLOW (the bound does not hold: w changes too
+//   much, footprint too large for shared memory, irregular grid, NaN).  64-byte descriptor per tile.
+//
+// warp_fast_kernel (one CTA per tile):
+//   1. staging: the source footprint (bounding box of the four mapped corners -- the image of a
+//      convex quad under a projective map with w > 0 is convex) is copied once from global memory
+//      into shared memory with 32-bit loads, re-laid-out as one 8-byte entry per source pixel x:
+//      (R[x] R[x+1] G[x] G[x+1]) (B[x] B[x+1] . .), i.e. horizontally adjacent taps already paired
+//      for the dot-product instruction.  Pixels outside the image and pixel (0,0) are staged as 0,
+//      which is exactly how the reference's samplers see them.
+//   2. sampling: every float32 term is tile-local (|di| <= 32, |rel| <= a few hundred), so rel has
+//      an absolute error of ~1e-5..1e-4 px although the image is thousands of pixels wide.  Per
+//      pixel: 3 FFMA + MUFU.RCP + 2 FMUL + 2 F2I give 16.16 fixed-point coordinates, two LDS.64
+//      fetch the four taps, and the blend is integer arithmetic with 16-bit weights that sum to
+//      exactly 65536 (IDP.2A, 2 per channel): flat regions are reproduced exactly and
+//      floor(v / 65536) is the reference's truncating astype(uint8).
+//   3. store: results are staged in shared memory (swizzled, conflict-free) and written with
+//      16-byte vector stores.
+//
+// Parity: mask decisions (bilinear: x > bw-1 | x < 0 ...; nn: the rounded index) are taken on the
+// float32 coordinates only when they are further than `band` from the decision boundary; pixels
+// inside the band, and every pixel of a SLOW tile, are evaluated by sample_store() in float64
+// exactly as warp_generic_kernel does.  nn output is therefore bit-identical to the reference;
+// bilinear output differs from the reference's float64 blend by < 0.05 grey levels before the
+// truncation, i.e. within +-1 after it (north_star tolerance), identical on flat regions and for
+// integer / dyadic translations.
+#pragma once
+
+#include "warp.cuh"
+
+namespace b200geo {
+
+#ifndef B2G_WP_OCC
+#define B2G_WP_OCC 3
+#endif
+#ifndef B2G_UNROLL_P
+#define B2G_UNROLL_P 4
+#endif
+constexpr int WF_UNROLL_P = B2G_UNROLL_P;   // rows of a thread's pixels unrolled together in the full-tile loop
+constexpr int WF_TW = 64;             // output tile width  (pixels)
+constexpr int WF_TH = 32;             // output tile height
+constexpr int WF_THREADS = 256;
+constexpr int WF_SRC_ENTRIES = 4096;  // staged source tile capacity: two planes of 16 KB (one 32-bit word per entry and plane)
+constexpr uint32_t WF_PLANE = WF_SRC_ENTRIES * 4u;   // byte offset of plane 1 (B pairs) from plane 0 (R/G pairs)
+constexpr float WF_MAX_REL = 1024.f;  // |rel| beyond this: SLOW (keeps the 16.16 conversion and the bound sane)
+constexpr float WF_MAX_BAND = 1.0f / 64.f;
+
+enum { WF_EMPTY = 0, WF_ZERO = 1, WF_INTERIOR = 2, WF_BORDER = 3, WF_SLOW = 4, WF_SPLIT = 5 };
+constexpr int WF_SUB_W = 32, WF_SUB_H = 16;   // SPLIT: the tile is redone as quadrants, each with its own (smaller) footprint
+constexpr int WF_TMA_BOX_W = 256;          // bytes per row of the 2-D TMA box (the hardware maximum for one dimension)
+constexpr int WF_TMA_BOX_H = 48;           // rows of the box: 12 KB per tile
+constexpr int WF_FLAG_TMA = 0x400;         // footprint fits the TMA box and the job lies in the described 2-D source array;
+                                           // `magic` then holds the array row of the footprint's first row
+constexpr int WF_FLAG_UNCHECKED = 0x100;   // footprint (+ read slack) lies inside the image and excludes pixel (0,0)
+
+struct __align__(16) WfDesc {
+    float nx0, ax, bx, ny0, ay, by, w0, gw, hw;   // w0, gw, hw pre-scaled by 2^-16: nx / w = rel * 65536
+    float band;                                   // ambiguity half-width, in rel * 65536 units
+    int xc, yc;                                   // anchor (absolute source pixel)
+    short ox, oy;                                 // staged tile origin, relative to the anchor
+    unsigned short P, rows;                       // staged tile pitch (entries, multiple of 4) and rows
+    int mode;                                     // WF_* | flags
+    unsigned magic;                               // ceil(2^32 / (P / 4)): division by the chunk count
+};
+static_assert(sizeof(WfDesc) == 64, "WfDesc is read as four 16-byte words");
+
+// Special registers read through volatile asm: the persistent loop is register-bound, and values
+// derived from %tid / %nctaid that the compiler hoists out of it end up spilled to local memory
+// (an LDL per tile on the critical path); re-deriving them per tile is a few ALU instructions.
+__device__ __forceinline__ int wf_tid()
+{
+    int v;
+    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(v));
+    return v;
+}
+__device__ __forceinline__ int wf_nctaid()
+{
+    int v;
+    asm volatile("mov.u32 %0, %%nctaid.x;" : "=r"(v));
+    return v;
+}
+
+__device__ __forceinline__ float wf_rcp(float x)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// rel * 65536 of output pixel (centre + di, centre + dj)
+__device__ __forceinline__ void wf_rel16(const WfDesc &T, float di, float dj, float &rx, float &ry)
+{
+    const float nx = __fmaf_rn(T.ax, di, __fmaf_rn(T.bx, dj, T.nx0));
+    const float ny = __fmaf_rn(T.ay, di, __fmaf_rn(T.by, dj, T.ny0));
+    const float w = __fmaf_rn(T.gw, di, __fmaf_rn(T.hw, dj, T.w0));
+    const float rw = wf_rcp(w);
+    rx = __fmul_rn(nx, rw);
+    ry = __fmul_rn(ny, rw);
+}
+
+// unmasked range of rel * 65536 for a tile anchored at (xc, yc)
+template <int BILINEAR>
+__device__ __forceinline__ void wf_bounds(int xc, int yc, int bw, int bh, float &lox, float &hix, float &loy, float &hiy)
+{
+    if (BILINEAR) {   // x > bw-1 | x < 0 | y > bh-1 | y < 0 -> masked (homography.py:126-130)
+        lox = (float)(0 - xc) * 65536.f; hix = (float)(bw - 1 - xc) * 65536.f;
+        loy = (float)(0 - yc) * 65536.f; hiy = (float)(bh - 1 - yc) * 65536.f;
+    } else {          // trunc(x + 0.5) in [0, bw-1]  <=>  x in (-1.5, bw - 0.5)   (homography.py:109-116)
+        lox = ((float)(0 - xc) - 1.5f) * 65536.f; hix = ((float)(bw - xc) - 0.5f) * 65536.f;
+        loy = ((float)(0 - yc) - 1.5f) * 65536.f; hiy = ((float)(bh - yc) - 0.5f) * 65536.f;
+    }
+}
+
+template <int BILINEAR>
+__device__ void wf_setup(const b200geo_warp_job &J, int c0, int r0, int tw, int th, long long tma_pitch, WfDesc &T)
+{
+    T.mode = WF_SLOW;
+    T.P = 0; T.rows = 0; T.ox = 0; T.oy = 0; T.xc = 0; T.yc = 0; T.band = 0.f; T.magic = 0u;
+    T.nx0 = T.ax = T.bx = T.ny0 = T.ay = T.by = T.gw = T.hw = 0.f; T.w0 = 1.f;
+    const int cm = c0 + WF_TW / 2, rm = r0 + WF_TH / 2;
+    const double Xm = (double)cm * J.dx + J.x0, Ym = (double)rm * J.dy + J.y0;
+    // the grid must be the arithmetic progression the tile-affine form assumes (np.linspace's
+    // forced last sample differs from it by an ulp; anything else goes the exact way)
+    const double exl = (double)(J.ow - 1) * J.dx + J.x0, eyl = (double)(J.oh - 1) * J.dy + J.y0;
+    bool ok = fabs(exl - J.x_last) <= 1e-9 * fmax(1.0, fabs(J.x_last)) && fabs(eyl - J.y_last) <= 1e-9 * fmax(1.0, fabs(J.y_last));
+    ok = ok && J.bw >= 2 && J.bh >= 2 && J.bw < (1 << 22) && J.bh < (1 << 22) && J.iw >= 1 && J.ih >= 1;
+    const double *h = J.invH;
+    const double zx = h[0] * Xm + h[1] * Ym + h[2];
+    const double zy = h[3] * Xm + h[4] * Ym + h[5];
+    const double zw = h[6] * Xm + h[7] * Ym + h[8];
+    ok = ok && fabs(zw) > 1e-200 && fabs(zw) < 1e200;
+    if (!ok) return;
+    const double s = 1.0 / zw;
+    const double xs = zx * s, ys = zy * s;
+    if (!(fabs(xs) < 4.0e6 && fabs(ys) < 4.0e6)) return;          // also NaN
+    const double xc = rint(xs), yc = rint(ys);
+    const double ax = (h[0] - xc * h[6]) * s * J.dx, bx = (h[1] - xc * h[7]) * s * J.dy;
+    const double ay = (h[3] - yc * h[6]) * s * J.dx, by = (h[4] - yc * h[7]) * s * J.dy;
+    const double gw = h[6] * s * J.dx, hw = h[7] * s * J.dy;
+    const double q = fabs(gw) * (WF_TW / 2) + fabs(hw) * (WF_TH / 2);   // |w - 1| over the tile
+    if (!(q <= 0.25)) return;
+    const double Sx = fabs(xs - xc) + fabs(ax) * (WF_TW / 2) + fabs(bx) * (WF_TH / 2);
+    const double Sy = fabs(ys - yc) + fabs(ay) * (WF_TW / 2) + fabs(by) * (WF_TH / 2);
+    if (!(Sx < 1.0e6 && Sy < 1.0e6)) return;
+    T.nx0 = (float)(xs - xc); T.ax = (float)ax; T.bx = (float)bx;
+    T.ny0 = (float)(ys - yc); T.ay = (float)ay; T.by = (float)by;
+    const double sc = 1.0 / 65536.0;
+    T.w0 = (float)sc; T.gw = (float)(gw * sc); T.hw = (float)(hw * sc);
+    T.xc = (int)xc; T.yc = (int)yc;
+
+    // four corners of the tile through the float32 formula the pixels use
+    float rxmin = 3.0e38f, rxmax = -3.0e38f, rymin = 3.0e38f, rymax = -3.0e38f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float di = (float)(((k & 1) ? tw - 1 : 0) - WF_TW / 2), dj = (float)(((k & 2) ? th - 1 : 0) - WF_TH / 2);
+        float rx, ry;
+        wf_rel16(T, di, dj, rx, ry);
+        rxmin = fminf(rxmin, rx); rxmax = fmaxf(rxmax, rx);
+        rymin = fminf(rymin, ry); rymax = fmaxf(rymax, ry);
+    }
+    const float R = fmaxf(fmaxf(fabsf(rxmin), fabsf(rxmax)), fmaxf(fabsf(rymin), fabsf(rymax))) * (1.0f / 65536.f);
+    if (!(R < WF_MAX_REL)) return;
+    // float32 error of rel (DESIGN.md "warp: coordinate error bound") with a 3.5x margin, plus the float64-side slack
+    const float band = 2.4e-7f * (6.f * (float)fmax(Sx, Sy) + 10.f * R) + 4.0e-6f;
+    if (!(band <= WF_MAX_BAND)) return;
+    const float B = band * 65536.f;
+    T.band = B;
+    float lox, hix, loy, hiy;
+    wf_bounds<BILINEAR>(T.xc, T.yc, J.bw, J.bh, lox, hix, loy, hiy);
+    // nn: an INTERIOR tile must also keep the rounded index non-negative (x > -0.5), so that the
+    // fast loop needs no trunc-toward-zero clamp
+    const float nn_lo = BILINEAR ? 0.f : 65536.f;
+    const bool all_in = rxmin >= lox + nn_lo + B && rxmax <= hix - B && rymin >= loy + nn_lo + B && rymax <= hiy - B;
+    const bool all_out = rxmax < lox - B || rxmin > hix + B || rymax < loy - B || rymin > hiy + B;
+    if (all_out) { T.mode = WF_ZERO; return; }
+    // index range of the entries the pixels can address (relative to the anchor); an entry holds x and x+1
+    int x_lo, x_hi, y_lo, y_hi;
+    if (BILINEAR) {
+        x_lo = __float2int_rd((rxmin - B) * (1.f / 65536.f)); x_hi = __float2int_rd((rxmax + B) * (1.f / 65536.f));
+        y_lo = __float2int_rd((rymin - B) * (1.f / 65536.f)); y_hi = __float2int_rd((rymax + B) * (1.f / 65536.f)) + 1;
+    } else {
+        x_lo = __float2int_rd((rxmin - B) * (1.f / 65536.f) + 0.5f) - 1; x_hi = __float2int_rd((rxmax + B) * (1.f / 65536.f) + 0.5f) + 1;
+        y_lo = __float2int_rd((rymin - B) * (1.f / 65536.f) + 0.5f) - 1; y_hi = __float2int_rd((rymax + B) * (1.f / 65536.f) + 0.5f) + 1;
+    }
+    if (!all_in) {   // clip to what an unmasked pixel can touch
+        x_lo = max(x_lo, 0 - T.xc); x_hi = min(x_hi, J.bw - 1 - T.xc);
+        y_lo = max(y_lo, 0 - T.yc); y_hi = min(y_hi, J.bh - (BILINEAR ? 0 : 1) - T.yc);
+    }
+    if (x_hi < x_lo || y_hi < y_lo) { x_hi = x_lo; y_hi = y_lo; }
+    // absolute origin column: a multiple of 4 pixels = 12 bytes, so that every 4-entry chunk of a
+    // row starts on a 32-bit boundary relative to the row start
+    const bool tma_job = tma_pitch > 0 && J.src_pitch == tma_pitch && J.src_offset >= 0 && J.src_offset % tma_pitch == 0;
+    const int ax0 = (T.xc + x_lo) & ~3;
+    const int ox = ax0 - T.xc;
+    const long long width = (long long)x_hi - ox + 1, rows = (long long)y_hi - y_lo + 1;
+    const long long P = (width + 3) & ~3LL;
+    if (ox < -32000 || y_lo < -32000) return;
+    if (P * rows > WF_SRC_ENTRIES) { T.mode = WF_SPLIT; return; }        // footprint does not fit: the kernel retries per quadrant
+    T.ox = (short)ox;
+    T.oy = (short)y_lo;
+    T.P = (unsigned short)P;
+    T.rows = (unsigned short)rows;
+    const unsigned chunks = (unsigned)(P >> 2);
+    T.magic = chunks > 1 ? (unsigned)((0x100000000ULL + chunks - 1) / chunks) : 0u;
+    T.mode = all_in ? WF_INTERIOR : WF_BORDER;
+    // unchecked staging: every 16-byte read of the staging loop stays inside the image rows
+    const int ay0 = T.yc + y_lo;
+    if (ax0 >= 0 && (long long)ax0 + P + 3 <= J.iw && ay0 >= 0 && (long long)ay0 + rows <= J.ih && !(ax0 == 0 && ay0 == 0)) {
+        T.mode |= WF_FLAG_UNCHECKED;
+        // a 2-D TMA box must start on a 16-byte boundary of the global array (measured: an unaligned
+        // innermost coordinate faults): the box starts at (3*ax0) & ~15 and the rows carry a phase of 0/4/8/12 bytes
+        if (tma_job && ((3 * ax0) & 15) + 3 * (P + 1) <= WF_TMA_BOX_W && rows <= WF_TMA_BOX_H) {
+            T.mode |= WF_FLAG_TMA;
+            T.magic = (unsigned)(J.src_offset / tma_pitch + ay0);
+        }
+    }
+}
+
+// Grid: (ceil(tiles_x / 32), ceil(tiles_y / 8), n_jobs), block (32, 8): one thread per tile.
+template <int BILINEAR>
+__global__ void __launch_bounds__(256)
+warp_setup_kernel(const b200geo_warp_job *__restrict__ jobs, const uint8_t *__restrict__ src_base, long long tma_pitch,
+                  int tiles_x, int tiles_y, WfDesc *__restrict__ descs)
+{
+    const int tx = blockIdx.x * 32 + threadIdx.x, ty = blockIdx.y * 8 + threadIdx.y;
+    if (tx >= tiles_x || ty >= tiles_y) return;
+    const b200geo_warp_job &J = jobs[blockIdx.z];
+    WfDesc T;
+    const int c0 = tx * WF_TW, r0 = ty * WF_TH;
+    if (c0 >= J.ow || r0 >= J.oh) {
+        T.mode = WF_EMPTY;
+        T.P = 0; T.rows = 0; T.ox = 0; T.oy = 0; T.xc = 0; T.yc = 0; T.band = 0.f; T.magic = 0u;
+        T.nx0 = T.ax = T.bx = T.ny0 = T.ay = T.by = T.gw = T.hw = 0.f; T.w0 = 1.f;
+    } else {
+        wf_setup<BILINEAR>(J, c0, r0, min(WF_TW, J.ow - c0), min(WF_TH, J.oh - r0), tma_pitch, T);
+    }
+    const uint4 *s = reinterpret_cast<const uint4 *>(&T);
+    uint4 *d = reinterpret_cast<uint4 *>(descs + ((size_t)blockIdx.z * tiles_y + ty) * tiles_x + tx);
+    d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; d[3] = s[3];
+}
+
+// ------------------------------------------------------------------------------------------------
+// shared-memory helpers (explicit .shared addressing keeps the address arithmetic 32-bit)
+// ------------------------------------------------------------------------------------------------
+// entry e of a staged tile: plane 0 word e = (R[x] R[x+1] G[x] G[x+1]), plane 1 word e = (B[x] B[x+1] . .).
+// Two planes (instead of one 8-byte record) make a lane's four entries one contiguous 16-byte store
+// per plane -- conflict-free -- at the price of two 32-bit loads per tap pair instead of one 64-bit.
+__device__ __forceinline__ uint2 wf_lds_entry(uint32_t a)
+{
+    uint2 v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v.x) : "r"(a));
+    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v.y) : "r"(a), "n"(WF_PLANE));
+    return v;
+}
+__device__ __forceinline__ void wf_sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v)); }
+__device__ __forceinline__ void wf_sts128(uint32_t a, uint4 v)
+{
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
+}
+
+// word index of output pixel (row, col) in the swizzled output stage (copy-out reads it with
+// conflict-free 128-bit loads)
+__device__ __forceinline__ int wf_out_index(int row, int col)
+{
+    const int u = col >> 2;
+    return row * WF_TW + (((u ^ ((u >> 3) & 1) ^ ((row & 1) << 1)) << 2) | (col & 3));
+}
+
+// 16 raw bytes w0..w3 = pixels x..x+4 (15 bytes used) -> the chunk's four entries, one 16-byte store per plane
+__device__ __forceinline__ void wf_store_chunk(uint32_t d, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3)
+{
+    uint4 rg, bb;
+    rg.x = __byte_perm(w0, w1, 0x4130); bb.x = __byte_perm(w0, w1, 0x5252);
+    rg.y = __byte_perm(w0, w1, 0x7463); bb.y = __byte_perm(w1, w2, 0x4141);
+    rg.z = __byte_perm(w1, w2, 0x6352); bb.z = __byte_perm(w2, w2, 0x3030);
+    rg.w = __byte_perm(w2, w3, 0x5241); bb.w = __byte_perm(w2, w3, 0x6363);
+    wf_sts128(d, rg);
+    wf_sts128(d + WF_PLANE, bb);
+}
+
+// one source pixel as the reference's samplers see it: 0 outside the image and at (0,0)
+__device__ __forceinline__ uint32_t wf_src_px(const uint8_t *__restrict__ src, size_t spitch, int iw, int ih, int y, int x)
+{
+    if (y < 0 || y >= ih || x < 0 || x >= iw || (x == 0 && y == 0)) return 0u;
+    const uint8_t *p = src + (size_t)y * spitch + 3 * (size_t)x;
+    return (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16);
+}
+
+// Copy the source footprint into shared memory as paired entries.
+__device__ __forceinline__ void wf_stage(const WfDesc &T, const uint8_t *__restrict__ src, size_t spitch, int iw, int ih,
+                                         uint32_t s_src)
+{
+    const int P = T.P, chunks = P >> 2, total = (int)T.rows * chunks;
+    const int ay0 = T.yc + T.oy, ax0 = T.xc + T.ox;
+    if (T.mode & WF_FLAG_UNCHECKED) {
+        const uint8_t *base = src + (size_t)ay0 * spitch + 3 * (size_t)ax0;
+        const bool aligned = ((((size_t)base) | spitch) & 3) == 0;
+        const uint32_t pitch32 = (uint32_t)spitch;
+        for (int t = threadIdx.x; t < total; t += WF_THREADS) {
+            const int i = chunks > 1 ? (int)__umulhi((unsigned)t, T.magic) : t;
+            const int k = t - i * chunks;
+            const uint8_t *a = base + ((uint32_t)i * pitch32 + 12u * (uint32_t)k);
+            uint32_t w0, w1, w2, w3;
+            if (aligned) {
+                const uint32_t *a4 = reinterpret_cast<const uint32_t *>(a);
+                w0 = __ldg(a4); w1 = __ldg(a4 + 1); w2 = __ldg(a4 + 2); w3 = __ldg(a4 + 3);
+            } else {
+                const uint32_t sh = ((uint32_t)(size_t)a & 3u) * 8u;
+                const uint32_t *a4 = reinterpret_cast<const uint32_t *>((size_t)a & ~(size_t)3);
+                const uint32_t v0 = __ldg(a4), v1 = __ldg(a4 + 1), v2 = __ldg(a4 + 2), v3 = __ldg(a4 + 3);
+                const uint32_t v4 = sh ? __ldg(a4 + 4) : 0u;
+                w0 = __funnelshift_r(v0, v1, sh); w1 = __funnelshift_r(v1, v2, sh);
+                w2 = __funnelshift_r(v2, v3, sh); w3 = __funnelshift_r(v3, v4, sh);
+            }
+            wf_store_chunk(s_src + (uint32_t)(i * P + 4 * k) * 4u, w0, w1, w2, w3);
+        }
+    } else {
+        for (int t = threadIdx.x; t < total; t += WF_THREADS) {
+            const int i = chunks > 1 ? (int)__umulhi((unsigned)t, T.magic) : t;
+            const int k = t - i * chunks;
+            const int sy = ay0 + i, sx = ax0 + 4 * k;
+            uint32_t px[5];
+#pragma unroll
+            for (int e = 0; e < 5; ++e) px[e] = wf_src_px(src, spitch, iw, ih, sy, sx + e);
+            uint4 rg, bb;
+            rg.x = __byte_perm(px[0], px[1], 0x5140); bb.x = __byte_perm(px[0], px[1], 0x7362);
+            rg.y = __byte_perm(px[1], px[2], 0x5140); bb.y = __byte_perm(px[1], px[2], 0x7362);
+            rg.z = __byte_perm(px[2], px[3], 0x5140); bb.z = __byte_perm(px[2], px[3], 0x7362);
+            rg.w = __byte_perm(px[3], px[4], 0x5140); bb.w = __byte_perm(px[3], px[4], 0x7362);
+            const uint32_t d = s_src + (uint32_t)(i * P + 4 * k) * 4u;
+            wf_sts128(d, rg);
+            wf_sts128(d + WF_PLANE, bb);
+        }
+    }
+}
+
+// one pixel of a SLOW tile / inside the ambiguity band: float64, exactly as warp_generic_kernel
+template <int BILINEAR>
+__device__ __noinline__ uint32_t wf_exact_px(const b200geo_warp_job &J, const uint8_t *__restrict__ src, int c, int r)
+{
+    const double Xo = grid_coord(J.x0, J.dx, J.x_last, c, J.ow);
+    const double Yo = grid_coord(J.y0, J.dy, J.y_last, r, J.oh);
+    const double zx = fma(J.invH[2], 1.0, fma(J.invH[1], Yo, J.invH[0] * Xo));
+    const double zy = fma(J.invH[5], 1.0, fma(J.invH[4], Yo, J.invH[3] * Xo));
+    const double zw = fma(J.invH[8], 1.0, fma(J.invH[7], Yo, J.invH[6] * Xo));
+    uint8_t o[3];
+    sample_store<uint8_t, uint8_t, 3, BILINEAR>(src, (size_t)J.src_pitch, J.iw, J.ih, J.bw, J.bh, zx / zw, zy / zw, o);
+    return (uint32_t)o[0] | ((uint32_t)o[1] << 8) | ((uint32_t)o[2] << 16);
+}
+
+// bilinear blend of two staged entry pairs with 16-bit weights summing to 65536
+__device__ __forceinline__ uint32_t wf_blend(uint2 top, uint2 bot, uint32_t fx, uint32_t fy)
+{
+    const uint32_t w11 = (fx * fy) >> 16;
+    const uint32_t Wbot = w11 * 65535u + fy;                       // (fy - w11) | w11 << 16
+    const uint32_t Wtop = fx * 65535u + 65536u - Wbot;             // (65536 - fx - fy + w11) | (fx - w11) << 16
+    const uint32_t vr = __dp2a_lo(Wtop, top.x, __dp2a_lo(Wbot, bot.x, 0u));
+    const uint32_t vg = __dp2a_hi(Wtop, top.x, __dp2a_hi(Wbot, bot.x, 0u));
+    const uint32_t vb = __dp2a_lo(Wtop, top.y, __dp2a_lo(Wbot, bot.y, 0u));
+    // v = value * 65536: byte 2 is floor(value) = astype(uint8).  fx = fy = 0 is the one case where
+    // a weight (w00 = 65536) does not fit its 16-bit field: the result is the tap itself.
+    const uint32_t o = __byte_perm(__byte_perm(vr, vg, 0x4462), vb, 0x4610);
+    return (fx | fy) ? o : __byte_perm(top.x, top.y, 0x4420);
+}
+
+// Full INTERIOR tile: no bounds, no mask; everything unrolled (8 pixels per thread).
+template <int BILINEAR>
+__device__ __forceinline__ void wf_compute_full(const WfDesc &T, const b200geo_warp_job &J, const uint8_t *__restrict__ src,
+                                                uint32_t s_src, uint32_t s_out, int c0, int r0, unsigned &n_exact)
+{
+    const int tid_ = wf_tid();
+    const int lane = tid_ & 31, wrp = tid_ >> 5;
+    const float di0 = (float)(lane - WF_TW / 2), dj0 = (float)(wrp - WF_TH / 2);
+    // coefficients live in registers; (x, y) numerators are carried as one float2 (FFMA2 / FMUL2)
+    const float2 a2 = make_float2(T.ax, T.ay), b2 = make_float2(T.bx, T.by);
+    const float gw = T.gw, hw = T.hw;
+    const float2 nb = __ffma2_rn(a2, make_float2(di0, di0), __ffma2_rn(b2, make_float2(dj0, dj0), make_float2(T.nx0, T.ny0)));
+    const float wb = __fmaf_rn(gw, di0, __fmaf_rn(hw, dj0, T.w0));
+    const uint32_t P4 = (uint32_t)T.P * 4u;
+    const uint32_t base = s_src - (uint32_t)(((int)T.oy * (int)T.P + (int)T.ox) * 4);
+    uint32_t oaddr[WF_TW / 32];
+#pragma unroll
+    for (int hh = 0; hh < WF_TW / 32; ++hh) oaddr[hh] = s_out + 4u * (uint32_t)wf_out_index(wrp, lane + 32 * hh);
+    const int B16 = (int)T.band + 2;
+#pragma unroll WF_UNROLL_P
+    for (int p = 0; p < WF_TH / 8; ++p) {
+        const float2 np = p ? __ffma2_rn(b2, make_float2((float)(8 * p), (float)(8 * p)), nb) : nb;
+        const float wp = p ? __fmaf_rn(hw, (float)(8 * p), wb) : wb;
+#pragma unroll
+        for (int hh = 0; hh < WF_TW / 32; ++hh) {
+            const float2 n = hh ? __ffma2_rn(a2, make_float2((float)(32 * hh), (float)(32 * hh)), np) : np;
+            const float w = hh ? __fmaf_rn(gw, (float)(32 * hh), wp) : wp;
+            const float rw = wf_rcp(w);
+            const float2 r = __fmul2_rn(n, make_float2(rw, rw));
+            const int fxd = __float2int_rd(r.x), fyd = __float2int_rd(r.y);
+            uint32_t out;
+            if (BILINEAR) {
+                const uint32_t a = (uint32_t)(fyd >> 16) * P4 + base + ((uint32_t)(fxd >> 16) << 2);
+                const uint2 top = wf_lds_entry(a), bot = wf_lds_entry(a + P4);
+                out = wf_blend(top, bot, (uint32_t)fxd & 0xFFFFu, (uint32_t)fyd & 0xFFFFu);
+            } else {
+                const int hx = fxd + 32768, hy = fyd + 32768;
+                const uint32_t fx = (uint32_t)hx & 0xFFFFu, fy = (uint32_t)hy & 0xFFFFu;
+                if (fx - (uint32_t)B16 > (uint32_t)(65535 - 2 * B16) || fy - (uint32_t)B16 > (uint32_t)(65535 - 2 * B16)) {
+                    // within `band` of a rounding boundary: the float64 path decides
+                    out = wf_exact_px<BILINEAR>(J, src, c0 + lane + 32 * hh, r0 + wrp + 8 * p);
+                    ++n_exact;
+                } else {
+                    const uint2 e = wf_lds_entry((uint32_t)(hy >> 16) * P4 + base + ((uint32_t)(hx >> 16) << 2));
+                    out = __byte_perm(e.x, e.y, 0x4420);
+                }
+            }
+            // row = wrp + 8p keeps its parity, so the swizzle of oaddr[] holds for every p
+            wf_sts32(oaddr[hh] + (uint32_t)(p * 8 * WF_TW * 4), out);
+        }
+    }
+}
+
+// Any other staged tile: partial tiles and BORDER tiles (per-pixel mask with the ambiguity band).
+template <int BILINEAR, int BORDER>
+__device__ __forceinline__ void wf_compute_general(const WfDesc &T, const b200geo_warp_job &J, const uint8_t *__restrict__ src,
+                                                uint32_t s_src, uint32_t s_out, int c0, int r0, int tw, int th, unsigned &n_exact,
+                                                int col_off = 0, int row_off = 0)
+{
+    // (c0, r0) is the output pixel of local (0, 0); (col_off, row_off) its place inside the staged output tile
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    const int P4 = (int)T.P * 4;
+    const uint32_t base = s_src - (uint32_t)(((int)T.oy * (int)T.P + (int)T.ox) * 4);
+    const int B16 = (int)T.band + 2;
+    float lox = 0.f, hix = 0.f, loy = 0.f, hiy = 0.f;
+    if (BORDER) wf_bounds<BILINEAR>(T.xc, T.yc, J.bw, J.bh, lox, hix, loy, hiy);
+    for (int row = wrp; row < th; row += 8) {
+        const float dj = (float)(row - WF_TH / 2);
+        for (int col = lane; col < tw; col += 32) {
+            float rx, ry;
+            wf_rel16(T, (float)(col - WF_TW / 2), dj, rx, ry);
+            uint32_t out = 0u;
+            bool fast = true;
+            if (BORDER) {
+                const bool in = rx >= lox + T.band && rx <= hix - T.band && ry >= loy + T.band && ry <= hiy - T.band;
+                const bool outp = rx < lox - T.band || rx > hix + T.band || ry < loy - T.band || ry > hiy + T.band;
+                if (!in) {
+                    fast = false;
+                    if (!outp) { out = wf_exact_px<BILINEAR>(J, src, c0 + col, r0 + row); ++n_exact; }
+                }
+            }
+            if (fast) {
+                const int fxd = __float2int_rd(rx), fyd = __float2int_rd(ry);
+                if (BILINEAR) {
+                    const uint32_t a = base + (uint32_t)((fyd >> 16) * P4 + (fxd >> 16) * 4);
+                    const uint2 top = wf_lds_entry(a), bot = wf_lds_entry(a + (uint32_t)P4);
+                    out = wf_blend(top, bot, (uint32_t)fxd & 0xFFFFu, (uint32_t)fyd & 0xFFFFu);
+                } else {
+                    const int hx = fxd + 32768, hy = fyd + 32768;
+                    const uint32_t fx = (uint32_t)hx & 0xFFFFu, fy = (uint32_t)hy & 0xFFFFu;
+                    if (fx - (uint32_t)B16 > (uint32_t)(65535 - 2 * B16) || fy - (uint32_t)B16 > (uint32_t)(65535 - 2 * B16)) {
+                        out = wf_exact_px<BILINEAR>(J, src, c0 + col, r0 + row);
+                        ++n_exact;
+                    } else {
+                        const int xi = max(hx >> 16, -T.xc), yi = max(hy >> 16, -T.yc);   // trunc toward zero: (-1, 0) -> 0
+                        const uint2 e = wf_lds_entry(base + (uint32_t)(yi * P4 + xi * 4));
+                        out = __byte_perm(e.x, e.y, 0x4420);
+                    }
+                }
+            }
+            wf_sts32(s_out + 4u * (uint32_t)wf_out_index(row + row_off, col + col_off), out);
+        }
+    }
+}
+
+// SPLIT tile: four quadrants, each set up here (warp 0, float64, like warp_setup_kernel does per
+// tile), staged synchronously and sampled by the general loop.  `sync` is the barrier of the
+// calling kernel's sampling threads.  A quadrant whose footprint still does not fit is exact.
+template <int BILINEAR, typename Sync>
+__device__ __noinline__ void wf_split_tile(const b200geo_warp_job &J, const uint8_t *__restrict__ src, WfDesc *s_sub, uint32_t s_src,
+                                           uint32_t s_out, uint32_t *s_out_mem, int c0, int r0, int tw, int th, unsigned &n_exact, Sync sync)
+{
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    for (int q = 0; q < (WF_TW / WF_SUB_W) * (WF_TH / WF_SUB_H); ++q) {
+        const int co = (q % (WF_TW / WF_SUB_W)) * WF_SUB_W, ro = (q / (WF_TW / WF_SUB_W)) * WF_SUB_H;
+        const int stw = min(WF_SUB_W, tw - co), sth = min(WF_SUB_H, th - ro);
+        if (stw <= 0 || sth <= 0) continue;                       // uniform
+        sync();                                                   // previous quadrant done with s_sub / the staged entries
+        if (wrp == 0) {
+            WfDesc t;
+            wf_setup<BILINEAR>(J, c0 + co, r0 + ro, stw, sth, 0, t);
+            if ((t.mode & 0xFF) == WF_SPLIT) t.mode = WF_SLOW;
+            if (lane == 0) *s_sub = t;
+        }
+        sync();
+        const int m = s_sub->mode & 0xFF;
+        if (m == WF_INTERIOR || m == WF_BORDER) {
+            wf_stage(*s_sub, src, (size_t)J.src_pitch, J.iw, J.ih, s_src);
+            sync();
+            if (m == WF_INTERIOR) wf_compute_general<BILINEAR, 0>(*s_sub, J, src, s_src, s_out, c0 + co, r0 + ro, stw, sth, n_exact, co, ro);
+            else wf_compute_general<BILINEAR, 1>(*s_sub, J, src, s_src, s_out, c0 + co, r0 + ro, stw, sth, n_exact, co, ro);
+        } else {
+            for (int row = wrp; row < sth; row += 8)
+                for (int col = lane; col < stw; col += 32) {
+                    uint32_t v = 0u;
+                    if (m != WF_ZERO) { v = wf_exact_px<BILINEAR>(J, src, c0 + co + col, r0 + ro + row); ++n_exact; }
+                    s_out_mem[wf_out_index(row + ro, col + co)] = v;
+                }
+        }
+    }
+}
+
+// write the tile: RGBX words in shared memory -> packed RGB bytes in global memory
+__device__ __forceinline__ void wf_copy_out(uint8_t *__restrict__ dst_job, size_t dst_pitch, const uint32_t *s_out_mem, int c0, int r0,
+                                            int tw, int th)
+{
+    uint8_t *dst = dst_job + (size_t)r0 * dst_pitch + (size_t)c0 * 3;
+    const bool vec = (((size_t)dst | dst_pitch) & 15) == 0 && tw == WF_TW;
+    if (vec) {
+        // task = 8 pixels of one row = 24 bytes = three 8-byte stores; 256 tasks for a full tile
+        const int t = wf_tid();
+        if (t < th * (WF_TW / 8)) {
+            const int row = t >> 3, h = t & 7;
+            const int sw = (h >> 2) ^ ((row & 1) << 1);           // (u >> 3) & 1 with u = 2h + j
+            const uint4 *s = reinterpret_cast<const uint4 *>(s_out_mem + row * WF_TW);
+            const uint4 a = s[(2 * h + 0) ^ sw], b = s[(2 * h + 1) ^ sw];
+            // 4 pixels (x,y,z,w = R G B .) -> 3 words: RGBR GBRG BRGB
+            uint2 o0, o1, o2;
+            o0.x = __byte_perm(a.x, a.y, 0x4210); o0.y = __byte_perm(a.y, a.z, 0x5421); o1.x = __byte_perm(a.z, a.w, 0x6542);
+            o1.y = __byte_perm(b.x, b.y, 0x4210); o2.x = __byte_perm(b.y, b.z, 0x5421); o2.y = __byte_perm(b.z, b.w, 0x6542);
+            uint2 *q = reinterpret_cast<uint2 *>(dst + (size_t)row * dst_pitch + h * 24);
+            q[0] = o0; q[1] = o1; q[2] = o2;
+        }
+    } else {
+        for (int i = threadIdx.x; i < th * WF_TW; i += WF_THREADS) {
+            const int row = i >> 6, col = i & (WF_TW - 1);
+            if (col >= tw) continue;
+            const uint32_t v = s_out_mem[wf_out_index(row, col)];
+            uint8_t *q = dst + (size_t)row * dst_pitch + col * 3;
+            q[0] = (uint8_t)v; q[1] = (uint8_t)(v >> 8); q[2] = (uint8_t)(v >> 16);
+        }
+    }
+}
+
+// Grid: (tiles_x, tiles_y, n_jobs).  stats[0] += pixels evaluated in float64.
+#ifndef B2G_WF_OCC
+#define B2G_WF_OCC 4
+#endif
+template <int BILINEAR>
+__global__ void __launch_bounds__(WF_THREADS, B2G_WF_OCC)
+warp_fast_kernel(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst_base,
+                 const b200geo_warp_job *__restrict__ jobs, const WfDesc *__restrict__ descs,
+                 unsigned long long *__restrict__ stats)
+{
+    __shared__ __align__(16) uint32_t s_src_mem[2 * WF_SRC_ENTRIES];
+    __shared__ __align__(16) uint32_t s_out_mem[WF_TW * WF_TH];
+
+    const WfDesc &T = descs[((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x];
+    const int mode = T.mode & 0xFF;
+    if (mode == WF_EMPTY) return;
+    const b200geo_warp_job &J = jobs[blockIdx.z];
+    const int c0 = blockIdx.x * WF_TW, r0 = blockIdx.y * WF_TH;
+    const int tw = min(WF_TW, J.ow - c0), th = min(WF_TH, J.oh - r0);
+    const uint8_t *src = src_base + J.src_offset;
+    const uint32_t s_src = (uint32_t)__cvta_generic_to_shared(s_src_mem);
+    const uint32_t s_out = (uint32_t)__cvta_generic_to_shared(s_out_mem);
+    unsigned n_exact = 0;
+
+    if (mode == WF_INTERIOR || mode == WF_BORDER) {
+        wf_stage(T, src, (size_t)J.src_pitch, J.iw, J.ih, s_src);
+        __syncthreads();
+        if (mode == WF_INTERIOR && tw == WF_TW && th == WF_TH) wf_compute_full<BILINEAR>(T, J, src, s_src, s_out, c0, r0, n_exact);
+        else if (mode == WF_INTERIOR) wf_compute_general<BILINEAR, 0>(T, J, src, s_src, s_out, c0, r0, tw, th, n_exact);
+        else wf_compute_general<BILINEAR, 1>(T, J, src, s_src, s_out, c0, r0, tw, th, n_exact);
+    } else if (mode == WF_ZERO) {
+        for (int i = threadIdx.x; i < WF_TW * WF_TH; i += WF_THREADS) s_out_mem[i] = 0u;
+    } else if (mode == WF_SPLIT) {
+        __shared__ WfDesc s_sub;
+        wf_split_tile<BILINEAR>(J, src, &s_sub, s_src, s_out, s_out_mem, c0, r0, tw, th, n_exact, [] { __syncthreads(); });
+    } else {
+        const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+        for (int row = wrp; row < th; row += 8)
+            for (int col = lane; col < tw; col += 32) {
+                s_out_mem[wf_out_index(row, col)] = wf_exact_px<BILINEAR>(J, src, c0 + col, r0 + row);
+                ++n_exact;
+            }
+    }
+    __syncthreads();
+
+    wf_copy_out(dst_base + J.dst_offset, (size_t)J.dst_pitch, s_out_mem, c0, r0, tw, th);
+    if (stats && n_exact) atomicAdd(stats, (unsigned long long)n_exact);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Persistent, warp-specialised, software-pipelined form of warp_fast_kernel.
+//
+// warp_fast_kernel exposes two serial memory latencies per tile (descriptor, then the source rows
+// the descriptor points at) and hides them only with the 4 CTAs an SM holds.  Here each CTA walks
+// tiles  blockIdx.x, blockIdx.x + gridDim.x, ...  with 8 consumer warps and 1 producer warp:
+//
+//   producer: reads descriptor i (prefetched two tiles ahead), the job's geometry, decides how the
+//     tile is staged, publishes a WpTile record in shared memory, arms the stage's `full` mbarrier
+//     with the byte count and issues one TMA bulk copy (cp.async.bulk, SASS UBLKCP) per source
+//     row -- 16-byte aligned raw RGB bytes -- into the stage's raw buffer.  It runs up to two tiles
+//     ahead of the consumers, gated by the stage's `empty` mbarrier.
+//   consumers: wait on `full` (normally already complete), convert the raw rows to paired entries
+//     shared-to-shared, release the stage (`empty`), sample, and write the tile out.  They
+//     synchronise among themselves with a named barrier; the producer never joins it.
+//
+// Tiles whose rows cannot be copied in bulk (image edges, footprints larger than the raw buffer)
+// are staged synchronously by the consumers as in warp_fast_kernel.
+// ------------------------------------------------------------------------------------------------
+constexpr int WP_RAW_BYTES = 14336;   // one raw-row buffer (x2); >= WF_TMA_BOX_W * WF_TMA_BOX_H
+constexpr int WP_OCC = B2G_WP_OCC;    // CTAs per SM
+constexpr int WP_THREADS = WF_THREADS + 32;
+
+struct __align__(16) WpTile {
+    WfDesc T;
+    const uint8_t *src;      // image base (job offset applied)
+    const uint8_t *a0;       // address of source pixel (ay0, ax0)
+    uint8_t *dst;            // output base of the job
+    long long src_pitch, dst_pitch;
+    int iw, ih, c0, r0, tw, th, jz;
+    uint32_t RB;             // bytes per raw row in shared memory (multiple of 16)
+    int staged, bulk;
+    uint32_t magic;          // ceil(2^32 / (P / 4)): division by the chunk count (T.magic holds the array row for TMA tiles)
+    int tma;                 // raw rows arrive as one 2-D tensor copy: row stride WF_TMA_BOX_W, one phase
+};
+
+constexpr int WP_STAGES = 2;          // raw-row buffers in flight
+constexpr int WP_TILE_RING = 4;       // tile records: a record outlives its raw buffer (read until the copy-out)
+
+struct WpSmem {
+    uint8_t raw[WP_STAGES][WP_RAW_BYTES];
+    uint32_t pairs[2 * WF_SRC_ENTRIES];   // plane 0, plane 1
+    uint32_t out[WF_TW * WF_TH];
+    WpTile tile[WP_TILE_RING];
+    WfDesc sub;              // SPLIT tiles: the quadrant being processed
+    unsigned long long full[WP_STAGES], empty[WP_STAGES];
+};
+
+__device__ __forceinline__ void wp_mbar_init(uint32_t a, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
+}
+__device__ __forceinline__ void wp_mbar_expect_tx(uint32_t a, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void wp_mbar_arrive(uint32_t a)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory");
+}
+__device__ __forceinline__ void wp_mbar_wait(uint32_t a, uint32_t parity)
+{
+    unsigned spins = 0;
+    for (;;) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+        if (ok) return;
+        if (++spins > (1u << 24)) __trap();        // a lost copy / protocol error must not hang the GPU
+    }
+}
+__device__ __forceinline__ void wp_bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t mbar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ uint32_t wp_lds32(uint32_t a)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void wp_consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(WF_THREADS) : "memory"); }
+
+// Raw RGB rows in shared memory -> entries.  Row i of the footprint starts `(phase0 + i * pitch32) & 15`
+// bytes into its raw row (per-row bulk copies start at the row address rounded down to 16; a 2-D
+// tensor copy has one phase for all rows: pitch32 = 0).  ALIGNED: all phases are multiples of 4
+// (always true for the tensor copy, whose origin column is a multiple of 4 pixels).
+template <int ALIGNED>
+__device__ __forceinline__ void wp_convert(const WfDesc &T, uint32_t magic, uint32_t phase0, uint32_t pitch32, uint32_t RB, uint32_t s_raw,
+                                           uint32_t s_pairs)
+{
+    const int P = T.P, chunks = P >> 2, total = (int)T.rows * chunks;
+    for (int t = wf_tid(); t < total; t += WF_THREADS) {
+        const int i = chunks > 1 ? (int)__umulhi((unsigned)t, magic) : t;
+        const int k = t - i * chunks;
+        const uint32_t o = ((phase0 + (uint32_t)i * pitch32) & 15u) + 12u * (uint32_t)k;   // byte offset in the raw row
+        const uint32_t a = s_raw + (uint32_t)i * RB + (o & ~3u);
+        uint32_t w0 = wp_lds32(a), w1 = wp_lds32(a + 4), w2 = wp_lds32(a + 8), w3 = wp_lds32(a + 12);
+        if (!ALIGNED) {
+            const uint32_t sh = (o & 3u) * 8u, w4 = wp_lds32(a + 16);
+            w0 = __funnelshift_r(w0, w1, sh); w1 = __funnelshift_r(w1, w2, sh);
+            w2 = __funnelshift_r(w2, w3, sh); w3 = __funnelshift_r(w3, w4, sh);
+        }
+        wf_store_chunk(s_pairs + (uint32_t)(i * P + 4 * k) * 4u, w0, w1, w2, w3);
+    }
+}
+
+// Grid: min(n_tiles, SMs * WP_OCC) CTAs of WP_THREADS; dynamic shared memory sizeof(WpSmem).
+template <int BILINEAR>
+__global__ void __launch_bounds__(WP_THREADS, WP_OCC)
+warp_pipe_kernel(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst_base,
+                 const b200geo_warp_job *__restrict__ jobs, const WfDesc *__restrict__ descs,
+                 int n_tiles, int tiles_x, int tiles_y, unsigned long long *__restrict__ stats,
+                 const __grid_constant__ CUtensorMap tmap, int use_tmap)
+{
+    extern __shared__ __align__(16) unsigned char wp_smem[];
+    WpSmem &S = *reinterpret_cast<WpSmem *>(wp_smem);
+    const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+    const int first = blockIdx.x;
+    if (first >= n_tiles) return;
+    // shared-space addresses are computed, never held in (locally-indexed) arrays
+    const uint32_t s_raw0 = (uint32_t)__cvta_generic_to_shared(S.raw[0]);
+    const uint32_t s_full0 = (uint32_t)__cvta_generic_to_shared(&S.full[0]);
+    const uint32_t s_empty0 = (uint32_t)__cvta_generic_to_shared(&S.empty[0]);
+
+    if (tid == 0) {
+        for (int i = 0; i < WP_STAGES; ++i) {
+            wp_mbar_init(s_full0 + 8u * i, 1);
+            wp_mbar_init(s_empty0 + 8u * i, WF_THREADS / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (wrp == WF_THREADS / 32) {
+        // ---------------------------------------------------------------- producer warp
+        const int tpj = tiles_x * tiles_y;
+        uint4 nd0 = make_uint4(0u, 0u, 0u, 0u), nd1 = nd0;      // lanes 0..3: descriptors of the next two tiles
+        if (lane < 4) {
+            nd0 = __ldg(reinterpret_cast<const uint4 *>(descs + first) + lane);
+            if (first + (int)gridDim.x < n_tiles) nd1 = __ldg(reinterpret_cast<const uint4 *>(descs + first + gridDim.x) + lane);
+        }
+        int it = 0;
+        for (int tile = first; tile < n_tiles; ++it, tile += wf_nctaid()) {
+            const int b = it % WP_STAGES, use = it / WP_STAGES;
+            const uint32_t s_full = s_full0 + 8u * b, s_raw = s_raw0 + (uint32_t)WP_RAW_BYTES * b;
+            if (use >= 1) wp_mbar_wait(s_empty0 + 8u * b, (uint32_t)(use - 1) & 1u);
+            WpTile &W = S.tile[it % WP_TILE_RING];
+            if (lane < 4) reinterpret_cast<uint4 *>(&W.T)[lane] = nd0;
+            nd0 = nd1;
+            if (lane < 4 && tile + 2 * (int)gridDim.x < n_tiles) nd1 = __ldg(reinterpret_cast<const uint4 *>(descs + tile + 2 * gridDim.x) + lane);
+            __syncwarp();
+            const int jz = tile / tpj, rem = tile - jz * tpj;
+            const int ty = rem / tiles_x, tx = rem - ty * tiles_x;
+            const b200geo_warp_job &J = jobs[jz];
+            const int mode = W.T.mode & 0xFF;
+            const int P = W.T.P, rows = W.T.rows;
+            const uint8_t *src = src_base + J.src_offset;
+            const size_t pitch = (size_t)J.src_pitch;
+            const int ay0 = W.T.yc + W.T.oy, ax0 = W.T.xc + W.T.ox;
+            const uint8_t *a0 = src + (long long)ay0 * (long long)pitch + 3LL * ax0;
+            const uint32_t RB = (uint32_t)(15 + 3 * (P + 1) + 15) & ~15u;
+            const bool staged = mode == WF_INTERIOR || mode == WF_BORDER;
+            const uint32_t chunks = (uint32_t)P >> 2;
+            const size_t lo = (size_t)a0 & ~(size_t)15;
+            const size_t hi = ((size_t)a0 + (size_t)(rows - 1) * pitch) & ~(size_t)15;
+            const size_t img_end = (size_t)src + (size_t)(J.ih - 1) * pitch + 3 * (size_t)J.iw;
+            const bool tma = use_tmap && staged && (W.T.mode & WF_FLAG_TMA);
+            const bool bulk = tma || (staged && !(W.T.mode & WF_FLAG_TMA) && (W.T.mode & WF_FLAG_UNCHECKED) &&
+                                      (uint32_t)rows * RB <= (uint32_t)WP_RAW_BYTES && lo >= (size_t)src && hi + RB <= img_end);
+            if (lane == 0) {
+                W.src = src; W.a0 = a0; W.dst = dst_base + J.dst_offset;
+                W.src_pitch = J.src_pitch; W.dst_pitch = J.dst_pitch;
+                W.iw = J.iw; W.ih = J.ih; W.c0 = tx * WF_TW; W.r0 = ty * WF_TH;
+                W.tw = min(WF_TW, J.ow - tx * WF_TW); W.th = min(WF_TH, J.oh - ty * WF_TH);
+                W.jz = jz; W.RB = tma ? (uint32_t)WF_TMA_BOX_W : RB; W.staged = staged; W.bulk = bulk; W.tma = tma;
+                const int srow = (int)W.T.magic;                   // TMA tiles: array row of the footprint's first row
+                if (W.T.mode & WF_FLAG_TMA)                        // everyone downstream wants the chunk divisor
+                    W.T.magic = chunks > 1 ? (uint32_t)((0x100000000ULL + chunks - 1) / chunks) : 0u;
+                W.magic = W.T.magic;
+                if (tma) {
+                    wp_mbar_expect_tx(s_full, (uint32_t)(WF_TMA_BOX_W * WF_TMA_BOX_H));
+                    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                                 ::"r"(s_raw), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"((3 * ax0) & ~15), "r"(srow), "r"(s_full) : "memory");
+                } else if (bulk) wp_mbar_expect_tx(s_full, (uint32_t)rows * RB);
+                else wp_mbar_arrive(s_full);
+            }
+            __syncwarp();
+            if (bulk && !tma)
+                for (int r = lane; r < rows; r += 32) {
+                    const size_t ar = ((size_t)a0 + (size_t)r * pitch) & ~(size_t)15;
+                    wp_bulk_g2s(s_raw + (uint32_t)r * RB, reinterpret_cast<const void *>(ar), RB, s_full);
+                }
+        }
+        return;
+    }
+
+    // -------------------------------------------------------------------- consumer warps
+    const uint32_t s_pairs = (uint32_t)__cvta_generic_to_shared(S.pairs);
+    const uint32_t s_out = (uint32_t)__cvta_generic_to_shared(S.out);
+    unsigned n_exact = 0;
+    // the tile index itself travels in the WpTile record: the consumers only count iterations
+    const int n_iter = (n_tiles - first + (int)gridDim.x - 1) / (int)gridDim.x;
+    for (int it = 0; it < n_iter; ++it) {
+        const int b = it % WP_STAGES, use = it / WP_STAGES;
+        wp_mbar_wait(s_full0 + 8u * b, (uint32_t)use & 1u);
+        // the record's ring slot is rewritten WP_TILE_RING tiles later; the producer is at most
+        // WP_STAGES tiles ahead of the conversion below, so it stays valid through the copy-out
+        const WpTile &W = S.tile[it % WP_TILE_RING];
+        const int mode = W.T.mode & 0xFF;
+        if (W.tma) wp_convert<1>(W.T, W.magic, (uint32_t)(size_t)W.a0, 0u, W.RB, s_raw0 + (uint32_t)WP_RAW_BYTES * b, s_pairs);
+        else if (W.bulk) wp_convert<0>(W.T, W.magic, (uint32_t)(size_t)W.a0, (uint32_t)W.src_pitch, W.RB, s_raw0 + (uint32_t)WP_RAW_BYTES * b, s_pairs);
+        else if (W.staged) wf_stage(W.T, W.src, (size_t)W.src_pitch, W.iw, W.ih, s_pairs);
+        __syncwarp();
+        if (lane == 0) wp_mbar_arrive(s_empty0 + 8u * b);     // raw[b] may be refilled
+        wp_consumer_sync();     // entries visible; the previous tile's copy-out has finished reading S.out
+        if (mode != WF_EMPTY) {
+            const b200geo_warp_job &J = jobs[W.jz];
+            if (W.staged) {
+                if (mode == WF_INTERIOR && W.tw == WF_TW && W.th == WF_TH) wf_compute_full<BILINEAR>(W.T, J, W.src, s_pairs, s_out, W.c0, W.r0, n_exact);
+                else if (mode == WF_INTERIOR) wf_compute_general<BILINEAR, 0>(W.T, J, W.src, s_pairs, s_out, W.c0, W.r0, W.tw, W.th, n_exact);
+                else wf_compute_general<BILINEAR, 1>(W.T, J, W.src, s_pairs, s_out, W.c0, W.r0, W.tw, W.th, n_exact);
+            } else if (mode == WF_ZERO) {
+                for (int i = tid; i < WF_TW * WF_TH; i += WF_THREADS) S.out[i] = 0u;
+            } else if (mode == WF_SPLIT) {
+                wf_split_tile<BILINEAR>(J, W.src, &S.sub, s_pairs, s_out, S.out, W.c0, W.r0, W.tw, W.th, n_exact, [] { wp_consumer_sync(); });
+            } else {
+                for (int row = wrp; row < W.th; row += 8)
+                    for (int col = lane; col < W.tw; col += 32) {
+                        S.out[wf_out_index(row, col)] = wf_exact_px<BILINEAR>(J, W.src, W.c0 + col, W.r0 + row);
+                        ++n_exact;
+                    }
+            }
+        }
+        wp_consumer_sync();
+        if (mode != WF_EMPTY) wf_copy_out(W.dst, (size_t)W.dst_pitch, S.out, W.c0, W.r0, W.tw, W.th);
+    }
+    if (stats && n_exact) atomicAdd(stats, (unsigned long long)n_exact);
+}
+
+}  // namespace b200geo

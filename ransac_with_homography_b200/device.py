@@ -212,10 +212,18 @@ def upload_jobs(jobs: np.ndarray, device) -> torch.Tensor:
     return torch.from_numpy(np.ascontiguousarray(jobs).view(np.uint8).copy()).to(device)
 
 
-def warp_resident(src, dst, jobs_dev: torch.Tensor, n_jobs: int, max_ow: int, max_oh: int, channels=3, sampler="bilinear"):
-    """K4 with the job array already on the device: no host work per launch."""
+def warp_resident(src, dst, jobs_dev: torch.Tensor, n_jobs: int, max_ow: int, max_oh: int, channels=3, sampler="bilinear",
+                  layout=None):
+    """K4 with the job array already on the device: no host work per launch.  layout = (pitch_bytes,
+    rows) describes `src` as one 2-D byte array (frames stored back to back: rows = n_frames * height)
+    and lets the kernel fetch each tile's source footprint with one 2-D TMA copy."""
     ctx = _ctx(src)
-    _cabi.check(ctx.lib.b200geo_warp_jobs_dev(ctx.handle, _p(src), _p(dst), _p(jobs_dev), int(n_jobs), int(max_ow),
-                                              int(max_oh), channels, _TORCH_TYPE[src.dtype], _TORCH_TYPE[dst.dtype],
-                                              _cabi.SAMPLERS[sampler], _stream(src)))
+    lay = None
+    if layout is not None:
+        lay = _cabi.SrcLayout(int(layout[0]), int(layout[1]))
+    import ctypes as C
+    _cabi.check(ctx.lib.b200geo_warp_batch_dev(ctx.handle, _p(src), _p(dst), _p(jobs_dev), int(n_jobs), int(max_ow),
+                                               int(max_oh), channels, _TORCH_TYPE[src.dtype], _TORCH_TYPE[dst.dtype],
+                                               _cabi.SAMPLERS[sampler], C.byref(lay) if lay is not None else None,
+                                               _stream(src)))
     return dst
