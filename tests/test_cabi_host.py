@@ -178,3 +178,28 @@ def test_canvas_placement_all_sign_cases(golden):
         canvas[tsy:tey + 1, tsx:tex + 1] = oracle.to_u8(t)
         canvas[qsy:qey + 1, qsx:qex + 1] = w["img2"]
         assert np.array_equal(canvas, w[f"pano_{name}_paste"])
+
+
+def test_dropin_modules_resolve_under_the_reference_names():
+    """`from homography import transformImage` / `from ransac import stitching` (reference app.py:9-10)
+    must resolve to this package when dropin/ is on the path; importing needs no GPU."""
+    import importlib
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "dropin"))
+    saved = {k: sys.modules.pop(k, None) for k in ("homography", "ransac")}
+    try:
+        hg, rs = importlib.import_module("homography"), importlib.import_module("ransac")
+        import ransac_with_homography_b200.homography as ours_h
+        import ransac_with_homography_b200.ransac as ours_r
+        assert hg.transformImage is ours_h.transformImage and hg.transformImageH is ours_h.transformImageH
+        assert rs.stitching is ours_r.stitching and rs.RANSAC is ours_r.RANSAC and rs.HomoModel is ours_r.HomoModel
+        for name in ("calcHomography", "calcHomographyLinear", "wrapPerspective", "wrapPerspectiveScan", "nearestNeighbor",
+                     "bilinear", "stitchPanorama", "addAlpha", "BLENDDIR", "cylindericlMap"):
+            assert hasattr(hg, name), name
+    finally:
+        sys.path.pop(0)
+        for k, v in saved.items():
+            sys.modules.pop(k, None)
+            if v is not None:
+                sys.modules[k] = v
