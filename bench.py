@@ -71,6 +71,35 @@ def frame_homographies(n, h, w, jitter, seed=0):
     return Hs
 
 
+C5 = dict(pairs=1024, M=2000, K=8192, th=4.0, d=95.0, h=1080, w=1920, canvas=(2160, 3840))
+
+
+def stitch_pairs(p0, p1):
+    """C5 pairs p0..p1-1: per pair a near-identity homography (corner jitter +-10%, translation within
+    +-900 / +-500 px), M correspondences with 50% outliers and 0.5 px noise, K explicit sample sets."""
+    M, K, h, w = C5["M"], C5["K"], C5["h"], C5["w"]
+    n = p1 - p0
+    pts = np.empty((n, M, 4), np.float32)
+    idx = np.empty((n, K, 4), np.int32)
+    src = np.array([[0, 0], [w, 0], [w, h], [0, h]], np.float64)
+    for i, p in enumerate(range(p0, p1)):
+        rs = np.random.RandomState(1000 + p)
+        dst = src + rs.uniform(-0.1, 0.1, (4, 2)) * [w, h] + rs.uniform(-1, 1, 2) * [900, 500]
+        A = np.zeros((8, 8)); b = np.zeros(8)
+        for j, ((x, y), (X, Y)) in enumerate(zip(src, dst)):
+            A[2 * j] = [x, y, 1, 0, 0, 0, -x * X, -y * X]; A[2 * j + 1] = [0, 0, 0, x, y, 1, -x * Y, -y * Y]
+            b[2 * j], b[2 * j + 1] = X, Y
+        Ht = np.append(np.linalg.solve(A, b), 1).reshape(3, 3)
+        X = rs.rand(2, M) * np.array([[w], [h]], np.float64)
+        q = Ht @ np.vstack([X, np.ones(M)])
+        Y = q[:2] / q[2] + rs.randn(2, M) * 0.5
+        out = rs.rand(M) < 0.5
+        Y[:, out] = rs.rand(2, int(out.sum())) * np.array([[w], [h]])
+        pts[i, :, :2], pts[i, :, 2:] = X.T, Y.T
+        idx[i] = np.random.RandomState(p).randint(0, M, (K, 4))
+    return pts, idx
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -397,22 +426,22 @@ def bench_warp(torch, dist, rank, world, args, ctx, peaks, local_gpu):
             "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peaks['source']})", "algorithmic_bytes_per_pixel": 6.0,
             "kernel_ms": k_avg_s * 1e3, "kernel_share_of_step": 1.0}
 
-    # end to end on a bounded batch: pinned host frames -> device -> warp -> pinned host
+    # end to end on a bounded batch: pinned host frames in, pinned host frames out, through the host-buffer entry
+    # point b200geo_warp_batch_host (chunked host->device / warp / device->host pipeline inside the library)
     nb = min(64, n)
     pin_in = torch.empty((nb, h, w, 3), dtype=torch.uint8).pin_memory()
     pin_in.copy_(src[:nb])
     pin_out = torch.empty((nb, h, w, 3), dtype=torch.uint8).pin_memory()
-    d_in, d_out = torch.empty_like(src[:nb]), torch.empty_like(src[:nb])
     jb = device.scan_jobs(Hs[:nb], (h, w), (h, w))
 
     def e2e_step():
-        d_in.copy_(pin_in, non_blocking=True)
-        device.warp(d_in, d_out, jb, 3, "bilinear")
-        pin_out.copy_(d_out, non_blocking=True)
-        torch.cuda.synchronize()
+        device.warp_host(pin_in, pin_out, jb, 3, "bilinear", device=local_gpu)
     n_e2e = max(2, min(args.steps, 5))
     ems = timed_steps(torch, dist, world, e2e_step, n_e2e, 1)
     e2e_v = world * nb * h * w * n_e2e / (ems / 1e3) / 1e9
+    chk = torch.empty_like(src[:nb])
+    device.warp(src[:nb], chk, jb, 3, "bilinear")
+    assert torch.equal(chk.cpu(), pin_out), "host-batch pipeline and device-resident warp disagree"
     rec = {"metric": "warp_gpix_per_s", "value": value, "unit": "Gpix/s", "ms_per_step": ms / args.steps,
            "dtype": "u8 pixels; f64 per-tile set-up, f32 tile-relative coordinates, 16.16 integer blend",
            "config": {"workload": "C4 batched backward warp: 4096 synthetic 1920x1080 RGB uint8 frames, per-frame random homography "
@@ -421,11 +450,51 @@ def bench_warp(torch, dist, rank, world, args, ctx, peaks, local_gpu):
                       "l2": "inputs (25.5 GB per 4096 frames) are larger than L2"},
            "roofline": roof,
            "e2e": {"value": e2e_v, "unit": "Gpix/s", "h2d_bytes_per_step": int(nb * per_frame), "d2h_bytes_per_step": int(nb * per_frame),
-                   "ms_per_step": ems / n_e2e, "how": f"{nb} frames per rank per step: pinned host -> device.warp -> pinned host"},
+                   "ms_per_step": ems / n_e2e, "how": f"{nb} frames per rank per step: pinned host -> device.warp_host (b200geo_warp_batch_host: 8-frame chunks, "
+                                                        "copies and kernels overlapped on three streams) -> pinned host"},
            "gpu_launches": int(launches), "clocks": cs.summary()}
     del src, dst
     torch.cuda.empty_cache()
     return rec
+
+
+def bench_stitch(torch, dist, rank, world, args, ctx, peaks, local_gpu):
+    """C5: batched stitch pipeline, pairs sharded over the ranks, no communication."""
+    from ransac_with_homography_b200 import device
+    lo, hi = device.shard_range(C5["pairs"], rank, world)
+    n = hi - lo
+    h, w, (ch, cw) = C5["h"], C5["w"], C5["canvas"]
+    pts_h, idx_h = stitch_pairs(lo, hi)
+    pts, idx = torch.from_numpy(pts_h).cuda(), torch.from_numpy(idx_h).cuda()
+    frames = torch.empty((n, h, w, 3), dtype=torch.uint8, device="cuda")
+    g = torch.Generator(device="cuda")
+    for i in range(0, n, 64):
+        g.manual_seed(7000 + lo + i)
+        m = min(64, n - i)
+        frames[i:i + m] = torch.randint(0, 256, (m, h, w, 3), dtype=torch.uint8, device="cuda", generator=g)
+    canv = torch.zeros((n, ch, cw, 3), dtype=torch.uint8, device="cuda")
+    out = {}
+
+    def step():
+        out["r"] = device.stitch_batched(pts, idx, frames, C5["th"], C5["d"], (ch, cw), canvases=canv)
+    l0 = ctx.launch_count()
+    ms = timed_steps(torch, dist, world, step, args.steps, args.warmup, None)
+    launches = (ctx.launch_count() - l0) * args.steps // (args.steps + args.warmup)
+    _, boxes, results, _ = out["r"]
+    res = results.cpu().numpy()
+    pix = int((boxes[:, 2].astype(np.int64) * boxes[:, 3]).sum())
+    if world > 1:
+        t = torch.tensor([pix], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t)
+        pix = int(t.item())
+    s = ms / args.steps / 1e3
+    return {"metric": "stitch_pairs_per_s", "value": C5["pairs"] / s, "unit": "pairs/s", "ms_per_step": ms / args.steps,
+            "ransac_hyp_pts_per_s": C5["pairs"] * C5["M"] * C5["K"] / s, "warp_gpix_per_s": pix / s / 1e9,
+            "config": {"workload": f"C5 batched stitch: {C5['pairs']} pairs x {C5['M']} correspondences x {C5['K']} sample sets (fwd, th=4, d=95) "
+                                   "+ refit + bilinear bbox warp of a 1080p frame into a 2160x3840 canvas slot; RANSAC and warp timed together "
+                                   "(the two rates above both divide by the whole step)",
+                       "sharding": f"pairs over {world} rank(s), no communication"},
+            "gpu_launches": int(launches), "pairs_ok": int((res[:, 2] == 0).sum()), "median_inliers": float(np.median(res[:, 1]))}
 
 
 def run_ours(args):
@@ -448,11 +517,21 @@ def run_ours(args):
         line = bench_ransac(torch, dist, rank, world, args, ctx, peaks, local)
     if args.workload in ("all", "warp"):
         warp_rec = bench_warp(torch, dist, rank, world, args, ctx, peaks, local)
+    stitch_rec = None
+    if args.workload in ("all", "stitch"):
+        torch.cuda.empty_cache()
+        stitch_rec = bench_stitch(torch, dist, rank, world, args, ctx, peaks, local)
+    if line is None and warp_rec is None:
+        line, stitch_rec = stitch_rec, None
+        line.setdefault("clocks", {"sm_mhz": None, "sm_max_mhz": None, "reasons": []})
     if line is None:
         line, warp_rec = warp_rec, None
     line.update({"n_gpus": world, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "strong",
                  "vs_baseline": None, "data": "synthetic"})
     line.setdefault("dtype", "f32")
+    if stitch_rec is not None:
+        line["stitch"] = stitch_rec
+        line["gpu_launches"] = line["gpu_launches"] + stitch_rec["gpu_launches"]
     if warp_rec is not None:
         line["warp"] = warp_rec
         line["clocks"] = merge_clocks(line["clocks"], warp_rec["clocks"])
@@ -486,7 +565,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="all", choices=["all", "ransac", "warp"])
+    ap.add_argument("--workload", default="all", choices=["all", "ransac", "warp", "stitch"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":

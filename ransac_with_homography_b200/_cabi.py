@@ -84,6 +84,7 @@ SIGNATURES = {
     "b200geo_warp_dev": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "b200geo_warp_jobs_dev": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "b200geo_warp_batch_dev": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "b200geo_warp_batch_host": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i]),
     "b200geo_warp_host": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i]),
     "b200geo_sample_host": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, C.c_longlong, _i, _i, _i, _i, _vp]),
 }

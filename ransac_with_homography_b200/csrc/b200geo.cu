@@ -58,6 +58,11 @@ int b200geo_destroy(b200geo_ctx *ctx)
         for (int i = 0; i < S_NUM; ++i)
             if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
         if (ctx->pinned) cudaFreeHost(ctx->pinned);
+        if (ctx->pipe_ready) {
+            for (int i = 0; i < 3; ++i) cudaStreamDestroy(ctx->pipe_stream[i]);
+            for (int i = 0; i < 3; ++i)
+                for (int b = 0; b < 2; ++b) cudaEventDestroy(ctx->pipe_event[i][b]);
+        }
     }
     delete ctx;
     return B200GEO_OK;
@@ -729,6 +734,90 @@ int b200geo_warp_dev(b200geo_ctx *ctx, const void *src, void *dst, const b200geo
     }
     B2G_CUDA(cudaMemcpyAsync(dj, hp, bytes, cudaMemcpyHostToDevice, st));
     return launch_warp(ctx, src, dst, dj, n_jobs, max_ow, max_oh, channels, src_type, dst_type, sampler, st, uniform ? &lay : nullptr);
+}
+
+int b200geo_warp_batch_host(b200geo_ctx *ctx, const void *src_host, void *dst_host, const b200geo_warp_job *jobs, int n_jobs,
+                            int channels, int src_type, int dst_type, int sampler, int chunk_jobs)
+{
+    B2G_ENTER(ctx);
+    B2G_ARG(src_host && dst_host && jobs && n_jobs >= 0);
+    B2G_ARG(sampler == B200GEO_NN || sampler == B200GEO_BILINEAR);
+    B2G_ARG(dst_type == B200GEO_U8 || dst_type == B200GEO_F32 || dst_type == B200GEO_F64);
+    if (n_jobs == 0) return B200GEO_OK;
+    if (chunk_jobs <= 0) chunk_jobs = 8;
+    if (chunk_jobs > n_jobs) chunk_jobs = n_jobs;
+    if (!ctx->pipe_ready) {
+        for (int i = 0; i < 3; ++i) B2G_CUDA(cudaStreamCreateWithFlags(&ctx->pipe_stream[i], cudaStreamNonBlocking));
+        for (int i = 0; i < 3; ++i)
+            for (int b = 0; b < 2; ++b) B2G_CUDA(cudaEventCreateWithFlags(&ctx->pipe_event[i][b], cudaEventDisableTiming));
+        ctx->pipe_ready = 1;
+    }
+    cudaStream_t s_in = ctx->pipe_stream[0], s_k = ctx->pipe_stream[1], s_out = ctx->pipe_stream[2];
+    // device images of one chunk are packed back to back (256-byte aligned); jobs are rebased onto them
+    const int n_chunks = (n_jobs + chunk_jobs - 1) / chunk_jobs;
+    std::vector<b200geo_warp_job> dj(jobs, jobs + n_jobs);
+    size_t max_src = 0, max_dst = 0;
+    bool uniform = true;
+    b200geo_src_layout lay = {jobs[0].src_pitch, 0};
+    for (int c = 0; c < n_chunks; ++c) {
+        size_t so = 0, dofs = 0;
+        for (int j = c * chunk_jobs; j < n_jobs && j < (c + 1) * chunk_jobs; ++j) {
+            B2G_ARG(jobs[j].ow > 0 && jobs[j].oh > 0 && jobs[j].iw > 0 && jobs[j].ih > 0 && jobs[j].src_pitch > 0 && jobs[j].dst_pitch > 0);
+            dj[j].src_offset = (int64_t)so;
+            dj[j].dst_offset = (int64_t)dofs;
+            if (jobs[j].src_pitch != lay.pitch || (so % (size_t)lay.pitch)) uniform = false;
+            so += ((size_t)jobs[j].src_pitch * jobs[j].ih + 255) & ~(size_t)255;
+            dofs += ((size_t)jobs[j].dst_pitch * jobs[j].oh + 255) & ~(size_t)255;
+        }
+        if (so > max_src) max_src = so;
+        if (dofs > max_dst) max_dst = dofs;
+    }
+    // (the 256-byte rounding keeps every image 16-byte aligned; a uniform pitch that divides the
+    // rounded size makes the chunk one 2-D array for the TMA path)
+    uint8_t *dsrc, *ddst;
+    b200geo_warp_job *djobs;
+    void *hp;
+    int rc;
+    if ((rc = scratch(ctx, S_PIPE_SRC, 2 * max_src, (void **)&dsrc))) return rc;
+    if ((rc = scratch(ctx, S_PIPE_DST, 2 * max_dst, (void **)&ddst))) return rc;
+    if ((rc = scratch(ctx, S_PIPE_JOBS, sizeof(b200geo_warp_job) * (size_t)n_jobs, (void **)&djobs))) return rc;
+    if ((rc = pinned(ctx, sizeof(b200geo_warp_job) * (size_t)n_jobs, &hp))) return rc;
+    B2G_CUDA(cudaStreamSynchronize(s_k));
+    memcpy(hp, dj.data(), sizeof(b200geo_warp_job) * (size_t)n_jobs);
+    B2G_CUDA(cudaMemcpyAsync(djobs, hp, sizeof(b200geo_warp_job) * (size_t)n_jobs, cudaMemcpyHostToDevice, s_k));
+    for (int c = 0; c < n_chunks; ++c) {
+        const int b = c & 1, j0 = c * chunk_jobs, j1 = (j0 + chunk_jobs < n_jobs) ? j0 + chunk_jobs : n_jobs;
+        uint8_t *cs = dsrc + (size_t)b * max_src, *cd = ddst + (size_t)b * max_dst;
+        // stage in: the slot's previous warp (chunk c-2) must have finished reading it
+        if (c >= 2) B2G_CUDA(cudaStreamWaitEvent(s_in, ctx->pipe_event[1][b], 0));
+        int max_ow = 0, max_oh = 0;
+        long long rows = 0;
+        for (int j = j0; j < j1; ++j) {
+            B2G_CUDA(cudaMemcpyAsync(cs + dj[j].src_offset, (const uint8_t *)src_host + jobs[j].src_offset,
+                                     (size_t)jobs[j].src_pitch * jobs[j].ih, cudaMemcpyHostToDevice, s_in));
+            if (jobs[j].ow > max_ow) max_ow = jobs[j].ow;
+            if (jobs[j].oh > max_oh) max_oh = jobs[j].oh;
+            if (uniform) rows = dj[j].src_offset / lay.pitch + jobs[j].ih;
+        }
+        B2G_CUDA(cudaEventRecord(ctx->pipe_event[0][b], s_in));
+        // warp: needs the inputs, and the slot's previous outputs (chunk c-2) copied out
+        B2G_CUDA(cudaStreamWaitEvent(s_k, ctx->pipe_event[0][b], 0));
+        if (c >= 2) B2G_CUDA(cudaStreamWaitEvent(s_k, ctx->pipe_event[2][b], 0));
+        lay.rows = rows;
+        if ((rc = launch_warp(ctx, cs, cd, djobs + j0, j1 - j0, max_ow, max_oh, channels, src_type, dst_type, sampler, s_k,
+                              uniform ? &lay : nullptr)))
+            return rc;
+        B2G_CUDA(cudaEventRecord(ctx->pipe_event[1][b], s_k));
+        // stage out
+        B2G_CUDA(cudaStreamWaitEvent(s_out, ctx->pipe_event[1][b], 0));
+        for (int j = j0; j < j1; ++j)
+            B2G_CUDA(cudaMemcpyAsync((uint8_t *)dst_host + jobs[j].dst_offset, cd + dj[j].dst_offset,
+                                     (size_t)jobs[j].dst_pitch * jobs[j].oh, cudaMemcpyDeviceToHost, s_out));
+        B2G_CUDA(cudaEventRecord(ctx->pipe_event[2][b], s_out));
+    }
+    B2G_CUDA(cudaStreamSynchronize(s_out));
+    B2G_CUDA(cudaStreamSynchronize(s_k));
+    return B200GEO_OK;
 }
 
 int b200geo_warp_host(b200geo_ctx *ctx, const void *src, void *dst, const b200geo_warp_job *job, int channels,

@@ -40,7 +40,7 @@ inline int fail(int code, const char *fmt, const char *a = "", const char *b = "
     } while (0)
 
 enum ScratchSlot {
-    S_PTS = 0, S_IDX, S_H, S_HINV, S_FLAGS, S_COUNTS, S_KEYS, S_RESULT, S_MASK, S_JOBS, S_SRC, S_DST, S_MISC, S_CMAX, S_STATS, S_WORKLIST, S_TILES,
+    S_PTS = 0, S_IDX, S_H, S_HINV, S_FLAGS, S_COUNTS, S_KEYS, S_RESULT, S_MASK, S_JOBS, S_SRC, S_DST, S_MISC, S_CMAX, S_STATS, S_WORKLIST, S_TILES, S_PIPE_SRC, S_PIPE_DST, S_PIPE_JOBS,
     S_NUM
 };
 
@@ -57,6 +57,9 @@ struct b200geo_ctx {
     int warp_exact;        // B200GEO_OPT_WARP_EXACT: warp uint8 images with the float64 kernel only
     int warp_variant;      // B200GEO_OPT_WARP_VARIANT: 0 = persistent TMA-pipelined kernel, 1 = one CTA per tile
     int warp_pipe_ready;   // dynamic shared memory attribute of warp_pipe_kernel set
+    cudaStream_t pipe_stream[3];   // b200geo_warp_batch_host: h2d, compute, d2h
+    cudaEvent_t pipe_event[3][2];  // [h2d done, compute done, d2h done][slot]
+    int pipe_ready;
     void *tmap_encode;     // cuTensorMapEncodeTiled (driver entry point), or NULL
     int tmap_probed;
     CUtensorMap tmap;      // cached 2-D tensor map of the last source layout

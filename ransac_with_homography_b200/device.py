@@ -207,6 +207,50 @@ def warp(src: torch.Tensor, dst: torch.Tensor, jobs: np.ndarray, channels: int =
     return dst
 
 
+def warp_host(src, dst, jobs: np.ndarray, channels: int = 3, sampler: str = "bilinear", chunk_jobs: int = 0, device: int | None = None):
+    """K4 over a batch of images in HOST memory (numpy arrays or CPU tensors; pinned memory gives
+    full overlap): chunks of jobs flow through a host->device / warp / device->host pipeline on
+    three streams (b200geo_warp_batch_host).  jobs' offsets index the host buffers.  Synchronous."""
+    assert jobs.dtype == _cabi.WARP_JOB_DTYPE
+    ctx = _cabi.context(device)
+    jobs = np.ascontiguousarray(jobs)
+
+    def _hp(a):
+        if isinstance(a, torch.Tensor):
+            assert not a.is_cuda and a.is_contiguous()
+            return _cabi._vp(a.data_ptr()), _TORCH_TYPE[a.dtype]
+        assert a.flags.c_contiguous
+        return _cabi._vp(a.ctypes.data), {np.dtype(np.uint8): _cabi.U8, np.dtype(np.float32): _cabi.F32, np.dtype(np.float64): _cabi.F64}[a.dtype]
+    sp, st = _hp(src)
+    dp, dt = _hp(dst)
+    _cabi.check(ctx.lib.b200geo_warp_batch_host(ctx.handle, sp, dp, _cabi._vp(jobs.ctypes.data), jobs.shape[0], channels, st, dt,
+                                                _cabi.SAMPLERS[sampler], int(chunk_jobs)))
+    return dst
+
+
+def stitch_batched(pts, idx, frames, th, d, canvas_hw, n=4, method="fwd", sampler="bilinear", canvases=None):
+    """Batched stitch pipeline (config "1024 pairs x 2k correspondences x 8192 hypotheses + warp to a
+    4K canvas"): for every pair b, RANSAC.run over pts[b] with the sample sets idx[b] (reference
+    ransac.py:159-213), then transformImageH(frames[b], H_b) (reference homography.py:230-242) into
+    canvas slot b, clipped to canvas_hw.  pts (B,M,4) f32, idx (B,K,4) i32, frames (B,h,w,3) u8, all
+    on the device.  One host round trip in the middle: the B refit homographies (72 B each) come
+    back so that the host can lay out the output rectangles exactly as the reference does
+    (bounding box of the warped corners, int() truncation).  Returns (canvases (B,H,W,3) u8,
+    boxes (B,4) = min_x, min_y, out_w, out_h, results (B,32) f64, masks (B,M) u8)."""
+    B, h, w, c = frames.shape
+    assert c == 3 and frames.dtype == torch.uint8 and frames.is_contiguous()
+    results, masks = ransac_batched(pts, idx, th, d, n, method)
+    res = results.cpu().numpy()
+    H = res[:, 12:21].reshape(B, 3, 3)
+    ok = (res[:, 2] == 0) & np.isfinite(H).all(axis=(1, 2))
+    H = np.where(ok[:, None, None], H, np.eye(3)[None])          # failed pairs: identity warp, flagged in results[:, 2]
+    jobs, boxes = bbox_jobs(H, (h, w), canvas_hw=canvas_hw)
+    if canvases is None:
+        canvases = torch.zeros((B, canvas_hw[0], canvas_hw[1], 3), dtype=torch.uint8, device=frames.device)
+    warp(frames, canvases, jobs, 3, sampler)
+    return canvases, boxes, results, masks
+
+
 def upload_jobs(jobs: np.ndarray, device) -> torch.Tensor:
     """Copy a job array to the device once (for repeated launches with b200geo_warp_jobs_dev)."""
     return torch.from_numpy(np.ascontiguousarray(jobs).view(np.uint8).copy()).to(device)

@@ -367,3 +367,44 @@ def test_fast_path_equals_reference_order_chain(ctx):
             assert n_shell >= 64 * 0.15 * M        # the constructed shell really exercised the exact path
             sub = np.arange(0, len(H), 37)
             assert np.array_equal(fast[sub], oracle.score_counts(pts, H[sub], 3.0))
+
+
+def test_batched_stitch_pipeline_matches_per_pair_path():
+    """Config-5 shape at reduced size: device.stitch_batched (batched RANSAC + refit + bbox warp into
+    canvas slots) against the per-pair drop-in calls (RANSAC.run + transformImageH), which are
+    themselves checked against the oracle above."""
+    import torch
+    from ransac_with_homography_b200 import device
+    from ransac_with_homography_b200.homography import transformImageH
+    from ransac_with_homography_b200.ransac import HomoModel, RANSAC
+    import io
+    from contextlib import redirect_stdout
+    rs = np.random.RandomState(9)
+    B, M, K, h, w, canvas = 5, 300, 512, 96, 160, (192, 320)
+    pts = np.empty((B, M, 4), np.float32)
+    idx = np.empty((B, K, 4), np.int32)
+    for b in range(B):
+        X = rs.rand(2, M) * [[w], [h]]
+        Ht = np.array([[1 + rs.uniform(-.05, .05), rs.uniform(-.05, .05), rs.uniform(-40, 40)],
+                       [rs.uniform(-.05, .05), 1 + rs.uniform(-.05, .05), rs.uniform(-30, 30)],
+                       [rs.uniform(-2e-4, 2e-4), rs.uniform(-2e-4, 2e-4), 1.0]])
+        q = Ht @ np.vstack([X, np.ones(M)])
+        Y = q[:2] / q[2] + rs.randn(2, M) * 0.3
+        out = rs.rand(M) < 0.4
+        Y[:, out] = rs.rand(2, int(out.sum())) * [[w], [h]]
+        pts[b, :, :2], pts[b, :, 2:] = X.T, Y.T
+        idx[b] = rs.randint(0, M, (K, 4))
+    frames = rs.randint(0, 256, (B, h, w, 3)).astype(np.uint8)
+    canv, boxes, results, masks = device.stitch_batched(torch.from_numpy(pts).cuda(), torch.from_numpy(idx).cuda(),
+                                                        torch.from_numpy(frames).cuda(), 4.0, 95.0, canvas)
+    canv, res, masks = canv.cpu().numpy(), results.cpu().numpy(), masks.cpu().numpy()
+    for b in range(B):
+        with redirect_stdout(io.StringIO()):
+            H, inl, cnt = RANSAC(HomoModel(th=4, d=95, n=4), k=K).run([pts[b, :, :2].T, pts[b, :, 2:].T], method="fwd", idx=idx[b])
+        assert int(res[b, 1]) == int(cnt) and np.array_equal(np.where(masks[b])[0], inl[0])
+        np.testing.assert_allclose(res[b, 12:21].reshape(3, 3), H, rtol=1e-12, atol=1e-12)
+        img, mx, my = transformImageH(frames[b].copy(), H)
+        assert boxes[b, :2].tolist() == [mx, my]
+        oh, ow = min(img.shape[0], canvas[0]), min(img.shape[1], canvas[1])
+        assert boxes[b, 2:].tolist() == [ow, oh]
+        assert np.array_equal(canv[b, :oh, :ow], img[:oh, :ow])
