@@ -42,7 +42,7 @@
 namespace b200geo {
 
 #ifndef B2G_WP_OCC
-#define B2G_WP_OCC 3
+#define B2G_WP_OCC 2
 #endif
 #ifndef B2G_UNROLL_P
 #define B2G_UNROLL_P 4
@@ -382,31 +382,38 @@ __device__ __forceinline__ void wf_compute_full(const WfDesc &T, const b200geo_w
     const int tid_ = wf_tid();
     const int lane = tid_ & 31, wrp = tid_ >> 5;
     const float di0 = (float)(lane - WF_TW / 2), dj0 = (float)(wrp - WF_TH / 2);
-    // coefficients live in registers; (x, y) numerators are carried as one float2 (FFMA2 / FMUL2)
-    const float2 a2 = make_float2(T.ax, T.ay), b2 = make_float2(T.bx, T.by);
-    const float gw = T.gw, hw = T.hw;
-    const float2 nb = __ffma2_rn(a2, make_float2(di0, di0), __ffma2_rn(b2, make_float2(dj0, dj0), make_float2(T.nx0, T.ny0)));
+    // coefficients live in registers; the two quotients of a pixel are one FMUL2
+    const float ax = T.ax, ay = T.ay, bx = T.bx, by = T.by, gw = T.gw, hw = T.hw;
+    const float nxb = __fmaf_rn(ax, di0, __fmaf_rn(bx, dj0, T.nx0));
+    const float nyb = __fmaf_rn(ay, di0, __fmaf_rn(by, dj0, T.ny0));
     const float wb = __fmaf_rn(gw, di0, __fmaf_rn(hw, dj0, T.w0));
     const uint32_t P4 = (uint32_t)T.P * 4u;
     const uint32_t base = s_src - (uint32_t)(((int)T.oy * (int)T.P + (int)T.ox) * 4);
     uint32_t oaddr[WF_TW / 32];
 #pragma unroll
-    for (int hh = 0; hh < WF_TW / 32; ++hh) oaddr[hh] = s_out + 4u * (uint32_t)wf_out_index(wrp, lane + 32 * hh);
+    for (int hh = 0; hh < WF_TW / 32; ++hh) {
+        oaddr[hh] = s_out + 4u * (uint32_t)wf_out_index(wrp, lane + 32 * hh);
+        asm volatile("" : "+r"(oaddr[hh]));      // opaque: keep it in a register instead of re-deriving the swizzle per pixel
+    }
     const int B16 = (int)T.band + 2;
 #pragma unroll WF_UNROLL_P
     for (int p = 0; p < WF_TH / 8; ++p) {
-        const float2 np = p ? __ffma2_rn(b2, make_float2((float)(8 * p), (float)(8 * p)), nb) : nb;
+        const float nxp = p ? __fmaf_rn(bx, (float)(8 * p), nxb) : nxb;
+        const float nyp = p ? __fmaf_rn(by, (float)(8 * p), nyb) : nyb;
         const float wp = p ? __fmaf_rn(hw, (float)(8 * p), wb) : wb;
 #pragma unroll
         for (int hh = 0; hh < WF_TW / 32; ++hh) {
-            const float2 n = hh ? __ffma2_rn(a2, make_float2((float)(32 * hh), (float)(32 * hh)), np) : np;
+            const float nx = hh ? __fmaf_rn(ax, (float)(32 * hh), nxp) : nxp;
+            const float ny = hh ? __fmaf_rn(ay, (float)(32 * hh), nyp) : nyp;
             const float w = hh ? __fmaf_rn(gw, (float)(32 * hh), wp) : wp;
             const float rw = wf_rcp(w);
-            const float2 r = __fmul2_rn(n, make_float2(rw, rw));
+            const float2 r = __fmul2_rn(make_float2(nx, ny), make_float2(rw, rw));
             const int fxd = __float2int_rd(r.x), fyd = __float2int_rd(r.y);
             uint32_t out;
             if (BILINEAR) {
-                const uint32_t a = (uint32_t)(fyd >> 16) * P4 + base + ((uint32_t)(fxd >> 16) << 2);
+                // integer parts: one PRMT each (sign-extended upper half), then IMAD + LEA
+                const int xi = (int)__byte_perm((uint32_t)fxd, 0u, 0xBB32), yi = (int)__byte_perm((uint32_t)fyd, 0u, 0xBB32);
+                const uint32_t a = (uint32_t)yi * P4 + base + ((uint32_t)xi << 2);
                 const uint2 top = wf_lds_entry(a), bot = wf_lds_entry(a + P4);
                 out = wf_blend(top, bot, (uint32_t)fxd & 0xFFFFu, (uint32_t)fyd & 0xFFFFu);
             } else {
@@ -417,12 +424,17 @@ __device__ __forceinline__ void wf_compute_full(const WfDesc &T, const b200geo_w
                     out = wf_exact_px<BILINEAR>(J, src, c0 + lane + 32 * hh, r0 + wrp + 8 * p);
                     ++n_exact;
                 } else {
-                    const uint2 e = wf_lds_entry((uint32_t)(hy >> 16) * P4 + base + ((uint32_t)(hx >> 16) << 2));
+                    const int xi = (int)__byte_perm((uint32_t)hx, 0u, 0xBB32), yi = (int)__byte_perm((uint32_t)hy, 0u, 0xBB32);
+                    const uint2 e = wf_lds_entry((uint32_t)yi * P4 + base + ((uint32_t)xi << 2));
                     out = __byte_perm(e.x, e.y, 0x4420);
                 }
             }
             // row = wrp + 8p keeps its parity, so the swizzle of oaddr[] holds for every p
-            wf_sts32(oaddr[hh] + (uint32_t)(p * 8 * WF_TW * 4), out);
+            asm volatile("st.shared.u32 [%0+%1], %2;" ::"r"(oaddr[hh]), "n"(0), "r"(out));
+            if (hh == WF_TW / 32 - 1) {
+#pragma unroll
+                for (int k = 0; k < WF_TW / 32; ++k) oaddr[k] += (uint32_t)(8 * WF_TW * 4);
+            }
         }
     }
 }
@@ -618,7 +630,7 @@ warp_fast_kernel(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst
 // are staged synchronously by the consumers as in warp_fast_kernel.
 // ------------------------------------------------------------------------------------------------
 constexpr int WP_RAW_BYTES = 14336;   // one raw-row buffer (x2); >= WF_TMA_BOX_W * WF_TMA_BOX_H
-constexpr int WP_OCC = B2G_WP_OCC;    // CTAs per SM
+constexpr int WP_OCC = B2G_WP_OCC;    // CTAs per SM (shared memory: 2 x raw 14 KB + 2 x entries 32 KB + 2 x output 8 KB)
 constexpr int WP_THREADS = WF_THREADS + 32;
 
 struct __align__(16) WpTile {
@@ -639,11 +651,12 @@ constexpr int WP_TILE_RING = 4;       // tile records: a record outlives its raw
 
 struct WpSmem {
     uint8_t raw[WP_STAGES][WP_RAW_BYTES];
-    uint32_t pairs[2 * WF_SRC_ENTRIES];   // plane 0, plane 1
-    uint32_t out[WF_TW * WF_TH];
+    uint32_t pairs[2][2 * WF_SRC_ENTRIES];   // double-buffered; each: plane 0, plane 1
+    uint32_t out[2][WF_TW * WF_TH];          // double-buffered output stage
     WpTile tile[WP_TILE_RING];
     WfDesc sub;              // SPLIT tiles: the quadrant being processed
     unsigned long long full[WP_STAGES], empty[WP_STAGES];
+    unsigned long long conv[2], samp[2];     // consumer-side: entries of buffer s complete / output stage s complete
 };
 
 __device__ __forceinline__ void wp_mbar_init(uint32_t a, uint32_t count)
@@ -663,10 +676,11 @@ __device__ __forceinline__ void wp_mbar_wait(uint32_t a, uint32_t parity)
     unsigned spins = 0;
     for (;;) {
         uint32_t ok;
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+        // the suspend-time hint lets the warp sleep in hardware until the phase completes instead of re-polling
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(a), "r"(parity), "r"(0x989680u) : "memory");
         if (ok) return;
-        if (++spins > (1u << 24)) __trap();        // a lost copy / protocol error must not hang the GPU
+        if (++spins > (1u << 20)) __trap();        // a lost copy / protocol error must not hang the GPU
     }
 }
 __device__ __forceinline__ void wp_bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t mbar)
@@ -691,6 +705,7 @@ __device__ __forceinline__ void wp_convert(const WfDesc &T, uint32_t magic, uint
                                            uint32_t s_pairs)
 {
     const int P = T.P, chunks = P >> 2, total = (int)T.rows * chunks;
+#pragma unroll 2
     for (int t = wf_tid(); t < total; t += WF_THREADS) {
         const int i = chunks > 1 ? (int)__umulhi((unsigned)t, magic) : t;
         const int k = t - i * chunks;
@@ -728,6 +743,10 @@ warp_pipe_kernel(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst
         for (int i = 0; i < WP_STAGES; ++i) {
             wp_mbar_init(s_full0 + 8u * i, 1);
             wp_mbar_init(s_empty0 + 8u * i, WF_THREADS / 32);
+        }
+        for (int i = 0; i < 2; ++i) {
+            wp_mbar_init((uint32_t)__cvta_generic_to_shared(&S.conv[i]), WF_THREADS / 32);
+            wp_mbar_init((uint32_t)__cvta_generic_to_shared(&S.samp[i]), WF_THREADS / 32);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -798,24 +817,51 @@ warp_pipe_kernel(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst
     }
 
     // -------------------------------------------------------------------- consumer warps
-    const uint32_t s_pairs = (uint32_t)__cvta_generic_to_shared(S.pairs);
-    const uint32_t s_out = (uint32_t)__cvta_generic_to_shared(S.out);
+    // Per warp and tile `it` (buffer s = it & 1):
+    //     wait conv[s]  -> sample tile it (entries[s] -> out[s]) -> arrive samp[s]
+    //                   -> convert tile it+1 (raw -> entries[s^1]) -> release raw stage -> arrive conv[s^1]
+    //     wait samp[s]  -> copy out[s] to global memory
+    // The warps only meet at the two waits, and there is a whole phase of other work between each
+    // arrive and its wait: a warp that finishes sampling early goes straight on to the (shared-
+    // memory-bound) conversion of the next tile while slower warps still sample (issue-bound).
+    // Hazards: entries[s^1] is rewritten after conv[s] completed, i.e. after every warp converted
+    // tile it, which each does after sampling tile it-1 (the last reader of entries[s^1]); out[s] is
+    // rewritten after conv[s] of tile it+2, which every warp arrives at after its copy-out of tile it.
+    const uint32_t s_pairs0 = (uint32_t)__cvta_generic_to_shared(S.pairs[0]);
+    const uint32_t s_out0 = (uint32_t)__cvta_generic_to_shared(S.out[0]);
+    const uint32_t s_conv0 = (uint32_t)__cvta_generic_to_shared(&S.conv[0]);
+    const uint32_t s_samp0 = (uint32_t)__cvta_generic_to_shared(&S.samp[0]);
+    constexpr uint32_t PAIRS_BYTES = 2u * WF_SRC_ENTRIES * 4u, OUT_BYTES = WF_TW * WF_TH * 4u;
     unsigned n_exact = 0;
     // the tile index itself travels in the WpTile record: the consumers only count iterations
     const int n_iter = (n_tiles - first + (int)gridDim.x - 1) / (int)gridDim.x;
-    for (int it = 0; it < n_iter; ++it) {
-        const int b = it % WP_STAGES, use = it / WP_STAGES;
+
+    auto convert = [&](int t) {        // raw stage t % WP_STAGES -> entries[t & 1]
+        const int b = t % WP_STAGES, use = t / WP_STAGES;
         wp_mbar_wait(s_full0 + 8u * b, (uint32_t)use & 1u);
         // the record's ring slot is rewritten WP_TILE_RING tiles later; the producer is at most
-        // WP_STAGES tiles ahead of the conversion below, so it stays valid through the copy-out
-        const WpTile &W = S.tile[it % WP_TILE_RING];
-        const int mode = W.T.mode & 0xFF;
-        if (W.tma) wp_convert<1>(W.T, W.magic, (uint32_t)(size_t)W.a0, 0u, W.RB, s_raw0 + (uint32_t)WP_RAW_BYTES * b, s_pairs);
-        else if (W.bulk) wp_convert<0>(W.T, W.magic, (uint32_t)(size_t)W.a0, (uint32_t)W.src_pitch, W.RB, s_raw0 + (uint32_t)WP_RAW_BYTES * b, s_pairs);
+        // WP_STAGES tiles ahead of this conversion, so the record stays valid through the copy-out
+        const WpTile &W = S.tile[t % WP_TILE_RING];
+        const uint32_t s_pairs = s_pairs0 + PAIRS_BYTES * (uint32_t)(t & 1), s_raw = s_raw0 + (uint32_t)WP_RAW_BYTES * b;
+        if (W.tma) wp_convert<1>(W.T, W.magic, (uint32_t)(size_t)W.a0, 0u, W.RB, s_raw, s_pairs);
+        else if (W.bulk) wp_convert<0>(W.T, W.magic, (uint32_t)(size_t)W.a0, (uint32_t)W.src_pitch, W.RB, s_raw, s_pairs);
         else if (W.staged) wf_stage(W.T, W.src, (size_t)W.src_pitch, W.iw, W.ih, s_pairs);
         __syncwarp();
-        if (lane == 0) wp_mbar_arrive(s_empty0 + 8u * b);     // raw[b] may be refilled
-        wp_consumer_sync();     // entries visible; the previous tile's copy-out has finished reading S.out
+        if (lane == 0) {
+            wp_mbar_arrive(s_empty0 + 8u * b);                 // raw[b] may be refilled
+            wp_mbar_arrive(s_conv0 + 8u * (uint32_t)(t & 1));
+        }
+    };
+
+    convert(0);
+    for (int it = 0; it < n_iter; ++it) {
+        const int s = it & 1;
+        const uint32_t par = (uint32_t)(it >> 1) & 1u;
+        const uint32_t s_pairs = s_pairs0 + PAIRS_BYTES * (uint32_t)s, s_out = s_out0 + OUT_BYTES * (uint32_t)s;
+        uint32_t *const out_mem = S.out[s];
+        const WpTile &W = S.tile[it % WP_TILE_RING];
+        const int mode = W.T.mode & 0xFF;
+        wp_mbar_wait(s_conv0 + 8u * (uint32_t)s, par);
         if (mode != WF_EMPTY) {
             const b200geo_warp_job &J = jobs[W.jz];
             if (W.staged) {
@@ -823,19 +869,22 @@ warp_pipe_kernel(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst
                 else if (mode == WF_INTERIOR) wf_compute_general<BILINEAR, 0>(W.T, J, W.src, s_pairs, s_out, W.c0, W.r0, W.tw, W.th, n_exact);
                 else wf_compute_general<BILINEAR, 1>(W.T, J, W.src, s_pairs, s_out, W.c0, W.r0, W.tw, W.th, n_exact);
             } else if (mode == WF_ZERO) {
-                for (int i = tid; i < WF_TW * WF_TH; i += WF_THREADS) S.out[i] = 0u;
+                for (int i = tid; i < WF_TW * WF_TH; i += WF_THREADS) out_mem[i] = 0u;
             } else if (mode == WF_SPLIT) {
-                wf_split_tile<BILINEAR>(J, W.src, &S.sub, s_pairs, s_out, S.out, W.c0, W.r0, W.tw, W.th, n_exact, [] { wp_consumer_sync(); });
+                wf_split_tile<BILINEAR>(J, W.src, &S.sub, s_pairs, s_out, out_mem, W.c0, W.r0, W.tw, W.th, n_exact, [] { wp_consumer_sync(); });
             } else {
                 for (int row = wrp; row < W.th; row += 8)
                     for (int col = lane; col < W.tw; col += 32) {
-                        S.out[wf_out_index(row, col)] = wf_exact_px<BILINEAR>(J, W.src, W.c0 + col, W.r0 + row);
+                        out_mem[wf_out_index(row, col)] = wf_exact_px<BILINEAR>(J, W.src, W.c0 + col, W.r0 + row);
                         ++n_exact;
                     }
             }
         }
-        wp_consumer_sync();
-        if (mode != WF_EMPTY) wf_copy_out(W.dst, (size_t)W.dst_pitch, S.out, W.c0, W.r0, W.tw, W.th);
+        __syncwarp();
+        if (lane == 0) wp_mbar_arrive(s_samp0 + 8u * (uint32_t)s);
+        if (it + 1 < n_iter) convert(it + 1);
+        wp_mbar_wait(s_samp0 + 8u * (uint32_t)s, par);
+        if (mode != WF_EMPTY) wf_copy_out(W.dst, (size_t)W.dst_pitch, out_mem, W.c0, W.r0, W.tw, W.th);
     }
     if (stats && n_exact) atomicAdd(stats, (unsigned long long)n_exact);
 }
