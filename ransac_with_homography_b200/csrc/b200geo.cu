@@ -210,7 +210,8 @@ int launch_score(b200geo_ctx *ctx, const float *pts, int M, const float *H, cons
     int rc;
     if ((rc = scratch(ctx, S_CMAX, sizeof(float) * (size_t)B, (void **)&cmax))) return rc;
     if ((rc = ensure_stats(ctx, st, &stats))) return rc;
-    cmax_kernel<<<B, 256, 0, st>>>((const float4 *)pts, M, cmax);
+    B2G_CUDA(cudaMemsetAsync(cmax, 0, sizeof(float) * (size_t)B, st));
+    cmax_kernel<<<dim3((M + 2047) / 2048, B), 256, 0, st>>>((const float4 *)pts, M, cmax);
     B2G_CHECK_LAUNCH(ctx);
 
     const int per_cta = FAST_THREADS * FAST_T;

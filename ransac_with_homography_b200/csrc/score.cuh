@@ -162,12 +162,14 @@ __device__ __forceinline__ float fast_band(const float (&h)[9], float C, float T
 // the FAST_CHUNK-sized chunk in which some |q| fell inside the shell.
 struct FastDeferred { unsigned slot, j0; };
 
-// largest |coordinate| of each correspondence set (NaN -> inf); grid (B), block 256
+// largest |coordinate| of each correspondence set (NaN -> inf); grid (ceil(M / 2048), B), block 256;
+// cmax[] must be zero beforehand (non-negative floats order like their bit patterns: atomicMax on int)
 __global__ void __launch_bounds__(256) cmax_kernel(const float4 *__restrict__ pts, int M, float *__restrict__ cmax)
 {
-    pts += (size_t)blockIdx.x * M;
+    pts += (size_t)blockIdx.y * M;
     float m = 0.f;
-    for (int i = threadIdx.x; i < M; i += blockDim.x) {
+    const int end = min(M, (int)(blockIdx.x + 1) * 2048);
+    for (int i = blockIdx.x * 2048 + threadIdx.x; i < end; i += 256) {
         float4 p = __ldg(pts + i);
         float v = fmaxf(fmaxf(fabsf(p.x), fabsf(p.y)), fmaxf(fabsf(p.z), fabsf(p.w)));
         if (p.x != p.x || p.y != p.y || p.z != p.z || p.w != p.w) v = __int_as_float(0x7f800000);
@@ -175,13 +177,7 @@ __global__ void __launch_bounds__(256) cmax_kernel(const float4 *__restrict__ pt
     }
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s));
-    __shared__ float sm[8];
-    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int w = 1; w < 8; ++w) m = fmaxf(m, sm[w]);
-        cmax[blockIdx.x] = m;
-    }
+    if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int *>(cmax) + blockIdx.y, __float_as_int(m));
 }
 
 // Grid: (ceil(nk / (FAST_THREADS*FAST_T)), point_splits, B).  METHOD is FWD or BACKWARD; for

@@ -3,12 +3,12 @@
 // Replaces calc_corresp + calcHomography (homography.py:4-14, 71-88) as called per RANSAC iteration
 // (ransac.py:177-180).  The reference takes the null vector of the raw 8x9 float32 matrix by LAPACK
 // SVD; for four points in general position that vector, scaled to h22 = 1, is the solution of the
-// 8x8 system of homography.py:16-28.  Here each thread holds the whole augmented 8x9 system in
-// registers: similarity-normalised coordinates (translate to the centroid, scale to unit box),
-// Gaussian elimination with partial pivoting (fully unrolled, row swaps as selects so nothing
-// spills to local memory), back substitution, de-normalisation, division by h22.
-// T = double is the default (FP64 is 1:2 on B200 and K1 is <3% of a search); T = float is the
-// literal "FP32 registers" variant.
+// 8x8 system of homography.py:16-28.  Per hypothesis that system is solved in closed form
+// (dlt4_closed: two square-to-quadrilateral maps composed, ~200 flops, registers only) in
+// similarity-normalised coordinates (translate to the centroid, scale to unit box), then
+// de-normalised and divided by h22.  dlt4_solve (Gaussian elimination with partial pivoting on the
+// 8x9 augmented matrix) serves the single explicit Scanner system and the refit.
+// T = double is the default (FP64 is 1:2 on B200); T = float is the literal "FP32 registers" variant.
 #pragma once
 
 #include "common.cuh"
@@ -115,6 +115,83 @@ __device__ __forceinline__ bool dlt4_solve(const T (&x)[4], const T (&y)[4], con
     return ok;
 }
 
+// Unit square (0,0) (1,0) (1,1) (0,1) -> quadrilateral p0 p1 p2 p3 (Heckbert's closed form of the
+// same 8x8 system): S = [[a b c] [d e f] [g h 1]].  Returns the denominator whose vanishing means
+// p1, p2, p3 are collinear.
+template <typename T>
+__device__ __forceinline__ T square_to_quad(const T (&x)[4], const T (&y)[4], T (&S)[9])
+{
+    const T dx1 = x[1] - x[2], dx2 = x[3] - x[2], dx3 = x[0] - x[1] + x[2] - x[3];
+    const T dy1 = y[1] - y[2], dy2 = y[3] - y[2], dy3 = y[0] - y[1] + y[2] - y[3];
+    const T den = dx1 * dy2 - dy1 * dx2;
+    const T r = T(1) / den;
+    const T g = (dx3 * dy2 - dy3 * dx2) * r, h = (dx1 * dy3 - dy1 * dx3) * r;
+    S[0] = x[1] - x[0] + g * x[1]; S[1] = x[3] - x[0] + h * x[3]; S[2] = x[0];
+    S[3] = y[1] - y[0] + g * y[1]; S[4] = y[3] - y[0] + h * y[3]; S[5] = y[0];
+    S[6] = g; S[7] = h; S[8] = T(1);
+    return den;
+}
+
+// 4 correspondences -> H by composing two square-to-quad maps: H = S_dst * adj(S_src), h22 = 1.
+// The solution of the same 8x8 system dlt4_solve() eliminates (~1200 flops, 72-entry matrix), in
+// ~200 flops and a few dozen registers; used per RANSAC hypothesis.  Similarity normalisation as in
+// dlt4_solve keeps the differences well scaled.
+template <typename T>
+__device__ __forceinline__ bool dlt4_closed(const T (&x)[4], const T (&y)[4], const T (&X)[4], const T (&Y)[4], T (&H)[9])
+{
+    T cx = (x[0] + x[1] + x[2] + x[3]) * T(0.25), cy = (y[0] + y[1] + y[2] + y[3]) * T(0.25);
+    T cX = (X[0] + X[1] + X[2] + X[3]) * T(0.25), cY = (Y[0] + Y[1] + Y[2] + Y[3]) * T(0.25);
+    T ds = T(0), dd = T(0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        ds = Real<T>::max(ds, Real<T>::max(Real<T>::abs(x[i] - cx), Real<T>::abs(y[i] - cy)));
+        dd = Real<T>::max(dd, Real<T>::max(Real<T>::abs(X[i] - cX), Real<T>::abs(Y[i] - cY)));
+    }
+    bool ok = (ds > T(0)) && (dd > T(0));
+    const T ss = T(1) / ds, sd = T(1) / dd;
+    T u[4], v[4], U[4], V[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        u[i] = (x[i] - cx) * ss; v[i] = (y[i] - cy) * ss;
+        U[i] = (X[i] - cX) * sd; V[i] = (Y[i] - cY) * sd;
+    }
+    T A[9], B[9];
+    const T da = square_to_quad<T>(u, v, A), db = square_to_quad<T>(U, V, B);
+    ok = ok && (Real<T>::abs(da) > T(0)) && (Real<T>::abs(db) > T(0));
+    // adj(A)
+    T a[9];
+    a[0] = A[4] * A[8] - A[5] * A[7]; a[1] = A[2] * A[7] - A[1] * A[8]; a[2] = A[1] * A[5] - A[2] * A[4];
+    a[3] = A[5] * A[6] - A[3] * A[8]; a[4] = A[0] * A[8] - A[2] * A[6]; a[5] = A[2] * A[3] - A[0] * A[5];
+    a[6] = A[3] * A[7] - A[4] * A[6]; a[7] = A[1] * A[6] - A[0] * A[7]; a[8] = A[0] * A[4] - A[1] * A[3];
+    // g = B * adj(A): normalised-coordinate homography (any scale)
+    T g[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) g[3 * r + c] = B[3 * r] * a[c] + B[3 * r + 1] * a[3 + c] + B[3 * r + 2] * a[6 + c];
+    // H = Td^-1 * g * Ts,  Ts = [ss 0 -ss*cx; 0 ss -ss*cy; 0 0 1],  Td^-1 = [dd 0 cX; 0 dd cY; 0 0 1]
+    T m[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        m[3 * r] = g[3 * r] * ss; m[3 * r + 1] = g[3 * r + 1] * ss;
+        m[3 * r + 2] = g[3 * r + 2] - (g[3 * r] * cx + g[3 * r + 1] * cy) * ss;
+    }
+    T n[9];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        n[j] = m[j] * dd + cX * m[6 + j];
+        n[3 + j] = m[3 + j] * dd + cY * m[6 + j];
+        n[6 + j] = m[6 + j];
+    }
+    const T inv = T(1) / n[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) H[j] = n[j] * inv;
+    H[8] = T(1);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ok = ok && (Real<T>::abs(H[j]) <= T(3.0e38));   // false for NaN / inf
+    return ok;
+}
+
 // 3x3 inverse by the adjugate (np.linalg.inv(self.val), ransac.py:74)
 template <typename T>
 __device__ __forceinline__ void invert3(const T (&h)[9], T (&o)[9])
@@ -142,7 +219,7 @@ __device__ __forceinline__ bool solve_sample(const float4 *__restrict__ pts, int
     T Y[4] = {T(p0.w), T(p1.w), T(p2.w), T(p3.w)};
     bool dup = (id.x == id.y) | (id.x == id.z) | (id.x == id.w) | (id.y == id.z) | (id.y == id.w) | (id.z == id.w);
     T H[9];
-    bool ok = dlt4_solve<T>(x, y, X, Y, H) && !dup;
+    bool ok = dlt4_closed<T>(x, y, X, Y, H) && !dup;
     const float qnan = __int_as_float(0x7fc00000);
     if (want_inv) {
         T Hi[9];

@@ -1,0 +1,61 @@
+"""Latency of the reference app's two single-frame configurations (BASELINE.json configs 1 and 2)
+through the drop-in Python API (host numpy arrays in and out), beside the numpy port on the host.
+
+    python tools/bench_app.py            # prints one JSON object
+
+C1: RANSAC on the reference's fixture (185 matches; settings A: th=5,d=70,k=1000 of ransac.example0
+    and B: th=4,d=95,k=1500 of app.py:364-367) + stitchPanorama warp of a 683x1024 RGB image by the
+    fitted H (synthetic pixels of the reference's shapes: the JPEGs do not travel to the GPU box).
+C2: Scanner: 4-point rectification of a 755x1226 image to A4 at 300 dpi (2480x3508), bilinear."""
+import io, json, os, sys, time
+from contextlib import redirect_stdout
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from oracle import ref_numpy as port
+from ransac_with_homography_b200 import homography as hg
+from ransac_with_homography_b200.ransac import HomoModel, RANSAC
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def best(fn, n=5):
+    ts = []
+    for _ in range(n):
+        t = time.perf_counter(); fn(); ts.append(time.perf_counter() - t)
+    return min(ts) * 1e3
+
+
+z = np.load(os.path.join(ROOT, "tests", "golden", "fixture_points.npz"))
+A, B = z["ptsA"], z["ptsB"]
+rs = np.random.RandomState(0)
+imgT = rs.randint(0, 256, (683, 1024, 3)).astype(np.uint8)
+imgQ = rs.randint(0, 256, (683, 1024, 3)).astype(np.uint8)
+out = {}
+for tag, (th, d, k) in {"A": (5, 70, 1000), "B": (4, 95, 1500)}.items():
+    idx = np.random.RandomState(1).randint(0, A.shape[0], (k, 4))
+    res = {}
+
+    def ours():
+        with redirect_stdout(io.StringIO()):
+            res["H"] = RANSAC(HomoModel(th=th, d=d, n=4), k=k).run([A.T, B.T], method="fwd", idx=idx)[0]
+
+    def ref():
+        res["Hr"] = port.ransac_run(A.T, B.T, th=th, d=d, n=4, k=k, method="fwd", idx=idx)[0]
+    ours()
+    out[f"C1_ransac_{tag}_ms"] = {"ours": best(ours), "numpy_port": best(ref, 3)}
+H = res["H"]
+hg.stitchPanorama(imgQ.copy(), imgT.copy(), H)
+out["C1_stitchPanorama_ms"] = {"ours": best(lambda: hg.stitchPanorama(imgQ.copy(), imgT.copy(), H)),
+                               "numpy_port_warp_only": best(lambda: port.warp_bbox(imgT.copy(), H, True)[0].astype(np.uint8), 2)}
+img = rs.randint(0, 256, (755, 1226, 3)).astype(np.uint8)
+u = np.array([[100, 560, 740, 80], [160, 125, 490, 555], [1, 1, 1, 1]], np.float64)
+v = np.array([[0, 2480, 2480, 0], [0, 0, 3508, 3508], [1, 1, 1, 1]], np.float64)
+hg.transformImage(img.copy(), u, v, box=[3508, 2480])
+Hs = port.homography_normal_eq(u.T[:, :2], v.T[:, :2])
+out["C2_scanner_2480x3508_ms"] = {"ours": best(lambda: hg.transformImage(img.copy(), u, v, box=[3508, 2480])),
+                                  "numpy_port": best(lambda: port.warp_scan(img.copy(), Hs, [3508, 2480], True)[0].astype(np.uint8), 1)}
+v2 = np.array([[0, 840, 840, 0], [0, 0, 1188, 1188], [1, 1, 1, 1]], np.float64)
+hg.transformImage(img.copy(), u, v2, box=[1188, 840])
+out["C2_scanner_840x1188_ms"] = {"ours": best(lambda: hg.transformImage(img.copy(), u, v2, box=[1188, 840]))}
+out["host_cores"] = os.cpu_count()
+print(json.dumps(out))
