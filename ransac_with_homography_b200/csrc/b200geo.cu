@@ -201,8 +201,7 @@ int launch_score(b200geo_ctx *ctx, const float *pts, int M, const float *H, cons
 {
     int nk = k_end - k_begin;
     if (nk <= 0 || B <= 0) return B200GEO_OK;
-    const bool fast_ok = (method == B200GEO_FWD || method == B200GEO_BACKWARD) && th > 0.f && th < 1.0e15f && M > 0 &&
-                         !ctx->force_exact;
+    const bool fast_ok = th > 0.f && th < 1.0e15f && M > 0 && !ctx->force_exact && (method != B200GEO_REPROJ || Hinv != nullptr);
     if (!fast_ok) return launch_score_exact(ctx, pts, M, H, Hinv, flags, k_begin, k_end, K_stride, B, th, method, counts, st);
 
     float *cmax;
@@ -213,6 +212,39 @@ int launch_score(b200geo_ctx *ctx, const float *pts, int M, const float *H, cons
     B2G_CUDA(cudaMemsetAsync(cmax, 0, sizeof(float) * (size_t)B, st));
     cmax_kernel<<<dim3((M + 2047) / 2048, B), 256, 0, st>>>((const float4 *)pts, M, cmax);
     B2G_CHECK_LAUNCH(ctx);
+
+    if (method == B200GEO_REPROJ) {
+        // two-sided bracket of the sum of the two errors (score_fast2_kernel), same deferred exact list
+        const int per_cta2 = FAST2_THREADS * 2;
+        int gx2 = (nk + per_cta2 - 1) / per_cta2;
+        long long blocks2 = (long long)gx2 * B, want2 = 16LL * 2 * ctx->sm_count;
+        int max_splits2 = (M + FAST2_TILE - 1) / FAST2_TILE, splits2 = 1;
+        if (blocks2 < want2) {
+            splits2 = (int)((want2 + blocks2 - 1) / blocks2);
+            if (splits2 > max_splits2) splits2 = max_splits2;
+        }
+        int per2 = (M + splits2 - 1) / splits2;
+        per2 = ((per2 + FAST2_TILE - 1) / FAST2_TILE) * FAST2_TILE;
+        splits2 = (M + per2 - 1) / per2;
+        if (splits2 > 1)
+            for (int b = 0; b < B; ++b)
+                B2G_CUDA(cudaMemsetAsync(counts + (size_t)b * K_stride + k_begin, 0, sizeof(int32_t) * (size_t)nk, st));
+        unsigned long long cap2 = (unsigned long long)nk * B * (unsigned long long)((M + FAST_CHUNK - 1) / FAST_CHUNK) / 32;
+        if (cap2 < (1ull << 20)) cap2 = 1ull << 20;
+        if (cap2 > (1ull << 26)) cap2 = 1ull << 26;
+        FastDeferred *wl2;
+        unsigned *wl2_count = (unsigned *)(stats + 1);
+        if ((rc = scratch(ctx, S_WORKLIST, cap2 * sizeof(FastDeferred), (void **)&wl2))) return rc;
+        unsigned wl2_cap = (unsigned)(ctx->scratch_cap[S_WORKLIST] / sizeof(FastDeferred));
+        B2G_CUDA(cudaMemsetAsync(wl2_count, 0, sizeof(unsigned), st));
+        score_fast2_kernel<<<dim3(gx2, splits2, B), FAST2_THREADS, 0, st>>>((const float4 *)pts, M, H, Hinv, flags, k_begin, k_end, K_stride, th,
+                                                                            cmax, per2, counts, wl2, wl2_count, wl2_cap);
+        B2G_CHECK_LAUNCH(ctx);
+        score_fixup2_kernel<<<8 * ctx->sm_count, 256, 0, st>>>((const float4 *)pts, M, H, Hinv, K_stride, th, cmax, wl2, wl2_count, wl2_cap,
+                                                               counts, stats);
+        B2G_CHECK_LAUNCH(ctx);
+        return B200GEO_OK;
+    }
 
     const int per_cta = FAST_THREADS * FAST_T;
     int gx = (nk + per_cta - 1) / per_cta;

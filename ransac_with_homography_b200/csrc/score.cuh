@@ -359,6 +359,224 @@ score_fixup_kernel(const float4 *__restrict__ pts, int M, const float *__restric
     if (stat_ambiguous && local) atomicAdd(stat_ambiguous, (unsigned long long)local);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Fast scoring kernel for the reproj loss (RANSAC.run's default method, ransac.py:91-95):
+//     loss = e_fwd + e_bwd ,  e_fwd = |H x - x'| ,  e_bwd = |H^-1 x' - x|     (each a float32 sqrt)
+// The sum of two square roots has no polynomial form, but both sides of the threshold are
+// bracketed by two division-free tests per direction, evaluated from the same a, b, w:
+//     accept:  e_fwd < T/2  and  e_bwd < T/2      =>  fl(e_fwd + e_bwd) <= 2 pred(T/2) = pred(T) < T
+//     reject:  e_fwd >= T   or   e_bwd >= T       =>  fl(e_fwd + e_bwd) >= T   (the other term is >= 0)
+// With the rows scaled by Th = T/2:  q = a^2 + b^2 - (Th w)^2 < 0  <=>  e < T/2 ,  and
+// r = q - 3 (Th w)^2 = a^2 + b^2 - (T w)^2 >= 0  <=>  e >= T.  12 FMA-pipe operations per direction,
+// packed two hypotheses per instruction (FFMA2).  Inliers of a good hypothesis (noise << T/2) are
+// accepted, outliers rejected; what falls between -- or within the rounding band of either test --
+// goes to the same deferred exact work list as in score_fast_kernel, so the counts are those of
+// the reference-order chain.
+// ------------------------------------------------------------------------------------------------
+constexpr int FAST2_THREADS = 256;
+constexpr int FAST2_TILE = 512;    // correspondences per tile: 64 bytes each -> 32 KB
+
+struct Fast2Q { float2 q1, r1, q2, r2; };
+
+__device__ __forceinline__ Fast2Q fast2_q(const float2 (&hf)[9], const float2 (&hb)[9], float4 a0, float4 a1, float4 b0, float4 b1)
+{
+    Fast2Q o;
+    {
+        const float2 xx = make_float2(a0.x, a0.y), yy = make_float2(a0.z, a0.w), nX = make_float2(a1.x, a1.y), nY = make_float2(a1.z, a1.w);
+        const float2 w = __ffma2_rn(hf[6], xx, __ffma2_rn(hf[7], yy, hf[8]));
+        const float2 a = __ffma2_rn(hf[0], xx, __ffma2_rn(hf[1], yy, __ffma2_rn(nX, w, hf[2])));
+        const float2 b = __ffma2_rn(hf[3], xx, __ffma2_rn(hf[4], yy, __ffma2_rn(nY, w, hf[5])));
+        const float2 t = __fmul2_rn(w, w);
+        o.q1 = __ffma2_rn(a, a, __ffma2_rn(b, b, neg2(t)));
+        o.r1 = __ffma2_rn(make_float2(-3.f, -3.f), t, o.q1);
+    }
+    {
+        const float2 xx = make_float2(b0.x, b0.y), yy = make_float2(b0.z, b0.w), nX = make_float2(b1.x, b1.y), nY = make_float2(b1.z, b1.w);
+        const float2 w = __ffma2_rn(hb[6], xx, __ffma2_rn(hb[7], yy, hb[8]));
+        const float2 a = __ffma2_rn(hb[0], xx, __ffma2_rn(hb[1], yy, __ffma2_rn(nX, w, hb[2])));
+        const float2 b = __ffma2_rn(hb[3], xx, __ffma2_rn(hb[4], yy, __ffma2_rn(nY, w, hb[5])));
+        const float2 t = __fmul2_rn(w, w);
+        o.q2 = __ffma2_rn(a, a, __ffma2_rn(b, b, neg2(t)));
+        o.r2 = __ffma2_rn(make_float2(-3.f, -3.f), t, o.q2);
+    }
+    return o;
+}
+
+// scalar twin for one hypothesis and one direction (bit-identical per lane): returns q, r
+__device__ __forceinline__ void fast2_q1(const float (&h)[9], float x, float y, float nX, float nY, float &q, float &r)
+{
+    const float w = __fmaf_rn(h[6], x, __fmaf_rn(h[7], y, h[8]));
+    const float a = __fmaf_rn(h[0], x, __fmaf_rn(h[1], y, __fmaf_rn(nX, w, h[2])));
+    const float b = __fmaf_rn(h[3], x, __fmaf_rn(h[4], y, __fmaf_rn(nY, w, h[5])));
+    const float t = __fmul_rn(w, w);
+    q = __fmaf_rn(a, a, __fmaf_rn(b, b, -t));
+    r = __fmaf_rn(-3.f, t, q);
+}
+
+// bands of the two tests of one direction: accept at Th = T/2, reject at T (the latter also covers
+// forming r from q and the rounded square)
+__device__ __forceinline__ void fast2_bands(const float (&h)[9], float C, float T, float &accept_band, float &reject_band)
+{
+    const float u = 5.9604645e-8f;
+    const float S2 = (fabsf(h[6]) + fabsf(h[7])) * C + fabsf(h[8]);
+    accept_band = fast_band(h, C, 0.5f * T);
+    reject_band = fast_band(h, C, T) + 8.f * u * T * T * S2 * S2;
+}
+
+// 0 = rejected, 1 = accepted, 2 = undecided (exact chain needed); NaN anywhere -> undecided
+__device__ __forceinline__ int fast2_decide(float q1, float r1, float q2, float r2, float a1, float rj1, float a2, float rj2)
+{
+    const bool acc = (q1 < -a1) && (q2 < -a2);
+    const bool rej = (r1 > rj1) || (r2 > rj2);
+    return acc ? 1 : (rej ? 0 : 2);
+}
+
+// Grid: (ceil(nk / (2*FAST2_THREADS)), point_splits, B).  T > 0 and finite; H and Hinv both required.
+__global__ void __launch_bounds__(FAST2_THREADS, 2)
+score_fast2_kernel(const float4 *__restrict__ pts, int M, const float *__restrict__ H, const float *__restrict__ Hinv,
+                   const uint8_t *__restrict__ flags, int k_begin, int k_end, int K_stride, float T, const float *__restrict__ cmax,
+                   int pts_per_split, int32_t *__restrict__ counts, FastDeferred *__restrict__ wl, unsigned *__restrict__ wl_count,
+                   unsigned wl_cap)
+{
+    __shared__ float4 tile[4 * FAST2_TILE];
+    const int b = blockIdx.z;
+    pts += (size_t)b * M;
+    const float C = cmax[b];
+    const float Th = 0.5f * T, invTh = 1.0f / Th;
+
+    // this thread's two hypotheses: k = base and base + FAST2_THREADS
+    const int base = k_begin + blockIdx.x * (FAST2_THREADS * 2) + threadIdx.x;
+    float2 hf[9], hb[9];
+    float ba1[2], br1[2], ba2[2], br2[2];
+    bool live[2], dead[2];
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+        const int k = base + t * FAST2_THREADS;
+        live[t] = k < k_end;
+        const size_t o = (size_t)b * K_stride + (live[t] ? k : k_begin);
+        bool bad = flags ? (flags[o] != 0) : false;
+        float f[9], g[9];
+#pragma unroll
+        for (int j = 0; j < 9; ++j) {
+            f[j] = __ldg(H + o * 9 + j);
+            g[j] = __ldg(Hinv + o * 9 + j);
+            bad = bad || !(fabsf(f[j]) <= 3.0e38f) || !(fabsf(g[j]) <= 3.0e38f);
+        }
+        dead[t] = bad || !live[t];
+        if (dead[t]) {
+#pragma unroll
+            for (int j = 0; j < 9; ++j) f[j] = g[j] = (j == 0 || j == 4 || j == 8) ? 1.f : 0.f;
+        }
+        fast2_bands(f, C, T, ba1[t], br1[t]);
+        fast2_bands(g, C, T, ba2[t], br2[t]);
+#pragma unroll
+        for (int j = 6; j < 9; ++j) { f[j] = __fmul_rn(Th, f[j]); g[j] = __fmul_rn(Th, g[j]); }
+#pragma unroll
+        for (int j = 0; j < 9; ++j) {
+            if (t == 0) { hf[j].x = f[j]; hb[j].x = g[j]; }
+            else { hf[j].y = f[j]; hb[j].y = g[j]; }
+        }
+    }
+    unsigned cnt[2] = {0u, 0u};
+    const int j_begin = blockIdx.y * pts_per_split;
+    const int j_end = min(M, j_begin + pts_per_split);
+    for (int t0 = j_begin; t0 < j_end; t0 += FAST2_TILE) {
+        const int n = min(FAST2_TILE, j_end - t0);
+        const int n_pad = (n + FAST_CHUNK - 1) / FAST_CHUNK * FAST_CHUNK;
+        __syncthreads();
+        for (int i = threadIdx.x; i < n_pad; i += FAST2_THREADS) {
+            // padding: a correspondence every hypothesis rejects outright (huge error both ways)
+            float4 p = i < n ? __ldg(pts + t0 + i) : make_float4(0.f, 0.f, 1.0e18f, 1.0e18f);
+            tile[4 * i + 0] = make_float4(p.x, p.x, p.y, p.y);
+            const float nX = -__fmul_rn(p.z, invTh), nY = -__fmul_rn(p.w, invTh);
+            tile[4 * i + 1] = make_float4(nX, nX, nY, nY);
+            tile[4 * i + 2] = make_float4(p.z, p.z, p.w, p.w);
+            const float nx = -__fmul_rn(p.x, invTh), ny = -__fmul_rn(p.y, invTh);
+            tile[4 * i + 3] = make_float4(nx, nx, ny, ny);
+        }
+        __syncthreads();
+        for (int i = 0; i < n_pad; i += FAST_CHUNK) {
+            bool und[2] = {false, false};
+#pragma unroll
+            for (int u = 0; u < FAST_CHUNK; ++u) {
+                const Fast2Q q = fast2_q(hf, hb, tile[4 * (i + u)], tile[4 * (i + u) + 1], tile[4 * (i + u) + 2], tile[4 * (i + u) + 3]);
+                const int d0 = fast2_decide(q.q1.x, q.r1.x, q.q2.x, q.r2.x, ba1[0], br1[0], ba2[0], br2[0]);
+                const int d1 = fast2_decide(q.q1.y, q.r1.y, q.q2.y, q.r2.y, ba1[1], br1[1], ba2[1], br2[1]);
+                cnt[0] += (d0 == 1); und[0] = und[0] || (d0 == 2);
+                cnt[1] += (d1 == 1); und[1] = und[1] || (d1 == 2);
+            }
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                if (!und[t] || dead[t]) continue;
+                // some correspondence of this chunk is undecided: defer the chunk to score_fixup2_kernel
+                const size_t o = (size_t)b * K_stride + base + t * FAST2_THREADS;
+                const unsigned w = atomicAdd(wl_count, 1u);
+                if (w < wl_cap) {
+                    wl[w].slot = (unsigned)o;
+                    wl[w].j0 = (unsigned)(t0 + i);
+                    continue;
+                }
+                // list full: settle the chunk here
+                float hx[9], hix[9];
+#pragma unroll
+                for (int j = 0; j < 9; ++j) { hx[j] = __ldg(H + o * 9 + j); hix[j] = __ldg(Hinv + o * 9 + j); }
+                for (int u = 0; u < FAST_CHUNK; ++u) {
+                    const int jj = t0 + i + u;
+                    if (jj >= j_end) break;
+                    const Fast2Q q = fast2_q(hf, hb, tile[4 * (i + u)], tile[4 * (i + u) + 1], tile[4 * (i + u) + 2], tile[4 * (i + u) + 3]);
+                    const int d = t == 0 ? fast2_decide(q.q1.x, q.r1.x, q.q2.x, q.r2.x, ba1[0], br1[0], ba2[0], br2[0])
+                                         : fast2_decide(q.q1.y, q.r1.y, q.q2.y, q.r2.y, ba1[1], br1[1], ba2[1], br2[1]);
+                    if (d != 2) continue;
+                    cnt[t] += exact_loss<B200GEO_REPROJ>(hx, hix, __ldg(pts + jj)) < T ? 1u : 0u;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+        if (!live[t]) continue;
+        const size_t o = (size_t)b * K_stride + base + t * FAST2_THREADS;
+        const int c = dead[t] ? 0 : (int)cnt[t];
+        if (gridDim.y > 1) { if (c) atomicAdd(counts + o, c); }
+        else counts[o] = c;
+    }
+}
+
+// Exact settlement of the deferred reproj chunks: one thread per (deferred chunk, correspondence).
+__global__ void __launch_bounds__(256)
+score_fixup2_kernel(const float4 *__restrict__ pts, int M, const float *__restrict__ H, const float *__restrict__ Hinv, int K_stride,
+                    float T, const float *__restrict__ cmax, const FastDeferred *__restrict__ wl, const unsigned *__restrict__ wl_count,
+                    unsigned wl_cap, int32_t *__restrict__ counts, unsigned long long *__restrict__ stat_ambiguous)
+{
+    const unsigned n = min(*wl_count, wl_cap);
+    const unsigned long long total = (unsigned long long)n * FAST_CHUNK;
+    const float Th = 0.5f * T, invTh = 1.0f / Th;
+    unsigned local = 0;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < total;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const FastDeferred e = wl[i / FAST_CHUNK];
+        const unsigned j = e.j0 + (unsigned)(i % FAST_CHUNK);
+        if (j >= (unsigned)M) continue;
+        const unsigned b = e.slot / (unsigned)K_stride;
+        float hx[9], hix[9], f[9], g[9];
+#pragma unroll
+        for (int c = 0; c < 9; ++c) { hx[c] = f[c] = __ldg(H + (size_t)e.slot * 9 + c); hix[c] = g[c] = __ldg(Hinv + (size_t)e.slot * 9 + c); }
+        float a1, r1b, a2, r2b;
+        fast2_bands(hx, cmax[b], T, a1, r1b);
+        fast2_bands(hix, cmax[b], T, a2, r2b);
+#pragma unroll
+        for (int c = 6; c < 9; ++c) { f[c] = __fmul_rn(Th, f[c]); g[c] = __fmul_rn(Th, g[c]); }
+        const float4 p = __ldg(pts + (size_t)b * M + j);
+        float q1, r1, q2, r2;
+        fast2_q1(f, p.x, p.y, -__fmul_rn(p.z, invTh), -__fmul_rn(p.w, invTh), q1, r1);
+        fast2_q1(g, p.z, p.w, -__fmul_rn(p.x, invTh), -__fmul_rn(p.y, invTh), q2, r2);
+        if (fast2_decide(q1, r1, q2, r2, a1, r1b, a2, r2b) != 2) continue;
+        if (exact_loss<B200GEO_REPROJ>(hx, hix, p) < T) atomicAdd(counts + e.slot, 1);
+        ++local;
+    }
+    if (stat_ambiguous && local) atomicAdd(stat_ambiguous, (unsigned long long)local);
+}
+
 // per-point loss of one hypothesis (HomoModel.computeLoss, ransac.py:84-98)
 __global__ void loss_kernel(const float4 *__restrict__ pts, int M, const float *__restrict__ H,
                             const float *__restrict__ Hinv, int method, float *__restrict__ err)
