@@ -375,9 +375,15 @@ __device__ __forceinline__ uint32_t wf_blend(uint2 top, uint2 bot, uint32_t fx, 
 }
 
 // Full INTERIOR tile: no bounds, no mask; everything unrolled (8 pixels per thread).
-template <int BILINEAR>
+// DIRECT = 1: results go straight to global memory.  Four neighbouring lanes hold four RGBX pixels =
+// 12 output bytes = three 32-bit words: each lane fetches its right neighbour's pixel (one SHFL),
+// builds one word with a lane-dependent PRMT, and three of every four lanes store it -- 96
+// contiguous bytes per warp and store instruction.  Requires dst_tile and dst_pitch 4-byte aligned.
+// DIRECT = 0: results go to the swizzled shared-memory stage `s_out` (copied out by wf_copy_out).
+template <int BILINEAR, int DIRECT>
 __device__ __forceinline__ void wf_compute_full(const WfDesc &T, const b200geo_warp_job &J, const uint8_t *__restrict__ src,
-                                                uint32_t s_src, uint32_t s_out, int c0, int r0, unsigned &n_exact)
+                                                uint32_t s_src, uint32_t s_out, int c0, int r0, unsigned &n_exact,
+                                                uint8_t *__restrict__ dst_tile = nullptr, size_t dst_pitch = 0)
 {
     const int tid_ = wf_tid();
     const int lane = tid_ & 31, wrp = tid_ >> 5;
@@ -395,6 +401,9 @@ __device__ __forceinline__ void wf_compute_full(const WfDesc &T, const b200geo_w
         oaddr[hh] = s_out + 4u * (uint32_t)wf_out_index(wrp, lane + 32 * hh);
         asm volatile("" : "+r"(oaddr[hh]));      // opaque: keep it in a register instead of re-deriving the swizzle per pixel
     }
+    // DIRECT: word (lane & 3) of the 12 bytes of pixels 4*(lane>>2) .. +3:  RGBR | GBRG | BRGB
+    const uint32_t psel = (lane & 3) == 0 ? 0x4210u : ((lane & 3) == 1 ? 0x5421u : 0x6542u);
+    uint8_t *gptr = dst_tile + (size_t)wrp * dst_pitch + (size_t)(12 * (lane >> 2) + 4 * (lane & 3));
     const int B16 = (int)T.band + 2;
 #pragma unroll WF_UNROLL_P
     for (int p = 0; p < WF_TH / 8; ++p) {
@@ -429,11 +438,18 @@ __device__ __forceinline__ void wf_compute_full(const WfDesc &T, const b200geo_w
                     out = __byte_perm(e.x, e.y, 0x4420);
                 }
             }
-            // row = wrp + 8p keeps its parity, so the swizzle of oaddr[] holds for every p
-            asm volatile("st.shared.u32 [%0+%1], %2;" ::"r"(oaddr[hh]), "n"(0), "r"(out));
-            if (hh == WF_TW / 32 - 1) {
+            if (DIRECT) {
+                const uint32_t nb = __shfl_down_sync(0xffffffffu, out, 1);
+                const uint32_t word = __byte_perm(out, nb, psel);
+                if ((lane & 3) != 3) *reinterpret_cast<uint32_t *>(gptr + 96 * hh) = word;
+                if (hh == WF_TW / 32 - 1) gptr += 8 * dst_pitch;
+            } else {
+                // row = wrp + 8p keeps its parity, so the swizzle of oaddr[] holds for every p
+                asm volatile("st.shared.u32 [%0+%1], %2;" ::"r"(oaddr[hh]), "n"(0), "r"(out));
+                if (hh == WF_TW / 32 - 1) {
 #pragma unroll
-                for (int k = 0; k < WF_TW / 32; ++k) oaddr[k] += (uint32_t)(8 * WF_TW * 4);
+                    for (int k = 0; k < WF_TW / 32; ++k) oaddr[k] += (uint32_t)(8 * WF_TW * 4);
+                }
             }
         }
     }
@@ -587,7 +603,7 @@ warp_fast_kernel(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst
     if (mode == WF_INTERIOR || mode == WF_BORDER) {
         wf_stage(T, src, (size_t)J.src_pitch, J.iw, J.ih, s_src);
         __syncthreads();
-        if (mode == WF_INTERIOR && tw == WF_TW && th == WF_TH) wf_compute_full<BILINEAR>(T, J, src, s_src, s_out, c0, r0, n_exact);
+        if (mode == WF_INTERIOR && tw == WF_TW && th == WF_TH) wf_compute_full<BILINEAR, 0>(T, J, src, s_src, s_out, c0, r0, n_exact);
         else if (mode == WF_INTERIOR) wf_compute_general<BILINEAR, 0>(T, J, src, s_src, s_out, c0, r0, tw, th, n_exact);
         else wf_compute_general<BILINEAR, 1>(T, J, src, s_src, s_out, c0, r0, tw, th, n_exact);
     } else if (mode == WF_ZERO) {
@@ -630,7 +646,7 @@ warp_fast_kernel(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst
 // are staged synchronously by the consumers as in warp_fast_kernel.
 // ------------------------------------------------------------------------------------------------
 constexpr int WP_RAW_BYTES = 14336;   // one raw-row buffer (x2); >= WF_TMA_BOX_W * WF_TMA_BOX_H
-constexpr int WP_OCC = B2G_WP_OCC;    // CTAs per SM (shared memory: 2 x raw 14 KB + 2 x entries 32 KB + 2 x output 8 KB)
+constexpr int WP_OCC = B2G_WP_OCC;    // CTAs per SM (shared memory: 2 x raw 14 KB + 2 x entries 32 KB + output 8 KB)
 constexpr int WP_THREADS = WF_THREADS + 32;
 
 struct __align__(16) WpTile {
@@ -652,11 +668,11 @@ constexpr int WP_TILE_RING = 4;       // tile records: a record outlives its raw
 struct WpSmem {
     uint8_t raw[WP_STAGES][WP_RAW_BYTES];
     uint32_t pairs[2][2 * WF_SRC_ENTRIES];   // double-buffered; each: plane 0, plane 1
-    uint32_t out[2][WF_TW * WF_TH];          // double-buffered output stage
+    uint32_t out[WF_TW * WF_TH];             // output stage of the tiles that are not written directly
     WpTile tile[WP_TILE_RING];
     WfDesc sub;              // SPLIT tiles: the quadrant being processed
     unsigned long long full[WP_STAGES], empty[WP_STAGES];
-    unsigned long long conv[2], samp[2];     // consumer-side: entries of buffer s complete / output stage s complete
+    unsigned long long conv[2];              // consumer-side: entries of buffer s complete
 };
 
 __device__ __forceinline__ void wp_mbar_init(uint32_t a, uint32_t count)
@@ -746,7 +762,6 @@ warp_pipe_kernel(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst
         }
         for (int i = 0; i < 2; ++i) {
             wp_mbar_init((uint32_t)__cvta_generic_to_shared(&S.conv[i]), WF_THREADS / 32);
-            wp_mbar_init((uint32_t)__cvta_generic_to_shared(&S.samp[i]), WF_THREADS / 32);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -818,20 +833,18 @@ warp_pipe_kernel(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst
 
     // -------------------------------------------------------------------- consumer warps
     // Per warp and tile `it` (buffer s = it & 1):
-    //     wait conv[s]  -> sample tile it (entries[s] -> out[s]) -> arrive samp[s]
-    //                   -> convert tile it+1 (raw -> entries[s^1]) -> release raw stage -> arrive conv[s^1]
-    //     wait samp[s]  -> copy out[s] to global memory
-    // The warps only meet at the two waits, and there is a whole phase of other work between each
-    // arrive and its wait: a warp that finishes sampling early goes straight on to the (shared-
-    // memory-bound) conversion of the next tile while slower warps still sample (issue-bound).
-    // Hazards: entries[s^1] is rewritten after conv[s] completed, i.e. after every warp converted
-    // tile it, which each does after sampling tile it-1 (the last reader of entries[s^1]); out[s] is
-    // rewritten after conv[s] of tile it+2, which every warp arrives at after its copy-out of tile it.
+    //     wait conv[s] -> sample tile it from entries[s], storing straight to global memory
+    //                  -> convert tile it+1 (raw -> entries[s^1]) -> release the raw stage -> arrive conv[s^1]
+    // The warps meet only at that one wait, a whole phase after the arrive: a warp that finishes
+    // sampling early goes straight on to the (shared-memory-bound) conversion of the next tile
+    // while slower warps still sample (issue-bound).  entries[s^1] is rewritten only after conv[s]
+    // completed, i.e. after every warp converted tile it, which each does after sampling tile it-1
+    // (the last reader of entries[s^1]).  Tiles that are not full INTERIOR tiles (9 % on the
+    // benchmark) go through the shared output stage between two consumer barriers.
     const uint32_t s_pairs0 = (uint32_t)__cvta_generic_to_shared(S.pairs[0]);
-    const uint32_t s_out0 = (uint32_t)__cvta_generic_to_shared(S.out[0]);
+    const uint32_t s_out = (uint32_t)__cvta_generic_to_shared(S.out);
     const uint32_t s_conv0 = (uint32_t)__cvta_generic_to_shared(&S.conv[0]);
-    const uint32_t s_samp0 = (uint32_t)__cvta_generic_to_shared(&S.samp[0]);
-    constexpr uint32_t PAIRS_BYTES = 2u * WF_SRC_ENTRIES * 4u, OUT_BYTES = WF_TW * WF_TH * 4u;
+    constexpr uint32_t PAIRS_BYTES = 2u * WF_SRC_ENTRIES * 4u;
     unsigned n_exact = 0;
     // the tile index itself travels in the WpTile record: the consumers only count iterations
     const int n_iter = (n_tiles - first + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -856,35 +869,41 @@ warp_pipe_kernel(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst
     convert(0);
     for (int it = 0; it < n_iter; ++it) {
         const int s = it & 1;
-        const uint32_t par = (uint32_t)(it >> 1) & 1u;
-        const uint32_t s_pairs = s_pairs0 + PAIRS_BYTES * (uint32_t)s, s_out = s_out0 + OUT_BYTES * (uint32_t)s;
-        uint32_t *const out_mem = S.out[s];
+        const uint32_t s_pairs = s_pairs0 + PAIRS_BYTES * (uint32_t)s;
         const WpTile &W = S.tile[it % WP_TILE_RING];
         const int mode = W.T.mode & 0xFF;
-        wp_mbar_wait(s_conv0 + 8u * (uint32_t)s, par);
+        wp_mbar_wait(s_conv0 + 8u * (uint32_t)s, (uint32_t)(it >> 1) & 1u);
+        uint8_t *const dst_tile = W.dst + (size_t)W.r0 * (size_t)W.dst_pitch + (size_t)W.c0 * 3;
+        const bool direct = mode == WF_INTERIOR && W.tw == WF_TW && W.th == WF_TH && ((((size_t)dst_tile) | (size_t)W.dst_pitch) & 3) == 0;
+        if (direct) {
+            wf_compute_full<BILINEAR, 1>(W.T, jobs[W.jz], W.src, s_pairs, 0u, W.c0, W.r0, n_exact, dst_tile, (size_t)W.dst_pitch);
+            if (it + 1 < n_iter) convert(it + 1);
+            continue;
+        }
+        // staged tiles: every consumer warp takes this branch for the same tiles (the record is shared)
         if (mode != WF_EMPTY) {
             const b200geo_warp_job &J = jobs[W.jz];
+            wp_consumer_sync();          // the previous staged tile's copy-out has finished reading S.out
             if (W.staged) {
-                if (mode == WF_INTERIOR && W.tw == WF_TW && W.th == WF_TH) wf_compute_full<BILINEAR>(W.T, J, W.src, s_pairs, s_out, W.c0, W.r0, n_exact);
+                // (a full tile whose destination is not 4-byte aligned takes the same arithmetic as the direct path)
+                if (mode == WF_INTERIOR && W.tw == WF_TW && W.th == WF_TH) wf_compute_full<BILINEAR, 0>(W.T, J, W.src, s_pairs, s_out, W.c0, W.r0, n_exact);
                 else if (mode == WF_INTERIOR) wf_compute_general<BILINEAR, 0>(W.T, J, W.src, s_pairs, s_out, W.c0, W.r0, W.tw, W.th, n_exact);
                 else wf_compute_general<BILINEAR, 1>(W.T, J, W.src, s_pairs, s_out, W.c0, W.r0, W.tw, W.th, n_exact);
             } else if (mode == WF_ZERO) {
-                for (int i = tid; i < WF_TW * WF_TH; i += WF_THREADS) out_mem[i] = 0u;
+                for (int i = tid; i < WF_TW * WF_TH; i += WF_THREADS) S.out[i] = 0u;
             } else if (mode == WF_SPLIT) {
-                wf_split_tile<BILINEAR>(J, W.src, &S.sub, s_pairs, s_out, out_mem, W.c0, W.r0, W.tw, W.th, n_exact, [] { wp_consumer_sync(); });
+                wf_split_tile<BILINEAR>(J, W.src, &S.sub, s_pairs, s_out, S.out, W.c0, W.r0, W.tw, W.th, n_exact, [] { wp_consumer_sync(); });
             } else {
                 for (int row = wrp; row < W.th; row += 8)
                     for (int col = lane; col < W.tw; col += 32) {
-                        out_mem[wf_out_index(row, col)] = wf_exact_px<BILINEAR>(J, W.src, W.c0 + col, W.r0 + row);
+                        S.out[wf_out_index(row, col)] = wf_exact_px<BILINEAR>(J, W.src, W.c0 + col, W.r0 + row);
                         ++n_exact;
                     }
             }
+            wp_consumer_sync();
         }
-        __syncwarp();
-        if (lane == 0) wp_mbar_arrive(s_samp0 + 8u * (uint32_t)s);
         if (it + 1 < n_iter) convert(it + 1);
-        wp_mbar_wait(s_samp0 + 8u * (uint32_t)s, par);
-        if (mode != WF_EMPTY) wf_copy_out(W.dst, (size_t)W.dst_pitch, out_mem, W.c0, W.r0, W.tw, W.th);
+        if (mode != WF_EMPTY) wf_copy_out(W.dst, (size_t)W.dst_pitch, S.out, W.c0, W.r0, W.tw, W.th);
     }
     if (stats && n_exact) atomicAdd(stats, (unsigned long long)n_exact);
 }
