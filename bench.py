@@ -36,6 +36,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FLOP_PER_PAIR = 25.0          # algorithmic FLOP per hypothesis x correspondence, fwd loss
+# DRAM traffic of the dominant kernels from the committed ncu --set full captures (dram__bytes_read + write):
+#   warp_pipe_kernel, profiles/r01_warp_pipe_v12.ncu-rep: 416.9 MB + 364.5 MB for 64 frames 1080p = 5.89 B per output pixel
+#   score_fast_kernel, profiles/r01_score_fast_K200k.ncu-rep: 8.6 MB for 200k x 20k pairs (FP32-bound: traffic is incidental)
+WARP_TRAFFIC_B_PER_PIXEL = (416.917760e6 + 364.532736e6) / (64 * 1080 * 1920)
+SCORE_TRAFFIC_B_PER_PAIR = 8.584448e6 / (200000 * 20000)
 C3 = dict(M=20000, K=1_000_000, th=3.0, d=99.0, seed=1, idx_seed=0)
 C4 = dict(frames=4096, h=1080, w=1920, jitter=0.05)
 
@@ -333,7 +338,8 @@ def bench_ransac(torch, dist, rank, world, args, ctx, peaks, local_gpu):
     peak_tflops = 148 * 128 * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12
     clocks = cs.summary()
     roof = {"bound": "fp32", "kernel": "score (K2)", "achieved": flops / k_avg_s / 1e12, "peak": peak_tflops, "unit": "TFLOP/s",
-            "frac": flops / k_avg_s / 1e12 / peak_tflops, "traffic": None,
+            "frac": flops / k_avg_s / 1e12 / peak_tflops, "traffic": SCORE_TRAFFIC_B_PER_PAIR * (hi - lo) * M,
+            "traffic_source": "ncu dram bytes per pair (profiles/r01_score_fast_K200k.ncu-rep) x pairs of this launch",
             "peak_source": f"148 SM x 128 FP32 lanes x 2 x sm_max_mhz ({peaks['sm_max_mhz']:.0f} MHz, MEASURED_PEAKS.json: {peaks['source']})",
             "algorithmic_flop_per_hyp_pt": FLOP_PER_PAIR, "kernel_ms": k_avg_s * 1e3,
             "kernel_share_of_step": (k_avg_s * 1e3) / (ms / args.steps)}
@@ -422,7 +428,8 @@ def bench_warp(torch, dist, rank, world, args, ctx, peaks, local_gpu):
     bytes_per_launch = 2.0 * n * per_frame                      # each source byte once + each output byte once
     k_avg_s = ms / args.steps / 1e3
     roof = {"bound": "hbm", "kernel": "warp_pipe_kernel (K4, bilinear u8 RGB; + warp_setup_kernel, <1% of the step)", "achieved": bytes_per_launch / k_avg_s / 1e9, "peak": peaks["hbm_gbs"],
-            "unit": "GB/s", "frac": bytes_per_launch / k_avg_s / 1e9 / peaks["hbm_gbs"], "traffic": None,
+            "unit": "GB/s", "frac": bytes_per_launch / k_avg_s / 1e9 / peaks["hbm_gbs"], "traffic": WARP_TRAFFIC_B_PER_PIXEL * n * h * w,
+            "traffic_source": "ncu dram bytes per output pixel (profiles/r01_warp_pipe_v12.ncu-rep, 64 frames) x pixels of this launch",
             "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peaks['source']})", "algorithmic_bytes_per_pixel": 6.0,
             "kernel_ms": k_avg_s * 1e3, "kernel_share_of_step": 1.0}
 
