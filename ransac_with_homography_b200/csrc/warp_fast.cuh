@@ -49,9 +49,18 @@ namespace b200geo {
 #endif
 constexpr int WF_UNROLL_P = B2G_UNROLL_P;   // rows of a thread's pixels unrolled together in the full-tile loop
 constexpr int WF_TW = 64;             // output tile width  (pixels)
-constexpr int WF_TH = 32;             // output tile height
+#ifndef B2G_TH
+#define B2G_TH 32
+#endif
+#ifndef B2G_ENTRIES
+#define B2G_ENTRIES 4096
+#endif
+#ifndef B2G_BOX_H
+#define B2G_BOX_H 48
+#endif
+constexpr int WF_TH = B2G_TH;         // output tile height (multiple of 8)
 constexpr int WF_THREADS = 256;
-constexpr int WF_SRC_ENTRIES = 4096;  // staged source tile capacity: two planes of 16 KB (one 32-bit word per entry and plane)
+constexpr int WF_SRC_ENTRIES = B2G_ENTRIES;  // staged source tile capacity: two planes of 16 KB (one 32-bit word per entry and plane)
 constexpr uint32_t WF_PLANE = WF_SRC_ENTRIES * 4u;   // byte offset of plane 1 (B pairs) from plane 0 (R/G pairs)
 constexpr float WF_MAX_REL = 1024.f;  // |rel| beyond this: SLOW (keeps the 16.16 conversion and the bound sane)
 constexpr float WF_MAX_BAND = 1.0f / 64.f;
@@ -59,7 +68,7 @@ constexpr float WF_MAX_BAND = 1.0f / 64.f;
 enum { WF_EMPTY = 0, WF_ZERO = 1, WF_INTERIOR = 2, WF_BORDER = 3, WF_SLOW = 4, WF_SPLIT = 5 };
 constexpr int WF_SUB_W = 32, WF_SUB_H = 16;   // SPLIT: the tile is redone as quadrants, each with its own (smaller) footprint
 constexpr int WF_TMA_BOX_W = 256;          // bytes per row of the 2-D TMA box (the hardware maximum for one dimension)
-constexpr int WF_TMA_BOX_H = 48;           // rows of the box: 12 KB per tile
+constexpr int WF_TMA_BOX_H = B2G_BOX_H;    // rows of the box: 12 KB per tile at 48
 constexpr int WF_FLAG_TMA = 0x400;         // footprint fits the TMA box and the job lies in the described 2-D source array;
                                            // `magic` then holds the array row of the footprint's first row
 constexpr int WF_FLAG_UNCHECKED = 0x100;   // footprint (+ read slack) lies inside the image and excludes pixel (0,0)
@@ -515,7 +524,7 @@ __device__ __noinline__ void wf_split_tile(const b200geo_warp_job &J, const uint
                                            uint32_t s_out, uint32_t *s_out_mem, int c0, int r0, int tw, int th, unsigned &n_exact, Sync sync)
 {
     const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
-    for (int q = 0; q < (WF_TW / WF_SUB_W) * (WF_TH / WF_SUB_H); ++q) {
+    for (int q = 0; q < (WF_TW / WF_SUB_W) * ((WF_TH + WF_SUB_H - 1) / WF_SUB_H); ++q) {
         const int co = (q % (WF_TW / WF_SUB_W)) * WF_SUB_W, ro = (q / (WF_TW / WF_SUB_W)) * WF_SUB_H;
         const int stw = min(WF_SUB_W, tw - co), sth = min(WF_SUB_H, th - ro);
         if (stw <= 0 || sth <= 0) continue;                       // uniform
@@ -645,7 +654,10 @@ warp_fast_kernel(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst
 // Tiles whose rows cannot be copied in bulk (image edges, footprints larger than the raw buffer)
 // are staged synchronously by the consumers as in warp_fast_kernel.
 // ------------------------------------------------------------------------------------------------
-constexpr int WP_RAW_BYTES = 14336;   // one raw-row buffer (x2); >= WF_TMA_BOX_W * WF_TMA_BOX_H
+#ifndef B2G_RAW_SLACK
+#define B2G_RAW_SLACK 2048
+#endif
+constexpr int WP_RAW_BYTES = WF_TMA_BOX_W * WF_TMA_BOX_H + B2G_RAW_SLACK;   // one raw-row buffer (x2)
 constexpr int WP_OCC = B2G_WP_OCC;    // CTAs per SM (shared memory: 2 x raw 14 KB + 2 x entries 32 KB + output 8 KB)
 constexpr int WP_THREADS = WF_THREADS + 32;
 
@@ -687,17 +699,31 @@ __device__ __forceinline__ void wp_mbar_arrive(uint32_t a)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory");
 }
+__device__ __forceinline__ bool wp_mbar_try(uint32_t a, uint32_t parity)
+{
+    uint32_t ok;
+    // the suspend-time hint lets the warp sleep in hardware until the phase completes instead of re-polling
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(a), "r"(parity), "r"(0x989680u) : "memory");
+    return ok != 0;
+}
+__device__ __noinline__ void wp_mbar_wait_slow(uint32_t a, uint32_t parity)
+{
+    // a lost copy / protocol error must not hang the GPU: give up after 4 s of wall time (a legitimate
+    // wait lasts microseconds; the limit is on time, not on tries -- a try may return early)
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        if (wp_mbar_try(a, parity)) return;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 4000000000ull) __trap();
+    }
+}
 __device__ __forceinline__ void wp_mbar_wait(uint32_t a, uint32_t parity)
 {
-    unsigned spins = 0;
-    for (;;) {
-        uint32_t ok;
-        // the suspend-time hint lets the warp sleep in hardware until the phase completes instead of re-polling
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(a), "r"(parity), "r"(0x989680u) : "memory");
-        if (ok) return;
-        if (++spins > (1u << 20)) __trap();        // a lost copy / protocol error must not hang the GPU
-    }
+    if (wp_mbar_try(a, parity)) return;
+    if (wp_mbar_try(a, parity)) return;
+    wp_mbar_wait_slow(a, parity);
 }
 __device__ __forceinline__ void wp_bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t mbar)
 {
