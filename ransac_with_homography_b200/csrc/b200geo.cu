@@ -399,6 +399,14 @@ int launch_warp(b200geo_ctx *ctx, const void *src, void *dst, const b200geo_warp
         dim3 sgrid((tiles_x + 31) / 32, (tiles_y + 7) / 8, n_jobs), sblock(32, 8);
         const uint8_t *s8 = (const uint8_t *)src;
         uint8_t *d8 = (uint8_t *)dst;
+        // deferred float64 pixels: list sized for ~0.4 % of the output, settled by warp_fixup_kernel
+        unsigned long long fix_want = (unsigned long long)max_ow * max_oh * n_jobs / 256 + 65536;
+        if (fix_want > (1ull << 27)) fix_want = 1ull << 27;
+        WfFixEntry *fix_list;
+        if ((rc = scratch(ctx, S_WARPFIX, fix_want * sizeof(WfFixEntry), (void **)&fix_list))) return rc;
+        const unsigned fix_cap = (unsigned)(ctx->scratch_cap[S_WARPFIX] / sizeof(WfFixEntry));
+        unsigned *fix_count = (unsigned *)(stats + 3);
+        B2G_CUDA(cudaMemsetAsync(fix_count, 0, sizeof(unsigned), st));
         const int use_tmap = ctx->warp_variant == 0 ? prepare_tmap(ctx, src, layout) : 0;
         if (getenv("B200GEO_DEBUG"))
             fprintf(stderr, "[b200geo] warp: jobs %d tiles %dx%d sampler %d layout %p use_tmap %d (encode %p)\n", n_jobs, tiles_x, tiles_y,
@@ -410,8 +418,8 @@ int launch_warp(b200geo_ctx *ctx, const void *src, void *dst, const b200geo_warp
         if (ctx->warp_variant == 1) {
             // one CTA per tile (kept for comparison)
             dim3 grid(tiles_x, tiles_y, n_jobs);
-            if (sampler == B200GEO_BILINEAR) warp_fast_kernel<1><<<grid, WF_THREADS, 0, st>>>(s8, d8, jobs_dev, descs, stats + 2);
-            else warp_fast_kernel<0><<<grid, WF_THREADS, 0, st>>>(s8, d8, jobs_dev, descs, stats + 2);
+            if (sampler == B200GEO_BILINEAR) warp_fast_kernel<1><<<grid, WF_THREADS, 0, st>>>(s8, d8, jobs_dev, descs, stats + 2, fix_list, fix_count, fix_cap);
+            else warp_fast_kernel<0><<<grid, WF_THREADS, 0, st>>>(s8, d8, jobs_dev, descs, stats + 2, fix_list, fix_count, fix_cap);
         } else {
             // persistent CTAs, TMA bulk copies one tile ahead
             const long long n_tiles = (long long)tiles_x * tiles_y * n_jobs;
@@ -424,10 +432,13 @@ int launch_warp(b200geo_ctx *ctx, const void *src, void *dst, const b200geo_warp
             long long ctas = (long long)ctx->sm_count * WP_OCC;
             if (ctas > n_tiles) ctas = n_tiles;
             if (sampler == B200GEO_BILINEAR)
-                warp_pipe_kernel<1><<<(unsigned)ctas, WP_THREADS, sizeof(WpSmem), st>>>(s8, d8, jobs_dev, descs, (int)n_tiles, tiles_x, tiles_y, stats + 2, ctx->tmap, use_tmap);
+                warp_pipe_kernel<1><<<(unsigned)ctas, WP_THREADS, sizeof(WpSmem), st>>>(s8, d8, jobs_dev, descs, (int)n_tiles, tiles_x, tiles_y, stats + 2, ctx->tmap, use_tmap, fix_list, fix_count, fix_cap);
             else
-                warp_pipe_kernel<0><<<(unsigned)ctas, WP_THREADS, sizeof(WpSmem), st>>>(s8, d8, jobs_dev, descs, (int)n_tiles, tiles_x, tiles_y, stats + 2, ctx->tmap, use_tmap);
+                warp_pipe_kernel<0><<<(unsigned)ctas, WP_THREADS, sizeof(WpSmem), st>>>(s8, d8, jobs_dev, descs, (int)n_tiles, tiles_x, tiles_y, stats + 2, ctx->tmap, use_tmap, fix_list, fix_count, fix_cap);
         }
+        B2G_CHECK_LAUNCH(ctx);
+        if (sampler == B200GEO_BILINEAR) warp_fixup_kernel<1><<<2 * ctx->sm_count, 128, 0, st>>>(s8, d8, jobs_dev, fix_list, fix_count, fix_cap, stats + 2);
+        else warp_fixup_kernel<0><<<2 * ctx->sm_count, 128, 0, st>>>(s8, d8, jobs_dev, fix_list, fix_count, fix_cap, stats + 2);
         B2G_CHECK_LAUNCH(ctx);
         return B200GEO_OK;
     }

@@ -62,6 +62,7 @@ constexpr int WF_TH = B2G_TH;         // output tile height (multiple of 8)
 constexpr int WF_THREADS = 256;
 constexpr int WF_SRC_ENTRIES = B2G_ENTRIES;  // staged source tile capacity: two planes of 16 KB (one 32-bit word per entry and plane)
 constexpr uint32_t WF_PLANE = WF_SRC_ENTRIES * 4u;   // byte offset of plane 1 (B pairs) from plane 0 (R/G pairs)
+constexpr float WF_W0 = 1.0f / 65536.f;   // constant term of the scaled denominator
 constexpr float WF_MAX_REL = 1024.f;  // |rel| beyond this: SLOW (keeps the 16.16 conversion and the bound sane)
 constexpr float WF_MAX_BAND = 1.0f / 64.f;
 
@@ -69,12 +70,12 @@ enum { WF_EMPTY = 0, WF_ZERO = 1, WF_INTERIOR = 2, WF_BORDER = 3, WF_SLOW = 4, W
 constexpr int WF_SUB_W = 32, WF_SUB_H = 16;   // SPLIT: the tile is redone as quadrants, each with its own (smaller) footprint
 constexpr int WF_TMA_BOX_W = 256;          // bytes per row of the 2-D TMA box (the hardware maximum for one dimension)
 constexpr int WF_TMA_BOX_H = B2G_BOX_H;    // rows of the box: 12 KB per tile at 48
-constexpr int WF_FLAG_TMA = 0x400;         // footprint fits the TMA box and the job lies in the described 2-D source array;
-                                           // `magic` then holds the array row of the footprint's first row
+constexpr int WF_FLAG_TMA = 0x400;         // footprint fits the TMA box and the job lies in the described 2-D source array
 constexpr int WF_FLAG_UNCHECKED = 0x100;   // footprint (+ read slack) lies inside the image and excludes pixel (0,0)
 
 struct __align__(16) WfDesc {
-    float nx0, ax, bx, ny0, ay, by, w0, gw, hw;   // w0, gw, hw pre-scaled by 2^-16: nx / w = rel * 65536
+    float nx0, ax, bx, ny0, ay, by, gw, hw;       // gw, hw pre-scaled by 2^-16 (w0 = WF_W0): nx / w = rel * 65536
+    int srow;                                     // TMA tiles: row of the footprint's first row in the 2-D source array
     float band;                                   // ambiguity half-width, in rel * 65536 units
     int xc, yc;                                   // anchor (absolute source pixel)
     short ox, oy;                                 // staged tile origin, relative to the anchor
@@ -112,7 +113,7 @@ __device__ __forceinline__ void wf_rel16(const WfDesc &T, float di, float dj, fl
 {
     const float nx = __fmaf_rn(T.ax, di, __fmaf_rn(T.bx, dj, T.nx0));
     const float ny = __fmaf_rn(T.ay, di, __fmaf_rn(T.by, dj, T.ny0));
-    const float w = __fmaf_rn(T.gw, di, __fmaf_rn(T.hw, dj, T.w0));
+    const float w = __fmaf_rn(T.gw, di, __fmaf_rn(T.hw, dj, WF_W0));
     const float rw = wf_rcp(w);
     rx = __fmul_rn(nx, rw);
     ry = __fmul_rn(ny, rw);
@@ -136,7 +137,7 @@ __device__ void wf_setup(const b200geo_warp_job &J, int c0, int r0, int tw, int 
 {
     T.mode = WF_SLOW;
     T.P = 0; T.rows = 0; T.ox = 0; T.oy = 0; T.xc = 0; T.yc = 0; T.band = 0.f; T.magic = 0u;
-    T.nx0 = T.ax = T.bx = T.ny0 = T.ay = T.by = T.gw = T.hw = 0.f; T.w0 = 1.f;
+    T.nx0 = T.ax = T.bx = T.ny0 = T.ay = T.by = T.gw = T.hw = 0.f; T.srow = 0;
     const int cm = c0 + WF_TW / 2, rm = r0 + WF_TH / 2;
     const double Xm = (double)cm * J.dx + J.x0, Ym = (double)rm * J.dy + J.y0;
     // the grid must be the arithmetic progression the tile-affine form assumes (np.linspace's
@@ -165,7 +166,7 @@ __device__ void wf_setup(const b200geo_warp_job &J, int c0, int r0, int tw, int 
     T.nx0 = (float)(xs - xc); T.ax = (float)ax; T.bx = (float)bx;
     T.ny0 = (float)(ys - yc); T.ay = (float)ay; T.by = (float)by;
     const double sc = 1.0 / 65536.0;
-    T.w0 = (float)sc; T.gw = (float)(gw * sc); T.hw = (float)(hw * sc);
+    T.gw = (float)(gw * sc); T.hw = (float)(hw * sc);
     T.xc = (int)xc; T.yc = (int)yc;
 
     // four corners of the tile through the float32 formula the pixels use
@@ -231,7 +232,7 @@ __device__ void wf_setup(const b200geo_warp_job &J, int c0, int r0, int tw, int 
         // innermost coordinate faults): the box starts at (3*ax0) & ~15 and the rows carry a phase of 0/4/8/12 bytes
         if (tma_job && ((3 * ax0) & 15) + 3 * (P + 1) <= WF_TMA_BOX_W && rows <= WF_TMA_BOX_H) {
             T.mode |= WF_FLAG_TMA;
-            T.magic = (unsigned)(J.src_offset / tma_pitch + ay0);
+            T.srow = (int)(J.src_offset / tma_pitch + ay0);
         }
     }
 }
@@ -250,7 +251,7 @@ warp_setup_kernel(const b200geo_warp_job *__restrict__ jobs, const uint8_t *__re
     if (c0 >= J.ow || r0 >= J.oh) {
         T.mode = WF_EMPTY;
         T.P = 0; T.rows = 0; T.ox = 0; T.oy = 0; T.xc = 0; T.yc = 0; T.band = 0.f; T.magic = 0u;
-        T.nx0 = T.ax = T.bx = T.ny0 = T.ay = T.by = T.gw = T.hw = 0.f; T.w0 = 1.f;
+        T.nx0 = T.ax = T.bx = T.ny0 = T.ay = T.by = T.gw = T.hw = 0.f; T.srow = 0;
     } else {
         wf_setup<BILINEAR>(J, c0, r0, min(WF_TW, J.ow - c0), min(WF_TH, J.oh - r0), tma_pitch, T);
     }
@@ -368,6 +369,45 @@ __device__ __noinline__ uint32_t wf_exact_px(const b200geo_warp_job &J, const ui
     return (uint32_t)o[0] | ((uint32_t)o[1] << 8) | ((uint32_t)o[2] << 16);
 }
 
+// Pixels that need the float64 path are rare (within `band` of a mask / rounding boundary) but slow
+// (float64 divisions, dependent global loads): settling one inline stalls its warp -- and at the next
+// tile barrier its whole CTA -- for microseconds.  They are pushed to a global list instead and
+// settled by warp_fixup_kernel after the main kernel (stream order); the main kernel stores its
+// speculative value, the fix-up overwrites the three bytes.
+struct WfFixEntry { int job, c, r; };
+struct WfFix {
+    WfFixEntry *list;
+    unsigned *count;
+    unsigned cap;
+    int job;
+};
+__device__ __forceinline__ bool wf_defer(const WfFix &f, int c, int r)
+{
+    if (!f.list) return false;
+    const unsigned i = atomicAdd(f.count, 1u);
+    if (i >= f.cap) return false;          // list full: the caller settles the pixel inline
+    f.list[i].job = f.job; f.list[i].c = c; f.list[i].r = r;
+    return true;
+}
+
+// Grid: any; one thread per deferred pixel.  stats[0] += pixels settled.
+template <int BILINEAR>
+__global__ void __launch_bounds__(128)
+warp_fixup_kernel(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst_base, const b200geo_warp_job *__restrict__ jobs,
+                  const WfFixEntry *__restrict__ list, const unsigned *__restrict__ count, unsigned cap,
+                  unsigned long long *__restrict__ stats)
+{
+    const unsigned n = min(*count, cap);
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const WfFixEntry e = list[i];
+        const b200geo_warp_job &J = jobs[e.job];
+        const uint32_t v = wf_exact_px<BILINEAR>(J, src_base + J.src_offset, e.c, e.r);
+        uint8_t *q = dst_base + J.dst_offset + (size_t)e.r * (size_t)J.dst_pitch + (size_t)e.c * 3;
+        q[0] = (uint8_t)v; q[1] = (uint8_t)(v >> 8); q[2] = (uint8_t)(v >> 16);
+    }
+    if (stats && blockIdx.x == 0 && threadIdx.x == 0 && n) atomicAdd(stats, (unsigned long long)n);
+}
+
 // bilinear blend of two staged entry pairs with 16-bit weights summing to 65536
 __device__ __forceinline__ uint32_t wf_blend(uint2 top, uint2 bot, uint32_t fx, uint32_t fy)
 {
@@ -391,7 +431,7 @@ __device__ __forceinline__ uint32_t wf_blend(uint2 top, uint2 bot, uint32_t fx, 
 // DIRECT = 0: results go to the swizzled shared-memory stage `s_out` (copied out by wf_copy_out).
 template <int BILINEAR, int DIRECT>
 __device__ __forceinline__ void wf_compute_full(const WfDesc &T, const b200geo_warp_job &J, const uint8_t *__restrict__ src,
-                                                uint32_t s_src, uint32_t s_out, int c0, int r0, unsigned &n_exact,
+                                                uint32_t s_src, uint32_t s_out, int c0, int r0, unsigned &n_exact, const WfFix &fix,
                                                 uint8_t *__restrict__ dst_tile = nullptr, size_t dst_pitch = 0)
 {
     const int tid_ = wf_tid();
@@ -401,7 +441,7 @@ __device__ __forceinline__ void wf_compute_full(const WfDesc &T, const b200geo_w
     const float ax = T.ax, ay = T.ay, bx = T.bx, by = T.by, gw = T.gw, hw = T.hw;
     const float nxb = __fmaf_rn(ax, di0, __fmaf_rn(bx, dj0, T.nx0));
     const float nyb = __fmaf_rn(ay, di0, __fmaf_rn(by, dj0, T.ny0));
-    const float wb = __fmaf_rn(gw, di0, __fmaf_rn(hw, dj0, T.w0));
+    const float wb = __fmaf_rn(gw, di0, __fmaf_rn(hw, dj0, WF_W0));
     const uint32_t P4 = (uint32_t)T.P * 4u;
     const uint32_t base = s_src - (uint32_t)(((int)T.oy * (int)T.P + (int)T.ox) * 4);
     uint32_t oaddr[WF_TW / 32];
@@ -414,6 +454,9 @@ __device__ __forceinline__ void wf_compute_full(const WfDesc &T, const b200geo_w
     const uint32_t psel = (lane & 3) == 0 ? 0x4210u : ((lane & 3) == 1 ? 0x5421u : 0x6542u);
     uint8_t *gptr = dst_tile + (size_t)wrp * dst_pitch + (size_t)(12 * (lane >> 2) + 4 * (lane & 3));
     const int B16 = (int)T.band + 2;
+    constexpr int NPX = (WF_TH / 8) * (WF_TW / 32);
+    uint32_t outv[NPX];          // nn only
+    uint32_t amb = 0u;           // nn only: pixels to settle in float64
 #pragma unroll WF_UNROLL_P
     for (int p = 0; p < WF_TH / 8; ++p) {
         const float nxp = p ? __fmaf_rn(bx, (float)(8 * p), nxb) : nxb;
@@ -435,19 +478,20 @@ __device__ __forceinline__ void wf_compute_full(const WfDesc &T, const b200geo_w
                 const uint2 top = wf_lds_entry(a), bot = wf_lds_entry(a + P4);
                 out = wf_blend(top, bot, (uint32_t)fxd & 0xFFFFu, (uint32_t)fyd & 0xFFFFu);
             } else {
+                // nn: fetch speculatively (the footprint has a one-entry margin either way), remember
+                // which pixels lie within `band` of a rounding boundary; they are settled in float64
+                // after the branch-free pass so that the eight fetches of a thread stay interleaved
                 const int hx = fxd + 32768, hy = fyd + 32768;
                 const uint32_t fx = (uint32_t)hx & 0xFFFFu, fy = (uint32_t)hy & 0xFFFFu;
-                if (fx - (uint32_t)B16 > (uint32_t)(65535 - 2 * B16) || fy - (uint32_t)B16 > (uint32_t)(65535 - 2 * B16)) {
-                    // within `band` of a rounding boundary: the float64 path decides
-                    out = wf_exact_px<BILINEAR>(J, src, c0 + lane + 32 * hh, r0 + wrp + 8 * p);
-                    ++n_exact;
-                } else {
-                    const int xi = (int)__byte_perm((uint32_t)hx, 0u, 0xBB32), yi = (int)__byte_perm((uint32_t)hy, 0u, 0xBB32);
-                    const uint2 e = wf_lds_entry((uint32_t)yi * P4 + base + ((uint32_t)xi << 2));
-                    out = __byte_perm(e.x, e.y, 0x4420);
-                }
+                if (fx - (uint32_t)B16 > (uint32_t)(65535 - 2 * B16) || fy - (uint32_t)B16 > (uint32_t)(65535 - 2 * B16))
+                    amb |= 1u << (p * (WF_TW / 32) + hh);
+                const int xi = (int)__byte_perm((uint32_t)hx, 0u, 0xBB32), yi = (int)__byte_perm((uint32_t)hy, 0u, 0xBB32);
+                const uint2 e = wf_lds_entry((uint32_t)yi * P4 + base + ((uint32_t)xi << 2));
+                out = __byte_perm(e.x, e.y, 0x4420);
             }
-            if (DIRECT) {
+            if (!BILINEAR) {
+                outv[p * (WF_TW / 32) + hh] = out;
+            } else if (DIRECT) {
                 const uint32_t nb = __shfl_down_sync(0xffffffffu, out, 1);
                 const uint32_t word = __byte_perm(out, nb, psel);
                 if ((lane & 3) != 3) *reinterpret_cast<uint32_t *>(gptr + 96 * hh) = word;
@@ -462,13 +506,34 @@ __device__ __forceinline__ void wf_compute_full(const WfDesc &T, const b200geo_w
             }
         }
     }
+    if (!BILINEAR) {
+        if (amb) {
+#pragma unroll
+            for (int k = 0; k < NPX; ++k)
+                if (amb & (1u << k)) {
+                    const int c = c0 + lane + 32 * (k % (WF_TW / 32)), r = r0 + wrp + 8 * (k / (WF_TW / 32));
+                    if (!wf_defer(fix, c, r)) { outv[k] = wf_exact_px<BILINEAR>(J, src, c, r); ++n_exact; }
+                }
+        }
+#pragma unroll
+        for (int k = 0; k < NPX; ++k) {
+            const int hh = k % (WF_TW / 32), p = k / (WF_TW / 32);
+            if (DIRECT) {
+                const uint32_t nb = __shfl_down_sync(0xffffffffu, outv[k], 1);
+                const uint32_t word = __byte_perm(outv[k], nb, psel);
+                if ((lane & 3) != 3) *reinterpret_cast<uint32_t *>(gptr + (size_t)p * 8 * dst_pitch + 96 * hh) = word;
+            } else {
+                asm volatile("st.shared.u32 [%0+%1], %2;" ::"r"(oaddr[hh] + (uint32_t)(p * 8 * WF_TW * 4)), "n"(0), "r"(outv[k]));
+            }
+        }
+    }
 }
 
 // Any other staged tile: partial tiles and BORDER tiles (per-pixel mask with the ambiguity band).
 template <int BILINEAR, int BORDER>
 __device__ __forceinline__ void wf_compute_general(const WfDesc &T, const b200geo_warp_job &J, const uint8_t *__restrict__ src,
                                                 uint32_t s_src, uint32_t s_out, int c0, int r0, int tw, int th, unsigned &n_exact,
-                                                int col_off = 0, int row_off = 0)
+                                                const WfFix &fix, int col_off = 0, int row_off = 0)
 {
     // (c0, r0) is the output pixel of local (0, 0); (col_off, row_off) its place inside the staged output tile
     const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
@@ -489,7 +554,7 @@ __device__ __forceinline__ void wf_compute_general(const WfDesc &T, const b200ge
                 const bool outp = rx < lox - T.band || rx > hix + T.band || ry < loy - T.band || ry > hiy + T.band;
                 if (!in) {
                     fast = false;
-                    if (!outp) { out = wf_exact_px<BILINEAR>(J, src, c0 + col, r0 + row); ++n_exact; }
+                    if (!outp && !wf_defer(fix, c0 + col, r0 + row)) { out = wf_exact_px<BILINEAR>(J, src, c0 + col, r0 + row); ++n_exact; }
                 }
             }
             if (fast) {
@@ -502,8 +567,7 @@ __device__ __forceinline__ void wf_compute_general(const WfDesc &T, const b200ge
                     const int hx = fxd + 32768, hy = fyd + 32768;
                     const uint32_t fx = (uint32_t)hx & 0xFFFFu, fy = (uint32_t)hy & 0xFFFFu;
                     if (fx - (uint32_t)B16 > (uint32_t)(65535 - 2 * B16) || fy - (uint32_t)B16 > (uint32_t)(65535 - 2 * B16)) {
-                        out = wf_exact_px<BILINEAR>(J, src, c0 + col, r0 + row);
-                        ++n_exact;
+                        if (!wf_defer(fix, c0 + col, r0 + row)) { out = wf_exact_px<BILINEAR>(J, src, c0 + col, r0 + row); ++n_exact; }
                     } else {
                         const int xi = max(hx >> 16, -T.xc), yi = max(hy >> 16, -T.yc);   // trunc toward zero: (-1, 0) -> 0
                         const uint2 e = wf_lds_entry(base + (uint32_t)(yi * P4 + xi * 4));
@@ -521,7 +585,8 @@ __device__ __forceinline__ void wf_compute_general(const WfDesc &T, const b200ge
 // calling kernel's sampling threads.  A quadrant whose footprint still does not fit is exact.
 template <int BILINEAR, typename Sync>
 __device__ __noinline__ void wf_split_tile(const b200geo_warp_job &J, const uint8_t *__restrict__ src, WfDesc *s_sub, uint32_t s_src,
-                                           uint32_t s_out, uint32_t *s_out_mem, int c0, int r0, int tw, int th, unsigned &n_exact, Sync sync)
+                                           uint32_t s_out, uint32_t *s_out_mem, int c0, int r0, int tw, int th, unsigned &n_exact,
+                                           const WfFix &fix, Sync sync)
 {
     const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
     for (int q = 0; q < (WF_TW / WF_SUB_W) * ((WF_TH + WF_SUB_H - 1) / WF_SUB_H); ++q) {
@@ -540,8 +605,8 @@ __device__ __noinline__ void wf_split_tile(const b200geo_warp_job &J, const uint
         if (m == WF_INTERIOR || m == WF_BORDER) {
             wf_stage(*s_sub, src, (size_t)J.src_pitch, J.iw, J.ih, s_src);
             sync();
-            if (m == WF_INTERIOR) wf_compute_general<BILINEAR, 0>(*s_sub, J, src, s_src, s_out, c0 + co, r0 + ro, stw, sth, n_exact, co, ro);
-            else wf_compute_general<BILINEAR, 1>(*s_sub, J, src, s_src, s_out, c0 + co, r0 + ro, stw, sth, n_exact, co, ro);
+            if (m == WF_INTERIOR) wf_compute_general<BILINEAR, 0>(*s_sub, J, src, s_src, s_out, c0 + co, r0 + ro, stw, sth, n_exact, fix, co, ro);
+            else wf_compute_general<BILINEAR, 1>(*s_sub, J, src, s_src, s_out, c0 + co, r0 + ro, stw, sth, n_exact, fix, co, ro);
         } else {
             for (int row = wrp; row < sth; row += 8)
                 for (int col = lane; col < stw; col += 32) {
@@ -593,7 +658,7 @@ template <int BILINEAR>
 __global__ void __launch_bounds__(WF_THREADS, B2G_WF_OCC)
 warp_fast_kernel(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst_base,
                  const b200geo_warp_job *__restrict__ jobs, const WfDesc *__restrict__ descs,
-                 unsigned long long *__restrict__ stats)
+                 unsigned long long *__restrict__ stats, WfFixEntry *__restrict__ fix_list, unsigned *__restrict__ fix_count, unsigned fix_cap)
 {
     __shared__ __align__(16) uint32_t s_src_mem[2 * WF_SRC_ENTRIES];
     __shared__ __align__(16) uint32_t s_out_mem[WF_TW * WF_TH];
@@ -608,18 +673,19 @@ warp_fast_kernel(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst
     const uint32_t s_src = (uint32_t)__cvta_generic_to_shared(s_src_mem);
     const uint32_t s_out = (uint32_t)__cvta_generic_to_shared(s_out_mem);
     unsigned n_exact = 0;
+    const WfFix fix = {fix_list, fix_count, fix_cap, (int)blockIdx.z};
 
     if (mode == WF_INTERIOR || mode == WF_BORDER) {
         wf_stage(T, src, (size_t)J.src_pitch, J.iw, J.ih, s_src);
         __syncthreads();
-        if (mode == WF_INTERIOR && tw == WF_TW && th == WF_TH) wf_compute_full<BILINEAR, 0>(T, J, src, s_src, s_out, c0, r0, n_exact);
-        else if (mode == WF_INTERIOR) wf_compute_general<BILINEAR, 0>(T, J, src, s_src, s_out, c0, r0, tw, th, n_exact);
-        else wf_compute_general<BILINEAR, 1>(T, J, src, s_src, s_out, c0, r0, tw, th, n_exact);
+        if (mode == WF_INTERIOR && tw == WF_TW && th == WF_TH) wf_compute_full<BILINEAR, 0>(T, J, src, s_src, s_out, c0, r0, n_exact, fix);
+        else if (mode == WF_INTERIOR) wf_compute_general<BILINEAR, 0>(T, J, src, s_src, s_out, c0, r0, tw, th, n_exact, fix);
+        else wf_compute_general<BILINEAR, 1>(T, J, src, s_src, s_out, c0, r0, tw, th, n_exact, fix);
     } else if (mode == WF_ZERO) {
         for (int i = threadIdx.x; i < WF_TW * WF_TH; i += WF_THREADS) s_out_mem[i] = 0u;
     } else if (mode == WF_SPLIT) {
         __shared__ WfDesc s_sub;
-        wf_split_tile<BILINEAR>(J, src, &s_sub, s_src, s_out, s_out_mem, c0, r0, tw, th, n_exact, [] { __syncthreads(); });
+        wf_split_tile<BILINEAR>(J, src, &s_sub, s_src, s_out, s_out_mem, c0, r0, tw, th, n_exact, fix, [] { __syncthreads(); });
     } else {
         const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
         for (int row = wrp; row < th; row += 8)
@@ -670,12 +736,15 @@ struct __align__(16) WpTile {
     int iw, ih, c0, r0, tw, th, jz;
     uint32_t RB;             // bytes per raw row in shared memory (multiple of 16)
     int staged, bulk;
-    uint32_t magic;          // ceil(2^32 / (P / 4)): division by the chunk count (T.magic holds the array row for TMA tiles)
+    int pad0;
     int tma;                 // raw rows arrive as one 2-D tensor copy: row stride WF_TMA_BOX_W, one phase
 };
 
-constexpr int WP_STAGES = 2;          // raw-row buffers in flight
-constexpr int WP_TILE_RING = 4;       // tile records: a record outlives its raw buffer (read until the copy-out)
+#ifndef B2G_STAGES
+#define B2G_STAGES 2
+#endif
+constexpr int WP_STAGES = B2G_STAGES; // raw-row buffers in flight
+constexpr int WP_TILE_RING = 8;       // tile records: a record outlives its raw buffer (read until the copy-out); >= WP_STAGES + 2
 
 struct WpSmem {
     uint8_t raw[WP_STAGES][WP_RAW_BYTES];
@@ -715,6 +784,9 @@ __device__ __noinline__ void wp_mbar_wait_slow(uint32_t a, uint32_t parity)
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     for (;;) {
         if (wp_mbar_try(a, parity)) return;
+        // measured: try_wait returns at once even with a suspend hint, and a hot spin takes issue slots from the
+        // warps that work (half of all executed instructions in one nn capture) -- back off explicitly
+        __nanosleep(64);
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
         if (t1 - t0 > 4000000000ull) __trap();
     }
@@ -769,7 +841,8 @@ __global__ void __launch_bounds__(WP_THREADS, WP_OCC)
 warp_pipe_kernel(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst_base,
                  const b200geo_warp_job *__restrict__ jobs, const WfDesc *__restrict__ descs,
                  int n_tiles, int tiles_x, int tiles_y, unsigned long long *__restrict__ stats,
-                 const __grid_constant__ CUtensorMap tmap, int use_tmap)
+                 const __grid_constant__ CUtensorMap tmap, int use_tmap,
+                 WfFixEntry *__restrict__ fix_list, unsigned *__restrict__ fix_count, unsigned fix_cap)
 {
     extern __shared__ __align__(16) unsigned char wp_smem[];
     WpSmem &S = *reinterpret_cast<WpSmem *>(wp_smem);
@@ -802,51 +875,62 @@ warp_pipe_kernel(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst
             nd0 = __ldg(reinterpret_cast<const uint4 *>(descs + first) + lane);
             if (first + (int)gridDim.x < n_tiles) nd1 = __ldg(reinterpret_cast<const uint4 *>(descs + first + gridDim.x) + lane);
         }
+        // tile -> (job, tile row, tile column), advanced incrementally (no division per tile)
+        const int step = (int)gridDim.x;
+        const int d_jz = step / tpj, d_rem = step - d_jz * tpj, d_ty = d_rem / tiles_x, d_tx = d_rem - d_ty * tiles_x;
+        int jz = first / tpj, ty = (first - jz * tpj) / tiles_x, tx = first - jz * tpj - ty * tiles_x;
+        // geometry of the current job, reloaded only when the job changes
+        int cur = -1, Jow = 0, Joh = 0, Jiw = 0, Jih = 0;
+        long long Jsp = 0, Jdp = 0;
+        const uint8_t *src = nullptr;
+        uint8_t *dstj = nullptr;
         int it = 0;
-        for (int tile = first; tile < n_tiles; ++it, tile += wf_nctaid()) {
+        for (int tile = first; tile < n_tiles; ++it, tile += step) {
             const int b = it % WP_STAGES, use = it / WP_STAGES;
             const uint32_t s_full = s_full0 + 8u * b, s_raw = s_raw0 + (uint32_t)WP_RAW_BYTES * b;
+            if (jz != cur) {
+                const b200geo_warp_job &J = jobs[jz];
+                cur = jz; Jow = J.ow; Joh = J.oh; Jiw = J.iw; Jih = J.ih; Jsp = J.src_pitch; Jdp = J.dst_pitch;
+                src = src_base + J.src_offset; dstj = dst_base + J.dst_offset;
+            }
             if (use >= 1) wp_mbar_wait(s_empty0 + 8u * b, (uint32_t)(use - 1) & 1u);
             WpTile &W = S.tile[it % WP_TILE_RING];
             if (lane < 4) reinterpret_cast<uint4 *>(&W.T)[lane] = nd0;
             nd0 = nd1;
-            if (lane < 4 && tile + 2 * (int)gridDim.x < n_tiles) nd1 = __ldg(reinterpret_cast<const uint4 *>(descs + tile + 2 * gridDim.x) + lane);
+            if (lane < 4 && tile + 2 * step < n_tiles) nd1 = __ldg(reinterpret_cast<const uint4 *>(descs + tile + 2 * step) + lane);
             __syncwarp();
-            const int jz = tile / tpj, rem = tile - jz * tpj;
-            const int ty = rem / tiles_x, tx = rem - ty * tiles_x;
-            const b200geo_warp_job &J = jobs[jz];
             const int mode = W.T.mode & 0xFF;
             const int P = W.T.P, rows = W.T.rows;
-            const uint8_t *src = src_base + J.src_offset;
-            const size_t pitch = (size_t)J.src_pitch;
+            const size_t pitch = (size_t)Jsp;
             const int ay0 = W.T.yc + W.T.oy, ax0 = W.T.xc + W.T.ox;
             const uint8_t *a0 = src + (long long)ay0 * (long long)pitch + 3LL * ax0;
             const uint32_t RB = (uint32_t)(15 + 3 * (P + 1) + 15) & ~15u;
             const bool staged = mode == WF_INTERIOR || mode == WF_BORDER;
-            const uint32_t chunks = (uint32_t)P >> 2;
-            const size_t lo = (size_t)a0 & ~(size_t)15;
-            const size_t hi = ((size_t)a0 + (size_t)(rows - 1) * pitch) & ~(size_t)15;
-            const size_t img_end = (size_t)src + (size_t)(J.ih - 1) * pitch + 3 * (size_t)J.iw;
             const bool tma = use_tmap && staged && (W.T.mode & WF_FLAG_TMA);
-            const bool bulk = tma || (staged && !(W.T.mode & WF_FLAG_TMA) && (W.T.mode & WF_FLAG_UNCHECKED) &&
-                                      (uint32_t)rows * RB <= (uint32_t)WP_RAW_BYTES && lo >= (size_t)src && hi + RB <= img_end);
+            bool bulk = tma;
+            if (!tma && staged && !(W.T.mode & WF_FLAG_TMA) && (W.T.mode & WF_FLAG_UNCHECKED) && (uint32_t)rows * RB <= (uint32_t)WP_RAW_BYTES) {
+                const size_t lo = (size_t)a0 & ~(size_t)15;
+                const size_t hi = ((size_t)a0 + (size_t)(rows - 1) * pitch) & ~(size_t)15;
+                const size_t img_end = (size_t)src + (size_t)(Jih - 1) * pitch + 3 * (size_t)Jiw;
+                bulk = lo >= (size_t)src && hi + RB <= img_end;
+            }
             if (lane == 0) {
-                W.src = src; W.a0 = a0; W.dst = dst_base + J.dst_offset;
-                W.src_pitch = J.src_pitch; W.dst_pitch = J.dst_pitch;
-                W.iw = J.iw; W.ih = J.ih; W.c0 = tx * WF_TW; W.r0 = ty * WF_TH;
-                W.tw = min(WF_TW, J.ow - tx * WF_TW); W.th = min(WF_TH, J.oh - ty * WF_TH);
+                W.src = src; W.a0 = a0; W.dst = dstj;
+                W.src_pitch = Jsp; W.dst_pitch = Jdp;
+                W.iw = Jiw; W.ih = Jih; W.c0 = tx * WF_TW; W.r0 = ty * WF_TH;
+                W.tw = min(WF_TW, Jow - tx * WF_TW); W.th = min(WF_TH, Joh - ty * WF_TH);
                 W.jz = jz; W.RB = tma ? (uint32_t)WF_TMA_BOX_W : RB; W.staged = staged; W.bulk = bulk; W.tma = tma;
-                const int srow = (int)W.T.magic;                   // TMA tiles: array row of the footprint's first row
-                if (W.T.mode & WF_FLAG_TMA)                        // everyone downstream wants the chunk divisor
-                    W.T.magic = chunks > 1 ? (uint32_t)((0x100000000ULL + chunks - 1) / chunks) : 0u;
-                W.magic = W.T.magic;
                 if (tma) {
                     wp_mbar_expect_tx(s_full, (uint32_t)(WF_TMA_BOX_W * WF_TMA_BOX_H));
                     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                                 ::"r"(s_raw), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"((3 * ax0) & ~15), "r"(srow), "r"(s_full) : "memory");
+                                 ::"r"(s_raw), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"((3 * ax0) & ~15), "r"(W.T.srow), "r"(s_full) : "memory");
                 } else if (bulk) wp_mbar_expect_tx(s_full, (uint32_t)rows * RB);
                 else wp_mbar_arrive(s_full);
             }
+            // next tile of this CTA
+            jz += d_jz; ty += d_ty; tx += d_tx;
+            if (tx >= tiles_x) { tx -= tiles_x; ++ty; }
+            if (ty >= tiles_y) { ty -= tiles_y; ++jz; }
             __syncwarp();
             if (bulk && !tma)
                 for (int r = lane; r < rows; r += 32) {
@@ -882,8 +966,8 @@ warp_pipe_kernel(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst
         // WP_STAGES tiles ahead of this conversion, so the record stays valid through the copy-out
         const WpTile &W = S.tile[t % WP_TILE_RING];
         const uint32_t s_pairs = s_pairs0 + PAIRS_BYTES * (uint32_t)(t & 1), s_raw = s_raw0 + (uint32_t)WP_RAW_BYTES * b;
-        if (W.tma) wp_convert<1>(W.T, W.magic, (uint32_t)(size_t)W.a0, 0u, W.RB, s_raw, s_pairs);
-        else if (W.bulk) wp_convert<0>(W.T, W.magic, (uint32_t)(size_t)W.a0, (uint32_t)W.src_pitch, W.RB, s_raw, s_pairs);
+        if (W.tma) wp_convert<1>(W.T, W.T.magic, (uint32_t)(size_t)W.a0, 0u, W.RB, s_raw, s_pairs);
+        else if (W.bulk) wp_convert<0>(W.T, W.T.magic, (uint32_t)(size_t)W.a0, (uint32_t)W.src_pitch, W.RB, s_raw, s_pairs);
         else if (W.staged) wf_stage(W.T, W.src, (size_t)W.src_pitch, W.iw, W.ih, s_pairs);
         __syncwarp();
         if (lane == 0) {
@@ -901,8 +985,9 @@ warp_pipe_kernel(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst
         wp_mbar_wait(s_conv0 + 8u * (uint32_t)s, (uint32_t)(it >> 1) & 1u);
         uint8_t *const dst_tile = W.dst + (size_t)W.r0 * (size_t)W.dst_pitch + (size_t)W.c0 * 3;
         const bool direct = mode == WF_INTERIOR && W.tw == WF_TW && W.th == WF_TH && ((((size_t)dst_tile) | (size_t)W.dst_pitch) & 3) == 0;
+        const WfFix fix = {fix_list, fix_count, fix_cap, W.jz};
         if (direct) {
-            wf_compute_full<BILINEAR, 1>(W.T, jobs[W.jz], W.src, s_pairs, 0u, W.c0, W.r0, n_exact, dst_tile, (size_t)W.dst_pitch);
+            wf_compute_full<BILINEAR, 1>(W.T, jobs[W.jz], W.src, s_pairs, 0u, W.c0, W.r0, n_exact, fix, dst_tile, (size_t)W.dst_pitch);
             if (it + 1 < n_iter) convert(it + 1);
             continue;
         }
@@ -912,13 +997,13 @@ warp_pipe_kernel(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst
             wp_consumer_sync();          // the previous staged tile's copy-out has finished reading S.out
             if (W.staged) {
                 // (a full tile whose destination is not 4-byte aligned takes the same arithmetic as the direct path)
-                if (mode == WF_INTERIOR && W.tw == WF_TW && W.th == WF_TH) wf_compute_full<BILINEAR, 0>(W.T, J, W.src, s_pairs, s_out, W.c0, W.r0, n_exact);
-                else if (mode == WF_INTERIOR) wf_compute_general<BILINEAR, 0>(W.T, J, W.src, s_pairs, s_out, W.c0, W.r0, W.tw, W.th, n_exact);
-                else wf_compute_general<BILINEAR, 1>(W.T, J, W.src, s_pairs, s_out, W.c0, W.r0, W.tw, W.th, n_exact);
+                if (mode == WF_INTERIOR && W.tw == WF_TW && W.th == WF_TH) wf_compute_full<BILINEAR, 0>(W.T, J, W.src, s_pairs, s_out, W.c0, W.r0, n_exact, fix);
+                else if (mode == WF_INTERIOR) wf_compute_general<BILINEAR, 0>(W.T, J, W.src, s_pairs, s_out, W.c0, W.r0, W.tw, W.th, n_exact, fix);
+                else wf_compute_general<BILINEAR, 1>(W.T, J, W.src, s_pairs, s_out, W.c0, W.r0, W.tw, W.th, n_exact, fix);
             } else if (mode == WF_ZERO) {
                 for (int i = tid; i < WF_TW * WF_TH; i += WF_THREADS) S.out[i] = 0u;
             } else if (mode == WF_SPLIT) {
-                wf_split_tile<BILINEAR>(J, W.src, &S.sub, s_pairs, s_out, S.out, W.c0, W.r0, W.tw, W.th, n_exact, [] { wp_consumer_sync(); });
+                wf_split_tile<BILINEAR>(J, W.src, &S.sub, s_pairs, s_out, S.out, W.c0, W.r0, W.tw, W.th, n_exact, fix, [] { wp_consumer_sync(); });
             } else {
                 for (int row = wrp; row < W.th; row += 8)
                     for (int col = lane; col < W.tw; col += 32) {
