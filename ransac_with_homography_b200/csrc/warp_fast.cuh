@@ -1,7 +1,7 @@
 // warp_fast.cuh -- K4 fast path: backward warp of uint8 RGB images to uint8 RGB, bilinear or nn.
 //
 // Same element semantics as warp.cuh (reference homography.py:108-209 + astype(uint8) of :225/:241),
-// organised for throughput.  The output is cut into 64 x 32 tiles; two kernels:
+// organised for throughput.  The output is cut into 64 x 40 tiles (WF_TW x WF_TH); two kernels:
 //
 // warp_setup_kernel (one THREAD per tile, float64): re-expresses the projective map of the tile
 //   around the tile's centre pixel and an integer anchor (xc, yc) next to the centre's source
@@ -50,7 +50,7 @@ namespace b200geo {
 constexpr int WF_UNROLL_P = B2G_UNROLL_P;   // rows of a thread's pixels unrolled together in the full-tile loop
 constexpr int WF_TW = 64;             // output tile width  (pixels)
 #ifndef B2G_TH
-#define B2G_TH 32
+#define B2G_TH 40       // 1080 = 27 x 40: no partial tile row at the benchmark's frame height (32 and 48 measured slower there)
 #endif
 #ifndef B2G_ENTRIES
 #define B2G_ENTRIES 4096
@@ -59,6 +59,7 @@ constexpr int WF_TW = 64;             // output tile width  (pixels)
 #define B2G_BOX_H 48
 #endif
 constexpr int WF_TH = B2G_TH;         // output tile height (multiple of 8)
+static_assert(B2G_TH % 8 == 0 && B2G_TH >= 16 && B2G_TH <= 64, "tile height");
 constexpr int WF_THREADS = 256;
 constexpr int WF_SRC_ENTRIES = B2G_ENTRIES;  // staged source tile capacity: two planes of 16 KB (one 32-bit word per entry and plane)
 constexpr uint32_t WF_PLANE = WF_SRC_ENTRIES * 4u;   // byte offset of plane 1 (B pairs) from plane 0 (R/G pairs)
@@ -408,19 +409,22 @@ warp_fixup_kernel(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ ds
     if (stats && blockIdx.x == 0 && threadIdx.x == 0 && n) atomicAdd(stats, (unsigned long long)n);
 }
 
-// bilinear blend of two staged entry pairs with 16-bit weights summing to 65536
+// bilinear blend of two staged entry pairs with 16-bit weights.  The four weights sum to 65535 (not
+// 65536) so that every one of them fits its 16-bit field for every (fx, fy) -- no special case for
+// fx = fy = 0 -- and the accumulators start at 255:  v = 65535 * value + 255 = 65536 * value + (255 - value),
+// whose byte 2 is floor(value) whenever `value` is an integer (flat regions, integer and dyadic
+// translations stay exact) and floor(value + eps), 0 <= eps < 0.004, otherwise.
+//   w11 = ceil(fx * fy / 65536) keeps w00 = 65535 - fx - fy + w11 >= 0:  (N - fx)(N - fy) >= 0 with N = 65535
+//   gives fx * fy / N >= fx + fy - N, and fx * fy / 65536 > fx * fy / N - 1.
 __device__ __forceinline__ uint32_t wf_blend(uint2 top, uint2 bot, uint32_t fx, uint32_t fy)
 {
-    const uint32_t w11 = (fx * fy) >> 16;
+    const uint32_t w11 = (fx * fy + 65535u) >> 16;
     const uint32_t Wbot = w11 * 65535u + fy;                       // (fy - w11) | w11 << 16
-    const uint32_t Wtop = fx * 65535u + 65536u - Wbot;             // (65536 - fx - fy + w11) | (fx - w11) << 16
-    const uint32_t vr = __dp2a_lo(Wtop, top.x, __dp2a_lo(Wbot, bot.x, 0u));
-    const uint32_t vg = __dp2a_hi(Wtop, top.x, __dp2a_hi(Wbot, bot.x, 0u));
-    const uint32_t vb = __dp2a_lo(Wtop, top.y, __dp2a_lo(Wbot, bot.y, 0u));
-    // v = value * 65536: byte 2 is floor(value) = astype(uint8).  fx = fy = 0 is the one case where
-    // a weight (w00 = 65536) does not fit its 16-bit field: the result is the tap itself.
-    const uint32_t o = __byte_perm(__byte_perm(vr, vg, 0x4462), vb, 0x4610);
-    return (fx | fy) ? o : __byte_perm(top.x, top.y, 0x4420);
+    const uint32_t Wtop = fx * 65535u + 65535u - Wbot;             // (65535 - fx - fy + w11) | (fx - w11) << 16
+    const uint32_t vr = __dp2a_lo(Wtop, top.x, __dp2a_lo(Wbot, bot.x, 255u));
+    const uint32_t vg = __dp2a_hi(Wtop, top.x, __dp2a_hi(Wbot, bot.x, 255u));
+    const uint32_t vb = __dp2a_lo(Wtop, top.y, __dp2a_lo(Wbot, bot.y, 255u));
+    return __byte_perm(__byte_perm(vr, vg, 0x4462), vb, 0x4610);
 }
 
 // Full INTERIOR tile: no bounds, no mask; everything unrolled (8 pixels per thread).
@@ -439,8 +443,9 @@ __device__ __forceinline__ void wf_compute_full(const WfDesc &T, const b200geo_w
     const float di0 = (float)(lane - WF_TW / 2), dj0 = (float)(wrp - WF_TH / 2);
     // coefficients live in registers; the two quotients of a pixel are one FMUL2
     const float ax = T.ax, ay = T.ay, bx = T.bx, by = T.by, gw = T.gw, hw = T.hw;
-    const float nxb = __fmaf_rn(ax, di0, __fmaf_rn(bx, dj0, T.nx0));
-    const float nyb = __fmaf_rn(ay, di0, __fmaf_rn(by, dj0, T.ny0));
+    // (nx, ny) travel as one register pair: each step is one packed FFMA2 (same roundings as two FFMAs)
+    const float2 A2 = make_float2(ax, ay), B2 = make_float2(bx, by);
+    const float2 nb = __ffma2_rn(A2, make_float2(di0, di0), __ffma2_rn(B2, make_float2(dj0, dj0), make_float2(T.nx0, T.ny0)));
     const float wb = __fmaf_rn(gw, di0, __fmaf_rn(hw, dj0, WF_W0));
     const uint32_t P4 = (uint32_t)T.P * 4u;
     const uint32_t base = s_src - (uint32_t)(((int)T.oy * (int)T.P + (int)T.ox) * 4);
@@ -459,16 +464,14 @@ __device__ __forceinline__ void wf_compute_full(const WfDesc &T, const b200geo_w
     uint32_t amb = 0u;           // nn only: pixels to settle in float64
 #pragma unroll WF_UNROLL_P
     for (int p = 0; p < WF_TH / 8; ++p) {
-        const float nxp = p ? __fmaf_rn(bx, (float)(8 * p), nxb) : nxb;
-        const float nyp = p ? __fmaf_rn(by, (float)(8 * p), nyb) : nyb;
+        const float2 np_ = p ? __ffma2_rn(B2, make_float2((float)(8 * p), (float)(8 * p)), nb) : nb;
         const float wp = p ? __fmaf_rn(hw, (float)(8 * p), wb) : wb;
 #pragma unroll
         for (int hh = 0; hh < WF_TW / 32; ++hh) {
-            const float nx = hh ? __fmaf_rn(ax, (float)(32 * hh), nxp) : nxp;
-            const float ny = hh ? __fmaf_rn(ay, (float)(32 * hh), nyp) : nyp;
+            const float2 n2 = hh ? __ffma2_rn(A2, make_float2((float)(32 * hh), (float)(32 * hh)), np_) : np_;
             const float w = hh ? __fmaf_rn(gw, (float)(32 * hh), wp) : wp;
             const float rw = wf_rcp(w);
-            const float2 r = __fmul2_rn(make_float2(nx, ny), make_float2(rw, rw));
+            const float2 r = __fmul2_rn(n2, make_float2(rw, rw));
             const int fxd = __float2int_rd(r.x), fyd = __float2int_rd(r.y);
             uint32_t out;
             if (BILINEAR) {
@@ -526,6 +529,92 @@ __device__ __forceinline__ void wf_compute_full(const WfDesc &T, const b200geo_w
                 asm volatile("st.shared.u32 [%0+%1], %2;" ::"r"(oaddr[hh] + (uint32_t)(p * 8 * WF_TW * 4)), "n"(0), "r"(outv[k]));
             }
         }
+    }
+}
+
+// Bilinear, full INTERIOR tile, direct stores: the same arithmetic as wf_compute_full<1, 1>, software-
+// pipelined by hand.  The kernel is latency-bound, not issue-bound (4 consumer warps per scheduler,
+// ~30-cycle shared-memory loads feeding a dependent integer chain): the eight tap loads of row p + 1
+// are issued (coordinates, addresses, LDS) before the blend of row p, so that a warp always has the
+// taps of two to four pixels in flight.
+#ifndef B2G_SWP
+#define B2G_SWP 1
+#endif
+#ifndef B2G_FUSE
+#define B2G_FUSE 0
+#endif
+#ifndef B2G_DIAG
+#define B2G_DIAG 0      // diagnostics only: 1 = no sampling arithmetic, 2 = no conversion, 4 = no global stores
+#endif
+// Conversion work fused into the sampling loop (tensor-copy tiles only): chunk t = tid + 256 * p of the
+// NEXT tile is converted between the rows of this one, so that every warp's instruction stream mixes
+// the shared-memory-bound conversion with the issue-bound sampling at a fine grain (as separate
+// phases the two only overlap across the SM's two CTAs).  total = 0: nothing fused.
+struct WfConv {
+    uint32_t a0, D, magic, dst;     // source = a0 + 12 t + (t / chunks) * D, destination = dst + 16 t   (see wp_convert)
+    int chunks, total;
+};
+static_assert(WF_SRC_ENTRIES / 4 <= (WF_TH / 8) * WF_THREADS, "fused conversion: one chunk per thread and row step");
+
+__device__ __forceinline__ void wf_full_bilinear_direct(const WfDesc &T, uint32_t s_src, uint8_t *__restrict__ dst_tile, size_t dst_pitch,
+                                                        const WfConv &cv)
+{
+    const int tid_ = wf_tid();
+    const int lane = tid_ & 31, wrp = tid_ >> 5;
+    const float di0 = (float)(lane - WF_TW / 2), dj0 = (float)(wrp - WF_TH / 2);
+    const float gw = T.gw, hw = T.hw;
+    const float2 A2 = make_float2(T.ax, T.ay), B2 = make_float2(T.bx, T.by);
+    const float2 nb = __ffma2_rn(A2, make_float2(di0, di0), __ffma2_rn(B2, make_float2(dj0, dj0), make_float2(T.nx0, T.ny0)));
+    const float wb = __fmaf_rn(gw, di0, __fmaf_rn(hw, dj0, WF_W0));
+    const uint32_t P4 = (uint32_t)T.P * 4u;
+    const uint32_t base = s_src - (uint32_t)(((int)T.oy * (int)T.P + (int)T.ox) * 4);
+    const uint32_t psel = (lane & 3) == 0 ? 0x4210u : ((lane & 3) == 1 ? 0x5421u : 0x6542u);
+    uint8_t *gptr = dst_tile + (size_t)wrp * dst_pitch + (size_t)(12 * (lane >> 2) + 4 * (lane & 3));
+    constexpr int G = WF_TW / 32, R = WF_TH / 8;
+    uint32_t fx[2][G], fy[2][G];
+    uint2 top[2][G], bot[2][G];
+    auto fetch = [&](int p, int b) {
+        const float2 np_ = p ? __ffma2_rn(B2, make_float2((float)(8 * p), (float)(8 * p)), nb) : nb;
+        const float wp = p ? __fmaf_rn(hw, (float)(8 * p), wb) : wb;
+#pragma unroll
+        for (int hh = 0; hh < G; ++hh) {
+            const float2 n2 = hh ? __ffma2_rn(A2, make_float2((float)(32 * hh), (float)(32 * hh)), np_) : np_;
+            const float w = hh ? __fmaf_rn(gw, (float)(32 * hh), wp) : wp;
+            const float rw = wf_rcp(w);
+            const float2 r = __fmul2_rn(n2, make_float2(rw, rw));
+            const int fxd = __float2int_rd(r.x), fyd = __float2int_rd(r.y);
+            const int xi = (int)__byte_perm((uint32_t)fxd, 0u, 0xBB32), yi = (int)__byte_perm((uint32_t)fyd, 0u, 0xBB32);
+            const uint32_t a = (uint32_t)yi * P4 + base + ((uint32_t)xi << 2);
+            top[b][hh] = wf_lds_entry(a);
+            bot[b][hh] = wf_lds_entry(a + P4);
+            fx[b][hh] = (uint32_t)fxd & 0xFFFFu;
+            fy[b][hh] = (uint32_t)fyd & 0xFFFFu;
+        }
+    };
+    if (!(B2G_DIAG & 1)) fetch(0, 0);
+#pragma unroll
+    for (int p = 0; p < R; ++p) {
+        const int t = tid_ + WF_THREADS * p;
+        const bool cvt = t < cv.total;
+        uint32_t w0 = 0u, w1 = 0u, w2 = 0u, w3 = 0u;
+        if (cvt) {
+            const uint32_t i = cv.chunks > 1 ? __umulhi((unsigned)t, cv.magic) : (uint32_t)t;
+            const uint32_t a = cv.a0 + 12u * (uint32_t)t + i * cv.D;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(a));
+            asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(w1) : "r"(a));
+            asm volatile("ld.shared.u32 %0, [%1+8];" : "=r"(w2) : "r"(a));
+            asm volatile("ld.shared.u32 %0, [%1+12];" : "=r"(w3) : "r"(a));
+        }
+        if (p + 1 < R && !(B2G_DIAG & 1)) fetch(p + 1, (p + 1) & 1);
+#pragma unroll
+        for (int hh = 0; hh < G; ++hh) {
+            const uint32_t out = (B2G_DIAG & 1) ? (uint32_t)(lane + p) : wf_blend(top[p & 1][hh], bot[p & 1][hh], fx[p & 1][hh], fy[p & 1][hh]);
+            const uint32_t nbr = __shfl_down_sync(0xffffffffu, out, 1);
+            const uint32_t word = __byte_perm(out, nbr, psel);
+            if ((B2G_DIAG & 4) ? word == 0x12345678u : (lane & 3) != 3) *reinterpret_cast<uint32_t *>(gptr + 96 * hh) = word;
+        }
+        gptr += 8 * dst_pitch;
+        if (cvt) wf_store_chunk(cv.dst + 16u * (uint32_t)t, w0, w1, w2, w3);
     }
 }
 
@@ -626,8 +715,8 @@ __device__ __forceinline__ void wf_copy_out(uint8_t *__restrict__ dst_job, size_
     const bool vec = (((size_t)dst | dst_pitch) & 15) == 0 && tw == WF_TW;
     if (vec) {
         // task = 8 pixels of one row = 24 bytes = three 8-byte stores; 256 tasks for a full tile
-        const int t = wf_tid();
-        if (t < th * (WF_TW / 8)) {
+#pragma unroll 1
+        for (int t = wf_tid(); t < th * (WF_TW / 8); t += WF_THREADS) {
             const int row = t >> 3, h = t & 7;
             const int sw = (h >> 2) ^ ((row & 1) << 1);           // (u >> 3) & 1 with u = 2h + j
             const uint4 *s = reinterpret_cast<const uint4 *>(s_out_mem + row * WF_TW);
@@ -746,9 +835,12 @@ struct __align__(16) WpTile {
 constexpr int WP_STAGES = B2G_STAGES; // raw-row buffers in flight
 constexpr int WP_TILE_RING = 8;       // tile records: a record outlives its raw buffer (read until the copy-out); >= WP_STAGES + 2
 
+#ifndef B2G_PAIRS
+#define B2G_PAIRS 2     // entry buffers: 2 = conversion of tile i+1 overlaps sampling of tile i inside a CTA; 1 = serialised (less shared memory)
+#endif
 struct WpSmem {
     uint8_t raw[WP_STAGES][WP_RAW_BYTES];
-    uint32_t pairs[2][2 * WF_SRC_ENTRIES];   // double-buffered; each: plane 0, plane 1
+    uint32_t pairs[B2G_PAIRS][2 * WF_SRC_ENTRIES];   // double-buffered; each: plane 0, plane 1
     uint32_t out[WF_TW * WF_TH];             // output stage of the tiles that are not written directly
     WpTile tile[WP_TILE_RING];
     WfDesc sub;              // SPLIT tiles: the quadrant being processed
@@ -768,12 +860,24 @@ __device__ __forceinline__ void wp_mbar_arrive(uint32_t a)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory");
 }
+#ifndef B2G_WAIT
+#define B2G_WAIT 1      // 0: try_wait with a 10 ms suspend hint + nanosleep back-off; 1: plain try_wait loop; 2: test_wait spin
+#endif
 __device__ __forceinline__ bool wp_mbar_try(uint32_t a, uint32_t parity)
 {
     uint32_t ok;
-    // the suspend-time hint lets the warp sleep in hardware until the phase completes instead of re-polling
+#if B2G_WAIT == 0
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                  : "=r"(ok) : "r"(a), "r"(parity), "r"(0x989680u) : "memory");
+#elif B2G_WAIT == 1
+    // no suspend-time hint: the hardware's default (short) suspend window; measured on B200, the hinted
+    // form (SASS NANOSLEEP.SYNCS <hint>) wakes late enough to cost ~0.5 us per tile of pure protocol time
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+#else
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+#endif
     return ok != 0;
 }
 __device__ __noinline__ void wp_mbar_wait_slow(uint32_t a, uint32_t parity)
@@ -783,10 +887,15 @@ __device__ __noinline__ void wp_mbar_wait_slow(uint32_t a, uint32_t parity)
     unsigned long long t0, t1;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     for (;;) {
-        if (wp_mbar_try(a, parity)) return;
-        // measured: try_wait returns at once even with a suspend hint, and a hot spin takes issue slots from the
-        // warps that work (half of all executed instructions in one nn capture) -- back off explicitly
-        __nanosleep(64);
+#pragma unroll 1
+        for (int i = 0; i < 64; ++i) {
+            if (wp_mbar_try(a, parity)) return;
+#if B2G_WAIT == 0
+            __nanosleep(64);
+#elif B2G_WAIT == 2
+            __nanosleep(20);
+#endif
+        }
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
         if (t1 - t0 > 4000000000ull) __trap();
     }
@@ -818,7 +927,20 @@ template <int ALIGNED>
 __device__ __forceinline__ void wp_convert(const WfDesc &T, uint32_t magic, uint32_t phase0, uint32_t pitch32, uint32_t RB, uint32_t s_raw,
                                            uint32_t s_pairs)
 {
-    const int P = T.P, chunks = P >> 2, total = (int)T.rows * chunks;
+    const int P = T.P, chunks = P >> 2, total = (B2G_DIAG & 2) ? 0 : (int)T.rows * chunks;
+    if (ALIGNED && pitch32 == 0u) {
+        // one phase for all rows (tensor copy): with t = i * chunks + k the source address is
+        // linear in t plus a per-row term, and the destination is 16 * t (P = 4 * chunks)
+        const uint32_t D = RB - 12u * (uint32_t)chunks, a0 = s_raw + (phase0 & 15u);
+#pragma unroll 2
+        for (int t = wf_tid(); t < total; t += WF_THREADS) {
+            const uint32_t i = chunks > 1 ? __umulhi((unsigned)t, magic) : (uint32_t)t;
+            const uint32_t a = a0 + 12u * (uint32_t)t + i * D;
+            const uint32_t w0 = wp_lds32(a), w1 = wp_lds32(a + 4), w2 = wp_lds32(a + 8), w3 = wp_lds32(a + 12);
+            wf_store_chunk(s_pairs + 16u * (uint32_t)t, w0, w1, w2, w3);
+        }
+        return;
+    }
 #pragma unroll 2
     for (int t = wf_tid(); t < total; t += WF_THREADS) {
         const int i = chunks > 1 ? (int)__umulhi((unsigned)t, magic) : t;
@@ -920,7 +1042,8 @@ warp_pipe_kernel(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst
                 W.iw = Jiw; W.ih = Jih; W.c0 = tx * WF_TW; W.r0 = ty * WF_TH;
                 W.tw = min(WF_TW, Jow - tx * WF_TW); W.th = min(WF_TH, Joh - ty * WF_TH);
                 W.jz = jz; W.RB = tma ? (uint32_t)WF_TMA_BOX_W : RB; W.staged = staged; W.bulk = bulk; W.tma = tma;
-                if (tma) {
+                if (tma && (B2G_DIAG & 8)) wp_mbar_arrive(s_full);
+                else if (tma) {
                     wp_mbar_expect_tx(s_full, (uint32_t)(WF_TMA_BOX_W * WF_TMA_BOX_H));
                     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                                  ::"r"(s_raw), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"((3 * ax0) & ~15), "r"(W.T.srow), "r"(s_full) : "memory");
@@ -965,7 +1088,8 @@ warp_pipe_kernel(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst
         // the record's ring slot is rewritten WP_TILE_RING tiles later; the producer is at most
         // WP_STAGES tiles ahead of this conversion, so the record stays valid through the copy-out
         const WpTile &W = S.tile[t % WP_TILE_RING];
-        const uint32_t s_pairs = s_pairs0 + PAIRS_BYTES * (uint32_t)(t & 1), s_raw = s_raw0 + (uint32_t)WP_RAW_BYTES * b;
+        const uint32_t s_pairs = s_pairs0 + PAIRS_BYTES * (uint32_t)(t & (B2G_PAIRS - 1)), s_raw = s_raw0 + (uint32_t)WP_RAW_BYTES * b;
+        if (B2G_PAIRS == 1 && t > 0) wp_consumer_sync();      // every warp is done sampling the previous tile from the one buffer
         if (W.tma) wp_convert<1>(W.T, W.T.magic, (uint32_t)(size_t)W.a0, 0u, W.RB, s_raw, s_pairs);
         else if (W.bulk) wp_convert<0>(W.T, W.T.magic, (uint32_t)(size_t)W.a0, (uint32_t)W.src_pitch, W.RB, s_raw, s_pairs);
         else if (W.staged) wf_stage(W.T, W.src, (size_t)W.src_pitch, W.iw, W.ih, s_pairs);
@@ -979,7 +1103,7 @@ warp_pipe_kernel(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst
     convert(0);
     for (int it = 0; it < n_iter; ++it) {
         const int s = it & 1;
-        const uint32_t s_pairs = s_pairs0 + PAIRS_BYTES * (uint32_t)s;
+        const uint32_t s_pairs = s_pairs0 + PAIRS_BYTES * (uint32_t)(s & (B2G_PAIRS - 1));
         const WpTile &W = S.tile[it % WP_TILE_RING];
         const int mode = W.T.mode & 0xFF;
         wp_mbar_wait(s_conv0 + 8u * (uint32_t)s, (uint32_t)(it >> 1) & 1u);
@@ -987,12 +1111,40 @@ warp_pipe_kernel(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst
         const bool direct = mode == WF_INTERIOR && W.tw == WF_TW && W.th == WF_TH && ((((size_t)dst_tile) | (size_t)W.dst_pitch) & 3) == 0;
         const WfFix fix = {fix_list, fix_count, fix_cap, W.jz};
         if (direct) {
+            if (BILINEAR && B2G_SWP) {
+                // the next tile's conversion rides inside this tile's sampling loop when its raw rows are a tensor-copy box
+                WfConv cv = {0u, 0u, 0u, 0u, 1, 0};
+                const int t1 = it + 1, b1 = t1 % WP_STAGES;
+                bool fused = false;
+                if (B2G_FUSE && t1 < n_iter) {
+                    wp_mbar_wait(s_full0 + 8u * b1, (uint32_t)(t1 / WP_STAGES) & 1u);      // record and raw rows of tile it + 1 are in
+                    const WpTile &W1 = S.tile[t1 % WP_TILE_RING];
+                    if (W1.tma) {
+                        fused = true;
+                        cv.chunks = (int)W1.T.P >> 2;
+                        cv.total = (int)W1.T.rows * cv.chunks;
+                        cv.a0 = s_raw0 + (uint32_t)WP_RAW_BYTES * b1 + ((uint32_t)(size_t)W1.a0 & 15u);
+                        cv.D = W1.RB - 12u * (uint32_t)cv.chunks;
+                        cv.magic = W1.T.magic;
+                        cv.dst = s_pairs0 + PAIRS_BYTES * (uint32_t)(t1 & (B2G_PAIRS - 1));
+                    }
+                }
+                wf_full_bilinear_direct(W.T, s_pairs, dst_tile, (size_t)W.dst_pitch, cv);
+                if (fused) {
+                    __syncwarp();
+                    if (lane == 0) {
+                        wp_mbar_arrive(s_empty0 + 8u * b1);
+                        wp_mbar_arrive(s_conv0 + 8u * (uint32_t)(t1 & 1));
+                    }
+                } else if (t1 < n_iter) convert(t1);
+                continue;
+            }
             wf_compute_full<BILINEAR, 1>(W.T, jobs[W.jz], W.src, s_pairs, 0u, W.c0, W.r0, n_exact, fix, dst_tile, (size_t)W.dst_pitch);
             if (it + 1 < n_iter) convert(it + 1);
             continue;
         }
         // staged tiles: every consumer warp takes this branch for the same tiles (the record is shared)
-        if (mode != WF_EMPTY) {
+        if (mode != WF_EMPTY && !(B2G_DIAG & 16)) {
             const b200geo_warp_job &J = jobs[W.jz];
             wp_consumer_sync();          // the previous staged tile's copy-out has finished reading S.out
             if (W.staged) {
@@ -1014,7 +1166,7 @@ warp_pipe_kernel(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst
             wp_consumer_sync();
         }
         if (it + 1 < n_iter) convert(it + 1);
-        if (mode != WF_EMPTY) wf_copy_out(W.dst, (size_t)W.dst_pitch, S.out, W.c0, W.r0, W.tw, W.th);
+        if (mode != WF_EMPTY && !(B2G_DIAG & 16)) wf_copy_out(W.dst, (size_t)W.dst_pitch, S.out, W.c0, W.r0, W.tw, W.th);
     }
     if (stats && n_exact) atomicAdd(stats, (unsigned long long)n_exact);
 }

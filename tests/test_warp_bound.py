@@ -1,6 +1,6 @@
 """CPU check of the fast warp kernel's coordinate error bound (csrc/warp_fast.cuh, wf_setup / wf_rel16).
 
-The kernel evaluates the source position of every pixel of a 64x32 tile in float32 from nine
+The kernel evaluates the source position of every pixel of a 64x40 tile in float32 from nine
 tile-local coefficients and decides masks / nn rounding on those coordinates only when they are
 further than `band` from the decision boundary.  This test mirrors the set-up arithmetic in numpy
 (float64 set-up, coefficients rounded to float32, float32 evaluation with fused multiply-adds and a
@@ -11,7 +11,7 @@ the float64 path.  No GPU needed: float32 fma / mul are IEEE and reproduced exac
 import numpy as np
 import pytest
 
-TW, TH = 64, 32
+TW, TH = 64, 40
 F = np.float32
 
 
