@@ -399,14 +399,20 @@ int launch_warp(b200geo_ctx *ctx, const void *src, void *dst, const b200geo_warp
         dim3 sgrid((tiles_x + 31) / 32, (tiles_y + 7) / 8, n_jobs), sblock(32, 8);
         const uint8_t *s8 = (const uint8_t *)src;
         uint8_t *d8 = (uint8_t *)dst;
-        // deferred float64 pixels: list sized for ~0.4 % of the output, settled by warp_fixup_kernel
+        // deferred float64 pixels: list sized for ~0.4 % of the output, settled by warp_fixup_kernel.  The
+        // scratch block starts with the per-segment counters (4 KB), the entries follow.
         unsigned long long fix_want = (unsigned long long)max_ow * max_oh * n_jobs / 256 + 65536;
         if (fix_want > (1ull << 27)) fix_want = 1ull << 27;
-        WfFixEntry *fix_list;
-        if ((rc = scratch(ctx, S_WARPFIX, fix_want * sizeof(WfFixEntry), (void **)&fix_list))) return rc;
-        const unsigned fix_cap = (unsigned)(ctx->scratch_cap[S_WARPFIX] / sizeof(WfFixEntry));
-        unsigned *fix_count = (unsigned *)(stats + 3);
+        constexpr size_t FIX_HDR = 4096;
+        char *fix_block;
+        if ((rc = scratch(ctx, S_WARPFIX, FIX_HDR + fix_want * sizeof(WfFixEntry), (void **)&fix_block))) return rc;
+        unsigned *fix_count = (unsigned *)fix_block;
+        WfFixEntry *fix_list = (WfFixEntry *)(fix_block + FIX_HDR);
+        const unsigned fix_cap = (unsigned)((ctx->scratch_cap[S_WARPFIX] - FIX_HDR) / sizeof(WfFixEntry));
+        unsigned *tile_counter = (unsigned *)(stats + 3);       // dynamic tile tickets of the persistent kernel
+        B2G_CUDA(cudaMemsetAsync(tile_counter, 0, sizeof(unsigned), st));
         B2G_CUDA(cudaMemsetAsync(fix_count, 0, sizeof(unsigned), st));
+        unsigned n_seg = 1, seg_cap = fix_cap;
         const int use_tmap = ctx->warp_variant == 0 ? prepare_tmap(ctx, src, layout) : 0;
         if (getenv("B200GEO_DEBUG"))
             fprintf(stderr, "[b200geo] warp: jobs %d tiles %dx%d sampler %d layout %p use_tmap %d (encode %p)\n", n_jobs, tiles_x, tiles_y,
@@ -431,14 +437,17 @@ int launch_warp(b200geo_ctx *ctx, const void *src, void *dst, const b200geo_warp
             }
             long long ctas = (long long)ctx->sm_count * WP_OCC;
             if (ctas > n_tiles) ctas = n_tiles;
+            if (ctas > (long long)(FIX_HDR / sizeof(unsigned))) ctas = FIX_HDR / sizeof(unsigned);
+            n_seg = (unsigned)ctas; seg_cap = fix_cap / n_seg;
             if (sampler == B200GEO_BILINEAR)
-                warp_pipe_kernel<1><<<(unsigned)ctas, WP_THREADS, sizeof(WpSmem), st>>>(s8, d8, jobs_dev, descs, (int)n_tiles, tiles_x, tiles_y, stats + 2, ctx->tmap, use_tmap, fix_list, fix_count, fix_cap);
+                warp_pipe_kernel<1><<<(unsigned)ctas, WP_THREADS, sizeof(WpSmem), st>>>(s8, d8, jobs_dev, descs, (int)n_tiles, tiles_x, tiles_y, stats + 2, ctx->tmap, use_tmap, fix_list, fix_count, seg_cap, tile_counter);
             else
-                warp_pipe_kernel<0><<<(unsigned)ctas, WP_THREADS, sizeof(WpSmem), st>>>(s8, d8, jobs_dev, descs, (int)n_tiles, tiles_x, tiles_y, stats + 2, ctx->tmap, use_tmap, fix_list, fix_count, fix_cap);
+                warp_pipe_kernel<0><<<(unsigned)ctas, WP_THREADS, sizeof(WpSmem), st>>>(s8, d8, jobs_dev, descs, (int)n_tiles, tiles_x, tiles_y, stats + 2, ctx->tmap, use_tmap, fix_list, fix_count, seg_cap, tile_counter);
         }
         B2G_CHECK_LAUNCH(ctx);
-        if (sampler == B200GEO_BILINEAR) warp_fixup_kernel<1><<<2 * ctx->sm_count, 128, 0, st>>>(s8, d8, jobs_dev, fix_list, fix_count, fix_cap, stats + 2);
-        else warp_fixup_kernel<0><<<2 * ctx->sm_count, 128, 0, st>>>(s8, d8, jobs_dev, fix_list, fix_count, fix_cap, stats + 2);
+        const dim3 fgrid(n_seg == 1 ? 2 * ctx->sm_count : 2, n_seg);
+        if (sampler == B200GEO_BILINEAR) warp_fixup_kernel<1><<<fgrid, 128, 0, st>>>(s8, d8, jobs_dev, fix_list, fix_count, n_seg, seg_cap, stats + 2);
+        else warp_fixup_kernel<0><<<fgrid, 128, 0, st>>>(s8, d8, jobs_dev, fix_list, fix_count, n_seg, seg_cap, stats + 2);
         B2G_CHECK_LAUNCH(ctx);
         return B200GEO_OK;
     }

@@ -67,7 +67,7 @@ constexpr float WF_W0 = 1.0f / 65536.f;   // constant term of the scaled denomin
 constexpr float WF_MAX_REL = 1024.f;  // |rel| beyond this: SLOW (keeps the 16.16 conversion and the bound sane)
 constexpr float WF_MAX_BAND = 1.0f / 64.f;
 
-enum { WF_EMPTY = 0, WF_ZERO = 1, WF_INTERIOR = 2, WF_BORDER = 3, WF_SLOW = 4, WF_SPLIT = 5 };
+enum { WF_EMPTY = 0, WF_ZERO = 1, WF_INTERIOR = 2, WF_BORDER = 3, WF_SLOW = 4, WF_SPLIT = 5, WF_DONE = 6 /* pipeline sentinel, never in a descriptor */ };
 constexpr int WF_SUB_W = 32, WF_SUB_H = 16;   // SPLIT: the tile is redone as quadrants, each with its own (smaller) footprint
 constexpr int WF_TMA_BOX_W = 256;          // bytes per row of the 2-D TMA box (the hardware maximum for one dimension)
 constexpr int WF_TMA_BOX_H = B2G_BOX_H;    // rows of the box: 12 KB per tile at 48
@@ -391,22 +391,31 @@ __device__ __forceinline__ bool wf_defer(const WfFix &f, int c, int r)
     return true;
 }
 
-// Grid: any; one thread per deferred pixel.  stats[0] += pixels settled.
+// The list is cut into n_seg segments of seg_cap entries, segment s holding min(counts[s], seg_cap) of
+// them: the persistent kernel gives every CTA its own segment and counts in shared memory (one global
+// counter made every deferred pixel wait for a returning atomic on one address -- measured: nn 25 %
+// slower than bilinear); the one-CTA-per-tile kernel uses a single segment with a global counter.
+// Grid: (x: any, y: <= n_seg); one thread per deferred pixel.  stats[0] += pixels settled.
 template <int BILINEAR>
 __global__ void __launch_bounds__(128)
 warp_fixup_kernel(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst_base, const b200geo_warp_job *__restrict__ jobs,
-                  const WfFixEntry *__restrict__ list, const unsigned *__restrict__ count, unsigned cap,
+                  const WfFixEntry *__restrict__ list, const unsigned *__restrict__ counts, unsigned n_seg, unsigned seg_cap,
                   unsigned long long *__restrict__ stats)
 {
-    const unsigned n = min(*count, cap);
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const WfFixEntry e = list[i];
-        const b200geo_warp_job &J = jobs[e.job];
-        const uint32_t v = wf_exact_px<BILINEAR>(J, src_base + J.src_offset, e.c, e.r);
-        uint8_t *q = dst_base + J.dst_offset + (size_t)e.r * (size_t)J.dst_pitch + (size_t)e.c * 3;
-        q[0] = (uint8_t)v; q[1] = (uint8_t)(v >> 8); q[2] = (uint8_t)(v >> 16);
+    unsigned long long settled = 0;
+    for (unsigned sgm = blockIdx.y; sgm < n_seg; sgm += gridDim.y) {
+        const unsigned n = min(counts[sgm], seg_cap);
+        const WfFixEntry *seg = list + (size_t)sgm * seg_cap;
+        for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+            const WfFixEntry e = seg[i];
+            const b200geo_warp_job &J = jobs[e.job];
+            const uint32_t v = wf_exact_px<BILINEAR>(J, src_base + J.src_offset, e.c, e.r);
+            uint8_t *q = dst_base + J.dst_offset + (size_t)e.r * (size_t)J.dst_pitch + (size_t)e.c * 3;
+            q[0] = (uint8_t)v; q[1] = (uint8_t)(v >> 8); q[2] = (uint8_t)(v >> 16);
+        }
+        if (blockIdx.x == 0 && threadIdx.x == 0) settled += n;
     }
-    if (stats && blockIdx.x == 0 && threadIdx.x == 0 && n) atomicAdd(stats, (unsigned long long)n);
+    if (stats && settled) atomicAdd(stats, settled);
 }
 
 // bilinear blend of two staged entry pairs with 16-bit weights.  The four weights sum to 65535 (not
@@ -615,6 +624,77 @@ __device__ __forceinline__ void wf_full_bilinear_direct(const WfDesc &T, uint32_
         }
         gptr += 8 * dst_pitch;
         if (cvt) wf_store_chunk(cv.dst + 16u * (uint32_t)t, w0, w1, w2, w3);
+    }
+}
+
+// Nearest neighbour, full INTERIOR tile, direct stores: same decisions as wf_compute_full<0, 1>, laid out
+// like the bilinear loop (the fetches of row p + 1 precede the stores of row p).  Every pixel is stored
+// speculatively; the ones within `band` of a rounding boundary are pushed to the fix-up list
+// (warp_fixup_kernel overwrites them in float64 after this kernel) or, if the list is full, settled here.
+template <int DUMMY = 0>
+__device__ __forceinline__ void wf_full_nn_direct(const WfDesc &T, const b200geo_warp_job &J, const uint8_t *__restrict__ src, uint32_t s_src,
+                                                  int c0, int r0, unsigned &n_exact, const WfFix &fix, uint8_t *__restrict__ dst_tile,
+                                                  size_t dst_pitch)
+{
+    const int tid_ = wf_tid();
+    const int lane = tid_ & 31, wrp = tid_ >> 5;
+    const float di0 = (float)(lane - WF_TW / 2), dj0 = (float)(wrp - WF_TH / 2);
+    const float gw = T.gw, hw = T.hw;
+    const float2 A2 = make_float2(T.ax, T.ay), B2 = make_float2(T.bx, T.by);
+    const float2 nb = __ffma2_rn(A2, make_float2(di0, di0), __ffma2_rn(B2, make_float2(dj0, dj0), make_float2(T.nx0, T.ny0)));
+    const float wb = __fmaf_rn(gw, di0, __fmaf_rn(hw, dj0, WF_W0));
+    const uint32_t P4 = (uint32_t)T.P * 4u;
+    const uint32_t base = s_src - (uint32_t)(((int)T.oy * (int)T.P + (int)T.ox) * 4);
+    const uint32_t psel = (lane & 3) == 0 ? 0x4210u : ((lane & 3) == 1 ? 0x5421u : 0x6542u);
+    uint8_t *gptr = dst_tile + (size_t)wrp * dst_pitch + (size_t)(12 * (lane >> 2) + 4 * (lane & 3));
+    const uint32_t B16 = (uint32_t)((int)T.band + 2);
+    constexpr int G = WF_TW / 32, R = WF_TH / 8;
+    uint2 e[2][G];
+    uint32_t amb = 0u;
+    auto fetch = [&](int p, int b) {
+        const float2 np_ = p ? __ffma2_rn(B2, make_float2((float)(8 * p), (float)(8 * p)), nb) : nb;
+        const float wp = p ? __fmaf_rn(hw, (float)(8 * p), wb) : wb;
+#pragma unroll
+        for (int hh = 0; hh < G; ++hh) {
+            const float2 n2 = hh ? __ffma2_rn(A2, make_float2((float)(32 * hh), (float)(32 * hh)), np_) : np_;
+            const float w = hh ? __fmaf_rn(gw, (float)(32 * hh), wp) : wp;
+            const float rw = wf_rcp(w);
+            const float2 r = __fmul2_rn(n2, make_float2(rw, rw));
+            const int hx = __float2int_rd(r.x) + 32768, hy = __float2int_rd(r.y) + 32768;
+            const uint32_t fx = (uint32_t)hx & 0xFFFFu, fy = (uint32_t)hy & 0xFFFFu;
+            if (fx - B16 > 65535u - 2u * B16 || fy - B16 > 65535u - 2u * B16) amb |= 1u << (p * G + hh);
+            const int xi = (int)__byte_perm((uint32_t)hx, 0u, 0xBB32), yi = (int)__byte_perm((uint32_t)hy, 0u, 0xBB32);
+            e[b][hh] = wf_lds_entry((uint32_t)yi * P4 + base + ((uint32_t)xi << 2));
+        }
+    };
+    fetch(0, 0);
+#pragma unroll
+    for (int p = 0; p < R; ++p) {
+        if (p + 1 < R) fetch(p + 1, (p + 1) & 1);
+#pragma unroll
+        for (int hh = 0; hh < G; ++hh) {
+            const uint32_t out = __byte_perm(e[p & 1][hh].x, e[p & 1][hh].y, 0x4420);
+            const uint32_t nbr = __shfl_down_sync(0xffffffffu, out, 1);
+            const uint32_t word = __byte_perm(out, nbr, psel);
+            if ((lane & 3) != 3) *reinterpret_cast<uint32_t *>(gptr + 96 * hh) = word;
+        }
+        gptr += 8 * dst_pitch;
+    }
+    if (__any_sync(0xffffffffu, amb != 0u)) {
+        __syncwarp();                                   // the speculative word stores of every lane precede the byte stores below
+        if (amb) {
+#pragma unroll 1
+            for (int k = 0; k < R * G; ++k)
+                if (amb & (1u << k)) {
+                    const int col = lane + 32 * (k % G), row = wrp + 8 * (k / G);
+                    if (!wf_defer(fix, c0 + col, r0 + row)) {
+                        const uint32_t v = wf_exact_px<0>(J, src, c0 + col, r0 + row);
+                        ++n_exact;
+                        uint8_t *q = dst_tile + (size_t)row * dst_pitch + (size_t)col * 3;
+                        q[0] = (uint8_t)v; q[1] = (uint8_t)(v >> 8); q[2] = (uint8_t)(v >> 16);
+                    }
+                }
+        }
     }
 }
 
@@ -838,6 +918,16 @@ constexpr int WP_TILE_RING = 8;       // tile records: a record outlives its raw
 #ifndef B2G_PAIRS
 #define B2G_PAIRS 2     // entry buffers: 2 = conversion of tile i+1 overlaps sampling of tile i inside a CTA; 1 = serialised (less shared memory)
 #endif
+#ifndef B2G_PROF
+#define B2G_PROF 0      // diagnostics only: per-warp cycle accounting printed by a few CTAs
+#endif
+#if B2G_PROF
+#define WP_T(var) const long long var = clock64()
+#define WP_ACC(acc, a, b) acc += (b) - (a)
+#else
+#define WP_T(var)
+#define WP_ACC(acc, a, b)
+#endif
 struct WpSmem {
     uint8_t raw[WP_STAGES][WP_RAW_BYTES];
     uint32_t pairs[B2G_PAIRS][2 * WF_SRC_ENTRIES];   // double-buffered; each: plane 0, plane 1
@@ -846,6 +936,7 @@ struct WpSmem {
     WfDesc sub;              // SPLIT tiles: the quadrant being processed
     unsigned long long full[WP_STAGES], empty[WP_STAGES];
     unsigned long long conv[2];              // consumer-side: entries of buffer s complete
+    unsigned fix_n;                          // deferred float64 pixels of this CTA (its segment of the fix-up list)
 };
 
 __device__ __forceinline__ void wp_mbar_init(uint32_t a, uint32_t count)
@@ -923,6 +1014,9 @@ __device__ __forceinline__ void wp_consumer_sync() { asm volatile("bar.sync 1, %
 // bytes into its raw row (per-row bulk copies start at the row address rounded down to 16; a 2-D
 // tensor copy has one phase for all rows: pitch32 = 0).  ALIGNED: all phases are multiples of 4
 // (always true for the tensor copy, whose origin column is a multiple of 4 pixels).
+#ifndef B2G_CONV_BATCH
+#define B2G_CONV_BATCH 1      // 2 and 4 were measured slower: the extra live registers spill under the 96-register cap
+#endif
 template <int ALIGNED>
 __device__ __forceinline__ void wp_convert(const WfDesc &T, uint32_t magic, uint32_t phase0, uint32_t pitch32, uint32_t RB, uint32_t s_raw,
                                            uint32_t s_pairs)
@@ -932,12 +1026,25 @@ __device__ __forceinline__ void wp_convert(const WfDesc &T, uint32_t magic, uint
         // one phase for all rows (tensor copy): with t = i * chunks + k the source address is
         // linear in t plus a per-row term, and the destination is 16 * t (P = 4 * chunks)
         const uint32_t D = RB - 12u * (uint32_t)chunks, a0 = s_raw + (phase0 & 15u);
-#pragma unroll 2
-        for (int t = wf_tid(); t < total; t += WF_THREADS) {
-            const uint32_t i = chunks > 1 ? __umulhi((unsigned)t, magic) : (uint32_t)t;
-            const uint32_t a = a0 + 12u * (uint32_t)t + i * D;
-            const uint32_t w0 = wp_lds32(a), w1 = wp_lds32(a + 4), w2 = wp_lds32(a + 8), w3 = wp_lds32(a + 12);
-            wf_store_chunk(s_pairs + 16u * (uint32_t)t, w0, w1, w2, w3);
+        // the loop is latency-bound (LDS -> PRMT -> STS, ~3 trips per tile): all loads of up to B2G_CONV_BATCH
+        // chunks are issued before the first permute
+#pragma unroll 1
+        for (int t0 = wf_tid(); t0 < total; t0 += B2G_CONV_BATCH * WF_THREADS) {
+            uint32_t w[B2G_CONV_BATCH][4];
+#pragma unroll
+            for (int u = 0; u < B2G_CONV_BATCH; ++u) {
+                const int t = t0 + u * WF_THREADS;
+                if (t < total) {
+                    const uint32_t i = chunks > 1 ? __umulhi((unsigned)t, magic) : (uint32_t)t;
+                    const uint32_t a = a0 + 12u * (uint32_t)t + i * D;
+                    w[u][0] = wp_lds32(a); w[u][1] = wp_lds32(a + 4); w[u][2] = wp_lds32(a + 8); w[u][3] = wp_lds32(a + 12);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < B2G_CONV_BATCH; ++u) {
+                const int t = t0 + u * WF_THREADS;
+                if (t < total) wf_store_chunk(s_pairs + 16u * (uint32_t)t, w[u][0], w[u][1], w[u][2], w[u][3]);
+            }
         }
         return;
     }
@@ -958,13 +1065,15 @@ __device__ __forceinline__ void wp_convert(const WfDesc &T, uint32_t magic, uint
 }
 
 // Grid: min(n_tiles, SMs * WP_OCC) CTAs of WP_THREADS; dynamic shared memory sizeof(WpSmem).
+// Registers: 9 warps are allocated as 10 (pairs), so two CTAs per SM leave 65536 / (2 x 320) = 102 -> 96 per
+// thread, which is what __launch_bounds__ makes ptxas use (__maxnreg__(112) was measured: one CTA per SM).
 template <int BILINEAR>
 __global__ void __launch_bounds__(WP_THREADS, WP_OCC)
 warp_pipe_kernel(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst_base,
                  const b200geo_warp_job *__restrict__ jobs, const WfDesc *__restrict__ descs,
                  int n_tiles, int tiles_x, int tiles_y, unsigned long long *__restrict__ stats,
                  const __grid_constant__ CUtensorMap tmap, int use_tmap,
-                 WfFixEntry *__restrict__ fix_list, unsigned *__restrict__ fix_count, unsigned fix_cap)
+                 WfFixEntry *__restrict__ fix_list, unsigned *__restrict__ fix_counts, unsigned seg_cap, unsigned *__restrict__ tile_counter)
 {
     extern __shared__ __align__(16) unsigned char wp_smem[];
     WpSmem &S = *reinterpret_cast<WpSmem *>(wp_smem);
@@ -977,6 +1086,7 @@ warp_pipe_kernel(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst
     const uint32_t s_empty0 = (uint32_t)__cvta_generic_to_shared(&S.empty[0]);
 
     if (tid == 0) {
+        S.fix_n = 0u;
         for (int i = 0; i < WP_STAGES; ++i) {
             wp_mbar_init(s_full0 + 8u * i, 1);
             wp_mbar_init(s_empty0 + 8u * i, WF_THREADS / 32);
@@ -991,35 +1101,56 @@ warp_pipe_kernel(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst
 
     if (wrp == WF_THREADS / 32) {
         // ---------------------------------------------------------------- producer warp
+        // Tiles are claimed dynamically: the first one is blockIdx.x, every further one gridDim.x + a ticket
+        // from a global counter, drawn two tiles ahead (the descriptor prefetch distance).  Static striding
+        // left the CTAs 10 % apart at the end (BORDER / SPLIT / SLOW tiles cost several times a direct one).
         const int tpj = tiles_x * tiles_y;
+        auto claim = [&]() {
+            int v = 0;
+            if (lane == 0) v = (int)atomicAdd(tile_counter, 1u);
+            return __shfl_sync(0xffffffffu, v, 0) + (int)gridDim.x;
+        };
+        int t_cur = first, t_n1 = claim(), t_n2 = claim();
         uint4 nd0 = make_uint4(0u, 0u, 0u, 0u), nd1 = nd0;      // lanes 0..3: descriptors of the next two tiles
         if (lane < 4) {
-            nd0 = __ldg(reinterpret_cast<const uint4 *>(descs + first) + lane);
-            if (first + (int)gridDim.x < n_tiles) nd1 = __ldg(reinterpret_cast<const uint4 *>(descs + first + gridDim.x) + lane);
+            nd0 = __ldg(reinterpret_cast<const uint4 *>(descs + t_cur) + lane);
+            if (t_n1 < n_tiles) nd1 = __ldg(reinterpret_cast<const uint4 *>(descs + t_n1) + lane);
         }
-        // tile -> (job, tile row, tile column), advanced incrementally (no division per tile)
-        const int step = (int)gridDim.x;
-        const int d_jz = step / tpj, d_rem = step - d_jz * tpj, d_ty = d_rem / tiles_x, d_tx = d_rem - d_ty * tiles_x;
-        int jz = first / tpj, ty = (first - jz * tpj) / tiles_x, tx = first - jz * tpj - ty * tiles_x;
         // geometry of the current job, reloaded only when the job changes
         int cur = -1, Jow = 0, Joh = 0, Jiw = 0, Jih = 0;
         long long Jsp = 0, Jdp = 0;
         const uint8_t *src = nullptr;
         uint8_t *dstj = nullptr;
         int it = 0;
-        for (int tile = first; tile < n_tiles; ++it, tile += step) {
+#if B2G_PROF
+        long long prof_wait = 0;
+        const long long prof_t0 = clock64();
+#endif
+        for (;; ++it) {
             const int b = it % WP_STAGES, use = it / WP_STAGES;
             const uint32_t s_full = s_full0 + 8u * b, s_raw = s_raw0 + (uint32_t)WP_RAW_BYTES * b;
-            if (jz != cur) {
+            const int jz = t_cur / tpj, trem = t_cur - jz * tpj, ty = trem / tiles_x, tx = trem - ty * tiles_x;
+            if (t_cur < n_tiles && jz != cur) {
                 const b200geo_warp_job &J = jobs[jz];
                 cur = jz; Jow = J.ow; Joh = J.oh; Jiw = J.iw; Jih = J.ih; Jsp = J.src_pitch; Jdp = J.dst_pitch;
                 src = src_base + J.src_offset; dstj = dst_base + J.dst_offset;
             }
+            WP_T(tp0);
             if (use >= 1) wp_mbar_wait(s_empty0 + 8u * b, (uint32_t)(use - 1) & 1u);
+            WP_T(tp1);
+            WP_ACC(prof_wait, tp0, tp1);
             WpTile &W = S.tile[it % WP_TILE_RING];
+            if (t_cur >= n_tiles) {
+                // out of tiles: publish the sentinel the consumers stop at
+                if (lane == 0) {
+                    W.T.mode = WF_DONE; W.staged = 0; W.bulk = 0; W.tma = 0;
+                    wp_mbar_arrive(s_full);
+                }
+                break;
+            }
             if (lane < 4) reinterpret_cast<uint4 *>(&W.T)[lane] = nd0;
             nd0 = nd1;
-            if (lane < 4 && tile + 2 * step < n_tiles) nd1 = __ldg(reinterpret_cast<const uint4 *>(descs + tile + 2 * step) + lane);
+            if (lane < 4 && t_n2 < n_tiles) nd1 = __ldg(reinterpret_cast<const uint4 *>(descs + t_n2) + lane);
             __syncwarp();
             const int mode = W.T.mode & 0xFF;
             const int P = W.T.P, rows = W.T.rows;
@@ -1051,9 +1182,7 @@ warp_pipe_kernel(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst
                 else wp_mbar_arrive(s_full);
             }
             // next tile of this CTA
-            jz += d_jz; ty += d_ty; tx += d_tx;
-            if (tx >= tiles_x) { tx -= tiles_x; ++ty; }
-            if (ty >= tiles_y) { ty -= tiles_y; ++jz; }
+            t_cur = t_n1; t_n1 = t_n2; t_n2 = claim();
             __syncwarp();
             if (bulk && !tma)
                 for (int r = lane; r < rows; r += 32) {
@@ -1061,6 +1190,11 @@ warp_pipe_kernel(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst
                     wp_bulk_g2s(s_raw + (uint32_t)r * RB, reinterpret_cast<const void *>(ar), RB, s_full);
                 }
         }
+#if B2G_PROF
+        if (lane == 0 && (blockIdx.x % 97) == 0)
+            printf("cta %3d producer: tiles %d total %lld wait_empty %lld work/tile %lld\n", (int)blockIdx.x, it, clock64() - prof_t0, prof_wait,
+                   (clock64() - prof_t0 - prof_wait) / (it ? it : 1));
+#endif
         return;
     }
 
@@ -1079,12 +1213,18 @@ warp_pipe_kernel(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst
     const uint32_t s_conv0 = (uint32_t)__cvta_generic_to_shared(&S.conv[0]);
     constexpr uint32_t PAIRS_BYTES = 2u * WF_SRC_ENTRIES * 4u;
     unsigned n_exact = 0;
-    // the tile index itself travels in the WpTile record: the consumers only count iterations
-    const int n_iter = (n_tiles - first + (int)gridDim.x - 1) / (int)gridDim.x;
+    // the tile index itself travels in the WpTile record: the consumers only count iterations, up to the sentinel record
 
+#if B2G_PROF
+    long long prof_conv_wait = 0, prof_full_wait = 0, prof_sample = 0, prof_convert = 0, prof_staged = 0;
+    const long long prof_t0 = clock64();
+#endif
     auto convert = [&](int t) {        // raw stage t % WP_STAGES -> entries[t & 1]
         const int b = t % WP_STAGES, use = t / WP_STAGES;
+        WP_T(tc0);
         wp_mbar_wait(s_full0 + 8u * b, (uint32_t)use & 1u);
+        WP_T(tc1);
+        WP_ACC(prof_full_wait, tc0, tc1);
         // the record's ring slot is rewritten WP_TILE_RING tiles later; the producer is at most
         // WP_STAGES tiles ahead of this conversion, so the record stays valid through the copy-out
         const WpTile &W = S.tile[t % WP_TILE_RING];
@@ -1098,25 +1238,32 @@ warp_pipe_kernel(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst
             wp_mbar_arrive(s_empty0 + 8u * b);                 // raw[b] may be refilled
             wp_mbar_arrive(s_conv0 + 8u * (uint32_t)(t & 1));
         }
+        WP_T(tc2);
+        WP_ACC(prof_convert, tc1, tc2);
     };
 
     convert(0);
-    for (int it = 0; it < n_iter; ++it) {
+    int it = 0;
+    for (;; ++it) {
         const int s = it & 1;
         const uint32_t s_pairs = s_pairs0 + PAIRS_BYTES * (uint32_t)(s & (B2G_PAIRS - 1));
         const WpTile &W = S.tile[it % WP_TILE_RING];
         const int mode = W.T.mode & 0xFF;
+        WP_T(tw0);
         wp_mbar_wait(s_conv0 + 8u * (uint32_t)s, (uint32_t)(it >> 1) & 1u);
+        if (mode == WF_DONE) break;
+        WP_T(tw1);
+        WP_ACC(prof_conv_wait, tw0, tw1);
         uint8_t *const dst_tile = W.dst + (size_t)W.r0 * (size_t)W.dst_pitch + (size_t)W.c0 * 3;
         const bool direct = mode == WF_INTERIOR && W.tw == WF_TW && W.th == WF_TH && ((((size_t)dst_tile) | (size_t)W.dst_pitch) & 3) == 0;
-        const WfFix fix = {fix_list, fix_count, fix_cap, W.jz};
+        const WfFix fix = {fix_list + (size_t)blockIdx.x * seg_cap, &S.fix_n, seg_cap, W.jz};
         if (direct) {
             if (BILINEAR && B2G_SWP) {
                 // the next tile's conversion rides inside this tile's sampling loop when its raw rows are a tensor-copy box
                 WfConv cv = {0u, 0u, 0u, 0u, 1, 0};
                 const int t1 = it + 1, b1 = t1 % WP_STAGES;
                 bool fused = false;
-                if (B2G_FUSE && t1 < n_iter) {
+                if (B2G_FUSE) {
                     wp_mbar_wait(s_full0 + 8u * b1, (uint32_t)(t1 / WP_STAGES) & 1u);      // record and raw rows of tile it + 1 are in
                     const WpTile &W1 = S.tile[t1 % WP_TILE_RING];
                     if (W1.tma) {
@@ -1130,17 +1277,20 @@ warp_pipe_kernel(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst
                     }
                 }
                 wf_full_bilinear_direct(W.T, s_pairs, dst_tile, (size_t)W.dst_pitch, cv);
+                WP_T(tw2);
+                WP_ACC(prof_sample, tw1, tw2);
                 if (fused) {
                     __syncwarp();
                     if (lane == 0) {
                         wp_mbar_arrive(s_empty0 + 8u * b1);
                         wp_mbar_arrive(s_conv0 + 8u * (uint32_t)(t1 & 1));
                     }
-                } else if (t1 < n_iter) convert(t1);
+                } else convert(t1);
                 continue;
             }
-            wf_compute_full<BILINEAR, 1>(W.T, jobs[W.jz], W.src, s_pairs, 0u, W.c0, W.r0, n_exact, fix, dst_tile, (size_t)W.dst_pitch);
-            if (it + 1 < n_iter) convert(it + 1);
+            if (!BILINEAR && B2G_SWP) wf_full_nn_direct(W.T, jobs[W.jz], W.src, s_pairs, W.c0, W.r0, n_exact, fix, dst_tile, (size_t)W.dst_pitch);
+            else wf_compute_full<BILINEAR, 1>(W.T, jobs[W.jz], W.src, s_pairs, 0u, W.c0, W.r0, n_exact, fix, dst_tile, (size_t)W.dst_pitch);
+            convert(it + 1);
             continue;
         }
         // staged tiles: every consumer warp takes this branch for the same tiles (the record is shared)
@@ -1165,10 +1315,19 @@ warp_pipe_kernel(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst
             }
             wp_consumer_sync();
         }
-        if (it + 1 < n_iter) convert(it + 1);
+        WP_T(tw3);
+        WP_ACC(prof_staged, tw1, tw3);
+        convert(it + 1);
         if (mode != WF_EMPTY && !(B2G_DIAG & 16)) wf_copy_out(W.dst, (size_t)W.dst_pitch, S.out, W.c0, W.r0, W.tw, W.th);
     }
+#if B2G_PROF
+    if (lane == 0 && (blockIdx.x % 97) == 0 && (wrp == 0 || wrp == 7))
+        printf("cta %3d warp %d: tiles %d total %lld conv_wait %lld full_wait %lld sample %lld convert %lld staged %lld\n", (int)blockIdx.x, wrp,
+               it, clock64() - prof_t0, prof_conv_wait, prof_full_wait, prof_sample, prof_convert, prof_staged);
+#endif
     if (stats && n_exact) atomicAdd(stats, (unsigned long long)n_exact);
+    wp_consumer_sync();                                  // every consumer warp has pushed its last deferred pixel
+    if (tid == 0) fix_counts[blockIdx.x] = S.fix_n;
 }
 
 }  // namespace b200geo
