@@ -222,6 +222,35 @@ int b200geo_warp_batch_host(b200geo_ctx *ctx, const void *src_host, void *dst_ho
 int b200geo_warp_host(b200geo_ctx *ctx, const void *src, void *dst, const b200geo_warp_job *job,
                       int channels, int src_type, int dst_type, int sampler);
 
+/* ------------------------------------------------------------------------------------------------
+ * (4) stitch compose, fused with the warp -- replaces the body of stitchPanorama (homography.py:288-338)
+ *     for uint8 RGB images: addAlpha('Rate') (:250-286), transformImageH's bilinear bbox warp in float64
+ *     (:230-242), the canvas placement, paste or alpha blend, and the final astype(uint8).
+ *     `job` describes the warp of imgT exactly as for b200geo_warp_* (its ow x oh output is the warped
+ *     rectangle; dst_offset / dst_pitch are ignored), `p` where that rectangle and imgQ sit on the canvas
+ *     (homography.py:303-321).  blend = 0: canvas = 0, warped T pasted, Q pasted on top (:335-338).
+ *     blend = 1 ('Rate'): out = (aq/(aq+at)) Q + (at/(aq+at)) T in float64, through a float32 canvas
+ *     (:322-334); alpha_t / alpha_q / alpha_bg are the float32 values the reference stores:
+ *     float32(rate + 1e-10), float32(1 + 1e-10 - rate), float32(1e-10).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct b200geo_compose {
+    int32_t fw, fh;          /* canvas size */
+    int32_t tsx, tsy;        /* canvas position of the warped rectangle (job->ow x job->oh) */
+    int32_t qsx, qsy;        /* canvas position of imgQ */
+    int32_t qw, qh;          /* imgQ size */
+    int64_t q_pitch;         /* bytes per imgQ row */
+    int64_t canvas_pitch;    /* bytes per canvas row */
+    double alpha_t, alpha_q, alpha_bg;
+    int32_t blend;           /* 0 paste, 1 'Rate' blend */
+    int32_t reserved;
+} b200geo_compose;
+/* device buffers (uint8 RGB), asynchronous on `stream` */
+int b200geo_stitch_compose_dev(b200geo_ctx *ctx, const void *imgT, const void *imgQ, void *canvas,
+                               const b200geo_warp_job *job, const b200geo_compose *p, void *stream);
+/* host buffers: H2D of both images, one kernel, D2H of the canvas */
+int b200geo_stitch_compose_host(b200geo_ctx *ctx, const void *imgT, const void *imgQ, void *canvas,
+                                const b200geo_warp_job *job, const b200geo_compose *p);
+
 /* The samplers called on explicit coordinates: nearestNeighbor / bilinear(z_t, img, h, w, mh, mw)
  * (homography.py:108-138).  zx, zy: N float64 each (rows 0 and 1 of z_t); bh, bw: the bounds the
  * sampler tests against; dst: N*channels values of dst_type.  Host buffers. */

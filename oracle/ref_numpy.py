@@ -174,3 +174,49 @@ def warp_scan(img, H, res, bilinear=True):
     h, w = res
     zt = _backmap(H, np.linspace(0, w, w), np.linspace(0, h, h))
     return _sample(zt, img, h, w, h, w, bilinear), 0, 0
+
+
+# ------------------------------------------------------------------------------------------------
+# stitch compose (homography.py:250-338) -- the step after the warp
+# ------------------------------------------------------------------------------------------------
+def stitch_panorama(imgQ, imgT, H, blending=False, blendrate=0.2):
+    """stitchPanorama (homography.py:288-338) with addAlpha(method='Rate') (:250-259) and
+    transformImageH (:230-242) restated step for step: same dtypes, same order of the array
+    expressions.  `blending` is False or 'Rate'.  Returns the uint8 canvas.  imgT[0,0,:] of the
+    caller's array is zeroed in the paste path, as the reference does."""
+    if blending:
+        rgba = np.zeros(imgT.shape[:2] + (4,), dtype=np.float32)               # addAlpha :254-259
+        rgba[:, :, :3] = imgT
+        rgba[:, :, 3] = blendrate + 1e-10
+        img_t, mx, my = warp_bbox(rgba, H, True)                                # float64, 4 channels (:241-242)
+    else:
+        img_t, mx, my = warp_bbox(imgT, H, True)
+        img_t = img_t.astype(np.uint8)                                          # :240
+    ht, wt, ct = img_t.shape
+    hq, wq, _ = imgQ.shape
+    tsx, tsy, tex, tey = 0, 0, wt - 1, ht - 1
+    qsx, qsy, qex, qey = 0, 0, wq - 1, hq - 1
+    if mx < 0 and my < 0:                                                       # :309-321
+        qsx, qsy, qex, qey = -mx, -my, -mx + wq - 1, -my + hq - 1
+    elif mx < 0:
+        tsy, tey = my, my + ht - 1
+        qsx, qex = -mx, -mx + wq - 1
+    elif my < 0:
+        tsx, tex = mx, mx + wt - 1
+        qsy, qey = -my, -my + hq - 1
+    else:
+        tsx, tsy, tex, tey = mx, my, mx + wt - 1, my + ht - 1
+    fw, fh = max(tex + 1, qex + 1), max(tey + 1, qey + 1)
+    if blending:
+        imgn = np.zeros((fh, fw, ct), dtype=np.float32)                         # :323-334
+        imgn[qsy:qey + 1, qsx:qex + 1, :3] = imgQ[:, :, :3].astype(np.float32)
+        imgn[:, :, 3] += 1e-10
+        imgn[qsy:qey + 1, qsx:qex + 1, 3] = 1 + 1e-10 - blendrate
+        base = imgn[tsy:tey + 1, tsx:tex + 1, 3:4] + img_t[:, :, 3:4]
+        imgn[tsy:tey + 1, tsx:tex + 1, :3] = ((imgn[tsy:tey + 1, tsx:tex + 1, 3:4] / base) * imgn[tsy:tey + 1, tsx:tex + 1, :3]
+                                              + (img_t[:, :, 3:4] / base) * img_t[:, :, :3])
+        return imgn[:, :, :3].astype(np.uint8)
+    imgn = np.zeros((fh, fw, ct), dtype=np.uint8)                               # :335-338
+    imgn[tsy:tey + 1, tsx:tex + 1, :] = img_t
+    imgn[qsy:qey + 1, qsx:qex + 1, :] = imgQ
+    return imgn

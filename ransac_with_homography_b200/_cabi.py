@@ -49,6 +49,15 @@ WARP_JOB_DTYPE = np.dtype([("invH", np.float64, 9), ("x0", np.float64), ("dx", n
                            ("dst_offset", np.int64), ("dst_pitch", np.int64)])
 assert WARP_JOB_DTYPE.itemsize == C.sizeof(WarpJob) == 184
 
+class Compose(C.Structure):
+    """struct b200geo_compose (include/b200geo.h)"""
+    _fields_ = [("fw", C.c_int32), ("fh", C.c_int32), ("tsx", C.c_int32), ("tsy", C.c_int32),
+                ("qsx", C.c_int32), ("qsy", C.c_int32), ("qw", C.c_int32), ("qh", C.c_int32),
+                ("q_pitch", C.c_int64), ("canvas_pitch", C.c_int64),
+                ("alpha_t", C.c_double), ("alpha_q", C.c_double), ("alpha_bg", C.c_double),
+                ("blend", C.c_int32), ("reserved", C.c_int32)]
+
+
 class SrcLayout(C.Structure):
     """struct b200geo_src_layout (include/b200geo.h)"""
     _fields_ = [("pitch", C.c_int64), ("rows", C.c_int64)]
@@ -87,6 +96,8 @@ SIGNATURES = {
     "b200geo_warp_batch_host": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i]),
     "b200geo_warp_host": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i]),
     "b200geo_sample_host": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, C.c_longlong, _i, _i, _i, _i, _vp]),
+    "b200geo_stitch_compose_dev": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b200geo_stitch_compose_host": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
 }
 
 _lib = None

@@ -6,6 +6,7 @@
 #include "solve.cuh"
 #include "warp.cuh"
 #include "warp_fast.cuh"
+#include "compose.cuh"
 
 #include <new>
 #include <stdlib.h>
@@ -893,6 +894,45 @@ int b200geo_warp_host(b200geo_ctx *ctx, const void *src, void *dst, const b200ge
     B2G_CUDA(cudaMemcpyAsync(ds, (const uint8_t *)src + job->src_offset, sbytes, cudaMemcpyHostToDevice, 0));
     if ((rc = b200geo_warp_dev(ctx, ds, dd, &j, 1, channels, src_type, dst_type, sampler, nullptr))) return rc;
     B2G_CUDA(cudaMemcpyAsync((uint8_t *)dst + job->dst_offset, dd, dbytes, cudaMemcpyDeviceToHost, 0));
+    B2G_CUDA(cudaStreamSynchronize(0));
+    return B200GEO_OK;
+}
+
+int b200geo_stitch_compose_dev(b200geo_ctx *ctx, const void *imgT, const void *imgQ, void *canvas, const b200geo_warp_job *job,
+                               const b200geo_compose *p, void *stream)
+{
+    B2G_ENTER(ctx);
+    B2G_ARG(imgT && imgQ && canvas && job && p);
+    B2G_ARG(p->fw > 0 && p->fh > 0 && p->qw > 0 && p->qh > 0 && job->iw > 0 && job->ih > 0 && job->ow >= 0 && job->oh >= 0);
+    B2G_ARG(p->blend == 0 || p->blend == 1);
+    B2G_ARG((size_t)p->canvas_pitch >= (size_t)p->fw * 3 && (size_t)p->q_pitch >= (size_t)p->qw * 3 && (size_t)job->src_pitch >= (size_t)job->iw * 3);
+    cudaStream_t st = (cudaStream_t)stream;
+    const dim3 grid((p->fw + 31) / 32, (p->fh + 7) / 8), block(32, 8);
+    B2G_ARG(grid.y <= 65535);
+    if (p->blend) stitch_compose_kernel<1><<<grid, block, 0, st>>>((const uint8_t *)imgT, (const uint8_t *)imgQ, (uint8_t *)canvas, *job, *p);
+    else stitch_compose_kernel<0><<<grid, block, 0, st>>>((const uint8_t *)imgT, (const uint8_t *)imgQ, (uint8_t *)canvas, *job, *p);
+    B2G_CHECK_LAUNCH(ctx);
+    return B200GEO_OK;
+}
+
+int b200geo_stitch_compose_host(b200geo_ctx *ctx, const void *imgT, const void *imgQ, void *canvas, const b200geo_warp_job *job,
+                                const b200geo_compose *p)
+{
+    B2G_ENTER(ctx);
+    B2G_ARG(imgT && imgQ && canvas && job && p && p->fh > 0 && p->qh > 0 && job->ih > 0);
+    const size_t tbytes = (size_t)job->src_pitch * (size_t)job->ih, qbytes = (size_t)p->q_pitch * (size_t)p->qh;
+    const size_t cbytes = (size_t)p->canvas_pitch * (size_t)p->fh;
+    void *dt, *dq, *dc;
+    int rc;
+    if ((rc = scratch(ctx, S_SRC, tbytes, &dt))) return rc;
+    if ((rc = scratch(ctx, S_MISC, qbytes, &dq))) return rc;
+    if ((rc = scratch(ctx, S_DST, cbytes, &dc))) return rc;
+    b200geo_warp_job j = *job;
+    j.src_offset = 0;
+    B2G_CUDA(cudaMemcpyAsync(dt, (const uint8_t *)imgT + job->src_offset, tbytes, cudaMemcpyHostToDevice, 0));
+    B2G_CUDA(cudaMemcpyAsync(dq, imgQ, qbytes, cudaMemcpyHostToDevice, 0));
+    if ((rc = b200geo_stitch_compose_dev(ctx, dt, dq, dc, &j, p, nullptr))) return rc;
+    B2G_CUDA(cudaMemcpyAsync(canvas, dc, cbytes, cudaMemcpyDeviceToHost, 0));
     B2G_CUDA(cudaStreamSynchronize(0));
     return B200GEO_OK;
 }

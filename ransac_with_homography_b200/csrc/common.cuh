@@ -10,6 +10,7 @@
 #include "../../include/b200geo.h"
 
 static_assert(sizeof(b200geo_warp_job) == 184, "b200geo_warp_job layout is part of the ABI");
+static_assert(sizeof(b200geo_compose) == 80, "b200geo_compose layout is part of the ABI");
 
 namespace b200geo {
 

@@ -251,6 +251,42 @@ def stitch_batched(pts, idx, frames, th, d, canvas_hw, n=4, method="fwd", sample
     return canvases, boxes, results, masks
 
 
+def stitch_compose(imgQ: torch.Tensor, imgT: torch.Tensor, H, blending=False, blendrate=0.2, canvas: torch.Tensor | None = None):
+    """stitchPanorama (reference homography.py:288-338) on device-resident uint8 RGB images: warp of imgT by H,
+    canvas placement, paste (blending False) or 'Rate' alpha blend, uint8 canvas -- one kernel (K5), asynchronous on
+    the current stream.  Unlike the host entry point it does not write to imgT: the kernel itself reads source
+    pixel (0,0) as 0.  Returns the canvas tensor (fh, fw, 3)."""
+    from . import homography as hg
+    assert imgQ.dtype == torch.uint8 and imgT.dtype == torch.uint8 and imgQ.is_contiguous() and imgT.is_contiguous()
+    assert imgQ.ndim == 3 and imgT.ndim == 3 and imgQ.shape[2] == 3 and imgT.shape[2] == 3
+    assert not blending or blending == 'Rate'
+    H = np.asarray(H, dtype=np.float64)
+    h, w, _ = imgT.shape
+    hq, wq, _ = imgQ.shape
+    min_x, max_x, min_y, max_y = hg._bbox(np.empty((h, w, 0)), H, 0)
+    wt, ht = max_x - min_x + 1, max_y - min_y + 1
+    (tsx, tsy, _, _), (qsx, qsy, _, _), fw, fh = hg._placement(min_x, min_y, wt, ht, wq, hq)
+    if canvas is None:
+        canvas = torch.empty((fh, fw, 3), dtype=torch.uint8, device=imgT.device)
+    assert canvas.shape == (fh, fw, 3) and canvas.dtype == torch.uint8 and canvas.is_contiguous()
+    job = _cabi.WarpJob()
+    job.invH[:] = np.linalg.inv(H).reshape(9).tolist()
+    job.x0, job.dx, job.x_last = hg._linspace_params(min_x, max_x, wt)
+    job.y0, job.dy, job.y_last = hg._linspace_params(min_y, max_y, ht)
+    job.ow, job.oh, job.bw, job.bh, job.iw, job.ih = wt, ht, w, h, w, h
+    job.src_offset, job.src_pitch, job.dst_offset, job.dst_pitch = 0, w * 3, 0, 0
+    p = _cabi.Compose()
+    p.fw, p.fh, p.tsx, p.tsy, p.qsx, p.qsy, p.qw, p.qh = fw, fh, tsx, tsy, qsx, qsy, wq, hq
+    p.q_pitch, p.canvas_pitch = wq * 3, fw * 3
+    p.alpha_t, p.alpha_q = float(np.float32(blendrate + 1e-10)), float(np.float32(1 + 1e-10 - blendrate))
+    p.alpha_bg = float(np.float32(1e-10))
+    p.blend = 1 if blending else 0
+    import ctypes as C
+    ctx = _ctx(imgT)
+    _cabi.check(ctx.lib.b200geo_stitch_compose_dev(ctx.handle, _p(imgT), _p(imgQ), _p(canvas), C.byref(job), C.byref(p), _stream(imgT)))
+    return canvas
+
+
 def upload_jobs(jobs: np.ndarray, device) -> torch.Tensor:
     """Copy a job array to the device once (for repeated launches with b200geo_warp_jobs_dev)."""
     return torch.from_numpy(np.ascontiguousarray(jobs).view(np.uint8).copy()).to(device)

@@ -298,9 +298,11 @@ def transformImageH(img, H, method='bilinear'):
 
 
 # ------------------------------------------------------------------------------------------------
-# compose (reference homography.py:244-338).  Not one of the three hot-path kernels (SURVEY.md
-# section 8f-1): canvas placement and paste / alpha blend are slice assignments done on the host
-# around the GPU warp, exactly as the reference does them.
+# compose (reference homography.py:244-338).  For uint8 RGB images with
+# paste or 'Rate' blending, stitchPanorama is ONE fused kernel (K5, csrc/compose.cuh): warp of imgT,
+# canvas placement, paste / alpha blend and the uint8 conversion, with no intermediate RGBA image.
+# Other inputs (float images, 'Gradient' alpha) take the reference's own sequence of steps around
+# the GPU warp.
 # ------------------------------------------------------------------------------------------------
 class BLENDDIR(object):
     LEFT = 0
@@ -358,9 +360,51 @@ def _placement(mx, my, wt, ht, wq, hq):
     return (tsx, tsy, tex, tey), (qsx, qsy, qex, qey), max(tex + 1, qex + 1), max(tey + 1, qey + 1)
 
 
+def _fusable(imgQ, imgT, blending):
+    return (isinstance(imgQ, np.ndarray) and isinstance(imgT, np.ndarray) and imgQ.dtype == np.uint8 and imgT.dtype == np.uint8
+            and imgQ.ndim == 3 and imgT.ndim == 3 and imgQ.shape[2] == 3 and imgT.shape[2] == 3
+            and (not blending or (isinstance(blending, str) and blending == 'Rate')))
+
+
+def _stitch_fused(imgQ, imgT, H, blending, blendrate):
+    """stitchPanorama for uint8 RGB inputs as one kernel (b200geo_stitch_compose_host)."""
+    H = np.asarray(H, dtype=np.float64)
+    if blending:
+        print(blendrate + 1e-10)                 # addAlpha prints the rate it stores (reference homography.py:257)
+    else:
+        _zero_origin(imgT)                       # transformImageH(imgT) zeroes the caller's pixel; with blending it is addAlpha's copy
+    h, w, _ = imgT.shape
+    hq, wq, _ = imgQ.shape
+    min_x, max_x, min_y, max_y = _bbox(imgT, H, 0)
+    wt, ht = max_x - min_x + 1, max_y - min_y + 1
+    (tsx, tsy, tex, tey), (qsx, qsy, qex, qey), fw, fh = _placement(min_x, min_y, wt, ht, wq, hq)
+    canvas = np.empty((fh, fw, 3), np.uint8)
+    if wt <= 0 or ht <= 0 or fw <= 0 or fh <= 0 or min(tsx, tsy, qsx, qsy) < 0:
+        raise ValueError("stitchPanorama: empty or negative canvas placement")   # the reference's slice assignment fails here
+    src, q = np.ascontiguousarray(imgT), np.ascontiguousarray(imgQ)
+    job = _cabi.WarpJob()
+    job.invH[:] = np.linalg.inv(H).reshape(9).tolist()
+    job.x0, job.dx, job.x_last = _linspace_params(min_x, max_x, wt)
+    job.y0, job.dy, job.y_last = _linspace_params(min_y, max_y, ht)
+    job.ow, job.oh, job.bw, job.bh, job.iw, job.ih = wt, ht, w, h, w, h
+    job.src_offset, job.src_pitch, job.dst_offset, job.dst_pitch = 0, src.strides[0], 0, 0
+    p = _cabi.Compose()
+    p.fw, p.fh, p.tsx, p.tsy, p.qsx, p.qsy, p.qw, p.qh = fw, fh, tsx, tsy, qsx, qsy, wq, hq
+    p.q_pitch, p.canvas_pitch = q.strides[0], canvas.strides[0]
+    p.alpha_t = float(np.float32(blendrate + 1e-10))
+    p.alpha_q = float(np.float32(1 + 1e-10 - blendrate))
+    p.alpha_bg = float(np.float32(1e-10))
+    p.blend = 1 if blending else 0
+    ctx = _cabi.context()
+    _cabi.check(ctx.lib.b200geo_stitch_compose_host(ctx.handle, _cabi.ptr(src), _cabi.ptr(q), _cabi.ptr(canvas), C.byref(job), C.byref(p)))
+    return canvas
+
+
 def stitchPanorama(imgQ, imgT, H, method='bilinear', blending=False, blendrate=0.2):
     """Warp imgT by H (GPU) and compose it with imgQ on a common canvas
     (reference homography.py:288-338).  Returns uint8."""
+    if _fusable(imgQ, imgT, blending):
+        return _stitch_fused(imgQ, imgT, H, blending, blendrate)
     if blending:
         imgT = addAlpha(imgT, method=blending, rate=blendrate)
     img_t, mx, my = transformImageH(imgT, H)

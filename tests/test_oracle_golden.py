@@ -150,3 +150,13 @@ def test_port_warp_matches_reference(golden):
     assert np.array_equal(out.astype(np.uint8), w["bbox_rot_bilinear"])
     out, _, _ = port.warp_scan(w["img"].copy(), w["scan_s1_H"], [90, 64], False)
     assert np.array_equal(out, w["scan_s1_nn"])
+
+
+@pytest.mark.parametrize("name", ["pp", "nn_", "np_", "pn_"])
+def test_port_stitch_panorama_matches_reference(golden, name):
+    """The numpy restatement of stitchPanorama (paste and 'Rate' blend) against the live reference's canvases,
+    in the four sign cases of the warp offset (reference homography.py:309-321)."""
+    w = golden.file("warps")
+    H = w[f"pano_{name}_H"]
+    assert np.array_equal(port.stitch_panorama(w["img2"].copy(), w["img"].copy(), H), w[f"pano_{name}_paste"])
+    assert np.array_equal(port.stitch_panorama(w["img2"].copy(), w["img"].copy(), H, "Rate", 0.2), w[f"pano_{name}_blend"])
