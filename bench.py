@@ -414,7 +414,7 @@ def bench_warp(torch, dist, rank, world, args, ctx, peaks, local_gpu):
     jobs = device.scan_jobs(Hs, (h, w), (h, w))
     jobs_dev = device.upload_jobs(jobs, "cuda")
 
-    layout = (w * 3, n * h)          # the shard's frames are one 2-D byte array: rows = frames * height
+    layout = (w * 3, n * h, h, w * 3)          # the shard's frames are one 2-D byte array: rows = frames * height
 
     def step():
         device.warp_resident(src, dst, jobs_dev, n, w, h, 3, "bilinear", layout=layout)

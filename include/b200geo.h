@@ -204,8 +204,14 @@ int b200geo_warp_jobs_dev(b200geo_ctx *ctx, const void *src, void *dst, const b2
  * to back (the batched configs) are such an array with rows = n_frames * height.  Results do not
  * depend on the layout hint; layout == NULL is b200geo_warp_jobs_dev. */
 typedef struct b200geo_src_layout {
-    int64_t pitch;   /* bytes between rows */
-    int64_t rows;    /* number of rows readable from src */
+    int64_t pitch;       /* bytes between rows */
+    int64_t rows;        /* number of rows readable from src */
+    /* Optional (0 = unknown): every image occupies image_rows consecutive rows starting at a multiple of
+     * image_rows, each row holding row_bytes image bytes (= 3 * iw).  The array is then described to the TMA unit
+     * as row_bytes x image_rows x images, and footprints that hang over an image edge are fetched by tensor
+     * copy too, with hardware zero fill -- exactly the samplers' view of out-of-image pixels. */
+    int64_t image_rows;
+    int64_t row_bytes;
 } b200geo_src_layout;
 int b200geo_warp_batch_dev(b200geo_ctx *ctx, const void *src, void *dst, const b200geo_warp_job *jobs_dev,
                            int n_jobs, int max_ow, int max_oh, int channels, int src_type, int dst_type,

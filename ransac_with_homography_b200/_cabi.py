@@ -60,7 +60,7 @@ class Compose(C.Structure):
 
 class SrcLayout(C.Structure):
     """struct b200geo_src_layout (include/b200geo.h)"""
-    _fields_ = [("pitch", C.c_int64), ("rows", C.c_int64)]
+    _fields_ = [("pitch", C.c_int64), ("rows", C.c_int64), ("image_rows", C.c_int64), ("row_bytes", C.c_int64)]
 
 
 _vp, _i, _f, _d, _sz = C.c_void_p, C.c_int, C.c_float, C.c_double, C.c_size_t

@@ -351,7 +351,7 @@ int launch_warp_t(b200geo_ctx *ctx, const void *src, void *dst, const b200geo_wa
 }
 
 // 2-D tensor map over the source byte array (uint8, rows x pitch), box WF_TMA_BOX_W x WF_TMA_BOX_H.
-// Returns 1 and fills ctx->tmap when the layout is usable, 0 otherwise (never an error: the
+// Returns 2 (2-D) or 3 (3-D: per-image zero fill) and fills ctx->tmap when the layout is usable, 0 otherwise (never an error: the
 // kernels fall back to per-row bulk copies).
 int prepare_tmap(b200geo_ctx *ctx, const void *src, const b200geo_src_layout *layout)
 {
@@ -366,20 +366,26 @@ int prepare_tmap(b200geo_ctx *ctx, const void *src, const b200geo_src_layout *la
         cudaGetLastError();
     }
     if (!ctx->tmap_encode) return 0;
-    if (ctx->tmap_src == src && ctx->tmap_pitch == layout->pitch && ctx->tmap_rows == layout->rows) return 1;
+    const bool d3 = layout->image_rows >= WF_TMA_BOX_H && layout->rows % layout->image_rows == 0 && layout->row_bytes >= WF_TMA_BOX_W &&
+                    layout->row_bytes <= layout->pitch && layout->image_rows < (1 << 24) && layout->rows / layout->image_rows < (1 << 24);
+    const int mode = d3 ? 3 : 2;
+    if (ctx->tmap_src == src && ctx->tmap_pitch == layout->pitch && ctx->tmap_rows == layout->rows &&
+        ctx->tmap_image_rows == (d3 ? layout->image_rows : 0) && ctx->tmap_row_bytes == (d3 ? layout->row_bytes : 0)) return mode;
     typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-    const cuuint64_t gdim[2] = {(cuuint64_t)layout->pitch, (cuuint64_t)layout->rows};
-    const cuuint64_t gstride[1] = {(cuuint64_t)layout->pitch};
-    const cuuint32_t box[2] = {(cuuint32_t)WF_TMA_BOX_W, (cuuint32_t)WF_TMA_BOX_H};
-    const cuuint32_t estride[2] = {1, 1};
-    CUresult r = ((encode_fn)ctx->tmap_encode)(&ctx->tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(src), gdim, gstride, box,
+    const cuuint64_t gdim[3] = {(cuuint64_t)(d3 ? layout->row_bytes : layout->pitch), (cuuint64_t)(d3 ? layout->image_rows : layout->rows),
+                                (cuuint64_t)(d3 ? layout->rows / layout->image_rows : 1)};
+    const cuuint64_t gstride[2] = {(cuuint64_t)layout->pitch, (cuuint64_t)layout->pitch * (cuuint64_t)(d3 ? layout->image_rows : 1)};
+    const cuuint32_t box[3] = {(cuuint32_t)WF_TMA_BOX_W, (cuuint32_t)WF_TMA_BOX_H, 1};
+    const cuuint32_t estride[3] = {1, 1, 1};
+    CUresult r = ((encode_fn)ctx->tmap_encode)(&ctx->tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, d3 ? 3 : 2, const_cast<void *>(src), gdim, gstride, box,
                                                estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { ctx->tmap_src = nullptr; return 0; }
     ctx->tmap_src = src; ctx->tmap_pitch = layout->pitch; ctx->tmap_rows = layout->rows;
-    return 1;
+    ctx->tmap_image_rows = d3 ? layout->image_rows : 0; ctx->tmap_row_bytes = d3 ? layout->row_bytes : 0;
+    return mode;
 }
 
 int launch_warp(b200geo_ctx *ctx, const void *src, void *dst, const b200geo_warp_job *jobs_dev, int n_jobs, int max_ow,
@@ -418,9 +424,10 @@ int launch_warp(b200geo_ctx *ctx, const void *src, void *dst, const b200geo_warp
         if (getenv("B200GEO_DEBUG"))
             fprintf(stderr, "[b200geo] warp: jobs %d tiles %dx%d sampler %d layout %p use_tmap %d (encode %p)\n", n_jobs, tiles_x, tiles_y,
                     sampler, (const void *)layout, use_tmap, ctx->tmap_encode);
-        const long long tma_pitch = use_tmap ? layout->pitch : 0;
-        if (sampler == B200GEO_BILINEAR) warp_setup_kernel<1><<<sgrid, sblock, 0, st>>>(jobs_dev, s8, tma_pitch, tiles_x, tiles_y, descs);
-        else warp_setup_kernel<0><<<sgrid, sblock, 0, st>>>(jobs_dev, s8, tma_pitch, tiles_x, tiles_y, descs);
+        // use_tmap: 0 no tensor map, 2 the source as a 2-D array, 3 as (row_bytes x image_rows x images)
+        const WfTma tma = {use_tmap ? (long long)layout->pitch : 0LL, use_tmap == 3 ? (int)layout->image_rows : 0, use_tmap == 3 ? (int)layout->row_bytes : 0};
+        if (sampler == B200GEO_BILINEAR) warp_setup_kernel<1><<<sgrid, sblock, 0, st>>>(jobs_dev, s8, tma, tiles_x, tiles_y, descs);
+        else warp_setup_kernel<0><<<sgrid, sblock, 0, st>>>(jobs_dev, s8, tma, tiles_x, tiles_y, descs);
         B2G_CHECK_LAUNCH(ctx);
         if (ctx->warp_variant == 1) {
             // one CTA per tile (kept for comparison)
@@ -441,9 +448,9 @@ int launch_warp(b200geo_ctx *ctx, const void *src, void *dst, const b200geo_warp
             if (ctas > (long long)(FIX_HDR / sizeof(unsigned))) ctas = FIX_HDR / sizeof(unsigned);
             n_seg = (unsigned)ctas; seg_cap = fix_cap / n_seg;
             if (sampler == B200GEO_BILINEAR)
-                warp_pipe_kernel<1><<<(unsigned)ctas, WP_THREADS, sizeof(WpSmem), st>>>(s8, d8, jobs_dev, descs, (int)n_tiles, tiles_x, tiles_y, stats + 2, ctx->tmap, use_tmap, fix_list, fix_count, seg_cap, tile_counter);
+                warp_pipe_kernel<1><<<(unsigned)ctas, WP_THREADS, sizeof(WpSmem), st>>>(s8, d8, jobs_dev, descs, (int)n_tiles, tiles_x, tiles_y, stats + 2, ctx->tmap, use_tmap, tma.image_rows, fix_list, fix_count, seg_cap, tile_counter);
             else
-                warp_pipe_kernel<0><<<(unsigned)ctas, WP_THREADS, sizeof(WpSmem), st>>>(s8, d8, jobs_dev, descs, (int)n_tiles, tiles_x, tiles_y, stats + 2, ctx->tmap, use_tmap, fix_list, fix_count, seg_cap, tile_counter);
+                warp_pipe_kernel<0><<<(unsigned)ctas, WP_THREADS, sizeof(WpSmem), st>>>(s8, d8, jobs_dev, descs, (int)n_tiles, tiles_x, tiles_y, stats + 2, ctx->tmap, use_tmap, tma.image_rows, fix_list, fix_count, seg_cap, tile_counter);
         }
         B2G_CHECK_LAUNCH(ctx);
         const dim3 fgrid(n_seg == 1 ? 2 * ctx->sm_count : 2, n_seg);

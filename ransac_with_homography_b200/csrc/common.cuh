@@ -65,7 +65,7 @@ struct b200geo_ctx {
     int tmap_probed;
     CUtensorMap tmap;      // cached 2-D tensor map of the last source layout
     const void *tmap_src;
-    long long tmap_pitch, tmap_rows;
+    long long tmap_pitch, tmap_rows, tmap_image_rows, tmap_row_bytes;
     void *scratch[b200geo::S_NUM];
     size_t scratch_cap[b200geo::S_NUM];
     void *pinned;          // small pinned staging block for scalar results

@@ -133,8 +133,17 @@ __device__ __forceinline__ void wf_bounds(int xc, int yc, int bw, int bh, float 
     }
 }
 
+// How the source array is described to the TMA unit (b200geo_src_layout): pitch = 0: not at all; image_rows = 0:
+// one 2-D byte array (a box must lie inside the image: rows of the neighbouring image are not zeros);
+// image_rows > 0: a 3-D array (row_bytes x image_rows x images) -- a box may hang over any image edge, the
+// hardware fills the out-of-bounds part with zeros, which is how the samplers see it.
+struct WfTma {
+    long long pitch;
+    int image_rows, row_bytes;
+};
+
 template <int BILINEAR>
-__device__ void wf_setup(const b200geo_warp_job &J, int c0, int r0, int tw, int th, long long tma_pitch, WfDesc &T)
+__device__ void wf_setup(const b200geo_warp_job &J, int c0, int r0, int tw, int th, const WfTma &tma, WfDesc &T)
 {
     T.mode = WF_SLOW;
     T.P = 0; T.rows = 0; T.ox = 0; T.oy = 0; T.xc = 0; T.yc = 0; T.band = 0.f; T.magic = 0u;
@@ -211,6 +220,7 @@ __device__ void wf_setup(const b200geo_warp_job &J, int c0, int r0, int tw, int 
     if (x_hi < x_lo || y_hi < y_lo) { x_hi = x_lo; y_hi = y_lo; }
     // absolute origin column: a multiple of 4 pixels = 12 bytes, so that every 4-entry chunk of a
     // row starts on a 32-bit boundary relative to the row start
+    const long long tma_pitch = tma.pitch;
     const bool tma_job = tma_pitch > 0 && J.src_pitch == tma_pitch && J.src_offset >= 0 && J.src_offset % tma_pitch == 0;
     const int ax0 = (T.xc + x_lo) & ~3;
     const int ox = ax0 - T.xc;
@@ -227,13 +237,23 @@ __device__ void wf_setup(const b200geo_warp_job &J, int c0, int r0, int tw, int 
     T.mode = all_in ? WF_INTERIOR : WF_BORDER;
     // unchecked staging: every 16-byte read of the staging loop stays inside the image rows
     const int ay0 = T.yc + y_lo;
-    if (ax0 >= 0 && (long long)ax0 + P + 3 <= J.iw && ay0 >= 0 && (long long)ay0 + rows <= J.ih && !(ax0 == 0 && ay0 == 0)) {
-        T.mode |= WF_FLAG_UNCHECKED;
-        // a 2-D TMA box must start on a 16-byte boundary of the global array (measured: an unaligned
-        // innermost coordinate faults): the box starts at (3*ax0) & ~15 and the rows carry a phase of 0/4/8/12 bytes
-        if (tma_job && ((3 * ax0) & 15) + 3 * (P + 1) <= WF_TMA_BOX_W && rows <= WF_TMA_BOX_H) {
+    const bool inside = ax0 >= 0 && (long long)ax0 + P + 3 <= J.iw && ay0 >= 0 && (long long)ay0 + rows <= J.ih && !(ax0 == 0 && ay0 == 0);
+    if (inside) T.mode |= WF_FLAG_UNCHECKED;
+    // a TMA box must start on a 16-byte boundary of the global array (measured: an unaligned innermost
+    // coordinate faults): the box starts at (3*ax0) & ~15 and the rows carry a phase of 0/4/8/12 bytes
+    const bool box_ok = tma_job && ((3 * ax0) & 15) + 3 * (P + 1) <= WF_TMA_BOX_W && rows <= WF_TMA_BOX_H;
+    if (tma.image_rows <= 0) {
+        if (inside && box_ok) {
             T.mode |= WF_FLAG_TMA;
             T.srow = (int)(J.src_offset / tma_pitch + ay0);
+        }
+    } else {
+        // 3-D description: edge footprints too, except the one holding source pixel (0,0) (it must read as 0)
+        const bool has00 = ax0 <= 0 && (long long)ax0 + P + 1 > 0 && ay0 <= 0 && (long long)ay0 + rows > 0;
+        const bool img_ok = J.ih == tma.image_rows && 3LL * J.iw == tma.row_bytes && J.src_offset % (tma_pitch * tma.image_rows) == 0;
+        if (box_ok && img_ok && !has00 && ax0 > -(1 << 24) && ay0 > -(1 << 24)) {
+            T.mode |= WF_FLAG_TMA;
+            T.srow = ay0;                                 // row inside its image; the producer adds the image index
         }
     }
 }
@@ -241,7 +261,7 @@ __device__ void wf_setup(const b200geo_warp_job &J, int c0, int r0, int tw, int 
 // Grid: (ceil(tiles_x / 32), ceil(tiles_y / 8), n_jobs), block (32, 8): one thread per tile.
 template <int BILINEAR>
 __global__ void __launch_bounds__(256)
-warp_setup_kernel(const b200geo_warp_job *__restrict__ jobs, const uint8_t *__restrict__ src_base, long long tma_pitch,
+warp_setup_kernel(const b200geo_warp_job *__restrict__ jobs, const uint8_t *__restrict__ src_base, const WfTma tma,
                   int tiles_x, int tiles_y, WfDesc *__restrict__ descs)
 {
     const int tx = blockIdx.x * 32 + threadIdx.x, ty = blockIdx.y * 8 + threadIdx.y;
@@ -254,7 +274,7 @@ warp_setup_kernel(const b200geo_warp_job *__restrict__ jobs, const uint8_t *__re
         T.P = 0; T.rows = 0; T.ox = 0; T.oy = 0; T.xc = 0; T.yc = 0; T.band = 0.f; T.magic = 0u;
         T.nx0 = T.ax = T.bx = T.ny0 = T.ay = T.by = T.gw = T.hw = 0.f; T.srow = 0;
     } else {
-        wf_setup<BILINEAR>(J, c0, r0, min(WF_TW, J.ow - c0), min(WF_TH, J.oh - r0), tma_pitch, T);
+        wf_setup<BILINEAR>(J, c0, r0, min(WF_TW, J.ow - c0), min(WF_TH, J.oh - r0), tma, T);
     }
     const uint4 *s = reinterpret_cast<const uint4 *>(&T);
     uint4 *d = reinterpret_cast<uint4 *>(descs + ((size_t)blockIdx.z * tiles_y + ty) * tiles_x + tx);
@@ -549,24 +569,20 @@ __device__ __forceinline__ void wf_compute_full(const WfDesc &T, const b200geo_w
 #ifndef B2G_SWP
 #define B2G_SWP 1
 #endif
-#ifndef B2G_FUSE
-#define B2G_FUSE 0
-#endif
 #ifndef B2G_DIAG
 #define B2G_DIAG 0      // diagnostics only: 1 = no sampling arithmetic, 2 = no conversion, 4 = no global stores
 #endif
-// Conversion work fused into the sampling loop (tensor-copy tiles only): chunk t = tid + 256 * p of the
-// NEXT tile is converted between the rows of this one, so that every warp's instruction stream mixes
-// the shared-memory-bound conversion with the issue-bound sampling at a fine grain (as separate
-// phases the two only overlap across the SM's two CTAs).  total = 0: nothing fused.
-struct WfConv {
-    uint32_t a0, D, magic, dst;     // source = a0 + 12 t + (t / chunks) * D, destination = dst + 16 t   (see wp_convert)
-    int chunks, total;
-};
-static_assert(WF_SRC_ENTRIES / 4 <= (WF_TH / 8) * WF_THREADS, "fused conversion: one chunk per thread and row step");
-
-__device__ __forceinline__ void wf_full_bilinear_direct(const WfDesc &T, uint32_t s_src, uint8_t *__restrict__ dst_tile, size_t dst_pitch,
-                                                        const WfConv &cv)
+// BORDER = 1: the tile crosses the mask boundary of the sampler (x > bw-1 | x < 0 | y > bh-1 | y < 0 -> 0,
+// homography.py:126-130).  The decision is taken on the float32 coordinates where they are further than
+// `band` from the boundary; coordinates are clamped into the unmasked range before addressing (the staged
+// footprint of a BORDER tile is clipped to it), masked pixels are stored as 0, and pixels inside the band go
+// to the fix-up list (float64) -- or are settled here if the list is full.
+// DIRECT = 0: the tile's destination is not 4-byte aligned; same arithmetic, results go to the shared output
+// stage `s_out` (so that a tile's bytes never depend on buffer alignment).
+template <int BORDER, int DIRECT>
+__device__ __forceinline__ void wf_full_bilinear(const WfDesc &T, const b200geo_warp_job &J, const uint8_t *__restrict__ src,
+                                                 uint32_t s_src, int c0, int r0, unsigned &n_exact, const WfFix &fix,
+                                                 uint8_t *__restrict__ dst_tile, size_t dst_pitch, uint32_t s_out = 0u)
 {
     const int tid_ = wf_tid();
     const int lane = tid_ & 31, wrp = tid_ >> 5;
@@ -578,8 +594,12 @@ __device__ __forceinline__ void wf_full_bilinear_direct(const WfDesc &T, uint32_
     const uint32_t P4 = (uint32_t)T.P * 4u;
     const uint32_t base = s_src - (uint32_t)(((int)T.oy * (int)T.P + (int)T.ox) * 4);
     const uint32_t psel = (lane & 3) == 0 ? 0x4210u : ((lane & 3) == 1 ? 0x5421u : 0x6542u);
-    uint8_t *gptr = dst_tile + (size_t)wrp * dst_pitch + (size_t)(12 * (lane >> 2) + 4 * (lane & 3));
+    uint8_t *gptr = DIRECT ? dst_tile + (size_t)wrp * dst_pitch + (size_t)(12 * (lane >> 2) + 4 * (lane & 3)) : nullptr;
     constexpr int G = WF_TW / 32, R = WF_TH / 8;
+    float lox = 0.f, hix = 0.f, loy = 0.f, hiy = 0.f;
+    if (BORDER) wf_bounds<1>(T.xc, T.yc, J.bw, J.bh, lox, hix, loy, hiy);
+    const float band = T.band;
+    uint32_t inmask = 0u, amb = 0u;
     uint32_t fx[2][G], fy[2][G];
     uint2 top[2][G], bot[2][G];
     auto fetch = [&](int p, int b) {
@@ -590,7 +610,15 @@ __device__ __forceinline__ void wf_full_bilinear_direct(const WfDesc &T, uint32_
             const float2 n2 = hh ? __ffma2_rn(A2, make_float2((float)(32 * hh), (float)(32 * hh)), np_) : np_;
             const float w = hh ? __fmaf_rn(gw, (float)(32 * hh), wp) : wp;
             const float rw = wf_rcp(w);
-            const float2 r = __fmul2_rn(n2, make_float2(rw, rw));
+            float2 r = __fmul2_rn(n2, make_float2(rw, rw));
+            if (BORDER) {
+                const bool in = r.x >= lox + band && r.x <= hix - band && r.y >= loy + band && r.y <= hiy - band;
+                const bool outp = r.x < lox - band || r.x > hix + band || r.y < loy - band || r.y > hiy + band;
+                if (in) inmask |= 1u << (p * G + hh);
+                else if (!outp) amb |= 1u << (p * G + hh);          // also NaN coordinates
+                r.x = fminf(fmaxf(r.x, lox), hix);                  // (NaN -> lox)
+                r.y = fminf(fmaxf(r.y, loy), hiy);
+            }
             const int fxd = __float2int_rd(r.x), fyd = __float2int_rd(r.y);
             const int xi = (int)__byte_perm((uint32_t)fxd, 0u, 0xBB32), yi = (int)__byte_perm((uint32_t)fyd, 0u, 0xBB32);
             const uint32_t a = (uint32_t)yi * P4 + base + ((uint32_t)xi << 2);
@@ -603,27 +631,40 @@ __device__ __forceinline__ void wf_full_bilinear_direct(const WfDesc &T, uint32_
     if (!(B2G_DIAG & 1)) fetch(0, 0);
 #pragma unroll
     for (int p = 0; p < R; ++p) {
-        const int t = tid_ + WF_THREADS * p;
-        const bool cvt = t < cv.total;
-        uint32_t w0 = 0u, w1 = 0u, w2 = 0u, w3 = 0u;
-        if (cvt) {
-            const uint32_t i = cv.chunks > 1 ? __umulhi((unsigned)t, cv.magic) : (uint32_t)t;
-            const uint32_t a = cv.a0 + 12u * (uint32_t)t + i * cv.D;
-            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(a));
-            asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(w1) : "r"(a));
-            asm volatile("ld.shared.u32 %0, [%1+8];" : "=r"(w2) : "r"(a));
-            asm volatile("ld.shared.u32 %0, [%1+12];" : "=r"(w3) : "r"(a));
-        }
         if (p + 1 < R && !(B2G_DIAG & 1)) fetch(p + 1, (p + 1) & 1);
 #pragma unroll
         for (int hh = 0; hh < G; ++hh) {
-            const uint32_t out = (B2G_DIAG & 1) ? (uint32_t)(lane + p) : wf_blend(top[p & 1][hh], bot[p & 1][hh], fx[p & 1][hh], fy[p & 1][hh]);
-            const uint32_t nbr = __shfl_down_sync(0xffffffffu, out, 1);
-            const uint32_t word = __byte_perm(out, nbr, psel);
-            if ((B2G_DIAG & 4) ? word == 0x12345678u : (lane & 3) != 3) *reinterpret_cast<uint32_t *>(gptr + 96 * hh) = word;
+            uint32_t out = (B2G_DIAG & 1) ? (uint32_t)(lane + p) : wf_blend(top[p & 1][hh], bot[p & 1][hh], fx[p & 1][hh], fy[p & 1][hh]);
+            if (BORDER && !(inmask & (1u << (p * G + hh)))) out = 0u;
+            if (DIRECT) {
+                const uint32_t nbr = __shfl_down_sync(0xffffffffu, out, 1);
+                const uint32_t word = __byte_perm(out, nbr, psel);
+                if ((B2G_DIAG & 4) ? word == 0x12345678u : (lane & 3) != 3) *reinterpret_cast<uint32_t *>(gptr + 96 * hh) = word;
+            } else {
+                wf_sts32(s_out + 4u * (uint32_t)wf_out_index(wrp + 8 * p, lane + 32 * hh), out);
+            }
         }
-        gptr += 8 * dst_pitch;
-        if (cvt) wf_store_chunk(cv.dst + 16u * (uint32_t)t, w0, w1, w2, w3);
+        if (DIRECT) gptr += 8 * dst_pitch;
+    }
+    if (BORDER && __any_sync(0xffffffffu, amb != 0u)) {
+        __syncwarp();                                   // the word stores of every lane precede the byte stores below
+        if (amb) {
+#pragma unroll 1
+            for (int k = 0; k < R * G; ++k)
+                if (amb & (1u << k)) {
+                    const int col = lane + 32 * (k % G), row = wrp + 8 * (k / G);
+                    if (!wf_defer(fix, c0 + col, r0 + row)) {
+                        const uint32_t v = wf_exact_px<1>(J, src, c0 + col, r0 + row);
+                        ++n_exact;
+                        if (DIRECT) {
+                            uint8_t *q = dst_tile + (size_t)row * dst_pitch + (size_t)col * 3;
+                            q[0] = (uint8_t)v; q[1] = (uint8_t)(v >> 8); q[2] = (uint8_t)(v >> 16);
+                        } else {
+                            wf_sts32(s_out + 4u * (uint32_t)wf_out_index(row, col), v);
+                        }
+                    }
+                }
+        }
     }
 }
 
@@ -765,7 +806,7 @@ __device__ __noinline__ void wf_split_tile(const b200geo_warp_job &J, const uint
         sync();                                                   // previous quadrant done with s_sub / the staged entries
         if (wrp == 0) {
             WfDesc t;
-            wf_setup<BILINEAR>(J, c0 + co, r0 + ro, stw, sth, 0, t);
+            wf_setup<BILINEAR>(J, c0 + co, r0 + ro, stw, sth, WfTma{0, 0, 0}, t);
             if ((t.mode & 0xFF) == WF_SPLIT) t.mode = WF_SLOW;
             if (lane == 0) *s_sub = t;
         }
@@ -848,6 +889,8 @@ warp_fast_kernel(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst
         wf_stage(T, src, (size_t)J.src_pitch, J.iw, J.ih, s_src);
         __syncthreads();
         if (mode == WF_INTERIOR && tw == WF_TW && th == WF_TH) wf_compute_full<BILINEAR, 0>(T, J, src, s_src, s_out, c0, r0, n_exact, fix);
+        else if (BILINEAR && B2G_SWP && mode == WF_BORDER && tw == WF_TW && th == WF_TH)
+            wf_full_bilinear<1, 0>(T, J, src, s_src, c0, r0, n_exact, fix, nullptr, 0, s_out);
         else if (mode == WF_INTERIOR) wf_compute_general<BILINEAR, 0>(T, J, src, s_src, s_out, c0, r0, tw, th, n_exact, fix);
         else wf_compute_general<BILINEAR, 1>(T, J, src, s_src, s_out, c0, r0, tw, th, n_exact, fix);
     } else if (mode == WF_ZERO) {
@@ -1072,7 +1115,7 @@ __global__ void __launch_bounds__(WP_THREADS, WP_OCC)
 warp_pipe_kernel(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst_base,
                  const b200geo_warp_job *__restrict__ jobs, const WfDesc *__restrict__ descs,
                  int n_tiles, int tiles_x, int tiles_y, unsigned long long *__restrict__ stats,
-                 const __grid_constant__ CUtensorMap tmap, int use_tmap,
+                 const __grid_constant__ CUtensorMap tmap, int use_tmap, int tma_image_rows,
                  WfFixEntry *__restrict__ fix_list, unsigned *__restrict__ fix_counts, unsigned seg_cap, unsigned *__restrict__ tile_counter)
 {
     extern __shared__ __align__(16) unsigned char wp_smem[];
@@ -1117,7 +1160,7 @@ warp_pipe_kernel(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst
             if (t_n1 < n_tiles) nd1 = __ldg(reinterpret_cast<const uint4 *>(descs + t_n1) + lane);
         }
         // geometry of the current job, reloaded only when the job changes
-        int cur = -1, Jow = 0, Joh = 0, Jiw = 0, Jih = 0;
+        int cur = -1, Jow = 0, Joh = 0, Jiw = 0, Jih = 0, Jimg = 0;
         long long Jsp = 0, Jdp = 0;
         const uint8_t *src = nullptr;
         uint8_t *dstj = nullptr;
@@ -1134,6 +1177,7 @@ warp_pipe_kernel(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst
                 const b200geo_warp_job &J = jobs[jz];
                 cur = jz; Jow = J.ow; Joh = J.oh; Jiw = J.iw; Jih = J.ih; Jsp = J.src_pitch; Jdp = J.dst_pitch;
                 src = src_base + J.src_offset; dstj = dst_base + J.dst_offset;
+                if (tma_image_rows > 0 && Jsp > 0) Jimg = (int)(J.src_offset / (Jsp * tma_image_rows));
             }
             WP_T(tp0);
             if (use >= 1) wp_mbar_wait(s_empty0 + 8u * b, (uint32_t)(use - 1) & 1u);
@@ -1176,8 +1220,12 @@ warp_pipe_kernel(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst
                 if (tma && (B2G_DIAG & 8)) wp_mbar_arrive(s_full);
                 else if (tma) {
                     wp_mbar_expect_tx(s_full, (uint32_t)(WF_TMA_BOX_W * WF_TMA_BOX_H));
-                    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                                 ::"r"(s_raw), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"((3 * ax0) & ~15), "r"(W.T.srow), "r"(s_full) : "memory");
+                    if (tma_image_rows > 0)
+                        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                                     ::"r"(s_raw), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"((3 * ax0) & ~15), "r"(W.T.srow), "r"(Jimg), "r"(s_full) : "memory");
+                    else
+                        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                                     ::"r"(s_raw), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"((3 * ax0) & ~15), "r"(W.T.srow), "r"(s_full) : "memory");
                 } else if (bulk) wp_mbar_expect_tx(s_full, (uint32_t)rows * RB);
                 else wp_mbar_arrive(s_full);
             }
@@ -1255,41 +1303,17 @@ warp_pipe_kernel(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst
         WP_T(tw1);
         WP_ACC(prof_conv_wait, tw0, tw1);
         uint8_t *const dst_tile = W.dst + (size_t)W.r0 * (size_t)W.dst_pitch + (size_t)W.c0 * 3;
-        const bool direct = mode == WF_INTERIOR && W.tw == WF_TW && W.th == WF_TH && ((((size_t)dst_tile) | (size_t)W.dst_pitch) & 3) == 0;
+        const bool full_aligned = W.tw == WF_TW && W.th == WF_TH && ((((size_t)dst_tile) | (size_t)W.dst_pitch) & 3) == 0;
+        const bool direct = full_aligned && (mode == WF_INTERIOR || (BILINEAR && B2G_SWP && mode == WF_BORDER));
         const WfFix fix = {fix_list + (size_t)blockIdx.x * seg_cap, &S.fix_n, seg_cap, W.jz};
         if (direct) {
             if (BILINEAR && B2G_SWP) {
-                // the next tile's conversion rides inside this tile's sampling loop when its raw rows are a tensor-copy box
-                WfConv cv = {0u, 0u, 0u, 0u, 1, 0};
-                const int t1 = it + 1, b1 = t1 % WP_STAGES;
-                bool fused = false;
-                if (B2G_FUSE) {
-                    wp_mbar_wait(s_full0 + 8u * b1, (uint32_t)(t1 / WP_STAGES) & 1u);      // record and raw rows of tile it + 1 are in
-                    const WpTile &W1 = S.tile[t1 % WP_TILE_RING];
-                    if (W1.tma) {
-                        fused = true;
-                        cv.chunks = (int)W1.T.P >> 2;
-                        cv.total = (int)W1.T.rows * cv.chunks;
-                        cv.a0 = s_raw0 + (uint32_t)WP_RAW_BYTES * b1 + ((uint32_t)(size_t)W1.a0 & 15u);
-                        cv.D = W1.RB - 12u * (uint32_t)cv.chunks;
-                        cv.magic = W1.T.magic;
-                        cv.dst = s_pairs0 + PAIRS_BYTES * (uint32_t)(t1 & (B2G_PAIRS - 1));
-                    }
-                }
-                wf_full_bilinear_direct(W.T, s_pairs, dst_tile, (size_t)W.dst_pitch, cv);
-                WP_T(tw2);
-                WP_ACC(prof_sample, tw1, tw2);
-                if (fused) {
-                    __syncwarp();
-                    if (lane == 0) {
-                        wp_mbar_arrive(s_empty0 + 8u * b1);
-                        wp_mbar_arrive(s_conv0 + 8u * (uint32_t)(t1 & 1));
-                    }
-                } else convert(t1);
-                continue;
-            }
-            if (!BILINEAR && B2G_SWP) wf_full_nn_direct(W.T, jobs[W.jz], W.src, s_pairs, W.c0, W.r0, n_exact, fix, dst_tile, (size_t)W.dst_pitch);
+                if (mode == WF_INTERIOR) wf_full_bilinear<0, 1>(W.T, jobs[W.jz], W.src, s_pairs, W.c0, W.r0, n_exact, fix, dst_tile, (size_t)W.dst_pitch);
+                else wf_full_bilinear<1, 1>(W.T, jobs[W.jz], W.src, s_pairs, W.c0, W.r0, n_exact, fix, dst_tile, (size_t)W.dst_pitch);
+            } else if (!BILINEAR && B2G_SWP) wf_full_nn_direct(W.T, jobs[W.jz], W.src, s_pairs, W.c0, W.r0, n_exact, fix, dst_tile, (size_t)W.dst_pitch);
             else wf_compute_full<BILINEAR, 1>(W.T, jobs[W.jz], W.src, s_pairs, 0u, W.c0, W.r0, n_exact, fix, dst_tile, (size_t)W.dst_pitch);
+            WP_T(tw2);
+            WP_ACC(prof_sample, tw1, tw2);
             convert(it + 1);
             continue;
         }
@@ -1300,6 +1324,8 @@ warp_pipe_kernel(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst
             if (W.staged) {
                 // (a full tile whose destination is not 4-byte aligned takes the same arithmetic as the direct path)
                 if (mode == WF_INTERIOR && W.tw == WF_TW && W.th == WF_TH) wf_compute_full<BILINEAR, 0>(W.T, J, W.src, s_pairs, s_out, W.c0, W.r0, n_exact, fix);
+                else if (BILINEAR && B2G_SWP && mode == WF_BORDER && W.tw == WF_TW && W.th == WF_TH)
+                    wf_full_bilinear<1, 0>(W.T, J, W.src, s_pairs, W.c0, W.r0, n_exact, fix, nullptr, 0, s_out);
                 else if (mode == WF_INTERIOR) wf_compute_general<BILINEAR, 0>(W.T, J, W.src, s_pairs, s_out, W.c0, W.r0, W.tw, W.th, n_exact, fix);
                 else wf_compute_general<BILINEAR, 1>(W.T, J, W.src, s_pairs, s_out, W.c0, W.r0, W.tw, W.th, n_exact, fix);
             } else if (mode == WF_ZERO) {

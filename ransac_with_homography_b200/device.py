@@ -247,7 +247,9 @@ def stitch_batched(pts, idx, frames, th, d, canvas_hw, n=4, method="fwd", sample
     jobs, boxes = bbox_jobs(H, (h, w), canvas_hw=canvas_hw)
     if canvases is None:
         canvases = torch.zeros((B, canvas_hw[0], canvas_hw[1], 3), dtype=torch.uint8, device=frames.device)
-    warp(frames, canvases, jobs, 3, sampler)
+    # the frames are one 2-D byte array (rows = B * h): each tile's footprint arrives by one tensor copy
+    warp_resident(frames, canvases, upload_jobs(jobs, frames.device), B, int(boxes[:, 2].max()), int(boxes[:, 3].max()), 3, sampler,
+                  layout=(w * 3, B * h, h, w * 3))
     return canvases, boxes, results, masks
 
 
@@ -295,12 +297,14 @@ def upload_jobs(jobs: np.ndarray, device) -> torch.Tensor:
 def warp_resident(src, dst, jobs_dev: torch.Tensor, n_jobs: int, max_ow: int, max_oh: int, channels=3, sampler="bilinear",
                   layout=None):
     """K4 with the job array already on the device: no host work per launch.  layout = (pitch_bytes,
-    rows) describes `src` as one 2-D byte array (frames stored back to back: rows = n_frames * height)
-    and lets the kernel fetch each tile's source footprint with one 2-D TMA copy."""
+    rows[, image_rows, row_bytes]) describes `src` as one 2-D byte array (frames stored back to back:
+    rows = n_frames * height) and lets the kernel fetch each tile's source footprint with one TMA tensor
+    copy; with image_rows / row_bytes (equal frames of image_rows rows and row_bytes = 3 * width bytes)
+    footprints over a frame edge are fetched the same way, zero-filled by the hardware."""
     ctx = _ctx(src)
     lay = None
     if layout is not None:
-        lay = _cabi.SrcLayout(int(layout[0]), int(layout[1]))
+        lay = _cabi.SrcLayout(int(layout[0]), int(layout[1]), int(layout[2]) if len(layout) > 2 else 0, int(layout[3]) if len(layout) > 3 else 0)
     import ctypes as C
     _cabi.check(ctx.lib.b200geo_warp_batch_dev(ctx.handle, _p(src), _p(dst), _p(jobs_dev), int(n_jobs), int(max_ow),
                                                int(max_oh), channels, _TORCH_TYPE[src.dtype], _TORCH_TYPE[dst.dtype],

@@ -390,3 +390,33 @@ def test_device_stitch_compose_matches_host_entry(golden, capsys):
         assert np.array_equal(device.stitch_compose(q, t, H).cpu().numpy(), w[f"pano_{name}_paste"])
         assert np.array_equal(device.stitch_compose(q, t, H, "Rate", 0.2).cpu().numpy(), w[f"pano_{name}_blend"])
         assert np.array_equal(t.cpu().numpy(), w["img"])            # the device entry point leaves imgT untouched
+
+
+@pytest.mark.parametrize("kind", ["jitter", "rot", "zoom", "persp"])
+@pytest.mark.parametrize("sampler", ["nn", "bilinear"])
+def test_layout_hints_do_not_change_results(kind, sampler):
+    """b200geo_warp_batch_dev with no layout, the 2-D layout and the 3-D layout (per-image zero fill: edge
+    footprints arrive by tensor copy too) must produce identical bytes, and those match the float64 kernel."""
+    import torch
+    from ransac_with_homography_b200 import _cabi, device
+    ctx = _cabi.context()
+    rs = np.random.RandomState(hash((kind, sampler, "layout")) % 2**31)
+    for (h, w) in [(240, 320), (203, 332), (97, 128)]:
+        B = 4
+        frames = rs.randint(0, 256, (B, h, w, 3)).astype(np.uint8)
+        Hs = np.stack([_rand_h(rs, h, w, kind) for _ in range(B)])
+        src_t = torch.from_numpy(frames).cuda()
+        jobs = device.scan_jobs(Hs, (h, w), (h, w))
+        jd = device.upload_jobs(jobs, "cuda")
+        outs = []
+        for layout in (None, (w * 3, B * h), (w * 3, B * h, h, w * 3)):
+            dst_t = torch.full((B, h, w, 3), 9, dtype=torch.uint8, device="cuda")
+            device.warp_resident(src_t, dst_t, jd, B, w, h, 3, sampler, layout=layout)
+            outs.append(dst_t.cpu().numpy())
+        assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2]), (kind, h, w)
+        ctx.warp_exact(True)
+        dst_t = torch.full((B, h, w, 3), 9, dtype=torch.uint8, device="cuda")
+        device.warp_resident(src_t, dst_t, jd, B, w, h, 3, sampler)
+        ctx.warp_exact(False)
+        d = np.abs(outs[2].astype(np.int16) - dst_t.cpu().numpy().astype(np.int16))
+        assert d.max() <= (0 if sampler == "nn" else U8_TOL), (kind, h, w, int(d.max()))

@@ -17,7 +17,7 @@ ctx.warp_variant(int(os.environ.get("WARP_VARIANT", "0")))
 src = torch.randint(0, 256, (n, h, w, 3), dtype=torch.uint8, device="cuda")
 dst = torch.empty_like(src)
 jobs = device.upload_jobs(device.scan_jobs(frame_homographies(n, h, w, float(os.environ.get("JITTER", "0.05"))), (h, w), (h, w)), "cuda")
-LAYOUT = None if os.environ.get('NO_TMAP') else (w * 3, n * h)
+LAYOUT = None if os.environ.get('NO_TMAP') else ((w * 3, n * h, h, w * 3) if not os.environ.get('TMAP2D') else (w * 3, n * h))
 for _ in range(3):
     device.warp_resident(src, dst, jobs, n, w, h, 3, sampler, layout=LAYOUT)
 torch.cuda.synchronize()
