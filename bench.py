@@ -37,9 +37,9 @@ sys.path.insert(0, ROOT)
 
 FLOP_PER_PAIR = 25.0          # algorithmic FLOP per hypothesis x correspondence, fwd loss
 # DRAM traffic of the dominant kernels from the committed ncu --set full captures (dram__bytes_read + write):
-#   warp_pipe_kernel, profiles/r01_warp_pipe_v12.ncu-rep: 416.9 MB + 364.5 MB for 64 frames 1080p = 5.89 B per output pixel
+#   warp_pipe_kernel, profiles/r01_warp_pipe_v14.ncu-rep: 393.2 MB + 362.5 MB for 64 frames 1080p = 5.70 B per output pixel
 #   score_fast_kernel, profiles/r01_score_fast_K200k.ncu-rep: 8.6 MB for 200k x 20k pairs (FP32-bound: traffic is incidental)
-WARP_TRAFFIC_B_PER_PIXEL = (416.917760e6 + 364.532736e6) / (64 * 1080 * 1920)
+WARP_TRAFFIC_B_PER_PIXEL = (393.238016e6 + 362.524672e6) / (64 * 1080 * 1920)
 SCORE_TRAFFIC_B_PER_PAIR = 8.584448e6 / (200000 * 20000)
 C3 = dict(M=20000, K=1_000_000, th=3.0, d=99.0, seed=1, idx_seed=0)
 C4 = dict(frames=4096, h=1080, w=1920, jitter=0.05)
@@ -429,7 +429,7 @@ def bench_warp(torch, dist, rank, world, args, ctx, peaks, local_gpu):
     k_avg_s = ms / args.steps / 1e3
     roof = {"bound": "hbm", "kernel": "warp_pipe_kernel (K4, bilinear u8 RGB; + warp_setup_kernel, <1% of the step)", "achieved": bytes_per_launch / k_avg_s / 1e9, "peak": peaks["hbm_gbs"],
             "unit": "GB/s", "frac": bytes_per_launch / k_avg_s / 1e9 / peaks["hbm_gbs"], "traffic": WARP_TRAFFIC_B_PER_PIXEL * n * h * w,
-            "traffic_source": "ncu dram bytes per output pixel (profiles/r01_warp_pipe_v12.ncu-rep, 64 frames) x pixels of this launch",
+            "traffic_source": "ncu dram bytes per output pixel (profiles/r01_warp_pipe_v14.ncu-rep, 64 frames) x pixels of this launch",
             "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peaks['source']})", "algorithmic_bytes_per_pixel": 6.0,
             "kernel_ms": k_avg_s * 1e3, "kernel_share_of_step": 1.0}
 
