@@ -257,6 +257,17 @@ int b200geo_stitch_compose_dev(b200geo_ctx *ctx, const void *imgT, const void *i
 int b200geo_stitch_compose_host(b200geo_ctx *ctx, const void *imgT, const void *imgQ, void *canvas,
                                 const b200geo_warp_job *job, const b200geo_compose *p);
 
+/* ------------------------------------------------------------------------------------------------
+ * (5) brute-force Hamming matcher -- replaces cv2.BFMatcher(cv2.NORM_HAMMING, crossCheck).match(A, B) in
+ *     stitching() (ransac.py:258-259), the step between ORB and RANSAC.run.  descA: nA x desc_bytes, descB:
+ *     nB x desc_bytes (uint8, desc_bytes a multiple of 4, <= 256; ORB: 32).  train_idx[i] = index in B of the
+ *     nearest descriptor of A[i] (first index on ties, as OpenCV) or -1 (nB == 0, or rejected by the
+ *     cross-check: A[i] is not the nearest descriptor of that B entry); dist[i] = its Hamming distance.
+ *     Host buffers; train_idx and dist hold nA int32 each.
+ * ---------------------------------------------------------------------------------------------- */
+int b200geo_match_hamming_host(b200geo_ctx *ctx, const uint8_t *descA, int nA, const uint8_t *descB, int nB,
+                               int desc_bytes, int cross_check, int32_t *train_idx, int32_t *dist);
+
 /* The samplers called on explicit coordinates: nearestNeighbor / bilinear(z_t, img, h, w, mh, mw)
  * (homography.py:108-138).  zx, zy: N float64 each (rows 0 and 1 of z_t); bh, bw: the bounds the
  * sampler tests against; dst: N*channels values of dst_type.  Host buffers. */

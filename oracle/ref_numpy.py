@@ -220,3 +220,27 @@ def stitch_panorama(imgQ, imgT, H, blending=False, blendrate=0.2):
     imgn[tsy:tey + 1, tsx:tex + 1, :] = img_t
     imgn[qsy:qey + 1, qsx:qex + 1, :] = imgQ
     return imgn
+
+
+# ------------------------------------------------------------------------------------------------
+# brute-force Hamming matching (ransac.py:258-259: cv2.BFMatcher(cv2.NORM_HAMMING, crossCheck=True).match)
+# ------------------------------------------------------------------------------------------------
+def bf_match_hamming(A, B, cross_check=True):
+    """OpenCV 4.x BFMatcher.match semantics for NORM_HAMMING (third-party: modules/core/src/batch_distance.cpp,
+    K = 1): nearest train descriptor per query descriptor, the first index among equal distances; with
+    cross-check the pass is repeated with the roles swapped and (i, j) is kept iff best_of_train[j] == i.
+    Returns (queryIdx, trainIdx, distance) arrays in query order.  Pinned against cv2 itself by
+    tests/test_oracle_golden.py (cv2 is a library of the image, not part of the reference)."""
+    A, B = np.asarray(A, np.uint8), np.asarray(B, np.uint8)
+    if A.shape[0] == 0 or B.shape[0] == 0:
+        z = np.zeros(0, np.int64)
+        return z, z, z
+    bits = np.unpackbits(A, axis=1).astype(np.int32)[:, None, :] != np.unpackbits(B, axis=1).astype(np.int32)[None, :, :]
+    D = bits.sum(axis=2)
+    ja = D.argmin(axis=1)                     # numpy argmin = first index of the minimum
+    q = np.arange(A.shape[0])
+    keep = np.ones(A.shape[0], bool)
+    if cross_check:
+        ib = D.argmin(axis=0)
+        keep = ib[ja] == q
+    return q[keep], ja[keep], D[q, ja][keep]

@@ -7,6 +7,7 @@
 #include "warp.cuh"
 #include "warp_fast.cuh"
 #include "compose.cuh"
+#include "match.cuh"
 
 #include <new>
 #include <stdlib.h>
@@ -901,6 +902,46 @@ int b200geo_warp_host(b200geo_ctx *ctx, const void *src, void *dst, const b200ge
     B2G_CUDA(cudaMemcpyAsync(ds, (const uint8_t *)src + job->src_offset, sbytes, cudaMemcpyHostToDevice, 0));
     if ((rc = b200geo_warp_dev(ctx, ds, dd, &j, 1, channels, src_type, dst_type, sampler, nullptr))) return rc;
     B2G_CUDA(cudaMemcpyAsync((uint8_t *)dst + job->dst_offset, dd, dbytes, cudaMemcpyDeviceToHost, 0));
+    B2G_CUDA(cudaStreamSynchronize(0));
+    return B200GEO_OK;
+}
+
+int b200geo_match_hamming_host(b200geo_ctx *ctx, const uint8_t *descA, int nA, const uint8_t *descB, int nB, int desc_bytes,
+                               int cross_check, int32_t *train_idx, int32_t *dist)
+{
+    B2G_ENTER(ctx);
+    B2G_ARG(nA >= 0 && nB >= 0 && desc_bytes > 0 && desc_bytes % 4 == 0 && desc_bytes <= 4 * HM_MAX_WORDS);
+    B2G_ARG((nA == 0 || (descA && train_idx && dist)) && (nB == 0 || descB));
+    if (nA == 0) return B200GEO_OK;
+    if (nB == 0) {
+        for (int i = 0; i < nA; ++i) { train_idx[i] = -1; dist[i] = 0; }
+        return B200GEO_OK;
+    }
+    const int words = desc_bytes / 4;
+    const size_t abytes = (size_t)nA * desc_bytes, bbytes = (size_t)nB * desc_bytes;
+    uint8_t *dd;
+    int32_t *dr;
+    int rc;
+    if ((rc = scratch(ctx, S_SRC, ((abytes + 15) & ~(size_t)15) + bbytes, (void **)&dd))) return rc;
+    if ((rc = scratch(ctx, S_MISC, sizeof(int32_t) * (2 * (size_t)nA + (size_t)nB), (void **)&dr))) return rc;
+    uint8_t *dA = dd, *dB = dd + ((abytes + 15) & ~(size_t)15);
+    int32_t *bestA = dr, *distA = dr + nA, *bestB = dr + 2 * (size_t)nA;
+    B2G_CUDA(cudaMemcpyAsync(dA, descA, abytes, cudaMemcpyHostToDevice, 0));
+    B2G_CUDA(cudaMemcpyAsync(dB, descB, bbytes, cudaMemcpyHostToDevice, 0));
+    const int nmax = nA > nB ? nA : nB;
+    const dim3 grid((nmax + HM_THREADS - 1) / HM_THREADS, cross_check ? 2 : 1);
+    const size_t smem = (size_t)HM_TILE * words * sizeof(uint32_t);
+    if (words == 8)
+        hamming_best_kernel<8><<<grid, HM_THREADS, smem, 0>>>((const uint32_t *)dA, nA, (const uint32_t *)dB, nB, words, bestA, distA, bestB);
+    else
+        hamming_best_kernel<0><<<grid, HM_THREADS, smem, 0>>>((const uint32_t *)dA, nA, (const uint32_t *)dB, nB, words, bestA, distA, bestB);
+    B2G_CHECK_LAUNCH(ctx);
+    if (cross_check) {
+        hamming_cross_kernel<<<(nA + 255) / 256, 256, 0, 0>>>(bestA, bestB, nA);
+        B2G_CHECK_LAUNCH(ctx);
+    }
+    B2G_CUDA(cudaMemcpyAsync(train_idx, bestA, sizeof(int32_t) * (size_t)nA, cudaMemcpyDeviceToHost, 0));
+    B2G_CUDA(cudaMemcpyAsync(dist, distA, sizeof(int32_t) * (size_t)nA, cudaMemcpyDeviceToHost, 0));
     B2G_CUDA(cudaStreamSynchronize(0));
     return B200GEO_OK;
 }

@@ -200,6 +200,38 @@ def example0(FILE="matchespoints.npy"):
     print(0)
 
 
+class Match(object):
+    """One match, with cv2.DMatch's attribute names (the reference reads .queryIdx / .trainIdx / .distance,
+    ransac.py:260-266)."""
+    __slots__ = ("queryIdx", "trainIdx", "imgIdx", "distance")
+
+    def __init__(self, queryIdx, trainIdx, distance):
+        self.queryIdx, self.trainIdx, self.imgIdx, self.distance = int(queryIdx), int(trainIdx), 0, float(distance)
+
+    def __repr__(self):
+        return f"Match(queryIdx={self.queryIdx}, trainIdx={self.trainIdx}, distance={self.distance})"
+
+
+def match_hamming(featuresA, featuresB, crossCheck=True):
+    """cv2.BFMatcher(cv2.NORM_HAMMING, crossCheck).match(featuresA, featuresB) (reference ransac.py:258-259) on the
+    GPU (K6, b200geo_match_hamming_host): for every descriptor of A the nearest descriptor of B by Hamming distance,
+    first index on ties, kept only if mutual when crossCheck.  Returns a list of Match in query order, like OpenCV.
+    None inputs (ORB found nothing) give an empty list."""
+    if featuresA is None or featuresB is None:
+        return []
+    A = np.ascontiguousarray(featuresA, dtype=np.uint8)
+    B = np.ascontiguousarray(featuresB, dtype=np.uint8)
+    assert A.ndim == 2 and B.ndim == 2 and (A.shape[1] == B.shape[1] or A.shape[0] == 0 or B.shape[0] == 0)
+    nA, nB = A.shape[0], B.shape[0]
+    if nA == 0 or nB == 0:
+        return []
+    tr, ds = np.empty(nA, np.int32), np.empty(nA, np.int32)
+    ctx = _cabi.context()
+    _cabi.check(ctx.lib.b200geo_match_hamming_host(ctx.handle, _cabi.ptr(A), nA, _cabi.ptr(B), nB, A.shape[1], 1 if crossCheck else 0,
+                                                   _cabi.ptr(tr), _cabi.ptr(ds)))
+    return [Match(i, tr[i], ds[i]) for i in np.nonzero(tr >= 0)[0]]
+
+
 def stitching(trainImg, queryImg,
               ransacMet="fwd",
               th=5,
@@ -212,8 +244,8 @@ def stitching(trainImg, queryImg,
               override=0,
               cylinderT=1):
     """Stitch trainImg into queryImg's frame (reference ransac.py:235-283; called from app.py:364).
-    ORB detection and brute-force Hamming matching stay on OpenCV as in the reference (third-party,
-    SURVEY.md section 8f-2); RANSAC and the backward warp run on the GPU."""
+    ORB detection stays on OpenCV as in the reference (third-party); the brute-force
+    Hamming matcher with cross-check, RANSAC, the backward warp and the compose run on the GPU."""
     import cv2
     if override == 0:
         trainImg_gray = cv2.cvtColor(trainImg, cv2.COLOR_RGB2GRAY)
@@ -223,8 +255,7 @@ def stitching(trainImg, queryImg,
         (kpsA, featuresA) = descriptor.detectAndCompute(trainImg_gray, None)
         (kpsB, featuresB) = descriptor.detectAndCompute(queryImg_gray, None)
 
-        bf = cv2.BFMatcher(cv2.NORM_HAMMING, crossCheck=True)
-        matches = sorted(bf.match(featuresA, featuresB), key=lambda m: m.distance)
+        matches = sorted(match_hamming(featuresA, featuresB, crossCheck=True), key=lambda m: m.distance)
 
         kpsA = np.float32([kp.pt for kp in kpsA])
         kpsB = np.float32([kp.pt for kp in kpsB])

@@ -60,3 +60,15 @@ def synth_pair(seed, M, outlier_frac=0.5, noise=0.5):
     out = rs.rand(M) < outlier_frac
     Y[:, out] = rs.rand(2, int(out.sum())) * np.array([[1920.0], [1080.0]])
     return X, Y.astype(np.float32)
+
+
+def descriptors(rs, n, nbytes=32, dup=0.3):
+    """Random descriptors with many near-duplicates so that equal distances (tie-breaking) actually occur."""
+    d = rs.randint(0, 256, (n, nbytes)).astype(np.uint8)
+    for i in range(1, n):
+        if rs.rand() < dup:
+            d[i] = d[rs.randint(0, i)]
+            flips = rs.randint(0, 3)
+            for _ in range(flips):
+                d[i, rs.randint(0, nbytes)] ^= np.uint8(1 << rs.randint(0, 8))
+    return d

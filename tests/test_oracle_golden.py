@@ -5,7 +5,7 @@ import pytest
 
 import oracle
 from oracle import ref_numpy as port
-from conftest import FIXTURE_CASES, case_method
+from conftest import FIXTURE_CASES, case_method, descriptors as _descriptors
 
 
 @pytest.mark.parametrize("name", FIXTURE_CASES)
@@ -160,3 +160,17 @@ def test_port_stitch_panorama_matches_reference(golden, name):
     H = w[f"pano_{name}_H"]
     assert np.array_equal(port.stitch_panorama(w["img2"].copy(), w["img"].copy(), H), w[f"pano_{name}_paste"])
     assert np.array_equal(port.stitch_panorama(w["img2"].copy(), w["img"].copy(), H, "Rate", 0.2), w[f"pano_{name}_blend"])
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+@pytest.mark.parametrize("cross", [True, False])
+def test_port_hamming_matcher_equals_opencv(seed, cross):
+    """The numpy restatement of BFMatcher(NORM_HAMMING, crossCheck).match against OpenCV itself (ties included)."""
+    cv2 = pytest.importorskip("cv2")
+    rs = np.random.RandomState(seed)
+    A, B = _descriptors(rs, 157 + 40 * seed), _descriptors(rs, 203 - 30 * seed)
+    B[::7] = A[rs.randint(0, A.shape[0], B[::7].shape[0])]        # exact duplicates across the sets
+    m = cv2.BFMatcher(cv2.NORM_HAMMING, crossCheck=cross).match(A, B)
+    q, t, d = port.bf_match_hamming(A, B, cross)
+    assert [x.queryIdx for x in m] == q.tolist() and [x.trainIdx for x in m] == t.tolist()
+    assert [int(x.distance) for x in m] == d.tolist()
