@@ -1058,7 +1058,7 @@ __device__ __forceinline__ void wp_consumer_sync() { asm volatile("bar.sync 1, %
 // tensor copy has one phase for all rows: pitch32 = 0).  ALIGNED: all phases are multiples of 4
 // (always true for the tensor copy, whose origin column is a multiple of 4 pixels).
 #ifndef B2G_CONV_BATCH
-#define B2G_CONV_BATCH 1      // 2 and 4 were measured slower: the extra live registers spill under the 96-register cap
+#define B2G_CONV_BATCH 1      // 2 and 4 were measured slower (inline: spills under the 96-register cap; out of line: 361 / 338 vs 386 Gpix/s)
 #endif
 template <int ALIGNED>
 __device__ __forceinline__ void wp_convert(const WfDesc &T, uint32_t magic, uint32_t phase0, uint32_t pitch32, uint32_t RB, uint32_t s_raw,
@@ -1105,6 +1105,14 @@ __device__ __forceinline__ void wp_convert(const WfDesc &T, uint32_t magic, uint
         }
         wf_store_chunk(s_pairs + (uint32_t)(i * P + 4 * k) * 4u, w0, w1, w2, w3);
     }
+}
+
+// the rare ways of filling the entries (per-row bulk copies; synchronous staging at image edges without a 3-D tensor
+// map): out of line, so that they do not weigh on the register allocation of the consumer loop
+__device__ __noinline__ void wp_convert_cold(const WpTile &W, uint32_t s_raw, uint32_t s_pairs)
+{
+    if (W.bulk) wp_convert<0>(W.T, W.T.magic, (uint32_t)(size_t)W.a0, (uint32_t)W.src_pitch, W.RB, s_raw, s_pairs);
+    else if (W.staged) wf_stage(W.T, W.src, (size_t)W.src_pitch, W.iw, W.ih, s_pairs);
 }
 
 // Grid: min(n_tiles, SMs * WP_OCC) CTAs of WP_THREADS; dynamic shared memory sizeof(WpSmem).
@@ -1279,8 +1287,7 @@ warp_pipe_kernel(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst
         const uint32_t s_pairs = s_pairs0 + PAIRS_BYTES * (uint32_t)(t & (B2G_PAIRS - 1)), s_raw = s_raw0 + (uint32_t)WP_RAW_BYTES * b;
         if (B2G_PAIRS == 1 && t > 0) wp_consumer_sync();      // every warp is done sampling the previous tile from the one buffer
         if (W.tma) wp_convert<1>(W.T, W.T.magic, (uint32_t)(size_t)W.a0, 0u, W.RB, s_raw, s_pairs);
-        else if (W.bulk) wp_convert<0>(W.T, W.T.magic, (uint32_t)(size_t)W.a0, (uint32_t)W.src_pitch, W.RB, s_raw, s_pairs);
-        else if (W.staged) wf_stage(W.T, W.src, (size_t)W.src_pitch, W.iw, W.ih, s_pairs);
+        else wp_convert_cold(W, s_raw, s_pairs);
         __syncwarp();
         if (lane == 0) {
             wp_mbar_arrive(s_empty0 + 8u * b);                 // raw[b] may be refilled
