@@ -225,7 +225,7 @@ __device__ void wf_setup(const b200geo_warp_job &J, int c0, int r0, int tw, int 
     const int ax0 = (T.xc + x_lo) & ~3;
     const int ox = ax0 - T.xc;
     const long long width = (long long)x_hi - ox + 1, rows = (long long)y_hi - y_lo + 1;
-    const long long P = (width + 3) & ~3LL;
+    const long long P = max(8LL, (width + 3) & ~3LL);       // >= 2 chunks: the conversion's division by multiplication needs chunks > 1
     if (ox < -32000 || y_lo < -32000) return;
     if (P * rows > WF_SRC_ENTRIES) { T.mode = WF_SPLIT; return; }        // footprint does not fit: the kernel retries per quadrant
     T.ox = (short)ox;
@@ -577,11 +577,17 @@ __device__ __forceinline__ void wf_compute_full(const WfDesc &T, const b200geo_w
 // `band` from the boundary; coordinates are clamped into the unmasked range before addressing (the staged
 // footprint of a BORDER tile is clipped to it), masked pixels are stored as 0, and pixels inside the band go
 // to the fix-up list (float64) -- or are settled here if the list is full.
+// address of plane-0 entry (0, 0) relative to the anchor, for a tile staged at shared address s_src
+__device__ __forceinline__ uint32_t wf_entry_base(const WfDesc &T, uint32_t s_src)
+{
+    return s_src - (uint32_t)(((int)T.oy * (int)T.P + (int)T.ox) * 4);
+}
+
 // DIRECT = 0: the tile's destination is not 4-byte aligned; same arithmetic, results go to the shared output
 // stage `s_out` (so that a tile's bytes never depend on buffer alignment).
 template <int BORDER, int DIRECT>
 __device__ __forceinline__ void wf_full_bilinear(const WfDesc &T, const b200geo_warp_job &J, const uint8_t *__restrict__ src,
-                                                 uint32_t s_src, int c0, int r0, unsigned &n_exact, const WfFix &fix,
+                                                 uint32_t base, uint32_t P4, int c0, int r0, unsigned &n_exact, const WfFix &fix,
                                                  uint8_t *__restrict__ dst_tile, size_t dst_pitch, uint32_t s_out = 0u)
 {
     const int tid_ = wf_tid();
@@ -591,8 +597,6 @@ __device__ __forceinline__ void wf_full_bilinear(const WfDesc &T, const b200geo_
     const float2 A2 = make_float2(T.ax, T.ay), B2 = make_float2(T.bx, T.by);
     const float2 nb = __ffma2_rn(A2, make_float2(di0, di0), __ffma2_rn(B2, make_float2(dj0, dj0), make_float2(T.nx0, T.ny0)));
     const float wb = __fmaf_rn(gw, di0, __fmaf_rn(hw, dj0, WF_W0));
-    const uint32_t P4 = (uint32_t)T.P * 4u;
-    const uint32_t base = s_src - (uint32_t)(((int)T.oy * (int)T.P + (int)T.ox) * 4);
     const uint32_t psel = (lane & 3) == 0 ? 0x4210u : ((lane & 3) == 1 ? 0x5421u : 0x6542u);
     uint8_t *gptr = DIRECT ? dst_tile + (size_t)wrp * dst_pitch + (size_t)(12 * (lane >> 2) + 4 * (lane & 3)) : nullptr;
     constexpr int G = WF_TW / 32, R = WF_TH / 8;
@@ -673,8 +677,8 @@ __device__ __forceinline__ void wf_full_bilinear(const WfDesc &T, const b200geo_
 // speculatively; the ones within `band` of a rounding boundary are pushed to the fix-up list
 // (warp_fixup_kernel overwrites them in float64 after this kernel) or, if the list is full, settled here.
 template <int DUMMY = 0>
-__device__ __forceinline__ void wf_full_nn_direct(const WfDesc &T, const b200geo_warp_job &J, const uint8_t *__restrict__ src, uint32_t s_src,
-                                                  int c0, int r0, unsigned &n_exact, const WfFix &fix, uint8_t *__restrict__ dst_tile,
+__device__ __forceinline__ void wf_full_nn_direct(const WfDesc &T, const b200geo_warp_job &J, const uint8_t *__restrict__ src, uint32_t base,
+                                                  uint32_t P4, int c0, int r0, unsigned &n_exact, const WfFix &fix, uint8_t *__restrict__ dst_tile,
                                                   size_t dst_pitch)
 {
     const int tid_ = wf_tid();
@@ -684,8 +688,6 @@ __device__ __forceinline__ void wf_full_nn_direct(const WfDesc &T, const b200geo
     const float2 A2 = make_float2(T.ax, T.ay), B2 = make_float2(T.bx, T.by);
     const float2 nb = __ffma2_rn(A2, make_float2(di0, di0), __ffma2_rn(B2, make_float2(dj0, dj0), make_float2(T.nx0, T.ny0)));
     const float wb = __fmaf_rn(gw, di0, __fmaf_rn(hw, dj0, WF_W0));
-    const uint32_t P4 = (uint32_t)T.P * 4u;
-    const uint32_t base = s_src - (uint32_t)(((int)T.oy * (int)T.P + (int)T.ox) * 4);
     const uint32_t psel = (lane & 3) == 0 ? 0x4210u : ((lane & 3) == 1 ? 0x5421u : 0x6542u);
     uint8_t *gptr = dst_tile + (size_t)wrp * dst_pitch + (size_t)(12 * (lane >> 2) + 4 * (lane & 3));
     const uint32_t B16 = (uint32_t)((int)T.band + 2);
@@ -890,7 +892,7 @@ warp_fast_kernel(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst
         __syncthreads();
         if (mode == WF_INTERIOR && tw == WF_TW && th == WF_TH) wf_compute_full<BILINEAR, 0>(T, J, src, s_src, s_out, c0, r0, n_exact, fix);
         else if (BILINEAR && B2G_SWP && mode == WF_BORDER && tw == WF_TW && th == WF_TH)
-            wf_full_bilinear<1, 0>(T, J, src, s_src, c0, r0, n_exact, fix, nullptr, 0, s_out);
+            wf_full_bilinear<1, 0>(T, J, src, wf_entry_base(T, s_src), (uint32_t)T.P * 4u, c0, r0, n_exact, fix, nullptr, 0, s_out);
         else if (mode == WF_INTERIOR) wf_compute_general<BILINEAR, 0>(T, J, src, s_src, s_out, c0, r0, tw, th, n_exact, fix);
         else wf_compute_general<BILINEAR, 1>(T, J, src, s_src, s_out, c0, r0, tw, th, n_exact, fix);
     } else if (mode == WF_ZERO) {
@@ -948,8 +950,13 @@ struct __align__(16) WpTile {
     int iw, ih, c0, r0, tw, th, jz;
     uint32_t RB;             // bytes per raw row in shared memory (multiple of 16)
     int staged, bulk;
-    int pad0;
-    int tma;                 // raw rows arrive as one 2-D tensor copy: row stride WF_TMA_BOX_W, one phase
+    int direct;              // full tile on the unrolled loop, stored straight to global memory
+    int tma;                 // raw rows arrive as one tensor copy: row stride WF_TMA_BOX_W, one phase
+    // per-tile constants every consumer thread needs, computed once by the producer
+    uint8_t *dst_tile;       // address of the tile's first output byte
+    uint32_t sm_base, sm_P4; // entry (x, y) relative to the anchor lives at sm_base + y * sm_P4 + 4 x (plane 0)
+    uint32_t cv_a0, cv_D, cv_dst;   // tensor-copy tiles: chunk t = i * chunks + k is read at cv_a0 + 12 t + i * cv_D, written at cv_dst + 16 t
+    int cv_total;            // chunks to convert (0 unless tma)
 };
 
 #ifndef B2G_STAGES
@@ -1053,44 +1060,15 @@ __device__ __forceinline__ uint32_t wp_lds32(uint32_t a)
 }
 __device__ __forceinline__ void wp_consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(WF_THREADS) : "memory"); }
 
-// Raw RGB rows in shared memory -> entries.  Row i of the footprint starts `(phase0 + i * pitch32) & 15`
-// bytes into its raw row (per-row bulk copies start at the row address rounded down to 16; a 2-D
-// tensor copy has one phase for all rows: pitch32 = 0).  ALIGNED: all phases are multiples of 4
-// (always true for the tensor copy, whose origin column is a multiple of 4 pixels).
-#ifndef B2G_CONV_BATCH
-#define B2G_CONV_BATCH 1      // 2 and 4 were measured slower (inline: spills under the 96-register cap; out of line: 361 / 338 vs 386 Gpix/s)
-#endif
+// Raw RGB rows in shared memory -> entries, for rows that arrived by per-row bulk copies: row i of the footprint starts
+// `(phase0 + i * pitch32) & 15` bytes into its raw row (each copy starts at the row address rounded down to 16).
+// ALIGNED: all phases are multiples of 4.  (Tensor-copy tiles -- one phase for all rows -- are converted inline in
+// the consumer loop from constants the producer leaves in the tile record.)
 template <int ALIGNED>
 __device__ __forceinline__ void wp_convert(const WfDesc &T, uint32_t magic, uint32_t phase0, uint32_t pitch32, uint32_t RB, uint32_t s_raw,
                                            uint32_t s_pairs)
 {
     const int P = T.P, chunks = P >> 2, total = (B2G_DIAG & 2) ? 0 : (int)T.rows * chunks;
-    if (ALIGNED && pitch32 == 0u) {
-        // one phase for all rows (tensor copy): with t = i * chunks + k the source address is
-        // linear in t plus a per-row term, and the destination is 16 * t (P = 4 * chunks)
-        const uint32_t D = RB - 12u * (uint32_t)chunks, a0 = s_raw + (phase0 & 15u);
-        // the loop is latency-bound (LDS -> PRMT -> STS, ~3 trips per tile): all loads of up to B2G_CONV_BATCH
-        // chunks are issued before the first permute
-#pragma unroll 1
-        for (int t0 = wf_tid(); t0 < total; t0 += B2G_CONV_BATCH * WF_THREADS) {
-            uint32_t w[B2G_CONV_BATCH][4];
-#pragma unroll
-            for (int u = 0; u < B2G_CONV_BATCH; ++u) {
-                const int t = t0 + u * WF_THREADS;
-                if (t < total) {
-                    const uint32_t i = chunks > 1 ? __umulhi((unsigned)t, magic) : (uint32_t)t;
-                    const uint32_t a = a0 + 12u * (uint32_t)t + i * D;
-                    w[u][0] = wp_lds32(a); w[u][1] = wp_lds32(a + 4); w[u][2] = wp_lds32(a + 8); w[u][3] = wp_lds32(a + 12);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < B2G_CONV_BATCH; ++u) {
-                const int t = t0 + u * WF_THREADS;
-                if (t < total) wf_store_chunk(s_pairs + 16u * (uint32_t)t, w[u][0], w[u][1], w[u][2], w[u][3]);
-            }
-        }
-        return;
-    }
 #pragma unroll 2
     for (int t = wf_tid(); t < total; t += WF_THREADS) {
         const int i = chunks > 1 ? (int)__umulhi((unsigned)t, magic) : t;
@@ -1135,6 +1113,8 @@ warp_pipe_kernel(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst
     const uint32_t s_raw0 = (uint32_t)__cvta_generic_to_shared(S.raw[0]);
     const uint32_t s_full0 = (uint32_t)__cvta_generic_to_shared(&S.full[0]);
     const uint32_t s_empty0 = (uint32_t)__cvta_generic_to_shared(&S.empty[0]);
+    const uint32_t s_pairs0 = (uint32_t)__cvta_generic_to_shared(S.pairs[0]);
+    constexpr uint32_t PAIRS_BYTES = 2u * WF_SRC_ENTRIES * 4u;
 
     if (tid == 0) {
         S.fix_n = 0u;
@@ -1225,6 +1205,19 @@ warp_pipe_kernel(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst
                 W.iw = Jiw; W.ih = Jih; W.c0 = tx * WF_TW; W.r0 = ty * WF_TH;
                 W.tw = min(WF_TW, Jow - tx * WF_TW); W.th = min(WF_TH, Joh - ty * WF_TH);
                 W.jz = jz; W.RB = tma ? (uint32_t)WF_TMA_BOX_W : RB; W.staged = staged; W.bulk = bulk; W.tma = tma;
+                {
+                    const uint32_t pairs_it = s_pairs0 + PAIRS_BYTES * (uint32_t)(it & (B2G_PAIRS - 1));
+                    uint8_t *const dt = dstj + (long long)W.r0 * Jdp + 3LL * W.c0;
+                    W.dst_tile = dt;
+                    W.direct = (mode == WF_INTERIOR || (BILINEAR && B2G_SWP && mode == WF_BORDER)) && W.tw == WF_TW && W.th == WF_TH &&
+                               ((((size_t)dt) | (size_t)Jdp) & 3) == 0;
+                    W.sm_P4 = (uint32_t)P * 4u;
+                    W.sm_base = wf_entry_base(W.T, pairs_it);
+                    W.cv_total = tma ? rows * (P >> 2) : 0;
+                    W.cv_D = (uint32_t)WF_TMA_BOX_W - 12u * (uint32_t)(P >> 2);
+                    W.cv_a0 = s_raw + ((uint32_t)(size_t)a0 & 15u);
+                    W.cv_dst = pairs_it;
+                }
                 if (tma && (B2G_DIAG & 8)) wp_mbar_arrive(s_full);
                 else if (tma) {
                     wp_mbar_expect_tx(s_full, (uint32_t)(WF_TMA_BOX_W * WF_TMA_BOX_H));
@@ -1264,10 +1257,8 @@ warp_pipe_kernel(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst
     // completed, i.e. after every warp converted tile it, which each does after sampling tile it-1
     // (the last reader of entries[s^1]).  Tiles that are not full INTERIOR tiles (9 % on the
     // benchmark) go through the shared output stage between two consumer barriers.
-    const uint32_t s_pairs0 = (uint32_t)__cvta_generic_to_shared(S.pairs[0]);
     const uint32_t s_out = (uint32_t)__cvta_generic_to_shared(S.out);
     const uint32_t s_conv0 = (uint32_t)__cvta_generic_to_shared(&S.conv[0]);
-    constexpr uint32_t PAIRS_BYTES = 2u * WF_SRC_ENTRIES * 4u;
     unsigned n_exact = 0;
     // the tile index itself travels in the WpTile record: the consumers only count iterations, up to the sentinel record
 
@@ -1286,8 +1277,17 @@ warp_pipe_kernel(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst
         const WpTile &W = S.tile[t % WP_TILE_RING];
         const uint32_t s_pairs = s_pairs0 + PAIRS_BYTES * (uint32_t)(t & (B2G_PAIRS - 1)), s_raw = s_raw0 + (uint32_t)WP_RAW_BYTES * b;
         if (B2G_PAIRS == 1 && t > 0) wp_consumer_sync();      // every warp is done sampling the previous tile from the one buffer
-        if (W.tma) wp_convert<1>(W.T, W.T.magic, (uint32_t)(size_t)W.a0, 0u, W.RB, s_raw, s_pairs);
-        else wp_convert_cold(W, s_raw, s_pairs);
+        if (W.tma) {
+            // (chunk, row) from t by multiplication (chunks >= 2 by construction); all constants come from the tile record
+            const int total = (B2G_DIAG & 2) ? 0 : W.cv_total;
+            const uint32_t a0 = W.cv_a0, D = W.cv_D, dst = W.cv_dst, magic = W.T.magic;
+#pragma unroll 2
+            for (int tt = tid; tt < total; tt += WF_THREADS) {
+                const uint32_t a = a0 + 12u * (uint32_t)tt + __umulhi((unsigned)tt, magic) * D;
+                const uint32_t w0 = wp_lds32(a), w1 = wp_lds32(a + 4), w2 = wp_lds32(a + 8), w3 = wp_lds32(a + 12);
+                wf_store_chunk(dst + 16u * (uint32_t)tt, w0, w1, w2, w3);
+            }
+        } else wp_convert_cold(W, s_raw, s_pairs);
         __syncwarp();
         if (lane == 0) {
             wp_mbar_arrive(s_empty0 + 8u * b);                 // raw[b] may be refilled
@@ -1309,15 +1309,13 @@ warp_pipe_kernel(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst
         if (mode == WF_DONE) break;
         WP_T(tw1);
         WP_ACC(prof_conv_wait, tw0, tw1);
-        uint8_t *const dst_tile = W.dst + (size_t)W.r0 * (size_t)W.dst_pitch + (size_t)W.c0 * 3;
-        const bool full_aligned = W.tw == WF_TW && W.th == WF_TH && ((((size_t)dst_tile) | (size_t)W.dst_pitch) & 3) == 0;
-        const bool direct = full_aligned && (mode == WF_INTERIOR || (BILINEAR && B2G_SWP && mode == WF_BORDER));
+        uint8_t *const dst_tile = W.dst_tile;
         const WfFix fix = {fix_list + (size_t)blockIdx.x * seg_cap, &S.fix_n, seg_cap, W.jz};
-        if (direct) {
+        if (W.direct) {
             if (BILINEAR && B2G_SWP) {
-                if (mode == WF_INTERIOR) wf_full_bilinear<0, 1>(W.T, jobs[W.jz], W.src, s_pairs, W.c0, W.r0, n_exact, fix, dst_tile, (size_t)W.dst_pitch);
-                else wf_full_bilinear<1, 1>(W.T, jobs[W.jz], W.src, s_pairs, W.c0, W.r0, n_exact, fix, dst_tile, (size_t)W.dst_pitch);
-            } else if (!BILINEAR && B2G_SWP) wf_full_nn_direct(W.T, jobs[W.jz], W.src, s_pairs, W.c0, W.r0, n_exact, fix, dst_tile, (size_t)W.dst_pitch);
+                if (mode == WF_INTERIOR) wf_full_bilinear<0, 1>(W.T, jobs[W.jz], W.src, W.sm_base, W.sm_P4, W.c0, W.r0, n_exact, fix, dst_tile, (size_t)W.dst_pitch);
+                else wf_full_bilinear<1, 1>(W.T, jobs[W.jz], W.src, W.sm_base, W.sm_P4, W.c0, W.r0, n_exact, fix, dst_tile, (size_t)W.dst_pitch);
+            } else if (!BILINEAR && B2G_SWP) wf_full_nn_direct(W.T, jobs[W.jz], W.src, W.sm_base, W.sm_P4, W.c0, W.r0, n_exact, fix, dst_tile, (size_t)W.dst_pitch);
             else wf_compute_full<BILINEAR, 1>(W.T, jobs[W.jz], W.src, s_pairs, 0u, W.c0, W.r0, n_exact, fix, dst_tile, (size_t)W.dst_pitch);
             WP_T(tw2);
             WP_ACC(prof_sample, tw1, tw2);
@@ -1332,7 +1330,7 @@ warp_pipe_kernel(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst
                 // (a full tile whose destination is not 4-byte aligned takes the same arithmetic as the direct path)
                 if (mode == WF_INTERIOR && W.tw == WF_TW && W.th == WF_TH) wf_compute_full<BILINEAR, 0>(W.T, J, W.src, s_pairs, s_out, W.c0, W.r0, n_exact, fix);
                 else if (BILINEAR && B2G_SWP && mode == WF_BORDER && W.tw == WF_TW && W.th == WF_TH)
-                    wf_full_bilinear<1, 0>(W.T, J, W.src, s_pairs, W.c0, W.r0, n_exact, fix, nullptr, 0, s_out);
+                    wf_full_bilinear<1, 0>(W.T, J, W.src, W.sm_base, W.sm_P4, W.c0, W.r0, n_exact, fix, nullptr, 0, s_out);
                 else if (mode == WF_INTERIOR) wf_compute_general<BILINEAR, 0>(W.T, J, W.src, s_pairs, s_out, W.c0, W.r0, W.tw, W.th, n_exact, fix);
                 else wf_compute_general<BILINEAR, 1>(W.T, J, W.src, s_pairs, s_out, W.c0, W.r0, W.tw, W.th, n_exact, fix);
             } else if (mode == WF_ZERO) {

@@ -47,6 +47,26 @@ H = res["H"]
 hg.stitchPanorama(imgQ.copy(), imgT.copy(), H)
 out["C1_stitchPanorama_ms"] = {"ours": best(lambda: hg.stitchPanorama(imgQ.copy(), imgT.copy(), H)),
                                "numpy_port_warp_only": best(lambda: port.warp_bbox(imgT.copy(), H, True)[0].astype(np.uint8), 2)}
+with redirect_stdout(io.StringIO()):
+    hg.stitchPanorama(imgQ.copy(), imgT.copy(), H, blending="Rate", blendrate=0.2)
+
+    def ours_blend():
+        hg.stitchPanorama(imgQ.copy(), imgT.copy(), H, blending="Rate", blendrate=0.2)
+
+    def ref_blend():
+        port.stitch_panorama(imgQ.copy(), imgT.copy(), H, "Rate", 0.2)
+    out["C1_stitchPanorama_blend_ms"] = {"ours": best(ours_blend), "numpy_port": best(ref_blend, 1)}
+# the matcher between ORB and RANSAC (ransac.py:258-259): 500 x 500 ORB-sized descriptors, cross-check
+from ransac_with_homography_b200.ransac import match_hamming
+dA, dB = rs.randint(0, 256, (500, 32)).astype(np.uint8), rs.randint(0, 256, (500, 32)).astype(np.uint8)
+match_hamming(dA, dB)
+out["C1_match_500x500_ms"] = {"ours": best(lambda: match_hamming(dA, dB))}
+try:
+    import cv2
+    bf = cv2.BFMatcher(cv2.NORM_HAMMING, crossCheck=True)
+    out["C1_match_500x500_ms"]["opencv_cpu"] = best(lambda: bf.match(dA, dB))
+except ImportError:
+    pass
 img = rs.randint(0, 256, (755, 1226, 3)).astype(np.uint8)
 u = np.array([[100, 560, 740, 80], [160, 125, 490, 555], [1, 1, 1, 1]], np.float64)
 v = np.array([[0, 2480, 2480, 0], [0, 0, 3508, 3508], [1, 1, 1, 1]], np.float64)
