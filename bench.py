@@ -356,7 +356,7 @@ def bench_ransac(torch, dist, rank, world, args, ctx, peaks, local_gpu):
         def e2e_step():
             with redirect_stdout(io.StringIO()):
                 runner.run([X, Y], method="fwd", idx=idx_h)
-        d2h += K * 4                       # RANSAC.run also returns the per-hypothesis counts on request
+        d2h += 4                           # the last sample set's count, for the reference's closing warning (ransac.py:203-204)
         for _ in range(max(1, min(args.warmup, 2))):
             e2e_step()
         t0 = time.perf_counter()
@@ -364,7 +364,7 @@ def bench_ransac(torch, dist, rank, world, args, ctx, peaks, local_gpu):
         for _ in range(n_e2e):
             e2e_step()
         e2e_s = (time.perf_counter() - t0) / n_e2e
-        e2e_how = "ransac.RANSAC.run([X, Y], 'fwd', idx=...) on numpy arrays (b200geo_ransac_host)"
+        e2e_how = "ransac.RANSAC.run([X, Y], 'fwd', idx=...) on numpy arrays (b200geo_ransac_host: the sample sets past the first scoring wave are uploaded under that wave's scoring)"
     else:
         pin_p, pin_i = torch.from_numpy(pts_h).pin_memory(), torch.from_numpy(idx_h).pin_memory()
         out_h = torch.empty(32, dtype=torch.float64).pin_memory()

@@ -143,14 +143,18 @@ int b200geo_ransac_finish_dev(b200geo_ctx *ctx, const float *pts, int M, const i
                               const unsigned long long *keys, float th, int method,
                               double *result, uint8_t *mask, void *stream);
 
-/* Whole RANSAC.run (ransac.py:159-213) on host buffers: H2D, search, finish, D2H.
+/* Whole RANSAC.run (ransac.py:159-213) on host buffers: H2D, search, finish, D2H.  The sample sets are uploaded
+ * in chunks on a second stream while earlier chunks are being solved and scored.
  *   thr = M*d/100 + n as the reference computes it (ransac.py:169,186).
  *   out_H_best: 9 float32 (winning 4-point hypothesis), out_H: 9 float64 (refit, the reference's
- *   return value), out_mask: M uint8, out_winner / out_count: scalars, out_counts (optional): K.
+ *   return value), out_mask: M uint8, out_winner / out_count: scalars, out_counts (optional): K inlier counts,
+ *   out_last_count (optional): the count of sample set K-1 -- what the reference's closing warning tests when no
+ *   hypothesis met the threshold (ransac.py:203-204).
  *   Returns B200GEO_ERR_NOMODEL / B200GEO_ERR_SINGULAR where the reference raises. */
 int b200geo_ransac_host(b200geo_ctx *ctx, const float *pts, int M, const int32_t *idx, int K,
                         float th, double thr, int method, float *out_H_best, double *out_H,
-                        uint8_t *out_mask, int32_t *out_winner, int32_t *out_count, int32_t *out_counts);
+                        uint8_t *out_mask, int32_t *out_winner, int32_t *out_count, int32_t *out_counts,
+                        int32_t *out_last_count);
 
 /* Batched form (config "batched stitch pipeline"): B independent pairs, each with its own
  * correspondence set (M rows) and K sample sets; one launch sequence, no host round trips.

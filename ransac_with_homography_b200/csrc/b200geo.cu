@@ -669,9 +669,23 @@ int b200geo_ransac_finish_dev(b200geo_ctx *ctx, const float *pts, int M, const i
     return launch_finish(ctx, pts, M, idx, 0, 1, keys, th, method, result, mask, (cudaStream_t)stream);
 }
 
+namespace {
+// the three non-blocking streams (h2d, compute, d2h) and their events, shared by the host-buffer pipelines
+int ensure_pipe(b200geo_ctx *ctx)
+{
+    if (!ctx->pipe_ready) {
+        for (int i = 0; i < 3; ++i) B2G_CUDA(cudaStreamCreateWithFlags(&ctx->pipe_stream[i], cudaStreamNonBlocking));
+        for (int i = 0; i < 3; ++i)
+            for (int b = 0; b < 2; ++b) B2G_CUDA(cudaEventCreateWithFlags(&ctx->pipe_event[i][b], cudaEventDisableTiming));
+        ctx->pipe_ready = 1;
+    }
+    return B200GEO_OK;
+}
+}  // namespace
+
 int b200geo_ransac_host(b200geo_ctx *ctx, const float *pts, int M, const int32_t *idx, int K, float th, double thr,
                         int method, float *out_H_best, double *out_H, uint8_t *out_mask, int32_t *out_winner,
-                        int32_t *out_count, int32_t *out_counts)
+                        int32_t *out_count, int32_t *out_counts, int32_t *out_last_count)
 {
     B2G_ENTER(ctx);
     B2G_ARG(pts && idx && M > 0 && K > 0);
@@ -688,16 +702,33 @@ int b200geo_ransac_host(b200geo_ctx *ctx, const float *pts, int M, const int32_t
     if ((rc = scratch(ctx, S_KEYS, 16, (void **)&dk))) return rc;
     if ((rc = scratch(ctx, S_RESULT, 32 * 8, (void **)&dr))) return rc;
     if ((rc = scratch(ctx, S_MASK, (size_t)M, (void **)&dm))) return rc;
-    B2G_CUDA(cudaMemcpyAsync(dp, pts, (size_t)M * 16, cudaMemcpyHostToDevice, 0));
-    B2G_CUDA(cudaMemcpyAsync(di, idx, (size_t)K * 16, cudaMemcpyHostToDevice, 0));
-    B2G_CUDA(cudaMemsetAsync(dk, 0, 16, 0));
-    if ((rc = search(ctx, dp, M, di, 0, K, K, 1, th, thr, method, dk, dc, 0))) return rc;
-    if ((rc = launch_finish(ctx, dp, M, di, K, 1, dk, th, method, dr, dm, 0))) return rc;
-    double res[32];
-    B2G_CUDA(cudaMemcpyAsync(res, dr, sizeof res, cudaMemcpyDeviceToHost, 0));
-    if (out_mask) B2G_CUDA(cudaMemcpyAsync(out_mask, dm, (size_t)M, cudaMemcpyDeviceToHost, 0));
-    if (out_counts) B2G_CUDA(cudaMemcpyAsync(out_counts, dc, (size_t)K * 4, cudaMemcpyDeviceToHost, 0));
+    if ((rc = ensure_pipe(ctx))) return rc;
+    // earlier work of this context may still be running on the legacy stream the scratch blocks are shared with
     B2G_CUDA(cudaStreamSynchronize(0));
+    cudaStream_t s_in = ctx->pipe_stream[0], s_k = ctx->pipe_stream[1];
+    B2G_CUDA(cudaMemcpyAsync(dp, pts, (size_t)M * 16, cudaMemcpyHostToDevice, s_k));
+    B2G_CUDA(cudaMemsetAsync(dk, 0, 16, s_k));
+    // Sample sets in two chunks: the first is one full wave of the scoring kernel (2 CTAs per SM x FAST_T x FAST_THREADS
+    // hypotheses), the rest crosses the link while it is solved and scored (the keys accumulate).  Equal or smaller
+    // chunks were measured slower: each one pays its own partial wave and fix-up launches.
+    const long long wave = 2LL * ctx->sm_count * FAST_T * FAST_THREADS;
+    int cut[3] = {0, K, K};
+    int n_chunks = 1;
+    if ((long long)K >= 2 * wave) { cut[1] = (int)wave; n_chunks = 2; }
+    for (int c = 0; c < n_chunks; ++c) {
+        const int kb = cut[c], ke = cut[c + 1];
+        B2G_CUDA(cudaMemcpyAsync(di + (size_t)kb * 4, idx + (size_t)kb * 4, (size_t)(ke - kb) * 16, cudaMemcpyHostToDevice, s_in));
+        B2G_CUDA(cudaEventRecord(ctx->pipe_event[0][c & 1], s_in));
+        B2G_CUDA(cudaStreamWaitEvent(s_k, ctx->pipe_event[0][c & 1], 0));
+        if ((rc = search(ctx, dp, M, di, kb, ke, K, 1, th, thr, method, dk, dc, s_k))) return rc;
+    }
+    if ((rc = launch_finish(ctx, dp, M, di, K, 1, dk, th, method, dr, dm, s_k))) return rc;
+    double res[32];
+    B2G_CUDA(cudaMemcpyAsync(res, dr, sizeof res, cudaMemcpyDeviceToHost, s_k));
+    if (out_mask) B2G_CUDA(cudaMemcpyAsync(out_mask, dm, (size_t)M, cudaMemcpyDeviceToHost, s_k));
+    if (out_counts) B2G_CUDA(cudaMemcpyAsync(out_counts, dc, (size_t)K * 4, cudaMemcpyDeviceToHost, s_k));
+    if (out_last_count) B2G_CUDA(cudaMemcpyAsync(out_last_count, dc + (K - 1), 4, cudaMemcpyDeviceToHost, s_k));
+    B2G_CUDA(cudaStreamSynchronize(s_k));
     if (out_winner) *out_winner = (int32_t)res[0];
     if (out_count) *out_count = (int32_t)res[1];
     if (out_H_best) for (int j = 0; j < 9; ++j) out_H_best[j] = (float)res[3 + j];
@@ -808,12 +839,8 @@ int b200geo_warp_batch_host(b200geo_ctx *ctx, const void *src_host, void *dst_ho
     if (n_jobs == 0) return B200GEO_OK;
     if (chunk_jobs <= 0) chunk_jobs = 8;
     if (chunk_jobs > n_jobs) chunk_jobs = n_jobs;
-    if (!ctx->pipe_ready) {
-        for (int i = 0; i < 3; ++i) B2G_CUDA(cudaStreamCreateWithFlags(&ctx->pipe_stream[i], cudaStreamNonBlocking));
-        for (int i = 0; i < 3; ++i)
-            for (int b = 0; b < 2; ++b) B2G_CUDA(cudaEventCreateWithFlags(&ctx->pipe_event[i][b], cudaEventDisableTiming));
-        ctx->pipe_ready = 1;
-    }
+    int prc;
+    if ((prc = ensure_pipe(ctx))) return prc;
     cudaStream_t s_in = ctx->pipe_stream[0], s_k = ctx->pipe_stream[1], s_out = ctx->pipe_stream[2];
     // device images of one chunk are packed back to back (256-byte aligned); jobs are rebased onto them
     const int n_chunks = (n_jobs + chunk_jobs - 1) / chunk_jobs;

@@ -166,10 +166,12 @@ class RANSAC(object):
         mask = np.empty(mx, np.uint8)
         winner = np.zeros(1, np.int32)
         count = np.zeros(1, np.int32)
-        counts = np.empty(k, np.int32)
+        counts = np.empty(k, np.int32) if return_details else None       # K values back only when asked for
+        last_count = np.zeros(1, np.int32)
         rc = ctx.lib.b200geo_ransac_host(ctx.handle, _cabi.ptr(rows), mx, _cabi.ptr(idx), k, float(np.float32(self.th)),
                                          float(d + self.n), _cabi.METHODS[method], _cabi.ptr(H_best), _cabi.ptr(H),
-                                         _cabi.ptr(mask), _cabi.ptr(winner), _cabi.ptr(count), _cabi.ptr(counts))
+                                         _cabi.ptr(mask), _cabi.ptr(winner), _cabi.ptr(count),
+                                         _cabi.ptr(counts) if counts is not None else None, _cabi.ptr(last_count))
         if rc == _cabi.ERR_NOMODEL:
             # the reference reaches np.where(None) here (ransac.py:206)
             raise ValueError("RANSAC: no hypothesis has any inlier (" + _cabi.last_error() + ")")
@@ -177,8 +179,9 @@ class RANSAC(object):
         w = int(winner[0])
         totalfitLen = np.int64(count[0])
         # the reference's warning tests the LAST evaluated iteration's count (ransac.py:203-204)
-        last = w if counts[w] >= (d + self.n) else k - 1
-        if counts[last] < (d + self.n):
+        # (count[0] is the winner's count; if it met the threshold the loop broke there, else it ran to sample set k-1)
+        last_cnt = int(count[0]) if count[0] >= (d + self.n) else int(last_count[0])
+        if last_cnt < (d + self.n):
             print("Warning:: fitting model does not exceed required threshold %d vs %d" % (totalfitLen, d + self.n))
         inliers = np.where(mask.astype(bool))
         DEBUG("Fitting final model using all inliers")
