@@ -402,8 +402,12 @@ int launch_warp(b200geo_ctx *ctx, const void *src, void *dst, const b200geo_warp
         if ((rc = ensure_stats(ctx, st, &stats))) return rc;
         const int tiles_x = (max_ow + WF_TW - 1) / WF_TW, tiles_y = (max_oh + WF_TH - 1) / WF_TH;
         if (tiles_y > 65535) return fail(B200GEO_ERR_ARG, "output too tall for one launch%s%s");
-        WfDesc *descs;
-        if ((rc = scratch(ctx, S_TILES, sizeof(WfDesc) * (size_t)tiles_x * tiles_y * n_jobs, (void **)&descs))) return rc;
+        // tile records: 64-byte descriptors for the one-CTA-per-tile kernel, 192-byte pipeline records for the persistent one
+        const size_t tile_bytes = ctx->warp_variant == 1 ? sizeof(WfDesc) : sizeof(WpTile);
+        void *tile_mem;
+        if ((rc = scratch(ctx, S_TILES, tile_bytes * (size_t)tiles_x * tiles_y * n_jobs, &tile_mem))) return rc;
+        WfDesc *descs = (WfDesc *)tile_mem;
+        WpTile *tiles = (WpTile *)tile_mem;
         dim3 sgrid((tiles_x + 31) / 32, (tiles_y + 7) / 8, n_jobs), sblock(32, 8);
         const uint8_t *s8 = (const uint8_t *)src;
         uint8_t *d8 = (uint8_t *)dst;
@@ -427,8 +431,13 @@ int launch_warp(b200geo_ctx *ctx, const void *src, void *dst, const b200geo_warp
                     sampler, (const void *)layout, use_tmap, ctx->tmap_encode);
         // use_tmap: 0 no tensor map, 2 the source as a 2-D array, 3 as (row_bytes x image_rows x images)
         const WfTma tma = {use_tmap ? (long long)layout->pitch : 0LL, use_tmap == 3 ? (int)layout->image_rows : 0, use_tmap == 3 ? (int)layout->row_bytes : 0};
-        if (sampler == B200GEO_BILINEAR) warp_setup_kernel<1><<<sgrid, sblock, 0, st>>>(jobs_dev, s8, tma, tiles_x, tiles_y, descs);
-        else warp_setup_kernel<0><<<sgrid, sblock, 0, st>>>(jobs_dev, s8, tma, tiles_x, tiles_y, descs);
+        if (ctx->warp_variant == 1) {
+            if (sampler == B200GEO_BILINEAR) warp_setup_kernel<1><<<sgrid, sblock, 0, st>>>(jobs_dev, s8, tma, tiles_x, tiles_y, descs);
+            else warp_setup_kernel<0><<<sgrid, sblock, 0, st>>>(jobs_dev, s8, tma, tiles_x, tiles_y, descs);
+        } else {
+            if (sampler == B200GEO_BILINEAR) warp_tile_setup_kernel<1><<<sgrid, sblock, 0, st>>>(jobs_dev, s8, d8, tma, use_tmap, tiles_x, tiles_y, tiles);
+            else warp_tile_setup_kernel<0><<<sgrid, sblock, 0, st>>>(jobs_dev, s8, d8, tma, use_tmap, tiles_x, tiles_y, tiles);
+        }
         B2G_CHECK_LAUNCH(ctx);
         if (ctx->warp_variant == 1) {
             // one CTA per tile (kept for comparison)
@@ -449,9 +458,9 @@ int launch_warp(b200geo_ctx *ctx, const void *src, void *dst, const b200geo_warp
             if (ctas > (long long)(FIX_HDR / sizeof(unsigned))) ctas = FIX_HDR / sizeof(unsigned);
             n_seg = (unsigned)ctas; seg_cap = fix_cap / n_seg;
             if (sampler == B200GEO_BILINEAR)
-                warp_pipe_kernel<1><<<(unsigned)ctas, WP_THREADS, sizeof(WpSmem), st>>>(s8, d8, jobs_dev, descs, (int)n_tiles, tiles_x, tiles_y, stats + 2, ctx->tmap, use_tmap, tma.image_rows, fix_list, fix_count, seg_cap, tile_counter);
+                warp_pipe_kernel<1><<<(unsigned)ctas, WP_THREADS, sizeof(WpSmem), st>>>(s8, d8, jobs_dev, tiles, (int)n_tiles, tiles_x, tiles_y, stats + 2, ctx->tmap, use_tmap, tma.image_rows, fix_list, fix_count, seg_cap, tile_counter);
             else
-                warp_pipe_kernel<0><<<(unsigned)ctas, WP_THREADS, sizeof(WpSmem), st>>>(s8, d8, jobs_dev, descs, (int)n_tiles, tiles_x, tiles_y, stats + 2, ctx->tmap, use_tmap, tma.image_rows, fix_list, fix_count, seg_cap, tile_counter);
+                warp_pipe_kernel<0><<<(unsigned)ctas, WP_THREADS, sizeof(WpSmem), st>>>(s8, d8, jobs_dev, tiles, (int)n_tiles, tiles_x, tiles_y, stats + 2, ctx->tmap, use_tmap, tma.image_rows, fix_list, fix_count, seg_cap, tile_counter);
         }
         B2G_CHECK_LAUNCH(ctx);
         const dim3 fgrid(n_seg == 1 ? 2 * ctx->sm_count : 2, n_seg);

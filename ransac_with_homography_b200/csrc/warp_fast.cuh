@@ -941,23 +941,32 @@ constexpr int WP_RAW_BYTES = WF_TMA_BOX_W * WF_TMA_BOX_H + B2G_RAW_SLACK;   // o
 constexpr int WP_OCC = B2G_WP_OCC;    // CTAs per SM (shared memory: 2 x raw 14 KB + 2 x entries 32 KB + output 8 KB)
 constexpr int WP_THREADS = WF_THREADS + 32;
 
+// One tile of the persistent kernel: written to global memory by warp_tile_setup_kernel (192 bytes per tile), copied
+// into a shared-memory ring slot by the producer, which only adds the addresses that depend on the pipeline stage.
 struct __align__(16) WpTile {
     WfDesc T;
     const uint8_t *src;      // image base (job offset applied)
     const uint8_t *a0;       // address of source pixel (ay0, ax0)
     uint8_t *dst;            // output base of the job
+    uint8_t *dst_tile;       // address of the tile's first output byte
     long long src_pitch, dst_pitch;
-    int iw, ih, c0, r0, tw, th, jz;
+    int iw, ih, c0, r0;
+    int tw, th, jz, img;     // img: index of the job's image in the 3-D tensor map
     uint32_t RB;             // bytes per raw row in shared memory (multiple of 16)
     int staged, bulk;
-    int direct;              // full tile on the unrolled loop, stored straight to global memory
     int tma;                 // raw rows arrive as one tensor copy: row stride WF_TMA_BOX_W, one phase
-    // per-tile constants every consumer thread needs, computed once by the producer
-    uint8_t *dst_tile;       // address of the tile's first output byte
-    uint32_t sm_base, sm_P4; // entry (x, y) relative to the anchor lives at sm_base + y * sm_P4 + 4 x (plane 0)
-    uint32_t cv_a0, cv_D, cv_dst;   // tensor-copy tiles: chunk t = i * chunks + k is read at cv_a0 + 12 t + i * cv_D, written at cv_dst + 16 t
+    int direct;              // full tile on the unrolled loop, stored straight to global memory
+    int tma_x;               // tensor copy: first byte column of the box (multiple of 16, may be negative)
+    // entry (x, y) relative to the anchor lives at sm_base + y * sm_P4 + 4 x (plane 0); set-up leaves the offset
+    // relative to the entries buffer in sm_base, the producer adds the buffer's address
+    uint32_t sm_base, sm_P4;
+    // tensor-copy tiles: chunk t = i * chunks + k is read at cv_a0 + 12 t + i * cv_D, written at cv_dst + 16 t
+    // (set-up leaves the row phase in cv_a0; the producer adds the raw stage's address and sets cv_dst)
+    uint32_t cv_a0, cv_D, cv_dst;
     int cv_total;            // chunks to convert (0 unless tma)
 };
+static_assert(sizeof(WpTile) == 192, "WpTile is copied as twelve 16-byte words");
+constexpr int WP_TILE_WORDS = sizeof(WpTile) / 16;
 
 #ifndef B2G_STAGES
 #define B2G_STAGES 2
@@ -1094,12 +1103,75 @@ __device__ __noinline__ void wp_convert_cold(const WpTile &W, uint32_t s_raw, ui
 }
 
 // Grid: min(n_tiles, SMs * WP_OCC) CTAs of WP_THREADS; dynamic shared memory sizeof(WpSmem).
+// Grid: (ceil(tiles_x / 32), ceil(tiles_y / 8), n_jobs), block (32, 8): one thread per tile.  The whole tile record
+// (everything that does not depend on the pipeline stage) is prepared here, so that the producer warp of the
+// persistent kernel does no address arithmetic, divisions or job look-ups: measured, it had become the slowest warp.
+template <int BILINEAR>
+__global__ void __launch_bounds__(256)
+warp_tile_setup_kernel(const b200geo_warp_job *__restrict__ jobs, const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst_base,
+                       const WfTma tma, int use_tmap, int tiles_x, int tiles_y, WpTile *__restrict__ tiles)
+{
+    const int tx = blockIdx.x * 32 + threadIdx.x, ty = blockIdx.y * 8 + threadIdx.y;
+    if (tx >= tiles_x || ty >= tiles_y) return;
+    const b200geo_warp_job &J = jobs[blockIdx.z];
+    WpTile W;
+    {
+        uint4 *z = reinterpret_cast<uint4 *>(&W);
+#pragma unroll
+        for (int i = 0; i < WP_TILE_WORDS; ++i) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    const int c0 = tx * WF_TW, r0 = ty * WF_TH;
+    if (c0 >= J.ow || r0 >= J.oh) {
+        W.T.mode = WF_EMPTY;
+    } else {
+        wf_setup<BILINEAR>(J, c0, r0, min(WF_TW, J.ow - c0), min(WF_TH, J.oh - r0), tma, W.T);
+        const int mode = W.T.mode & 0xFF;
+        const int P = W.T.P, rows = W.T.rows;
+        const uint8_t *src = src_base + J.src_offset;
+        uint8_t *dstj = dst_base + J.dst_offset;
+        const int ay0 = W.T.yc + W.T.oy, ax0 = W.T.xc + W.T.ox;
+        const uint8_t *a0 = src + (long long)ay0 * J.src_pitch + 3LL * ax0;
+        const uint32_t RB = (uint32_t)(15 + 3 * (P + 1) + 15) & ~15u;
+        const bool staged = mode == WF_INTERIOR || mode == WF_BORDER;
+        const bool tm = use_tmap && staged && (W.T.mode & WF_FLAG_TMA);
+        bool bulk = tm;
+        if (!tm && staged && !(W.T.mode & WF_FLAG_TMA) && (W.T.mode & WF_FLAG_UNCHECKED) && (uint32_t)rows * RB <= (uint32_t)WP_RAW_BYTES) {
+            const size_t pitch = (size_t)J.src_pitch;
+            const size_t lo = (size_t)a0 & ~(size_t)15;
+            const size_t hi = ((size_t)a0 + (size_t)(rows - 1) * pitch) & ~(size_t)15;
+            const size_t img_end = (size_t)src + (size_t)(J.ih - 1) * pitch + 3 * (size_t)J.iw;
+            bulk = lo >= (size_t)src && hi + RB <= img_end;
+        }
+        W.src = src; W.a0 = a0; W.dst = dstj;
+        W.src_pitch = J.src_pitch; W.dst_pitch = J.dst_pitch;
+        W.iw = J.iw; W.ih = J.ih; W.c0 = c0; W.r0 = r0;
+        W.tw = min(WF_TW, J.ow - c0); W.th = min(WF_TH, J.oh - r0);
+        W.jz = (int)blockIdx.z;
+        W.img = (tma.image_rows > 0 && J.src_pitch > 0) ? (int)(J.src_offset / (J.src_pitch * tma.image_rows)) : 0;
+        W.RB = tm ? (uint32_t)WF_TMA_BOX_W : RB; W.staged = staged; W.bulk = bulk; W.tma = tm;
+        uint8_t *const dt = dstj + (long long)r0 * J.dst_pitch + 3LL * c0;
+        W.dst_tile = dt;
+        W.direct = (mode == WF_INTERIOR || (BILINEAR && B2G_SWP && mode == WF_BORDER)) && W.tw == WF_TW && W.th == WF_TH &&
+                   ((((size_t)dt) | (size_t)J.dst_pitch) & 3) == 0;
+        W.tma_x = (3 * ax0) & ~15;
+        W.sm_P4 = (uint32_t)P * 4u;
+        W.sm_base = wf_entry_base(W.T, 0u);
+        W.cv_total = tm ? rows * (P >> 2) : 0;
+        W.cv_D = (uint32_t)WF_TMA_BOX_W - 12u * (uint32_t)(P >> 2);
+        W.cv_a0 = (uint32_t)(size_t)a0 & 15u;
+    }
+    const uint4 *sv = reinterpret_cast<const uint4 *>(&W);
+    uint4 *d = reinterpret_cast<uint4 *>(tiles + ((size_t)blockIdx.z * tiles_y + ty) * tiles_x + tx);
+#pragma unroll
+    for (int i = 0; i < WP_TILE_WORDS; ++i) d[i] = sv[i];
+}
+
 // Registers: 9 warps are allocated as 10 (pairs), so two CTAs per SM leave 65536 / (2 x 320) = 102 -> 96 per
 // thread, which is what __launch_bounds__ makes ptxas use (__maxnreg__(112) was measured: one CTA per SM).
 template <int BILINEAR>
 __global__ void __launch_bounds__(WP_THREADS, WP_OCC)
 warp_pipe_kernel(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst_base,
-                 const b200geo_warp_job *__restrict__ jobs, const WfDesc *__restrict__ descs,
+                 const b200geo_warp_job *__restrict__ jobs, const WpTile *__restrict__ tiles,
                  int n_tiles, int tiles_x, int tiles_y, unsigned long long *__restrict__ stats,
                  const __grid_constant__ CUtensorMap tmap, int use_tmap, int tma_image_rows,
                  WfFixEntry *__restrict__ fix_list, unsigned *__restrict__ fix_counts, unsigned seg_cap, unsigned *__restrict__ tile_counter)
@@ -1133,40 +1205,32 @@ warp_pipe_kernel(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst
     if (wrp == WF_THREADS / 32) {
         // ---------------------------------------------------------------- producer warp
         // Tiles are claimed dynamically: the first one is blockIdx.x, every further one gridDim.x + a ticket
-        // from a global counter, drawn two tiles ahead (the descriptor prefetch distance).  Static striding
+        // from a global counter, drawn three tiles ahead (the record prefetch distance is two).  Static striding
         // left the CTAs 10 % apart at the end (BORDER / SPLIT / SLOW tiles cost several times a direct one).
-        const int tpj = tiles_x * tiles_y;
         auto claim = [&]() {
             int v = 0;
             if (lane == 0) v = (int)atomicAdd(tile_counter, 1u);
             return __shfl_sync(0xffffffffu, v, 0) + (int)gridDim.x;
         };
+        const uint4 *gt = reinterpret_cast<const uint4 *>(tiles);
         int t_cur = first, t_n1 = claim(), t_n2 = claim();
-        uint4 nd0 = make_uint4(0u, 0u, 0u, 0u), nd1 = nd0;      // lanes 0..3: descriptors of the next two tiles
-        if (lane < 4) {
-            nd0 = __ldg(reinterpret_cast<const uint4 *>(descs + t_cur) + lane);
-            if (t_n1 < n_tiles) nd1 = __ldg(reinterpret_cast<const uint4 *>(descs + t_n1) + lane);
+        uint4 nd0 = make_uint4(0u, 0u, 0u, 0u), nd1 = nd0;      // lanes 0..11: records of the next two tiles
+        if (lane < WP_TILE_WORDS) {
+            nd0 = __ldg(gt + (size_t)t_cur * WP_TILE_WORDS + lane);
+            if (t_n1 < n_tiles) nd1 = __ldg(gt + (size_t)t_n1 * WP_TILE_WORDS + lane);
         }
-        // geometry of the current job, reloaded only when the job changes
-        int cur = -1, Jow = 0, Joh = 0, Jiw = 0, Jih = 0, Jimg = 0;
-        long long Jsp = 0, Jdp = 0;
-        const uint8_t *src = nullptr;
-        uint8_t *dstj = nullptr;
         int it = 0;
 #if B2G_PROF
-        long long prof_wait = 0;
+        long long prof_wait = 0, prof_claim = 0, prof_build = 0;
         const long long prof_t0 = clock64();
 #endif
         for (;; ++it) {
+            // the ticket of the tile three iterations ahead: drawn here, read at the end of the iteration, so that
+            // the atomic's round trip is hidden
+            int ticket = 0;
+            if (lane == 0) ticket = (int)atomicAdd(tile_counter, 1u);
             const int b = it % WP_STAGES, use = it / WP_STAGES;
             const uint32_t s_full = s_full0 + 8u * b, s_raw = s_raw0 + (uint32_t)WP_RAW_BYTES * b;
-            const int jz = t_cur / tpj, trem = t_cur - jz * tpj, ty = trem / tiles_x, tx = trem - ty * tiles_x;
-            if (t_cur < n_tiles && jz != cur) {
-                const b200geo_warp_job &J = jobs[jz];
-                cur = jz; Jow = J.ow; Joh = J.oh; Jiw = J.iw; Jih = J.ih; Jsp = J.src_pitch; Jdp = J.dst_pitch;
-                src = src_base + J.src_offset; dstj = dst_base + J.dst_offset;
-                if (tma_image_rows > 0 && Jsp > 0) Jimg = (int)(J.src_offset / (Jsp * tma_image_rows));
-            }
             WP_T(tp0);
             if (use >= 1) wp_mbar_wait(s_empty0 + 8u * b, (uint32_t)(use - 1) & 1u);
             WP_T(tp1);
@@ -1180,59 +1244,39 @@ warp_pipe_kernel(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst
                 }
                 break;
             }
-            if (lane < 4) reinterpret_cast<uint4 *>(&W.T)[lane] = nd0;
+            if (lane < WP_TILE_WORDS) reinterpret_cast<uint4 *>(&W)[lane] = nd0;
             nd0 = nd1;
-            if (lane < 4 && t_n2 < n_tiles) nd1 = __ldg(reinterpret_cast<const uint4 *>(descs + t_n2) + lane);
+            if (lane < WP_TILE_WORDS && t_n2 < n_tiles) nd1 = __ldg(gt + (size_t)t_n2 * WP_TILE_WORDS + lane);
             __syncwarp();
-            const int mode = W.T.mode & 0xFF;
-            const int P = W.T.P, rows = W.T.rows;
-            const size_t pitch = (size_t)Jsp;
-            const int ay0 = W.T.yc + W.T.oy, ax0 = W.T.xc + W.T.ox;
-            const uint8_t *a0 = src + (long long)ay0 * (long long)pitch + 3LL * ax0;
-            const uint32_t RB = (uint32_t)(15 + 3 * (P + 1) + 15) & ~15u;
-            const bool staged = mode == WF_INTERIOR || mode == WF_BORDER;
-            const bool tma = use_tmap && staged && (W.T.mode & WF_FLAG_TMA);
-            bool bulk = tma;
-            if (!tma && staged && !(W.T.mode & WF_FLAG_TMA) && (W.T.mode & WF_FLAG_UNCHECKED) && (uint32_t)rows * RB <= (uint32_t)WP_RAW_BYTES) {
-                const size_t lo = (size_t)a0 & ~(size_t)15;
-                const size_t hi = ((size_t)a0 + (size_t)(rows - 1) * pitch) & ~(size_t)15;
-                const size_t img_end = (size_t)src + (size_t)(Jih - 1) * pitch + 3 * (size_t)Jiw;
-                bulk = lo >= (size_t)src && hi + RB <= img_end;
-            }
+            const bool tma = W.tma != 0, bulk = W.bulk != 0;
+            const int rows = W.T.rows;
+            const uint32_t RB = W.RB;
+            const uint8_t *a0 = W.a0;
+            const size_t pitch = (size_t)W.src_pitch;
             if (lane == 0) {
-                W.src = src; W.a0 = a0; W.dst = dstj;
-                W.src_pitch = Jsp; W.dst_pitch = Jdp;
-                W.iw = Jiw; W.ih = Jih; W.c0 = tx * WF_TW; W.r0 = ty * WF_TH;
-                W.tw = min(WF_TW, Jow - tx * WF_TW); W.th = min(WF_TH, Joh - ty * WF_TH);
-                W.jz = jz; W.RB = tma ? (uint32_t)WF_TMA_BOX_W : RB; W.staged = staged; W.bulk = bulk; W.tma = tma;
-                {
-                    const uint32_t pairs_it = s_pairs0 + PAIRS_BYTES * (uint32_t)(it & (B2G_PAIRS - 1));
-                    uint8_t *const dt = dstj + (long long)W.r0 * Jdp + 3LL * W.c0;
-                    W.dst_tile = dt;
-                    W.direct = (mode == WF_INTERIOR || (BILINEAR && B2G_SWP && mode == WF_BORDER)) && W.tw == WF_TW && W.th == WF_TH &&
-                               ((((size_t)dt) | (size_t)Jdp) & 3) == 0;
-                    W.sm_P4 = (uint32_t)P * 4u;
-                    W.sm_base = wf_entry_base(W.T, pairs_it);
-                    W.cv_total = tma ? rows * (P >> 2) : 0;
-                    W.cv_D = (uint32_t)WF_TMA_BOX_W - 12u * (uint32_t)(P >> 2);
-                    W.cv_a0 = s_raw + ((uint32_t)(size_t)a0 & 15u);
-                    W.cv_dst = pairs_it;
-                }
+                const uint32_t pairs_it = s_pairs0 + PAIRS_BYTES * (uint32_t)(it & (B2G_PAIRS - 1));
+                W.sm_base += pairs_it;
+                W.cv_a0 += s_raw;
+                W.cv_dst = pairs_it;
                 if (tma && (B2G_DIAG & 8)) wp_mbar_arrive(s_full);
                 else if (tma) {
                     wp_mbar_expect_tx(s_full, (uint32_t)(WF_TMA_BOX_W * WF_TMA_BOX_H));
                     if (tma_image_rows > 0)
                         asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                                     ::"r"(s_raw), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"((3 * ax0) & ~15), "r"(W.T.srow), "r"(Jimg), "r"(s_full) : "memory");
+                                     ::"r"(s_raw), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(W.tma_x), "r"(W.T.srow), "r"(W.img), "r"(s_full) : "memory");
                     else
                         asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                                     ::"r"(s_raw), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"((3 * ax0) & ~15), "r"(W.T.srow), "r"(s_full) : "memory");
+                                     ::"r"(s_raw), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(W.tma_x), "r"(W.T.srow), "r"(s_full) : "memory");
                 } else if (bulk) wp_mbar_expect_tx(s_full, (uint32_t)rows * RB);
                 else wp_mbar_arrive(s_full);
             }
+            WP_T(tp2);
             // next tile of this CTA
-            t_cur = t_n1; t_n1 = t_n2; t_n2 = claim();
+            t_cur = t_n1; t_n1 = t_n2; t_n2 = __shfl_sync(0xffffffffu, ticket, 0) + (int)gridDim.x;
             __syncwarp();
+            WP_T(tp3);
+            WP_ACC(prof_claim, tp2, tp3);
+            WP_ACC(prof_build, tp1, tp2);
             if (bulk && !tma)
                 for (int r = lane; r < rows; r += 32) {
                     const size_t ar = ((size_t)a0 + (size_t)r * pitch) & ~(size_t)15;
@@ -1241,8 +1285,8 @@ warp_pipe_kernel(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst
         }
 #if B2G_PROF
         if (lane == 0 && (blockIdx.x % 97) == 0)
-            printf("cta %3d producer: tiles %d total %lld wait_empty %lld work/tile %lld\n", (int)blockIdx.x, it, clock64() - prof_t0, prof_wait,
-                   (clock64() - prof_t0 - prof_wait) / (it ? it : 1));
+            printf("cta %3d producer: tiles %d total %lld wait_empty %lld work/tile %lld build/tile %lld claim/tile %lld\n", (int)blockIdx.x, it,
+                   clock64() - prof_t0, prof_wait, (clock64() - prof_t0 - prof_wait) / (it ? it : 1), prof_build / (it ? it : 1), prof_claim / (it ? it : 1));
 #endif
         return;
     }
