@@ -37,9 +37,9 @@ sys.path.insert(0, ROOT)
 
 FLOP_PER_PAIR = 25.0          # algorithmic FLOP per hypothesis x correspondence, fwd loss
 # DRAM traffic of the dominant kernels from the committed ncu --set full captures (dram__bytes_read + write):
-#   warp_pipe_kernel, profiles/r01_warp_pipe_v14.ncu-rep: 393.2 MB + 362.5 MB for 64 frames 1080p = 5.70 B per output pixel
+#   warp_pipe_kernel, profiles/r01_warp_pipe_v15.ncu-rep: 400.0 MB + 364.6 MB for 64 frames 1080p = 5.76 B per output pixel
 #   score_fast_kernel, profiles/r01_score_fast_K200k.ncu-rep: 8.6 MB for 200k x 20k pairs (FP32-bound: traffic is incidental)
-WARP_TRAFFIC_B_PER_PIXEL = (393.238016e6 + 362.524672e6) / (64 * 1080 * 1920)
+WARP_TRAFFIC_B_PER_PIXEL = (399.999232e6 + 364.638208e6) / (64 * 1080 * 1920)
 SCORE_TRAFFIC_B_PER_PAIR = 8.584448e6 / (200000 * 20000)
 C3 = dict(M=20000, K=1_000_000, th=3.0, d=99.0, seed=1, idx_seed=0)
 C4 = dict(frames=4096, h=1080, w=1920, jitter=0.05)
@@ -429,7 +429,7 @@ def bench_warp(torch, dist, rank, world, args, ctx, peaks, local_gpu):
     k_avg_s = ms / args.steps / 1e3
     roof = {"bound": "hbm", "kernel": "warp_pipe_kernel (K4, bilinear u8 RGB; + warp_setup_kernel, <1% of the step)", "achieved": bytes_per_launch / k_avg_s / 1e9, "peak": peaks["hbm_gbs"],
             "unit": "GB/s", "frac": bytes_per_launch / k_avg_s / 1e9 / peaks["hbm_gbs"], "traffic": WARP_TRAFFIC_B_PER_PIXEL * n * h * w,
-            "traffic_source": "ncu dram bytes per output pixel (profiles/r01_warp_pipe_v14.ncu-rep, 64 frames) x pixels of this launch",
+            "traffic_source": "ncu dram bytes per output pixel (profiles/r01_warp_pipe_v15.ncu-rep, 64 frames) x pixels of this launch",
             "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peaks['source']})", "algorithmic_bytes_per_pixel": 6.0,
             "kernel_ms": k_avg_s * 1e3, "kernel_share_of_step": 1.0}
 
@@ -452,7 +452,7 @@ def bench_warp(torch, dist, rank, world, args, ctx, peaks, local_gpu):
     rec = {"metric": "warp_gpix_per_s", "value": value, "unit": "Gpix/s", "ms_per_step": ms / args.steps,
            "dtype": "u8 pixels; f64 per-tile set-up, f32 tile-relative coordinates, 16.16 integer blend",
            "config": {"workload": "C4 batched backward warp: 4096 synthetic 1920x1080 RGB uint8 frames, per-frame random homography "
-                                  "(corner jitter +-5%), bilinear, fixed 1080x1920 output (wrapPerspectiveScan grid), two launches per step (tile set-up + warp)",
+                                  "(corner jitter +-5%), bilinear, fixed 1080x1920 output (wrapPerspectiveScan grid), three launches per step (tile set-up, warp, float64 fix-up)",
                       "sharding": f"frames over {world} rank(s), no communication",
                       "l2": "inputs (25.5 GB per 4096 frames) are larger than L2"},
            "roofline": roof,
