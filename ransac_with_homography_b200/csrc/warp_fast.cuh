@@ -59,7 +59,7 @@ constexpr int WF_TW = 64;             // output tile width  (pixels)
 #define B2G_BOX_H 48
 #endif
 constexpr int WF_TH = B2G_TH;         // output tile height (multiple of 8)
-static_assert(B2G_TH % 8 == 0 && B2G_TH >= 16 && B2G_TH <= 64, "tile height");
+static_assert(B2G_TH % 8 == 0 && B2G_TH >= 16 && B2G_TH <= 96, "tile height");
 constexpr int WF_THREADS = 256;
 constexpr int WF_SRC_ENTRIES = B2G_ENTRIES;  // staged source tile capacity: two planes of 16 KB (one 32-bit word per entry and plane)
 constexpr uint32_t WF_PLANE = WF_SRC_ENTRIES * 4u;   // byte offset of plane 1 (B pairs) from plane 0 (R/G pairs)
@@ -872,8 +872,11 @@ warp_fast_kernel(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst
                  const b200geo_warp_job *__restrict__ jobs, const WfDesc *__restrict__ descs,
                  unsigned long long *__restrict__ stats, WfFixEntry *__restrict__ fix_list, unsigned *__restrict__ fix_count, unsigned fix_cap)
 {
-    __shared__ __align__(16) uint32_t s_src_mem[2 * WF_SRC_ENTRIES];
-    __shared__ __align__(16) uint32_t s_out_mem[WF_TW * WF_TH];
+    // (static shared memory: the comparison kernel exists only for tile shapes whose buffers fit 48 KB)
+    constexpr bool FITS = (2 * WF_SRC_ENTRIES + WF_TW * WF_TH) * 4 <= 47 * 1024;
+    __shared__ __align__(16) uint32_t s_src_mem[FITS ? 2 * WF_SRC_ENTRIES : 4];
+    __shared__ __align__(16) uint32_t s_out_mem[FITS ? WF_TW * WF_TH : 4];
+    if (!FITS) { __trap(); }
 
     const WfDesc &T = descs[((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x];
     const int mode = T.mode & 0xFF;
