@@ -654,8 +654,9 @@ __device__ __forceinline__ void wf_full_bilinear(const WfDesc &T, const b200geo_
         __syncwarp();                                   // the word stores of every lane precede the byte stores below
         if (amb) {
 #pragma unroll 1
-            for (int k = 0; k < R * G; ++k)
-                if (amb & (1u << k)) {
+            for (uint32_t rest = amb; rest; rest &= rest - 1u) {
+                const int k = __ffs((int)rest) - 1;
+                {
                     const int col = lane + 32 * (k % G), row = wrp + 8 * (k / G);
                     if (!wf_defer(fix, c0 + col, r0 + row)) {
                         const uint32_t v = wf_exact_px<1>(J, src, c0 + col, r0 + row);
@@ -668,6 +669,7 @@ __device__ __forceinline__ void wf_full_bilinear(const WfDesc &T, const b200geo_
                         }
                     }
                 }
+            }
         }
     }
 }
@@ -676,7 +678,10 @@ __device__ __forceinline__ void wf_full_bilinear(const WfDesc &T, const b200geo_
 // like the bilinear loop (the fetches of row p + 1 precede the stores of row p).  Every pixel is stored
 // speculatively; the ones within `band` of a rounding boundary are pushed to the fix-up list
 // (warp_fixup_kernel overwrites them in float64 after this kernel) or, if the list is full, settled here.
-template <int DUMMY = 0>
+// BORDER = 1: the tile crosses the mask boundary (rounded index outside [0, bw-1] x [0, bh-1] -> 0, homography.py:109-116):
+// decided on the float32 coordinates where they are further than `band` from the boundary, indices clamped into the image
+// (which also performs the truncation toward zero of (-1, 0) -> 0), masked pixels stored as 0, the rest deferred.
+template <int BORDER>
 __device__ __forceinline__ void wf_full_nn_direct(const WfDesc &T, const b200geo_warp_job &J, const uint8_t *__restrict__ src, uint32_t base,
                                                   uint32_t P4, int c0, int r0, unsigned &n_exact, const WfFix &fix, uint8_t *__restrict__ dst_tile,
                                                   size_t dst_pitch)
@@ -692,8 +697,12 @@ __device__ __forceinline__ void wf_full_nn_direct(const WfDesc &T, const b200geo
     uint8_t *gptr = dst_tile + (size_t)wrp * dst_pitch + (size_t)(12 * (lane >> 2) + 4 * (lane & 3));
     const uint32_t B16 = (uint32_t)((int)T.band + 2);
     constexpr int G = WF_TW / 32, R = WF_TH / 8;
+    float lox = 0.f, hix = 0.f, loy = 0.f, hiy = 0.f;
+    if (BORDER) wf_bounds<0>(T.xc, T.yc, J.bw, J.bh, lox, hix, loy, hiy);
+    const float band = T.band;
+    const int xlo = -T.xc, xhi = J.bw - 1 - T.xc, ylo = -T.yc, yhi = J.bh - 1 - T.yc;
     uint2 e[2][G];
-    uint32_t amb = 0u;
+    uint32_t amb = 0u, inmask = 0u;
     auto fetch = [&](int p, int b) {
         const float2 np_ = p ? __ffma2_rn(B2, make_float2((float)(8 * p), (float)(8 * p)), nb) : nb;
         const float wp = p ? __fmaf_rn(hw, (float)(8 * p), wb) : wb;
@@ -702,11 +711,21 @@ __device__ __forceinline__ void wf_full_nn_direct(const WfDesc &T, const b200geo
             const float2 n2 = hh ? __ffma2_rn(A2, make_float2((float)(32 * hh), (float)(32 * hh)), np_) : np_;
             const float w = hh ? __fmaf_rn(gw, (float)(32 * hh), wp) : wp;
             const float rw = wf_rcp(w);
-            const float2 r = __fmul2_rn(n2, make_float2(rw, rw));
+            float2 r = __fmul2_rn(n2, make_float2(rw, rw));
+            bool in = true;
+            if (BORDER) {
+                in = r.x >= lox + band && r.x <= hix - band && r.y >= loy + band && r.y <= hiy - band;
+                const bool outp = r.x < lox - band || r.x > hix + band || r.y < loy - band || r.y > hiy + band;
+                if (in) inmask |= 1u << (p * G + hh);
+                else if (!outp) amb |= 1u << (p * G + hh);          // also NaN coordinates
+                r.x = fminf(fmaxf(r.x, lox), hix);                  // keeps the conversion below in range (NaN -> lox)
+                r.y = fminf(fmaxf(r.y, loy), hiy);
+            }
             const int hx = __float2int_rd(r.x) + 32768, hy = __float2int_rd(r.y) + 32768;
             const uint32_t fx = (uint32_t)hx & 0xFFFFu, fy = (uint32_t)hy & 0xFFFFu;
-            if (fx - B16 > 65535u - 2u * B16 || fy - B16 > 65535u - 2u * B16) amb |= 1u << (p * G + hh);
-            const int xi = (int)__byte_perm((uint32_t)hx, 0u, 0xBB32), yi = (int)__byte_perm((uint32_t)hy, 0u, 0xBB32);
+            if (in && (fx - B16 > 65535u - 2u * B16 || fy - B16 > 65535u - 2u * B16)) amb |= 1u << (p * G + hh);
+            int xi = (int)__byte_perm((uint32_t)hx, 0u, 0xBB32), yi = (int)__byte_perm((uint32_t)hy, 0u, 0xBB32);
+            if (BORDER) { xi = min(max(xi, xlo), xhi); yi = min(max(yi, ylo), yhi); }
             e[b][hh] = wf_lds_entry((uint32_t)yi * P4 + base + ((uint32_t)xi << 2));
         }
     };
@@ -716,7 +735,8 @@ __device__ __forceinline__ void wf_full_nn_direct(const WfDesc &T, const b200geo
         if (p + 1 < R) fetch(p + 1, (p + 1) & 1);
 #pragma unroll
         for (int hh = 0; hh < G; ++hh) {
-            const uint32_t out = __byte_perm(e[p & 1][hh].x, e[p & 1][hh].y, 0x4420);
+            uint32_t out = __byte_perm(e[p & 1][hh].x, e[p & 1][hh].y, 0x4420);
+            if (BORDER && !(inmask & (1u << (p * G + hh)))) out = 0u;
             const uint32_t nbr = __shfl_down_sync(0xffffffffu, out, 1);
             const uint32_t word = __byte_perm(out, nbr, psel);
             if ((lane & 3) != 3) *reinterpret_cast<uint32_t *>(gptr + 96 * hh) = word;
@@ -727,16 +747,16 @@ __device__ __forceinline__ void wf_full_nn_direct(const WfDesc &T, const b200geo
         __syncwarp();                                   // the speculative word stores of every lane precede the byte stores below
         if (amb) {
 #pragma unroll 1
-            for (int k = 0; k < R * G; ++k)
-                if (amb & (1u << k)) {
-                    const int col = lane + 32 * (k % G), row = wrp + 8 * (k / G);
-                    if (!wf_defer(fix, c0 + col, r0 + row)) {
-                        const uint32_t v = wf_exact_px<0>(J, src, c0 + col, r0 + row);
-                        ++n_exact;
-                        uint8_t *q = dst_tile + (size_t)row * dst_pitch + (size_t)col * 3;
-                        q[0] = (uint8_t)v; q[1] = (uint8_t)(v >> 8); q[2] = (uint8_t)(v >> 16);
-                    }
+            for (uint32_t rest = amb; rest; rest &= rest - 1u) {
+                const int k = __ffs((int)rest) - 1;
+                const int col = lane + 32 * (k % G), row = wrp + 8 * (k / G);
+                if (!wf_defer(fix, c0 + col, r0 + row)) {
+                    const uint32_t v = wf_exact_px<0>(J, src, c0 + col, r0 + row);
+                    ++n_exact;
+                    uint8_t *q = dst_tile + (size_t)row * dst_pitch + (size_t)col * 3;
+                    q[0] = (uint8_t)v; q[1] = (uint8_t)(v >> 8); q[2] = (uint8_t)(v >> 16);
                 }
+            }
         }
     }
 }
@@ -1154,7 +1174,7 @@ warp_tile_setup_kernel(const b200geo_warp_job *__restrict__ jobs, const uint8_t 
         W.RB = tm ? (uint32_t)WF_TMA_BOX_W : RB; W.staged = staged; W.bulk = bulk; W.tma = tm;
         uint8_t *const dt = dstj + (long long)r0 * J.dst_pitch + 3LL * c0;
         W.dst_tile = dt;
-        W.direct = (mode == WF_INTERIOR || (BILINEAR && B2G_SWP && mode == WF_BORDER)) && W.tw == WF_TW && W.th == WF_TH &&
+        W.direct = (mode == WF_INTERIOR || (B2G_SWP && mode == WF_BORDER)) && W.tw == WF_TW && W.th == WF_TH &&
                    ((((size_t)dt) | (size_t)J.dst_pitch) & 3) == 0;
         W.tma_x = (3 * ax0) & ~15;
         W.sm_P4 = (uint32_t)P * 4u;
@@ -1362,7 +1382,10 @@ warp_pipe_kernel(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst
             if (BILINEAR && B2G_SWP) {
                 if (mode == WF_INTERIOR) wf_full_bilinear<0, 1>(W.T, jobs[W.jz], W.src, W.sm_base, W.sm_P4, W.c0, W.r0, n_exact, fix, dst_tile, (size_t)W.dst_pitch);
                 else wf_full_bilinear<1, 1>(W.T, jobs[W.jz], W.src, W.sm_base, W.sm_P4, W.c0, W.r0, n_exact, fix, dst_tile, (size_t)W.dst_pitch);
-            } else if (!BILINEAR && B2G_SWP) wf_full_nn_direct(W.T, jobs[W.jz], W.src, W.sm_base, W.sm_P4, W.c0, W.r0, n_exact, fix, dst_tile, (size_t)W.dst_pitch);
+            } else if (!BILINEAR && B2G_SWP) {
+                if (mode == WF_INTERIOR) wf_full_nn_direct<0>(W.T, jobs[W.jz], W.src, W.sm_base, W.sm_P4, W.c0, W.r0, n_exact, fix, dst_tile, (size_t)W.dst_pitch);
+                else wf_full_nn_direct<1>(W.T, jobs[W.jz], W.src, W.sm_base, W.sm_P4, W.c0, W.r0, n_exact, fix, dst_tile, (size_t)W.dst_pitch);
+            }
             else wf_compute_full<BILINEAR, 1>(W.T, jobs[W.jz], W.src, s_pairs, 0u, W.c0, W.r0, n_exact, fix, dst_tile, (size_t)W.dst_pitch);
             WP_T(tw2);
             WP_ACC(prof_sample, tw1, tw2);
