@@ -1,40 +1,43 @@
 // warp_fast.cuh -- K4 fast path: backward warp of uint8 RGB images to uint8 RGB, bilinear or nn.
 //
 // Same element semantics as warp.cuh (reference homography.py:108-209 + astype(uint8) of :225/:241),
-// organised for throughput.  The output is cut into 64 x 40 tiles (WF_TW x WF_TH); two kernels:
+// organised for throughput.  The output is cut into 64 x 40 tiles (WF_TW x WF_TH).
 //
-// warp_setup_kernel (one THREAD per tile, float64): re-expresses the projective map of the tile
-//   around the tile's centre pixel and an integer anchor (xc, yc) next to the centre's source
-//   position,
+// Set-up (one THREAD per tile, float64; wf_setup): re-expresses the projective map of the tile around
+//   the tile's centre pixel and an integer anchor (xc, yc) next to the centre's source position,
 //       rel_x = x - xc = (nx0 + ax*di + bx*dj) / (1 + gw*di + hw*dj)        (di, dj = pixel - centre)
 //   rounds the nine coefficients to float32 once, bounds the float32 evaluation error of rel
 //   (`band`), maps the four tile corners and classifies the tile: ZERO (wholly masked), INTERIOR
-//   (wholly unmasked), BORDER (per-pixel mask) or SLOW (the bound does not hold: w changes too
-//   much, footprint too large for shared memory, irregular grid, NaN).  64-byte descriptor per tile.
+//   (wholly unmasked), BORDER (per-pixel mask), SPLIT (footprint too large: redone per quadrant) or
+//   SLOW (the bound does not hold: w changes too much, irregular grid, NaN -> float64 per pixel).
+//   warp_tile_setup_kernel writes a complete 192-byte record per tile for the persistent kernel,
+//   warp_setup_kernel the 64-byte descriptor alone for the one-CTA-per-tile comparison kernel.
 //
-// warp_fast_kernel (one CTA per tile):
+// Per tile (warp_pipe_kernel: persistent, warp-specialised, see the comment above it; warp_fast_kernel:
+// one CTA per tile, kept for comparison):
 //   1. staging: the source footprint (bounding box of the four mapped corners -- the image of a
-//      convex quad under a projective map with w > 0 is convex) is copied once from global memory
-//      into shared memory with 32-bit loads, re-laid-out as one 8-byte entry per source pixel x:
-//      (R[x] R[x+1] G[x] G[x+1]) (B[x] B[x+1] . .), i.e. horizontally adjacent taps already paired
-//      for the dot-product instruction.  Pixels outside the image and pixel (0,0) are staged as 0,
-//      which is exactly how the reference's samplers see them.
+//      convex quad under a projective map with w > 0 is convex) arrives in shared memory by one TMA
+//      tensor copy (or per-row bulk copies / plain loads) and is re-laid-out as one paired entry per
+//      source pixel x: plane 0 (R[x] R[x+1] G[x] G[x+1]), plane 1 (B[x] B[x+1] . .), i.e. horizontally
+//      adjacent taps already paired for the dot-product instruction.  Pixels outside the image and
+//      pixel (0,0) are staged as 0, which is exactly how the reference's samplers see them.
 //   2. sampling: every float32 term is tile-local (|di| <= 32, |rel| <= a few hundred), so rel has
 //      an absolute error of ~1e-5..1e-4 px although the image is thousands of pixels wide.  Per
-//      pixel: 3 FFMA + MUFU.RCP + 2 FMUL + 2 F2I give 16.16 fixed-point coordinates, two LDS.64
-//      fetch the four taps, and the blend is integer arithmetic with 16-bit weights that sum to
-//      exactly 65536 (IDP.2A, 2 per channel): flat regions are reproduced exactly and
-//      floor(v / 65536) is the reference's truncating astype(uint8).
-//   3. store: results are staged in shared memory (swizzled, conflict-free) and written with
-//      16-byte vector stores.
+//      pixel: FFMA + FFMA2 + MUFU.RCP + FMUL2 + 2 F2I give 16.16 fixed-point coordinates, four LDS.32
+//      fetch the taps, and the blend is integer arithmetic with 16-bit weights that sum to 65535
+//      plus a bias of 255 (IDP.2A, 2 per channel; see wf_blend): flat regions and integer / dyadic
+//      translations are reproduced exactly and byte 2 of the accumulator is the reference's
+//      truncating astype(uint8).
+//   3. store: full tiles write 96 contiguous bytes per warp and store instruction straight to global
+//      memory (SHFL + PRMT pack); other tiles go through a swizzled shared-memory output stage.
 //
 // Parity: mask decisions (bilinear: x > bw-1 | x < 0 ...; nn: the rounded index) are taken on the
 // float32 coordinates only when they are further than `band` from the decision boundary; pixels
 // inside the band, and every pixel of a SLOW tile, are evaluated by sample_store() in float64
-// exactly as warp_generic_kernel does.  nn output is therefore bit-identical to the reference;
-// bilinear output differs from the reference's float64 blend by < 0.05 grey levels before the
-// truncation, i.e. within +-1 after it (north_star tolerance), identical on flat regions and for
-// integer / dyadic translations.
+// exactly as warp_generic_kernel does (deferred to warp_fixup_kernel).  nn output is therefore
+// bit-identical to the reference; bilinear output differs from the reference's float64 blend by
+// < 0.05 grey levels before the truncation, i.e. within +-1 after it (north_star tolerance),
+// identical on flat regions and for integer / dyadic translations.
 #pragma once
 
 #include "warp.cuh"
