@@ -435,7 +435,7 @@ def bench_warp(torch, dist, rank, world, args, ctx, peaks, local_gpu):
 
     # end to end on a bounded batch: pinned host frames in, pinned host frames out, through the host-buffer entry
     # point b200geo_warp_batch_host (chunked host->device / warp / device->host pipeline inside the library)
-    nb = min(64, n)
+    nb = min(256, n)
     pin_in = torch.empty((nb, h, w, 3), dtype=torch.uint8).pin_memory()
     pin_in.copy_(src[:nb])
     pin_out = torch.empty((nb, h, w, 3), dtype=torch.uint8).pin_memory()
@@ -457,7 +457,7 @@ def bench_warp(torch, dist, rank, world, args, ctx, peaks, local_gpu):
                       "l2": "inputs (25.5 GB per 4096 frames) are larger than L2"},
            "roofline": roof,
            "e2e": {"value": e2e_v, "unit": "Gpix/s", "h2d_bytes_per_step": int(nb * per_frame), "d2h_bytes_per_step": int(nb * per_frame),
-                   "ms_per_step": ems / n_e2e, "how": f"{nb} frames per rank per step: pinned host -> device.warp_host (b200geo_warp_batch_host: 8-frame chunks, "
+                   "ms_per_step": ems / n_e2e, "how": f"{nb} frames per rank per step: pinned host -> device.warp_host (b200geo_warp_batch_host: 16-frame chunks, "
                                                         "copies and kernels overlapped on three streams) -> pinned host"},
            "gpu_launches": int(launches), "clocks": cs.summary()}
     del src, dst

@@ -846,7 +846,7 @@ int b200geo_warp_batch_host(b200geo_ctx *ctx, const void *src_host, void *dst_ho
     B2G_ARG(sampler == B200GEO_NN || sampler == B200GEO_BILINEAR);
     B2G_ARG(dst_type == B200GEO_U8 || dst_type == B200GEO_F32 || dst_type == B200GEO_F64);
     if (n_jobs == 0) return B200GEO_OK;
-    if (chunk_jobs <= 0) chunk_jobs = 8;
+    if (chunk_jobs <= 0) chunk_jobs = n_jobs >= 128 ? 16 : 8;     // measured on 1080p frames: 8 is best for 64 jobs, 16 for 256
     if (chunk_jobs > n_jobs) chunk_jobs = n_jobs;
     int prc;
     if ((prc = ensure_pipe(ctx))) return prc;
