@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/b200geo.h"
@@ -32,7 +33,11 @@ inline int fail(int code, const char *fmt, const char *a = "", const char *b = "
     do {                                                                                        \
         (ctx)->launches++;                                                                      \
         cudaError_t e__ = cudaGetLastError();                                                   \
-        if (e__ != cudaSuccess) return ::b200geo::fail(B200GEO_ERR_CUDA, "kernel launch: %s%s", cudaGetErrorString(e__)); \
+        if (e__ == cudaSuccess && getenv("B200GEO_SYNC_LAUNCHES")) e__ = cudaDeviceSynchronize();  /* debugging: fault attribution */ \
+        if (e__ != cudaSuccess) {                                                               \
+            if (getenv("B200GEO_SYNC_LAUNCHES")) fprintf(stderr, "[b200geo] %s:%d: %s\n", __FILE__, __LINE__, cudaGetErrorString(e__)); \
+            return ::b200geo::fail(B200GEO_ERR_CUDA, "kernel launch: %s%s", cudaGetErrorString(e__)); \
+        }                                                                                       \
     } while (0)
 
 #define B2G_ARG(cond)                                                                           \

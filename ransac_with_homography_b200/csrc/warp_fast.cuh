@@ -216,9 +216,18 @@ __device__ void wf_setup(const b200geo_warp_job &J, int c0, int r0, int tw, int 
         x_lo = __float2int_rd((rxmin - B) * (1.f / 65536.f) + 0.5f) - 1; x_hi = __float2int_rd((rxmax + B) * (1.f / 65536.f) + 0.5f) + 1;
         y_lo = __float2int_rd((rymin - B) * (1.f / 65536.f) + 0.5f) - 1; y_hi = __float2int_rd((rymax + B) * (1.f / 65536.f) + 0.5f) + 1;
     }
-    if (!all_in) {   // clip to what an unmasked pixel can touch
-        x_lo = max(x_lo, 0 - T.xc); x_hi = min(x_hi, J.bw - 1 - T.xc);
-        y_lo = max(y_lo, 0 - T.yc); y_hi = min(y_hi, J.bh - (BILINEAR ? 0 : 1) - T.yc);
+    if (!all_in) {
+        // Clip to what an unmasked pixel can touch.  The unrolled BORDER loops clamp every coordinate into the image
+        // before addressing, so the staged range must contain the clamped position of EVERY pixel of the tile: an axis
+        // whose range misses the image altogether (the tile is not ZERO only because of `band`) collapses onto the
+        // image edge the clamp produces (+ the second tap row for bilinear) instead of onto an arbitrary entry.
+        const int ix_lo = 0 - T.xc, ix_hi = J.bw - 1 - T.xc, iy_lo = 0 - T.yc, iy_hi = J.bh - 1 - T.yc, ytap = BILINEAR ? 1 : 0;
+        if (x_hi < ix_lo) x_lo = x_hi = ix_lo;
+        else if (x_lo > ix_hi) x_lo = x_hi = ix_hi;
+        else { x_lo = max(x_lo, ix_lo); x_hi = min(x_hi, ix_hi); }
+        if (y_hi < iy_lo) { y_lo = iy_lo; y_hi = iy_lo + ytap; }
+        else if (y_lo > iy_hi) { y_lo = iy_hi; y_hi = iy_hi + ytap; }
+        else { y_lo = max(y_lo, iy_lo); y_hi = min(y_hi, iy_hi + ytap); }
     }
     if (x_hi < x_lo || y_hi < y_lo) { x_hi = x_lo; y_hi = y_lo; }
     // absolute origin column: a multiple of 4 pixels = 12 bytes, so that every 4-entry chunk of a
@@ -507,8 +516,9 @@ __device__ __forceinline__ void wf_compute_full(const WfDesc &T, const b200geo_w
             const int fxd = __float2int_rd(r.x), fyd = __float2int_rd(r.y);
             uint32_t out;
             if (BILINEAR) {
-                // integer parts: one PRMT each (sign-extended upper half), then IMAD + LEA
-                const int xi = (int)__byte_perm((uint32_t)fxd, 0u, 0xBB32), yi = (int)__byte_perm((uint32_t)fyd, 0u, 0xBB32);
+                // integer parts by arithmetic shift (a PRMT with byte 3 replicated is only a sign extension for |rel| < 256 px:
+                // found by tools/fuzz_warp.py on coordinates clamped far outside a tile's own range), then IMAD + LEA
+                const int xi = fxd >> 16, yi = fyd >> 16;
                 const uint32_t a = (uint32_t)yi * P4 + base + ((uint32_t)xi << 2);
                 const uint2 top = wf_lds_entry(a), bot = wf_lds_entry(a + P4);
                 out = wf_blend(top, bot, (uint32_t)fxd & 0xFFFFu, (uint32_t)fyd & 0xFFFFu);
@@ -520,7 +530,7 @@ __device__ __forceinline__ void wf_compute_full(const WfDesc &T, const b200geo_w
                 const uint32_t fx = (uint32_t)hx & 0xFFFFu, fy = (uint32_t)hy & 0xFFFFu;
                 if (fx - (uint32_t)B16 > (uint32_t)(65535 - 2 * B16) || fy - (uint32_t)B16 > (uint32_t)(65535 - 2 * B16))
                     amb |= 1u << (p * (WF_TW / 32) + hh);
-                const int xi = (int)__byte_perm((uint32_t)hx, 0u, 0xBB32), yi = (int)__byte_perm((uint32_t)hy, 0u, 0xBB32);
+                const int xi = hx >> 16, yi = hy >> 16;
                 const uint2 e = wf_lds_entry((uint32_t)yi * P4 + base + ((uint32_t)xi << 2));
                 out = __byte_perm(e.x, e.y, 0x4420);
             }
@@ -627,7 +637,12 @@ __device__ __forceinline__ void wf_full_bilinear(const WfDesc &T, const b200geo_
                 r.y = fminf(fmaxf(r.y, loy), hiy);
             }
             const int fxd = __float2int_rd(r.x), fyd = __float2int_rd(r.y);
-            const int xi = (int)__byte_perm((uint32_t)fxd, 0u, 0xBB32), yi = (int)__byte_perm((uint32_t)fyd, 0u, 0xBB32);
+            const int xi = fxd >> 16, yi = fyd >> 16;
+#ifdef B2G_DEBUG_FOOT
+            if (xi < T.ox || xi >= T.ox + (int)T.P || yi < T.oy || yi + 1 >= T.oy + (int)T.rows)
+                printf("foot: border %d tile c0 %d r0 %d mode %x xi %d yi %d ox %d oy %d P %d rows %d xc %d yc %d r %g %g lo %g %g hi %g %g band %g\n", BORDER, c0, r0, T.mode,
+                       xi, yi, (int)T.ox, (int)T.oy, (int)T.P, (int)T.rows, T.xc, T.yc, r.x, r.y, lox, loy, hix, hiy, band);
+#endif
             const uint32_t a = (uint32_t)yi * P4 + base + ((uint32_t)xi << 2);
             top[b][hh] = wf_lds_entry(a);
             bot[b][hh] = wf_lds_entry(a + P4);
@@ -727,7 +742,7 @@ __device__ __forceinline__ void wf_full_nn_direct(const WfDesc &T, const b200geo
             const int hx = __float2int_rd(r.x) + 32768, hy = __float2int_rd(r.y) + 32768;
             const uint32_t fx = (uint32_t)hx & 0xFFFFu, fy = (uint32_t)hy & 0xFFFFu;
             if (in && (fx - B16 > 65535u - 2u * B16 || fy - B16 > 65535u - 2u * B16)) amb |= 1u << (p * G + hh);
-            int xi = (int)__byte_perm((uint32_t)hx, 0u, 0xBB32), yi = (int)__byte_perm((uint32_t)hy, 0u, 0xBB32);
+            int xi = hx >> 16, yi = hy >> 16;
             if (BORDER) { xi = min(max(xi, xlo), xhi); yi = min(max(yi, ylo), yhi); }
             e[b][hh] = wf_lds_entry((uint32_t)yi * P4 + base + ((uint32_t)xi << 2));
         }

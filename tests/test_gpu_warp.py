@@ -420,3 +420,42 @@ def test_layout_hints_do_not_change_results(kind, sampler):
         ctx.warp_exact(False)
         d = np.abs(outs[2].astype(np.int16) - dst_t.cpu().numpy().astype(np.int16))
         assert d.max() <= (0 if sampler == "nn" else U8_TOL), (kind, h, w, int(d.max()))
+
+
+def test_border_tile_far_from_its_anchor_regression():
+    """A strong-perspective frame whose BORDER tiles clamp coordinates more than 256 px away from the tile anchor:
+    the integer part of the 16.16 coordinate was once taken with a byte permute that only sign-extends 24-bit values
+    (illegal shared-memory address; found by tools/fuzz_warp.py, seed 1 case 261)."""
+    import torch
+    from ransac_with_homography_b200 import _cabi, device
+    ctx = _cabi.context()
+    h, w = 114, 744
+    H = np.array([[1.0, 0.1, 5.0], [0.05, 1.0, -7.0], [1.9822643559266172e-03, -7.9026834333958615e-04, 1.0]])
+    frames = np.random.RandomState(5).randint(0, 256, (1, h, w, 3)).astype(np.uint8)
+    jobs = device.scan_jobs(H[None], (h, w), (h, w))
+    src_t = torch.from_numpy(frames).cuda()
+    out = {}
+    for sampler in ("bilinear", "nn"):
+        for m in ("fast", "exact"):
+            ctx.warp_exact(m == "exact")
+            dst_t = torch.full((h * w * 3,), 7, dtype=torch.uint8, device="cuda")
+            device.warp(src_t, dst_t, jobs, 3, sampler)
+            torch.cuda.synchronize()
+            out[m] = dst_t.cpu().numpy().astype(np.int16)
+        ctx.warp_exact(False)
+        assert np.abs(out["fast"] - out["exact"]).max() <= (0 if sampler == "nn" else U8_TOL)
+
+
+def test_fuzz_fast_kernel_short():
+    """A short run of tools/fuzz_warp.py (random sizes, batches, homography families, samplers, grids, layout hints)."""
+    import importlib.util, os, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("fuzz_warp", os.path.join(root, "tools", "fuzz_warp.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    argv = sys.argv
+    try:
+        sys.argv = ["fuzz_warp.py", "80", "7"]
+        assert mod.main() == 0
+    finally:
+        sys.argv = argv
