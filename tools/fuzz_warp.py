@@ -78,9 +78,16 @@ def main():
         out = {}
         if os.environ.get("FUZZ_VERBOSE"):
             print(f"case {c}: {sampler} {form} {h}x{w} B={B} out {mh}x{mo} layout={layout}", flush=True)
+        host_pipe = rs.rand() < 0.2          # the host-buffer pipeline (three streams, chunked) instead of the device-resident call
+        chunk = int(rs.randint(1, 5))
         for m in (("exact", "fast") if os.environ.get("FUZZ_EXACT_FIRST") else ("fast", "exact")):
             ctx.warp_exact(m == "exact")
             ctx.warp_variant(int(os.environ.get("WARP_VARIANT", "0")))
+            if host_pipe and m == "fast":
+                out_h = np.full((total,), 7, np.uint8)
+                device.warp_host(frames, out_h, jobs, 3, sampler, chunk_jobs=chunk)
+                out[m] = out_h.astype(np.int16)
+                continue
             dst_t = torch.full((total,), 7, dtype=torch.uint8, device="cuda")
             device.warp_resident(src_t, dst_t, jd, B, mo, mh, 3, sampler, layout=layout if m == "fast" else None)
             torch.cuda.synchronize()
@@ -92,7 +99,7 @@ def main():
         worst = max(worst, share if sampler == "bilinear" else 0.0)
         if d.max() > tol or (sampler == "bilinear" and share > 0.03):
             bad += 1
-            print(f"FAIL case {c}: {sampler} {form} {h}x{w} B={B} layout={layout} max {int(d.max())} share {share:.4f}")
+            print(f"FAIL case {c}: {sampler} {form} {h}x{w} B={B} layout={layout} host_pipe={host_pipe}/{chunk} max {int(d.max())} share {share:.4f}")
     print(f"{cases} cases, {bad} failures, worst bilinear off-by-one share {worst:.4f}")
     return 1 if bad else 0
 
