@@ -12,6 +12,7 @@
 
 static_assert(sizeof(b200geo_warp_job) == 184, "b200geo_warp_job layout is part of the ABI");
 static_assert(sizeof(b200geo_compose) == 80, "b200geo_compose layout is part of the ABI");
+static_assert(sizeof(b200geo_src_layout) == 32, "b200geo_src_layout layout is part of the ABI");
 
 namespace b200geo {
 

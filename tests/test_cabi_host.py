@@ -55,6 +55,20 @@ def test_warp_job_struct_layout():
         assert getattr(_cabi.WarpJob, name).offset == _cabi.WARP_JOB_DTYPE.fields[name][1]
 
 
+def test_abi_struct_sizes_match_the_header():
+    """ctypes mirrors of the structs include/b200geo.h declares; the C side static_asserts the same sizes (csrc/common.cuh),
+    and the header must list the fields in the order the mirrors use."""
+    import ctypes as C
+    assert C.sizeof(_cabi.WarpJob) == 184 and C.sizeof(_cabi.Compose) == 80 and C.sizeof(_cabi.SrcLayout) == 32
+    hdr = open(os.path.join(ROOT, "include", "b200geo.h")).read()
+    for struct, cls in (("b200geo_compose", _cabi.Compose), ("b200geo_src_layout", _cabi.SrcLayout), ("b200geo_warp_job", _cabi.WarpJob)):
+        body = re.search(r"typedef struct " + struct + r" \{(.*?)\} " + struct + ";", hdr, flags=re.S).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        names = [n.split("[")[0] for decl in body.split(";") if decl.strip() for n in re.sub(r"^\s*\w+\s+", "", decl.strip()).replace(" ", "").split(",")]
+        mine = [n for n, _ in cls._fields_]
+        assert [n.replace("reserved0", "r0") for n in names] == [n.replace("reserved0", "r0") for n in mine], (struct, names, mine)
+
+
 @pytest.mark.parametrize("start,stop,num", [(0, 2480, 2480), (0, 1080, 1080), (-27, 170, 198), (5, 5, 1), (0, 7, 7), (-3, 69, 73)])
 def test_linspace_params_reproduce_numpy(start, stop, num):
     from ransac_with_homography_b200.homography import _linspace_params
