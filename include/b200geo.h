@@ -73,7 +73,8 @@ int b200geo_stats(b200geo_ctx *ctx, unsigned long long *exact_path_pairs, int re
 /* options */
 #define B200GEO_OPT_FORCE_EXACT 1   /* value != 0: score every pair with the reference-order chain */
 #define B200GEO_OPT_WARP_EXACT 2    /* value != 0: warp uint8 RGB with the float64 kernel (bit-exact bilinear) */
-#define B200GEO_OPT_WARP_VARIANT 3  /* fast uint8 warp: 0 = persistent TMA-pipelined kernel (default), 1 = one CTA per tile */
+#define B200GEO_OPT_WARP_VARIANT 3  /* fast uint8 warp: 0 = one warp per 32x20 strip where the layout allows, persistent tile kernel for the
+                                       rest (default); 1 = one CTA per tile; 2 = persistent tile kernel only */
 int b200geo_set_option(b200geo_ctx *ctx, int option, int value);
 /* Number of output pixels the fast uint8 warp kernel evaluated with the float64 reference-order
  * path (inside the coordinate-error band around a mask / rounding boundary, or in tiles where

@@ -6,6 +6,7 @@
 #include "solve.cuh"
 #include "warp.cuh"
 #include "warp_fast.cuh"
+#include "warp_strip.cuh"
 #include "compose.cuh"
 #include "match.cuh"
 
@@ -131,15 +132,16 @@ int b200geo_sync(b200geo_ctx *ctx, void *stream)
 // ------------------------------------------------------------------------------------------------
 namespace {
 
-// 64-byte statistics block: [0] score pairs taken by the exact chain, [1] deferred-work counter,
-// [2] warp pixels evaluated in float64 by the fast warp kernel
+// 128-byte statistics / counter block (8-byte words): [0] score pairs taken by the exact chain, [1] deferred-work counter,
+// [2] warp pixels evaluated in float64 by the fast warp kernel, [3] tile tickets of warp_pipe_kernel,
+// [4] routed launch: number of strip tiles, number of old-kernel tiles (2 x u32), [5] tile tickets of warp_strip_kernel
 int ensure_stats(b200geo_ctx *ctx, cudaStream_t st, unsigned long long **out)
 {
     if (ctx->scratch_cap[S_STATS] == 0) {
         void *p;
         int rc;
-        if ((rc = scratch(ctx, S_STATS, 64, &p))) return rc;
-        B2G_CUDA(cudaMemsetAsync(p, 0, 64, st));
+        if ((rc = scratch(ctx, S_STATS, 128, &p))) return rc;
+        B2G_CUDA(cudaMemsetAsync(p, 0, 128, st));
     }
     *out = (unsigned long long *)ctx->scratch[S_STATS];
     return B200GEO_OK;
@@ -384,6 +386,14 @@ int prepare_tmap(b200geo_ctx *ctx, const void *src, const b200geo_src_layout *la
                                                estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { ctx->tmap_src = nullptr; return 0; }
+    ctx->tmap_strip_ok = 0;
+    if (d3) {       // the per-warp strips of warp_strip_kernel fetch a 160-byte x 26-row box of the same array
+        const cuuint32_t sbox[3] = {(cuuint32_t)WS_RAW_W, (cuuint32_t)WS_ROWS, 1};
+        r = ((encode_fn)ctx->tmap_encode)(&ctx->tmap_strip, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void *>(src), gdim, gstride, sbox,
+                                          estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        ctx->tmap_strip_ok = r == CUDA_SUCCESS;
+    }
     ctx->tmap_src = src; ctx->tmap_pitch = layout->pitch; ctx->tmap_rows = layout->rows;
     ctx->tmap_image_rows = d3 ? layout->image_rows : 0; ctx->tmap_row_bytes = d3 ? layout->row_bytes : 0;
     return mode;
@@ -425,42 +435,69 @@ int launch_warp(b200geo_ctx *ctx, const void *src, void *dst, const b200geo_warp
         B2G_CUDA(cudaMemsetAsync(tile_counter, 0, sizeof(unsigned), st));
         B2G_CUDA(cudaMemsetAsync(fix_count, 0, sizeof(unsigned), st));
         unsigned n_seg = 1, seg_cap = fix_cap;
-        const int use_tmap = ctx->warp_variant == 0 ? prepare_tmap(ctx, src, layout) : 0;
+        const int use_tmap = ctx->warp_variant != 1 ? prepare_tmap(ctx, src, layout) : 0;
         if (getenv("B200GEO_DEBUG"))
             fprintf(stderr, "[b200geo] warp: jobs %d tiles %dx%d sampler %d layout %p use_tmap %d (encode %p)\n", n_jobs, tiles_x, tiles_y,
                     sampler, (const void *)layout, use_tmap, ctx->tmap_encode);
         // use_tmap: 0 no tensor map, 2 the source as a 2-D array, 3 as (row_bytes x image_rows x images)
         const WfTma tma = {use_tmap ? (long long)layout->pitch : 0LL, use_tmap == 3 ? (int)layout->image_rows : 0, use_tmap == 3 ? (int)layout->row_bytes : 0};
-        if (ctx->warp_variant == 1) {
-            if (sampler == B200GEO_BILINEAR) warp_setup_kernel<1><<<sgrid, sblock, 0, st>>>(jobs_dev, s8, tma, tiles_x, tiles_y, descs);
-            else warp_setup_kernel<0><<<sgrid, sblock, 0, st>>>(jobs_dev, s8, tma, tiles_x, tiles_y, descs);
-        } else {
-            if (sampler == B200GEO_BILINEAR) warp_tile_setup_kernel<1><<<sgrid, sblock, 0, st>>>(jobs_dev, s8, d8, tma, use_tmap, tiles_x, tiles_y, tiles);
-            else warp_tile_setup_kernel<0><<<sgrid, sblock, 0, st>>>(jobs_dev, s8, d8, tma, use_tmap, tiles_x, tiles_y, tiles);
+        const long long n_tiles = (long long)tiles_x * tiles_y * n_jobs;
+        if (n_tiles > 0x3fffffffLL) return fail(B200GEO_ERR_ARG, "too many warp tiles for one launch%s%s");
+        if (ctx->warp_variant != 1 && !ctx->warp_pipe_ready) {
+            B2G_CUDA(cudaFuncSetAttribute(warp_pipe_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WpSmem)));
+            B2G_CUDA(cudaFuncSetAttribute(warp_pipe_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WpSmem)));
+            B2G_CUDA(cudaFuncSetAttribute(warp_strip_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS_SMEM_BYTES));
+            B2G_CUDA(cudaFuncSetAttribute(warp_strip_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS_SMEM_BYTES));
+            ctx->warp_pipe_ready = 1;
         }
-        B2G_CHECK_LAUNCH(ctx);
         if (ctx->warp_variant == 1) {
             // one CTA per tile (kept for comparison)
+            if (sampler == B200GEO_BILINEAR) warp_setup_kernel<1><<<sgrid, sblock, 0, st>>>(jobs_dev, s8, tma, tiles_x, tiles_y, descs);
+            else warp_setup_kernel<0><<<sgrid, sblock, 0, st>>>(jobs_dev, s8, tma, tiles_x, tiles_y, descs);
+            B2G_CHECK_LAUNCH(ctx);
             dim3 grid(tiles_x, tiles_y, n_jobs);
             if (sampler == B200GEO_BILINEAR) warp_fast_kernel<1><<<grid, WF_THREADS, 0, st>>>(s8, d8, jobs_dev, descs, stats + 2, fix_list, fix_count, fix_cap);
             else warp_fast_kernel<0><<<grid, WF_THREADS, 0, st>>>(s8, d8, jobs_dev, descs, stats + 2, fix_list, fix_count, fix_cap);
+        } else if (use_tmap == 3 && ctx->tmap_strip_ok && ctx->warp_variant == 0) {
+            // routed: every 64 x 40 tile goes either to warp_strip_kernel (four 32 x 20 strips, one warp each) or, if one of its
+            // strips does not qualify, to warp_pipe_kernel; both lists are compact, their lengths stay on the device
+            WsStrip *strips;
+            if ((rc = scratch(ctx, S_STRIPS, 4 * sizeof(WsStrip) * (size_t)n_tiles, (void **)&strips))) return rc;
+            unsigned *route = (unsigned *)(stats + 4), *strip_ticket = (unsigned *)(stats + 5);
+            B2G_CUDA(cudaMemsetAsync(route, 0, 16, st));        // both counts and the strip ticket
+            if (sampler == B200GEO_BILINEAR) warp_route_setup_kernel<1><<<sgrid, sblock, 0, st>>>(jobs_dev, s8, d8, tma, use_tmap, tiles_x, tiles_y, strips, tiles, route);
+            else warp_route_setup_kernel<0><<<sgrid, sblock, 0, st>>>(jobs_dev, s8, d8, tma, use_tmap, tiles_x, tiles_y, strips, tiles, route);
+            B2G_CHECK_LAUNCH(ctx);
+            long long sctas = (n_tiles + WS_WARPS - 1) / WS_WARPS;
+            if (sctas > ctx->sm_count) sctas = ctx->sm_count;
+            long long pctas = (long long)ctx->sm_count * WP_OCC;
+            if (pctas > n_tiles) pctas = n_tiles;
+            n_seg = (unsigned)(sctas + pctas); seg_cap = fix_cap / n_seg;
+            if (n_seg * sizeof(unsigned) > FIX_HDR || seg_cap == 0) return fail(B200GEO_ERR_ARG, "fix-up list segments%s%s");
+            if (sampler == B200GEO_BILINEAR)
+                warp_strip_kernel<1><<<(unsigned)sctas, WS_THREADS, WS_SMEM_BYTES, st>>>(s8, jobs_dev, strips, route, ctx->tmap_strip, fix_list, fix_count, seg_cap, strip_ticket, stats + 2);
+            else
+                warp_strip_kernel<0><<<(unsigned)sctas, WS_THREADS, WS_SMEM_BYTES, st>>>(s8, jobs_dev, strips, route, ctx->tmap_strip, fix_list, fix_count, seg_cap, strip_ticket, stats + 2);
+            B2G_CHECK_LAUNCH(ctx);
+            WfFixEntry *fl = fix_list + (size_t)sctas * seg_cap;
+            unsigned *fc = fix_count + sctas;
+            if (sampler == B200GEO_BILINEAR)
+                warp_pipe_kernel<1><<<(unsigned)pctas, WP_THREADS, sizeof(WpSmem), st>>>(s8, d8, jobs_dev, tiles, 0, route + 1, tiles_x, tiles_y, stats + 2, ctx->tmap, use_tmap, tma.image_rows, fl, fc, seg_cap, tile_counter);
+            else
+                warp_pipe_kernel<0><<<(unsigned)pctas, WP_THREADS, sizeof(WpSmem), st>>>(s8, d8, jobs_dev, tiles, 0, route + 1, tiles_x, tiles_y, stats + 2, ctx->tmap, use_tmap, tma.image_rows, fl, fc, seg_cap, tile_counter);
         } else {
             // persistent CTAs, TMA bulk copies one tile ahead
-            const long long n_tiles = (long long)tiles_x * tiles_y * n_jobs;
-            if (n_tiles > 0x7fffffffLL) return fail(B200GEO_ERR_ARG, "too many warp tiles for one launch%s%s");
-            if (!ctx->warp_pipe_ready) {
-                B2G_CUDA(cudaFuncSetAttribute(warp_pipe_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WpSmem)));
-                B2G_CUDA(cudaFuncSetAttribute(warp_pipe_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WpSmem)));
-                ctx->warp_pipe_ready = 1;
-            }
+            if (sampler == B200GEO_BILINEAR) warp_tile_setup_kernel<1><<<sgrid, sblock, 0, st>>>(jobs_dev, s8, d8, tma, use_tmap, tiles_x, tiles_y, tiles);
+            else warp_tile_setup_kernel<0><<<sgrid, sblock, 0, st>>>(jobs_dev, s8, d8, tma, use_tmap, tiles_x, tiles_y, tiles);
+            B2G_CHECK_LAUNCH(ctx);
             long long ctas = (long long)ctx->sm_count * WP_OCC;
             if (ctas > n_tiles) ctas = n_tiles;
             if (ctas > (long long)(FIX_HDR / sizeof(unsigned))) ctas = FIX_HDR / sizeof(unsigned);
             n_seg = (unsigned)ctas; seg_cap = fix_cap / n_seg;
             if (sampler == B200GEO_BILINEAR)
-                warp_pipe_kernel<1><<<(unsigned)ctas, WP_THREADS, sizeof(WpSmem), st>>>(s8, d8, jobs_dev, tiles, (int)n_tiles, tiles_x, tiles_y, stats + 2, ctx->tmap, use_tmap, tma.image_rows, fix_list, fix_count, seg_cap, tile_counter);
+                warp_pipe_kernel<1><<<(unsigned)ctas, WP_THREADS, sizeof(WpSmem), st>>>(s8, d8, jobs_dev, tiles, (int)n_tiles, nullptr, tiles_x, tiles_y, stats + 2, ctx->tmap, use_tmap, tma.image_rows, fix_list, fix_count, seg_cap, tile_counter);
             else
-                warp_pipe_kernel<0><<<(unsigned)ctas, WP_THREADS, sizeof(WpSmem), st>>>(s8, d8, jobs_dev, tiles, (int)n_tiles, tiles_x, tiles_y, stats + 2, ctx->tmap, use_tmap, tma.image_rows, fix_list, fix_count, seg_cap, tile_counter);
+                warp_pipe_kernel<0><<<(unsigned)ctas, WP_THREADS, sizeof(WpSmem), st>>>(s8, d8, jobs_dev, tiles, (int)n_tiles, nullptr, tiles_x, tiles_y, stats + 2, ctx->tmap, use_tmap, tma.image_rows, fix_list, fix_count, seg_cap, tile_counter);
         }
         B2G_CHECK_LAUNCH(ctx);
         const dim3 fgrid(n_seg == 1 ? 2 * ctx->sm_count : 2, n_seg);
@@ -826,13 +863,19 @@ int b200geo_warp_dev(b200geo_ctx *ctx, const void *src, void *dst, const b200geo
     memcpy(hp, jobs, bytes);
     int max_ow = 0, max_oh = 0;
     // the jobs are visible here: describe the source as one 2-D byte array when they share a pitch
-    b200geo_src_layout lay = {jobs[0].src_pitch, 0};
-    bool uniform = true;
+    b200geo_src_layout lay = {jobs[0].src_pitch, 0, 0, 0};
+    bool uniform = true, same = channels == 3 && src_type == B200GEO_U8;     // same: equal images at multiples of their size -> 3-D tensor map
     for (int i = 0; i < n_jobs; ++i) {
         if (jobs[i].ow > max_ow) max_ow = jobs[i].ow;
         if (jobs[i].oh > max_oh) max_oh = jobs[i].oh;
         if (jobs[i].src_pitch != lay.pitch || lay.pitch <= 0 || jobs[i].src_offset < 0 || jobs[i].src_offset % lay.pitch) uniform = false;
         else if (jobs[i].src_offset / lay.pitch + jobs[i].ih > lay.rows) lay.rows = jobs[i].src_offset / lay.pitch + jobs[i].ih;
+        if (jobs[i].ih != jobs[0].ih || jobs[i].iw != jobs[0].iw || jobs[i].ih <= 0 || jobs[i].src_offset < 0 ||
+            (lay.pitch > 0 && jobs[i].src_offset % (lay.pitch * jobs[0].ih))) same = false;
+    }
+    if (uniform && same && lay.rows % jobs[0].ih == 0 && 3LL * jobs[0].iw <= lay.pitch) {
+        lay.image_rows = jobs[0].ih;
+        lay.row_bytes = 3LL * jobs[0].iw;
     }
     B2G_CUDA(cudaMemcpyAsync(dj, hp, bytes, cudaMemcpyHostToDevice, st));
     return launch_warp(ctx, src, dst, dj, n_jobs, max_ow, max_oh, channels, src_type, dst_type, sampler, st, uniform ? &lay : nullptr);
@@ -855,8 +898,15 @@ int b200geo_warp_batch_host(b200geo_ctx *ctx, const void *src_host, void *dst_ho
     const int n_chunks = (n_jobs + chunk_jobs - 1) / chunk_jobs;
     std::vector<b200geo_warp_job> dj(jobs, jobs + n_jobs);
     size_t max_src = 0, max_dst = 0;
-    bool uniform = true;
-    b200geo_src_layout lay = {jobs[0].src_pitch, 0};
+    bool uniform = true, same = channels == 3 && src_type == B200GEO_U8;
+    b200geo_src_layout lay = {jobs[0].src_pitch, 0, 0, 0};
+    for (int j = 0; j < n_jobs; ++j)
+        if (jobs[j].ih != jobs[0].ih || jobs[j].iw != jobs[0].iw || jobs[j].src_pitch != jobs[0].src_pitch) same = false;
+    if (same && (((size_t)jobs[0].src_pitch * jobs[0].ih) & 255) == 0 && 3LL * jobs[0].iw <= jobs[0].src_pitch) {
+        // equal images whose size is a multiple of the 256-byte packing granule: each chunk is (row_bytes x image_rows x images)
+        lay.image_rows = jobs[0].ih;
+        lay.row_bytes = 3LL * jobs[0].iw;
+    }
     for (int c = 0; c < n_chunks; ++c) {
         size_t so = 0, dofs = 0;
         for (int j = c * chunk_jobs; j < n_jobs && j < (c + 1) * chunk_jobs; ++j) {

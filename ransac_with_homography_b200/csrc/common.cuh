@@ -47,7 +47,7 @@ inline int fail(int code, const char *fmt, const char *a = "", const char *b = "
     } while (0)
 
 enum ScratchSlot {
-    S_PTS = 0, S_IDX, S_H, S_HINV, S_FLAGS, S_COUNTS, S_KEYS, S_RESULT, S_MASK, S_JOBS, S_SRC, S_DST, S_MISC, S_CMAX, S_STATS, S_WORKLIST, S_TILES, S_PIPE_SRC, S_PIPE_DST, S_PIPE_JOBS, S_WARPFIX,
+    S_PTS = 0, S_IDX, S_H, S_HINV, S_FLAGS, S_COUNTS, S_KEYS, S_RESULT, S_MASK, S_JOBS, S_SRC, S_DST, S_MISC, S_CMAX, S_STATS, S_WORKLIST, S_TILES, S_PIPE_SRC, S_PIPE_DST, S_PIPE_JOBS, S_WARPFIX, S_STRIPS,
     S_NUM
 };
 
@@ -62,14 +62,16 @@ struct b200geo_ctx {
     int64_t launches;
     int force_exact;       // B200GEO_OPT_FORCE_EXACT: score with the reference-order chain only
     int warp_exact;        // B200GEO_OPT_WARP_EXACT: warp uint8 images with the float64 kernel only
-    int warp_variant;      // B200GEO_OPT_WARP_VARIANT: 0 = persistent TMA-pipelined kernel, 1 = one CTA per tile
+    int warp_variant;      // B200GEO_OPT_WARP_VARIANT: 0 = strips per warp + persistent kernel for the rest, 1 = one CTA per tile, 2 = persistent kernel only
     int warp_pipe_ready;   // dynamic shared memory attribute of warp_pipe_kernel set
     cudaStream_t pipe_stream[3];   // b200geo_warp_batch_host: h2d, compute, d2h
     cudaEvent_t pipe_event[3][2];  // [h2d done, compute done, d2h done][slot]
     int pipe_ready;
     void *tmap_encode;     // cuTensorMapEncodeTiled (driver entry point), or NULL
     int tmap_probed;
-    CUtensorMap tmap;      // cached 2-D tensor map of the last source layout
+    CUtensorMap tmap;      // cached 2-D / 3-D tensor map of the last source layout (box of warp_pipe_kernel)
+    CUtensorMap tmap_strip; // same array, box of warp_strip_kernel (3-D layouts only)
+    int tmap_strip_ok;
     const void *tmap_src;
     long long tmap_pitch, tmap_rows, tmap_image_rows, tmap_row_bytes;
     void *scratch[b200geo::S_NUM];

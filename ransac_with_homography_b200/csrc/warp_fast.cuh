@@ -1147,6 +1147,53 @@ __device__ __noinline__ void wp_convert_cold(const WpTile &W, uint32_t s_raw, ui
 // Grid: (ceil(tiles_x / 32), ceil(tiles_y / 8), n_jobs), block (32, 8): one thread per tile.  The whole tile record
 // (everything that does not depend on the pipeline stage) is prepared here, so that the producer warp of the
 // persistent kernel does no address arithmetic, divisions or job look-ups: measured, it had become the slowest warp.
+// The complete record of one tile (everything that does not depend on the pipeline stage).
+template <int BILINEAR>
+__device__ __forceinline__ void wp_build_tile(const b200geo_warp_job &J, int jz, int c0, int r0, const uint8_t *__restrict__ src_base,
+                                              uint8_t *__restrict__ dst_base, const WfTma &tma, int use_tmap, WpTile &W)
+{
+    {
+        uint4 *z = reinterpret_cast<uint4 *>(&W);
+#pragma unroll
+        for (int i = 0; i < WP_TILE_WORDS; ++i) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    wf_setup<BILINEAR>(J, c0, r0, min(WF_TW, J.ow - c0), min(WF_TH, J.oh - r0), tma, W.T);
+    const int mode = W.T.mode & 0xFF;
+    const int P = W.T.P, rows = W.T.rows;
+    const uint8_t *src = src_base + J.src_offset;
+    uint8_t *dstj = dst_base + J.dst_offset;
+    const int ay0 = W.T.yc + W.T.oy, ax0 = W.T.xc + W.T.ox;
+    const uint8_t *a0 = src + (long long)ay0 * J.src_pitch + 3LL * ax0;
+    const uint32_t RB = (uint32_t)(15 + 3 * (P + 1) + 15) & ~15u;
+    const bool staged = mode == WF_INTERIOR || mode == WF_BORDER;
+    const bool tm = use_tmap && staged && (W.T.mode & WF_FLAG_TMA);
+    bool bulk = tm;
+    if (!tm && staged && !(W.T.mode & WF_FLAG_TMA) && (W.T.mode & WF_FLAG_UNCHECKED) && (uint32_t)rows * RB <= (uint32_t)WP_RAW_BYTES) {
+        const size_t pitch = (size_t)J.src_pitch;
+        const size_t lo = (size_t)a0 & ~(size_t)15;
+        const size_t hi = ((size_t)a0 + (size_t)(rows - 1) * pitch) & ~(size_t)15;
+        const size_t img_end = (size_t)src + (size_t)(J.ih - 1) * pitch + 3 * (size_t)J.iw;
+        bulk = lo >= (size_t)src && hi + RB <= img_end;
+    }
+    W.src = src; W.a0 = a0; W.dst = dstj;
+    W.src_pitch = J.src_pitch; W.dst_pitch = J.dst_pitch;
+    W.iw = J.iw; W.ih = J.ih; W.c0 = c0; W.r0 = r0;
+    W.tw = min(WF_TW, J.ow - c0); W.th = min(WF_TH, J.oh - r0);
+    W.jz = jz;
+    W.img = (tma.image_rows > 0 && J.src_pitch > 0) ? (int)(J.src_offset / (J.src_pitch * tma.image_rows)) : 0;
+    W.RB = tm ? (uint32_t)WF_TMA_BOX_W : RB; W.staged = staged; W.bulk = bulk; W.tma = tm;
+    uint8_t *const dt = dstj + (long long)r0 * J.dst_pitch + 3LL * c0;
+    W.dst_tile = dt;
+    W.direct = (mode == WF_INTERIOR || (B2G_SWP && mode == WF_BORDER)) && W.tw == WF_TW && W.th == WF_TH &&
+               ((((size_t)dt) | (size_t)J.dst_pitch) & 3) == 0;
+    W.tma_x = (3 * ax0) & ~15;
+    W.sm_P4 = (uint32_t)P * 4u;
+    W.sm_base = wf_entry_base(W.T, 0u);
+    W.cv_total = tm ? rows * (P >> 2) : 0;
+    W.cv_D = (uint32_t)WF_TMA_BOX_W - 12u * (uint32_t)(P >> 2);
+    W.cv_a0 = (uint32_t)(size_t)a0 & 15u;
+}
+
 template <int BILINEAR>
 __global__ void __launch_bounds__(256)
 warp_tile_setup_kernel(const b200geo_warp_job *__restrict__ jobs, const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst_base,
@@ -1156,50 +1203,14 @@ warp_tile_setup_kernel(const b200geo_warp_job *__restrict__ jobs, const uint8_t 
     if (tx >= tiles_x || ty >= tiles_y) return;
     const b200geo_warp_job &J = jobs[blockIdx.z];
     WpTile W;
-    {
+    const int c0 = tx * WF_TW, r0 = ty * WF_TH;
+    if (c0 >= J.ow || r0 >= J.oh) {
         uint4 *z = reinterpret_cast<uint4 *>(&W);
 #pragma unroll
         for (int i = 0; i < WP_TILE_WORDS; ++i) z[i] = make_uint4(0u, 0u, 0u, 0u);
-    }
-    const int c0 = tx * WF_TW, r0 = ty * WF_TH;
-    if (c0 >= J.ow || r0 >= J.oh) {
         W.T.mode = WF_EMPTY;
     } else {
-        wf_setup<BILINEAR>(J, c0, r0, min(WF_TW, J.ow - c0), min(WF_TH, J.oh - r0), tma, W.T);
-        const int mode = W.T.mode & 0xFF;
-        const int P = W.T.P, rows = W.T.rows;
-        const uint8_t *src = src_base + J.src_offset;
-        uint8_t *dstj = dst_base + J.dst_offset;
-        const int ay0 = W.T.yc + W.T.oy, ax0 = W.T.xc + W.T.ox;
-        const uint8_t *a0 = src + (long long)ay0 * J.src_pitch + 3LL * ax0;
-        const uint32_t RB = (uint32_t)(15 + 3 * (P + 1) + 15) & ~15u;
-        const bool staged = mode == WF_INTERIOR || mode == WF_BORDER;
-        const bool tm = use_tmap && staged && (W.T.mode & WF_FLAG_TMA);
-        bool bulk = tm;
-        if (!tm && staged && !(W.T.mode & WF_FLAG_TMA) && (W.T.mode & WF_FLAG_UNCHECKED) && (uint32_t)rows * RB <= (uint32_t)WP_RAW_BYTES) {
-            const size_t pitch = (size_t)J.src_pitch;
-            const size_t lo = (size_t)a0 & ~(size_t)15;
-            const size_t hi = ((size_t)a0 + (size_t)(rows - 1) * pitch) & ~(size_t)15;
-            const size_t img_end = (size_t)src + (size_t)(J.ih - 1) * pitch + 3 * (size_t)J.iw;
-            bulk = lo >= (size_t)src && hi + RB <= img_end;
-        }
-        W.src = src; W.a0 = a0; W.dst = dstj;
-        W.src_pitch = J.src_pitch; W.dst_pitch = J.dst_pitch;
-        W.iw = J.iw; W.ih = J.ih; W.c0 = c0; W.r0 = r0;
-        W.tw = min(WF_TW, J.ow - c0); W.th = min(WF_TH, J.oh - r0);
-        W.jz = (int)blockIdx.z;
-        W.img = (tma.image_rows > 0 && J.src_pitch > 0) ? (int)(J.src_offset / (J.src_pitch * tma.image_rows)) : 0;
-        W.RB = tm ? (uint32_t)WF_TMA_BOX_W : RB; W.staged = staged; W.bulk = bulk; W.tma = tm;
-        uint8_t *const dt = dstj + (long long)r0 * J.dst_pitch + 3LL * c0;
-        W.dst_tile = dt;
-        W.direct = (mode == WF_INTERIOR || (B2G_SWP && mode == WF_BORDER)) && W.tw == WF_TW && W.th == WF_TH &&
-                   ((((size_t)dt) | (size_t)J.dst_pitch) & 3) == 0;
-        W.tma_x = (3 * ax0) & ~15;
-        W.sm_P4 = (uint32_t)P * 4u;
-        W.sm_base = wf_entry_base(W.T, 0u);
-        W.cv_total = tm ? rows * (P >> 2) : 0;
-        W.cv_D = (uint32_t)WF_TMA_BOX_W - 12u * (uint32_t)(P >> 2);
-        W.cv_a0 = (uint32_t)(size_t)a0 & 15u;
+        wp_build_tile<BILINEAR>(J, (int)blockIdx.z, c0, r0, src_base, dst_base, tma, use_tmap, W);
     }
     const uint4 *sv = reinterpret_cast<const uint4 *>(&W);
     uint4 *d = reinterpret_cast<uint4 *>(tiles + ((size_t)blockIdx.z * tiles_y + ty) * tiles_x + tx);
@@ -1213,7 +1224,7 @@ template <int BILINEAR>
 __global__ void __launch_bounds__(WP_THREADS, WP_OCC)
 warp_pipe_kernel(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst_base,
                  const b200geo_warp_job *__restrict__ jobs, const WpTile *__restrict__ tiles,
-                 int n_tiles, int tiles_x, int tiles_y, unsigned long long *__restrict__ stats,
+                 int n_tiles_host, const unsigned *__restrict__ n_tiles_dev, int tiles_x, int tiles_y, unsigned long long *__restrict__ stats,
                  const __grid_constant__ CUtensorMap tmap, int use_tmap, int tma_image_rows,
                  WfFixEntry *__restrict__ fix_list, unsigned *__restrict__ fix_counts, unsigned seg_cap, unsigned *__restrict__ tile_counter)
 {
@@ -1221,7 +1232,12 @@ warp_pipe_kernel(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst
     WpSmem &S = *reinterpret_cast<WpSmem *>(wp_smem);
     const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
     const int first = blockIdx.x;
-    if (first >= n_tiles) return;
+    // routed launches (warp_strip.cuh) keep the tile list compact and its length on the device
+    const int n_tiles = n_tiles_dev ? (int)*n_tiles_dev : n_tiles_host;
+    if (first >= n_tiles) {
+        if (tid == 0) fix_counts[blockIdx.x] = 0u;
+        return;
+    }
     // shared-space addresses are computed, never held in (locally-indexed) arrays
     const uint32_t s_raw0 = (uint32_t)__cvta_generic_to_shared(S.raw[0]);
     const uint32_t s_full0 = (uint32_t)__cvta_generic_to_shared(&S.full[0]);

@@ -1,0 +1,563 @@
+// warp_strip.cuh -- K4 fast path, second generation: one WARP per 32 x 20 output strip, no CTA-wide lockstep.
+//
+// Same element semantics and the same parity rules as warp_fast.cuh (reference homography.py:108-209 + the
+// astype(uint8) of :225/:241); what changes is the organisation.  warp_pipe_kernel (warp_fast.cuh) walks 64 x 40
+// tiles with 8 sampling warps per CTA that meet at one barrier per tile, and spends 57 thread-instructions per
+// pixel, a quarter of them on the per-tile protocol (profiles/r01_warp_pipe_decomposition.md).  Here
+//
+//   * every warp owns a strip of 32 x 20 output pixels (lane = column, 20 pixels per lane): its own TMA tensor
+//     copy of the strip's source footprint (160 B x 26 rows, issued one strip ahead by the warp itself), its own
+//     staged entries (48 entries x 26 rows), its own mbarrier.  Warps never wait for each other: a 16-warp CTA
+//     is 16 independent pipelines that share only the tile-ticket counter and the fix-up list segment.
+//   * a 64 x 40 tile is four strips; a warp draws one tile ticket (global atomic) per four strips.  The strip
+//     records (80 B: coefficients, tensor-copy coordinates, destination, footprint shape) are written by the
+//     set-up kernel and fetched into shared memory one strip ahead with cp.async.
+//   * coordinates: the float32 tile-relative quotient is rounded to 16.16 fixed point by the FFMA that forms it
+//     (n/w + 1.5 * 2^23: the integer lands in the mantissa), so the two F2I, the integer-part shift of a signed
+//     value and the base subtraction of the old loop disappear: FFMA2 + FFMA + MUFU.RCP + FFMA2 per pixel.
+//     (The coefficients carry a bias of -1/4 unit so that the rounding is a floor for every exactly representable
+//     coordinate: integer and dyadic translations stay bit-exact; elsewhere the 16.16 value differs from the floor
+//     by at most one unit = 1.5e-5 px, which the ambiguity band covers.)
+//   * entries: per staged row 48 (R[x] R[x+1] G[x] G[x+1]) words followed by 48 (B[x] B[x+1] . .) words, row pitch
+//     384 B = 3 x 128: lanes that sit on different source rows never collide on a bank, the conversion's 16-byte
+//     stores are conflict-free, and the second tap row is the immediate offset +384.
+//
+// Strips that do not fit this scheme (partial strips, footprints wider than 44 entries or taller than 26 rows,
+// SLOW / SPLIT geometry, the footprint holding source pixel (0,0), unaligned destinations, sources without a 3-D
+// tensor map) are left to warp_pipe_kernel, tile by tile: the set-up kernel routes every 64 x 40 tile to exactly one
+// of the two kernels (compact lists, counts on the device).
+#pragma once
+
+#include "warp_fast.cuh"
+
+namespace b200geo {
+
+constexpr int WS_W = 32, WS_H = 20;          // strip size (a 64 x 40 tile = 2 x 2 strips)
+static_assert(WF_TW == 2 * WS_W && WF_TH == 2 * WS_H, "a tile is four strips");
+constexpr int WS_EPR = 48;                   // entries per staged row
+constexpr int WS_PLANE = WS_EPR * 4;         // byte offset of the B-pair words inside a staged row
+constexpr int WS_ROWB = WS_EPR * 8;          // staged row pitch: 384 B
+constexpr int WS_ROWS = 26;                  // staged rows
+constexpr int WS_RAW_W = 160;                // tensor-copy box: bytes per row (multiple of 16) ...
+constexpr int WS_MAXP = 44;                  // ... which holds 4 + 12 + 3 * (44 + 1) <= 160 bytes
+constexpr int WS_WARPS = 16;
+constexpr int WS_THREADS = WS_WARPS * 32;
+constexpr int WS_RAW_BYTES = ((WS_RAW_W * WS_ROWS + 127) / 128) * 128;
+constexpr int WS_ENT_BYTES = WS_ROWB * WS_ROWS;
+constexpr int WS_WARP_BYTES = WS_RAW_BYTES + WS_ENT_BYTES;
+static_assert(WS_WARP_BYTES % 128 == 0, "tensor-copy destinations are 128-byte aligned");
+constexpr int WS_REC_BYTES = 80;
+constexpr int WS_SMEM_BYTES = WS_WARPS * (WS_WARP_BYTES + 2 * WS_REC_BYTES + 8) + 16;
+static_assert(WS_SMEM_BYTES <= 227 * 1024, "one CTA per SM");
+constexpr float WS_MAGIC = 12582912.f;       // 1.5 * 2^23: float32(MAGIC + v) has the integer v in its low 23 bits for |v| < 2^22
+constexpr int WS_MAGIC_HI = 0x4B40;          // bits 16.. of MAGIC's pattern: the offset of the 16.16 integer part
+constexpr float WS_MAX_REL = 62.f;           // |rel| beyond this does not fit the 23-bit fixed point: old kernel
+
+struct __align__(16) WsStrip {
+    float nx0, ny0, ax, ay, bx, by, gw, hw;  // as WfDesc (x / y pairs adjacent: loaded as float2), n.. / a.. / b.. carrying the rounding bias
+    int tma_x, tma_y;                        // tensor-copy coordinates: byte column (multiple of 16), row inside the image
+    uint8_t *dst;                            // first output byte of the strip
+    int dst_pitch;
+    uint16_t img, job;                       // image index in the 3-D tensor map; job index
+    int8_t ox, oy;                           // staged origin relative to the anchor
+    uint8_t rows, chunks;                    // footprint rows, 4-entry chunks per row
+    uint8_t mode, phase;                     // WF_ZERO | WF_INTERIOR | WF_BORDER; byte offset of entry column 0 inside a raw row (0, 4, 8, 12)
+    uint16_t b16;                            // ambiguity half-width in units of 2^-16 px, rounded up (+2)
+    uint16_t c0, r0;                         // first output pixel of the strip
+    int xc, yc;                              // anchor (absolute source pixel)
+    uint32_t magic;                          // ceil(2^32 / chunks)
+};
+static_assert(sizeof(WsStrip) == WS_REC_BYTES, "strip records are fetched as five 16-byte words");
+
+// One strip: the analogue of wf_setup for a 32 x 20 strip.  Returns false if the strip must go to the old kernel.
+template <int BILINEAR>
+__device__ bool ws_setup(const b200geo_warp_job &J, int job, int c0, int r0, const WfTma &tma, uint8_t *__restrict__ dst_base, WsStrip &S)
+{
+    if (c0 + WS_W > J.ow || r0 + WS_H > J.oh) return false;                   // full strips only
+    if (tma.image_rows <= 0) return false;                                    // needs the 3-D tensor map
+    const int cm = c0 + WS_W / 2, rm = r0 + WS_H / 2;
+    const double Xm = (double)cm * J.dx + J.x0, Ym = (double)rm * J.dy + J.y0;
+    const double exl = (double)(J.ow - 1) * J.dx + J.x0, eyl = (double)(J.oh - 1) * J.dy + J.y0;
+    bool ok = fabs(exl - J.x_last) <= 1e-9 * fmax(1.0, fabs(J.x_last)) && fabs(eyl - J.y_last) <= 1e-9 * fmax(1.0, fabs(J.y_last));
+    ok = ok && J.bw >= 2 && J.bh >= 2 && J.bw < (1 << 22) && J.bh < (1 << 22) && J.iw >= 1 && J.ih >= 1;
+    const double *h = J.invH;
+    const double zx = h[0] * Xm + h[1] * Ym + h[2];
+    const double zy = h[3] * Xm + h[4] * Ym + h[5];
+    const double zw = h[6] * Xm + h[7] * Ym + h[8];
+    ok = ok && fabs(zw) > 1e-200 && fabs(zw) < 1e200;
+    if (!ok) return false;
+    const double s = 1.0 / zw;
+    const double xs = zx * s, ys = zy * s;
+    if (!(fabs(xs) < 4.0e6 && fabs(ys) < 4.0e6)) return false;
+    const double xc = rint(xs), yc = rint(ys);
+    const double ax = (h[0] - xc * h[6]) * s * J.dx, bx = (h[1] - xc * h[7]) * s * J.dy;
+    const double ay = (h[3] - yc * h[6]) * s * J.dx, by = (h[4] - yc * h[7]) * s * J.dy;
+    const double gw = h[6] * s * J.dx, hw = h[7] * s * J.dy;
+    const double q = fabs(gw) * (WS_W / 2) + fabs(hw) * (WS_H / 2);
+    if (!(q <= 0.25)) return false;
+    const double Sx = fabs(xs - xc) + fabs(ax) * (WS_W / 2) + fabs(bx) * (WS_H / 2);
+    const double Sy = fabs(ys - yc) + fabs(ay) * (WS_W / 2) + fabs(by) * (WS_H / 2);
+    if (!(Sx < 1.0e6 && Sy < 1.0e6)) return false;
+    const double sc = 1.0 / 65536.0;
+    WfDesc T;                                  // unbiased float32 coefficients: the corners through the pixels' formula
+    T.nx0 = (float)(xs - xc); T.ax = (float)ax; T.bx = (float)bx;
+    T.ny0 = (float)(ys - yc); T.ay = (float)ay; T.by = (float)by;
+    T.gw = (float)(gw * sc); T.hw = (float)(hw * sc);
+    T.xc = (int)xc; T.yc = (int)yc;
+    float rxmin = 3.0e38f, rxmax = -3.0e38f, rymin = 3.0e38f, rymax = -3.0e38f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float di = (float)(((k & 1) ? WS_W - 1 : 0) - WS_W / 2), dj = (float)(((k & 2) ? WS_H - 1 : 0) - WS_H / 2);
+        float rx, ry;
+        wf_rel16(T, di, dj, rx, ry);
+        rxmin = fminf(rxmin, rx); rxmax = fmaxf(rxmax, rx);
+        rymin = fminf(rymin, ry); rymax = fmaxf(rymax, ry);
+    }
+    const float R = fmaxf(fmaxf(fabsf(rxmin), fabsf(rxmax)), fmaxf(fabsf(rymin), fabsf(rymax))) * (1.0f / 65536.f);
+    if (!(R < WS_MAX_REL)) return false;
+    // float32 error of rel as in wf_setup, plus two units of 2^-16 px for the biased round-to-nearest of the fixed point
+    const float band = 2.4e-7f * (6.f * (float)fmax(Sx, Sy) + 10.f * R) + 4.0e-6f + 3.1e-5f;
+    if (!(band <= WF_MAX_BAND)) return false;
+    const float B = band * 65536.f;
+    float lox, hix, loy, hiy;
+    wf_bounds<BILINEAR>(T.xc, T.yc, J.bw, J.bh, lox, hix, loy, hiy);
+    const float nn_lo = BILINEAR ? 0.f : 65536.f;
+    const bool all_in = rxmin >= lox + nn_lo + B && rxmax <= hix - B && rymin >= loy + nn_lo + B && rymax <= hiy - B;
+    const bool all_out = rxmax < lox - B || rxmin > hix + B || rymax < loy - B || rymin > hiy + B;
+    // destination: 32-bit stores
+    if (J.dst_pitch <= 0 || J.dst_pitch >= (1LL << 31)) return false;
+    uint8_t *const dt = dst_base + J.dst_offset + (long long)r0 * J.dst_pitch + 3LL * c0;
+    if ((((size_t)dt) | (size_t)J.dst_pitch) & 3) return false;
+    if ((((size_t)dt) >> 32) != (((size_t)dt + (size_t)(WS_H - 1) * (size_t)J.dst_pitch + 3 * WS_W) >> 32)) return false;   // row steps add to the low word only
+    if (c0 > 65535 || r0 > 65535 || job > 65535) return false;
+    S.dst = dt; S.dst_pitch = (int)J.dst_pitch; S.job = (uint16_t)job; S.c0 = (uint16_t)c0; S.r0 = (uint16_t)r0;
+    S.xc = T.xc; S.yc = T.yc; S.b16 = (uint16_t)((int)B + 2);
+    S.tma_x = S.tma_y = 0; S.img = 0; S.phase = 0; S.ox = S.oy = 0; S.rows = 0; S.chunks = 2; S.magic = 0x80000000u;
+    S.nx0 = S.ax = S.bx = S.ny0 = S.ay = S.by = S.gw = S.hw = 0.f;
+    if (all_out) { S.mode = (uint8_t)WF_ZERO; return true; }
+    int x_lo, x_hi, y_lo, y_hi;
+    if (BILINEAR) {
+        x_lo = __float2int_rd((rxmin - B) * (1.f / 65536.f)); x_hi = __float2int_rd((rxmax + B) * (1.f / 65536.f));
+        y_lo = __float2int_rd((rymin - B) * (1.f / 65536.f)); y_hi = __float2int_rd((rymax + B) * (1.f / 65536.f)) + 1;
+    } else {
+        x_lo = __float2int_rd((rxmin - B) * (1.f / 65536.f) + 0.5f) - 1; x_hi = __float2int_rd((rxmax + B) * (1.f / 65536.f) + 0.5f) + 1;
+        y_lo = __float2int_rd((rymin - B) * (1.f / 65536.f) + 0.5f) - 1; y_hi = __float2int_rd((rymax + B) * (1.f / 65536.f) + 0.5f) + 1;
+    }
+    if (!all_in) {      // clip to what a clamped coordinate can touch (see wf_setup)
+        const int ix_lo = 0 - T.xc, ix_hi = J.bw - 1 - T.xc, iy_lo = 0 - T.yc, iy_hi = J.bh - 1 - T.yc, ytap = BILINEAR ? 1 : 0;
+        if (x_hi < ix_lo) x_lo = x_hi = ix_lo;
+        else if (x_lo > ix_hi) x_lo = x_hi = ix_hi;
+        else { x_lo = max(x_lo, ix_lo); x_hi = min(x_hi, ix_hi); }
+        if (y_hi < iy_lo) { y_lo = iy_lo; y_hi = iy_lo + ytap; }
+        else if (y_lo > iy_hi) { y_lo = iy_hi; y_hi = iy_hi + ytap; }
+        else { y_lo = max(y_lo, iy_lo); y_hi = min(y_hi, iy_hi + ytap); }
+    }
+    if (x_hi < x_lo || y_hi < y_lo) { x_hi = x_lo; y_hi = y_lo; }
+    const int ax0 = (T.xc + x_lo) & ~3;
+    const int ox = ax0 - T.xc;
+    const long long width = (long long)x_hi - ox + 1, rows = (long long)y_hi - y_lo + 1;
+    const long long P = max(8LL, (width + 3) & ~3LL);
+    if (P > WS_MAXP || rows > WS_ROWS) return false;
+    const int ay0 = T.yc + y_lo;
+    // the one footprint per image that holds source pixel (0,0) (it must read as 0) stays with the old kernel
+    const bool has00 = ax0 <= 0 && (long long)ax0 + P + 1 > 0 && ay0 <= 0 && (long long)ay0 + rows > 0;
+    const bool img_ok = J.ih == tma.image_rows && 3LL * J.iw == tma.row_bytes && J.src_pitch == tma.pitch && J.src_offset >= 0 &&
+                        J.src_offset % (tma.pitch * tma.image_rows) == 0;
+    if (has00 || !img_ok || !(ax0 > -(1 << 24) && ay0 > -(1 << 24))) return false;
+    const long long img = J.src_offset / (tma.pitch * tma.image_rows);
+    if (ox < -128 || y_lo < -128 || ox > 127 || y_lo > 127 || img > 65535) return false;
+    S.mode = all_in ? WF_INTERIOR : WF_BORDER;
+    S.ox = (int8_t)ox; S.oy = (int8_t)y_lo; S.rows = (uint8_t)rows; S.chunks = (uint8_t)(P >> 2);
+    S.magic = (unsigned)((0x100000000ULL + (unsigned)S.chunks - 1) / (unsigned)S.chunks);
+    S.tma_x = (3 * ax0) & ~15; S.phase = (uint8_t)((3 * ax0) & 15); S.tma_y = ay0;
+    S.img = (uint16_t)img;
+    // biased coefficients: n' = n + bias * w, so that  round(n' / w) = floor(n / w [+ 1/2 px for nn])  up to a quarter unit
+    const double bias = BILINEAR ? -0.25 : 32768.0 - 0.25;
+    S.nx0 = (float)((xs - xc) + bias * sc); S.ax = (float)(ax + bias * gw * sc); S.bx = (float)(bx + bias * hw * sc);
+    S.ny0 = (float)((ys - yc) + bias * sc); S.ay = (float)(ay + bias * gw * sc); S.by = (float)(by + bias * hw * sc);
+    S.gw = T.gw; S.hw = T.hw;
+    return true;
+}
+
+// Set-up of the routed launch.  One thread per 64 x 40 tile: the four strip records if all four strips qualify (appended to
+// `strips`, count in counts[0]), else the tile's WpTile record (appended to `tiles`, count in counts[1]).
+// Appends are aggregated per warp (one atomic per warp and list).
+template <int BILINEAR>
+__global__ void __launch_bounds__(256)
+warp_route_setup_kernel(const b200geo_warp_job *__restrict__ jobs, const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst_base,
+                        const WfTma tma, int use_tmap, int tiles_x, int tiles_y, WsStrip *__restrict__ strips, WpTile *__restrict__ tiles,
+                        unsigned *__restrict__ counts)
+{
+    const int tx = blockIdx.x * 32 + threadIdx.x, ty = blockIdx.y * 8 + threadIdx.y;
+    const int lane = threadIdx.x;
+    bool live = tx < tiles_x && ty < tiles_y;
+    const b200geo_warp_job &J = jobs[blockIdx.z];
+    const int c0 = tx * WF_TW, r0 = ty * WF_TH;
+    if (live && (c0 >= J.ow || r0 >= J.oh)) live = false;
+    WsStrip S[4];
+    bool fast = live;
+    if (fast) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (fast) fast = ws_setup<BILINEAR>(J, (int)blockIdx.z, c0 + (k & 1) * WS_W, r0 + (k >> 1) * WS_H, tma, dst_base, S[k]);
+    }
+    const unsigned m_fast = __ballot_sync(0xffffffffu, fast), m_old = __ballot_sync(0xffffffffu, live && !fast);
+    unsigned b_fast = 0, b_old = 0;
+    if (lane == 0) {
+        if (m_fast) b_fast = atomicAdd(counts + 0, (unsigned)__popc(m_fast));
+        if (m_old) b_old = atomicAdd(counts + 1, (unsigned)__popc(m_old));
+    }
+    b_fast = __shfl_sync(0xffffffffu, b_fast, 0);
+    b_old = __shfl_sync(0xffffffffu, b_old, 0);
+    const unsigned below = (1u << lane) - 1u;
+    if (fast) {
+        uint4 *d = reinterpret_cast<uint4 *>(strips + 4 * (size_t)(b_fast + __popc(m_fast & below)));
+        const uint4 *sv = reinterpret_cast<const uint4 *>(S);
+#pragma unroll
+        for (int i = 0; i < 4 * WS_REC_BYTES / 16; ++i) d[i] = sv[i];
+    } else if (live) {
+        WpTile W;
+        wp_build_tile<BILINEAR>(J, (int)blockIdx.z, c0, r0, src_base, dst_base, tma, use_tmap, W);
+        uint4 *d = reinterpret_cast<uint4 *>(tiles + (size_t)(b_old + __popc(m_old & below)));
+        const uint4 *sv = reinterpret_cast<const uint4 *>(&W);
+#pragma unroll
+        for (int i = 0; i < WP_TILE_WORDS; ++i) d[i] = sv[i];
+    }
+}
+
+__device__ __forceinline__ uint32_t ws_lds32(uint32_t a)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float ws_ldsf(uint32_t a)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t ws_ldsu8(uint32_t a)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ int ws_ldss8(uint32_t a)
+{
+    int v;
+    asm volatile("ld.shared.s8 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t ws_ldsu16(uint32_t a)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+template <int OFF>
+__device__ __forceinline__ uint32_t ws_lds32o(uint32_t a)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(a), "n"(OFF));
+    return v;
+}
+__device__ __forceinline__ void ws_stg32(uint8_t *p, uint32_t v)
+{
+    asm volatile("st.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+#define WS_REC(field) ((uint32_t)offsetof(WsStrip, field))
+
+// raw RGB rows (tensor copy: row pitch WS_RAW_W, entry column 0 at byte `phase`) -> staged entries of this warp
+__device__ __forceinline__ void ws_convert(uint32_t rec, uint32_t s_raw, uint32_t s_ent, int lane)
+{
+    const int rows = (int)ws_ldsu8(rec + WS_REC(rows)), chunks = (int)ws_ldsu8(rec + WS_REC(chunks));
+    const uint32_t magic = ws_lds32(rec + WS_REC(magic)), phase = ws_ldsu8(rec + WS_REC(phase));
+    const int total = rows * chunks;
+    const uint32_t Dr = (uint32_t)WS_RAW_W - 12u * (uint32_t)chunks, De = (uint32_t)WS_ROWB - 16u * (uint32_t)chunks;
+    uint32_t ra = s_raw + phase + 12u * (uint32_t)lane, ea = s_ent + 16u * (uint32_t)lane;
+#pragma unroll 2
+    for (int t = lane; t < total; t += 32) {
+        const uint32_t i = __umulhi((unsigned)t, magic);
+        const uint32_t a = ra + i * Dr;
+        const uint32_t w0 = ws_lds32(a), w1 = ws_lds32o<4>(a), w2 = ws_lds32o<8>(a), w3 = ws_lds32o<12>(a);
+        const uint32_t d = ea + i * De;
+        uint4 rg, bb;
+        rg.x = __byte_perm(w0, w1, 0x4130); bb.x = __byte_perm(w0, w1, 0x5252);
+        rg.y = __byte_perm(w0, w1, 0x7463); bb.y = __byte_perm(w1, w2, 0x4141);
+        rg.z = __byte_perm(w1, w2, 0x6352); bb.z = __byte_perm(w2, w2, 0x3030);
+        rg.w = __byte_perm(w2, w3, 0x5241); bb.w = __byte_perm(w2, w3, 0x6363);
+        wf_sts128(d, rg);
+        wf_sts128(d + WS_PLANE, bb);
+        ra += 32u * 12u; ea += 32u * 16u;
+    }
+}
+
+#ifndef B2G_WS_GROUP
+#define B2G_WS_GROUP 4      // rows of a lane whose taps are in flight together
+#endif
+#ifndef B2G_WS_UNROLL
+#define B2G_WS_UNROLL 1     // 1: the 20 rows of an INTERIOR strip fully unrolled (row index = immediate operand)
+#endif
+
+__device__ __forceinline__ float2 ws_ldsf2(uint32_t a)
+{
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+    return v;
+}
+// opaque to the optimiser's algebra: keeps "integer part, then scaled add" as SHF + IMAD / LEA
+__device__ __forceinline__ uint32_t ws_hi16(uint32_t v)
+{
+    uint32_t r;
+    asm("shr.u32 %0, %1, 16;" : "=r"(r) : "r"(v));
+    return r;
+}
+// 32-bit store through a pointer given as (low word, high word): the row step touches the low word only (the set-up
+// kernel routes a strip here only if its 20 rows do not cross a 4 GiB boundary)
+__device__ __forceinline__ void ws_stg32_lh(uint32_t lo, uint32_t hi, uint32_t v)
+{
+    asm volatile("{\n\t.reg .b64 a;\n\tmov.b64 a, {%0, %1};\n\tst.global.u32 [a], %2;\n\t}" ::"r"(lo), "r"(hi), "r"(v) : "memory");
+}
+
+// One strip: 20 pixels per lane (column c0 + lane, rows r0 .. r0+19).
+template <int BILINEAR, int BORDER>
+__device__ __forceinline__ void ws_sample(uint32_t rec, uint32_t s_ent, int lane, const b200geo_warp_job *__restrict__ jobs,
+                                          const uint8_t *__restrict__ src_base, const WfFix &fix0, unsigned &n_exact)
+{
+    const float2 A2 = ws_ldsf2(rec + WS_REC(ax)), B2 = ws_ldsf2(rec + WS_REC(bx));
+    const float gw = ws_ldsf(rec + WS_REC(gw)), hw = ws_ldsf(rec + WS_REC(hw));
+    const float di0 = (float)(lane - WS_W / 2);
+    const float2 nb = __ffma2_rn(A2, make_float2(di0, di0), ws_ldsf2(rec + WS_REC(nx0)));
+    const float wb = __fmaf_rn(gw, di0, WF_W0);
+    const int ox = ws_ldss8(rec + WS_REC(ox)), oy = ws_ldss8(rec + WS_REC(oy));
+    // plane-0 word of entry (xi, yi) [bit patterns of the magic-number fixed point, integer parts offset by WS_MAGIC_HI]
+    const uint32_t base = s_ent - (uint32_t)((WS_MAGIC_HI + oy) * WS_ROWB + (WS_MAGIC_HI + ox) * 4);
+    unsigned long long dstrip;             // first output byte of the strip
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(dstrip) : "r"(rec + WS_REC(dst)));
+    // word (lane & 3) of the 12 bytes of pixels 4 * (lane >> 2) .. + 3:  RGBR | GBRG | BRGB  (three of four lanes store)
+    uint32_t g_lo = (uint32_t)dstrip + (uint32_t)(12 * (lane >> 2) + 4 * (lane & 3));
+    const uint32_t g_hi = (uint32_t)(dstrip >> 32);
+    const uint32_t pitch = ws_lds32(rec + WS_REC(dst_pitch));
+    const uint32_t psel = (lane & 3) == 0 ? 0x4210u : ((lane & 3) == 1 ? 0x5421u : 0x6542u);
+    const bool st_lane = (lane & 3) != 3;
+    float lox = 0.f, hix = 0.f, loy = 0.f, hiy = 0.f, band = 0.f;
+    int xlo = 0, xhi = 0, ylo = 0, yhi = 0;
+    uint32_t B16 = 0u;
+    if (BORDER || !BILINEAR) {
+        B16 = ws_ldsu16(rec + WS_REC(b16));
+        band = (float)B16;
+    }
+    if (BORDER) {
+        const b200geo_warp_job &J = jobs[ws_ldsu16(rec + WS_REC(job))];
+        const int xc = (int)ws_lds32(rec + WS_REC(xc)), yc = (int)ws_lds32(rec + WS_REC(yc));
+        wf_bounds<BILINEAR>(xc, yc, J.bw, J.bh, lox, hix, loy, hiy);
+        xlo = -xc; xhi = J.bw - 1 - xc; ylo = -yc; yhi = J.bh - 1 - yc;
+        if (!BILINEAR) {     // the biased coordinate carries + 1/2 px
+            lox += 32768.f; hix += 32768.f; loy += 32768.f; hiy += 32768.f;
+        }
+    }
+    constexpr int G = B2G_WS_GROUP;
+    static_assert(WS_H % G == 0, "row groups");
+    uint32_t amb = 0u, inmask = 0u;
+    auto group = [&](const int g0, const float2 n2g, const float wg) {
+        // n2g, wg: numerators / denominator of row g0 (for the looped form: of row g0, the rows of the group add constants)
+        uint32_t t0[G], t1[G], t2[G], t3[G], bx_[G], by_[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const float dj = (float)g;
+            const float2 n2 = g ? __ffma2_rn(B2, make_float2(dj, dj), n2g) : n2g;
+            const float w = g ? __fmaf_rn(hw, dj, wg) : wg;
+            const float rw = wf_rcp(w);
+            uint32_t bxv, byv;
+            if (BORDER) {
+                float2 r = __fmul2_rn(n2, make_float2(rw, rw));
+                const bool in = r.x >= lox + band && r.x <= hix - band && r.y >= loy + band && r.y <= hiy - band;
+                const bool outp = r.x < lox - band || r.x > hix + band || r.y < loy - band || r.y > hiy + band;
+                if (in) inmask |= 1u << (g0 + g);
+                else if (!outp) amb |= 1u << (g0 + g);                 // also NaN coordinates
+                r.x = fminf(fmaxf(r.x, lox), hix);                     // (NaN -> lox)
+                r.y = fminf(fmaxf(r.y, loy), hiy);
+                const float2 f = __fadd2_rn(r, make_float2(WS_MAGIC, WS_MAGIC));
+                bxv = __float_as_uint(f.x); byv = __float_as_uint(f.y);
+            } else {
+                const float2 f = __ffma2_rn(n2, make_float2(rw, rw), make_float2(WS_MAGIC, WS_MAGIC));
+                bxv = __float_as_uint(f.x); byv = __float_as_uint(f.y);
+            }
+            uint32_t xi = ws_hi16(bxv), yi = ws_hi16(byv);
+            if (!BILINEAR) {
+                const uint32_t fx = bxv & 0xFFFFu, fy = byv & 0xFFFFu;
+                const bool near = fx - B16 > 65535u - 2u * B16 || fy - B16 > 65535u - 2u * B16;
+                if (BORDER) {
+                    if (near && (inmask >> (g0 + g) & 1u)) amb |= 1u << (g0 + g);
+                    xi = (uint32_t)(min(max((int)xi - WS_MAGIC_HI, xlo), xhi) + WS_MAGIC_HI);
+                    yi = (uint32_t)(min(max((int)yi - WS_MAGIC_HI, ylo), yhi) + WS_MAGIC_HI);
+                } else if (near) amb |= 1u << (g0 + g);
+            }
+            const uint32_t a = yi * (uint32_t)WS_ROWB + (xi * 4u + base);
+            t0[g] = ws_lds32(a);
+            t1[g] = ws_lds32o<WS_PLANE>(a);
+            if (BILINEAR) {
+                t2[g] = ws_lds32o<WS_ROWB>(a);
+                t3[g] = ws_lds32o<WS_ROWB + WS_PLANE>(a);
+            }
+            bx_[g] = bxv; by_[g] = byv;
+        }
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            uint32_t out;
+            if (BILINEAR) out = wf_blend(make_uint2(t0[g], t1[g]), make_uint2(t2[g], t3[g]), bx_[g] & 0xFFFFu, by_[g] & 0xFFFFu);
+            else out = __byte_perm(t0[g], t1[g], 0x4420);
+            if (BORDER && !(inmask >> (g0 + g) & 1u)) out = 0u;
+            const uint32_t nbr = __shfl_down_sync(0xffffffffu, out, 1);
+            const uint32_t word = __byte_perm(out, nbr, psel);
+            if (st_lane) ws_stg32_lh(g_lo, g_hi, word);
+            g_lo += pitch;
+        }
+    };
+    if (B2G_WS_UNROLL && !BORDER) {
+#pragma unroll
+        for (int g0 = 0; g0 < WS_H; g0 += G) {
+            const float dj = (float)(g0 - WS_H / 2);
+            group(g0, __ffma2_rn(B2, make_float2(dj, dj), nb), __fmaf_rn(hw, dj, wb));
+        }
+    } else {
+        float dj = (float)(-WS_H / 2);
+#pragma unroll 1
+        for (int g0 = 0; g0 < WS_H; g0 += G) {
+            group(g0, __ffma2_rn(B2, make_float2(dj, dj), nb), __fmaf_rn(hw, dj, wb));
+            dj += (float)G;
+        }
+    }
+    if (BORDER || !BILINEAR) {
+        if (__any_sync(0xffffffffu, amb != 0u)) {
+            __syncwarp();                                   // every lane's word stores precede the byte stores below
+            if (amb) {
+                const int job = (int)ws_ldsu16(rec + WS_REC(job));
+                const int c = (int)ws_ldsu16(rec + WS_REC(c0)) + lane, r0 = (int)ws_ldsu16(rec + WS_REC(r0));
+                WfFix fix = fix0;
+                fix.job = job;
+#pragma unroll 1
+                for (uint32_t rest = amb; rest; rest &= rest - 1u) {
+                    const int k = __ffs((int)rest) - 1;
+                    if (!wf_defer(fix, c, r0 + k)) {
+                        const b200geo_warp_job &J = jobs[job];
+                        const uint32_t v = wf_exact_px<BILINEAR>(J, src_base + J.src_offset, c, r0 + k);
+                        ++n_exact;
+                        uint8_t *p = reinterpret_cast<uint8_t *>(dstrip) + (long long)k * (int)pitch + 3 * lane;
+                        p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16);
+                    }
+                }
+            }
+        }
+    }
+}
+
+// Grid: min(ceil(n_tiles / 16), SMs) CTAs of 16 warps, dynamic shared memory WS_SMEM_BYTES (one CTA per SM).
+// counts[0] = number of routed tiles (four strip records each); ticket: global tile-ticket counter (zeroed by the host).
+template <int BILINEAR>
+__global__ void __launch_bounds__(WS_THREADS, 1)
+warp_strip_kernel(const uint8_t *__restrict__ src_base, const b200geo_warp_job *__restrict__ jobs, const WsStrip *__restrict__ strips,
+                  const unsigned *__restrict__ counts, const __grid_constant__ CUtensorMap tmap, WfFixEntry *__restrict__ fix_list,
+                  unsigned *__restrict__ fix_counts, unsigned seg_cap, unsigned *__restrict__ ticket, unsigned long long *__restrict__ stats)
+{
+    extern __shared__ __align__(128) unsigned char ws_smem[];
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(ws_smem);
+    const uint32_t s_raw = s0 + (uint32_t)(wrp * WS_WARP_BYTES), s_ent = s_raw + WS_RAW_BYTES;
+    const uint32_t s_recs = s0 + (uint32_t)(WS_WARPS * WS_WARP_BYTES) + (uint32_t)(wrp * 2 * WS_REC_BYTES);
+    const uint32_t s_bar = s0 + (uint32_t)(WS_WARPS * (WS_WARP_BYTES + 2 * WS_REC_BYTES)) + 8u * (uint32_t)wrp;
+    unsigned *const s_fix_n = reinterpret_cast<unsigned *>(ws_smem + WS_WARPS * (WS_WARP_BYTES + 2 * WS_REC_BYTES + 8));
+    if (threadIdx.x == 0) *s_fix_n = 0u;
+    if (lane == 0) {
+        wp_mbar_init(s_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+
+    const unsigned n_tiles = counts[0];
+    const unsigned n_warps = gridDim.x * WS_WARPS;
+    unsigned tile = blockIdx.x * WS_WARPS + wrp;
+    unsigned n_exact = 0;
+    const WfFix fix = {fix_list + (size_t)blockIdx.x * seg_cap, s_fix_n, seg_cap, 0};
+
+    auto fetch_record = [&](uint32_t slot, unsigned strip) {      // asynchronous: lanes 0..7 copy 16 bytes each
+        if (lane < WS_REC_BYTES / 16) {
+            const char *g = reinterpret_cast<const char *>(strips + strip) + 16 * lane;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(slot + 16u * (uint32_t)lane), "l"(g) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto issue_copy = [&](uint32_t slot) {                        // lane 0: tensor copy of the strip's footprint into this warp's raw rows
+        if (lane == 0 && (int)ws_ldsu8(slot + WS_REC(mode)) != WF_ZERO) {
+            const int x = (int)ws_lds32(slot + WS_REC(tma_x)), y = (int)ws_lds32(slot + WS_REC(tma_y)), z = (int)ws_ldsu16(slot + WS_REC(img));
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // this warp's generic reads of the raw rows precede the overwrite
+            wp_mbar_expect_tx(s_bar, (uint32_t)(WS_RAW_W * WS_ROWS));
+            asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                         ::"r"(s_raw), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(x), "r"(y), "r"(z), "r"(s_bar) : "memory");
+        }
+    };
+
+    if (tile < n_tiles) {
+        uint32_t slot_cur = s_recs, slot_nxt = s_recs + WS_REC_BYTES;
+        unsigned tk = 0;                                          // lane 0: ticket of the tile after `tile`
+        if (lane == 0) tk = atomicAdd(ticket, 1u);
+        fetch_record(slot_cur, tile * 4u);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+        issue_copy(slot_cur);
+        uint32_t ph = 0u;
+        int j = 0;
+        for (;;) {
+            unsigned nxt_tile = tile, nxt_strip;
+            bool has_next = true;
+            if (j < 3) nxt_strip = tile * 4u + (unsigned)(j + 1);
+            else {
+                nxt_tile = __shfl_sync(0xffffffffu, tk, 0) + n_warps;
+                has_next = nxt_tile < n_tiles;
+                nxt_strip = nxt_tile * 4u;
+            }
+            if (has_next) fetch_record(slot_nxt, nxt_strip);
+            const int mode = (int)ws_ldsu8(slot_cur + WS_REC(mode));
+            if (mode != WF_ZERO) {
+                wp_mbar_wait(s_bar, ph);
+                ph ^= 1u;
+                ws_convert(slot_cur, s_raw, s_ent, lane);
+            }
+            __syncwarp();                                         // entries written / raw rows read by every lane
+            if (has_next) {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                __syncwarp();
+                issue_copy(slot_nxt);
+            }
+            // (votes: the branch conditions are warp-uniform by construction, so the shuffles inside need no divergence check)
+            if (__all_sync(0xffffffffu, mode == WF_INTERIOR)) ws_sample<BILINEAR, 0>(slot_cur, s_ent, lane, jobs, src_base, fix, n_exact);
+            else if (__all_sync(0xffffffffu, mode == WF_BORDER)) ws_sample<BILINEAR, 1>(slot_cur, s_ent, lane, jobs, src_base, fix, n_exact);
+            else {
+                unsigned long long d;
+                asm volatile("ld.shared.u64 %0, [%1];" : "=l"(d) : "r"(slot_cur + WS_REC(dst)));
+                uint8_t *gp = reinterpret_cast<uint8_t *>(d) + 4 * lane;
+                const int pitch = (int)ws_lds32(slot_cur + WS_REC(dst_pitch));
+                if (lane < 24) {
+#pragma unroll 4
+                    for (int r = 0; r < WS_H; ++r) ws_stg32(gp + (long long)r * pitch, 0u);
+                }
+            }
+            if (!has_next) break;
+            __syncwarp();                                         // every lane is done with the entries and the current record
+            const uint32_t tmp = slot_cur; slot_cur = slot_nxt; slot_nxt = tmp;
+            if (j < 3) ++j;
+            else {
+                tile = nxt_tile; j = 0;
+                if (lane == 0) tk = atomicAdd(ticket, 1u);
+            }
+        }
+    }
+    if (stats && n_exact) atomicAdd(stats, (unsigned long long)n_exact);
+    __syncthreads();                                              // every warp has pushed its last deferred pixel
+    if (threadIdx.x == 0) fix_counts[blockIdx.x] = *s_fix_n;
+}
+
+}  // namespace b200geo

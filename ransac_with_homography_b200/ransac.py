@@ -5,7 +5,8 @@ the C ABI (include/b200geo.h).  No CPU fallback.
 
 Parallel form of the loop (reference ransac.py:176-202): the k sample sets are drawn up front from
 the same global ``np.random`` stream the reference consumes (``randint(0, M, (k, n))`` is
-stream-identical to k sequential ``randint(0, M, n)`` calls), all k hypotheses are solved and
+stream-identical to k sequential ``randint(0, M, n)`` calls; after an early exit the stream is rewound
+to where the reference's ``break`` leaves it), all k hypotheses are solved and
 scored at once, and the winner is the first iteration meeting ``M*d/100 + n`` if any (the
 reference's ``break``), else the lowest-index maximum (the reference's strict ``>``).
 """
@@ -155,7 +156,9 @@ class RANSAC(object):
         assert self.n == 4, "the homography model samples 4 correspondences"
         d = mx * self.d / 100
         k = int(self.k)
+        rng_state = None
         if idx is None:
+            rng_state = np.random.get_state()
             idx = np.random.randint(0, mx, (k, self.n))      # same stream as k draws of n (ransac.py:177)
         idx = np.ascontiguousarray(idx, dtype=np.int32).reshape(-1, 4)
         k = idx.shape[0]
@@ -178,6 +181,11 @@ class RANSAC(object):
         _cabi.check(rc)
         w = int(winner[0])
         totalfitLen = np.int64(count[0])
+        if rng_state is not None and count[0] >= (d + self.n) and w + 1 < k:
+            # the reference stops drawing at its `break` (ransac.py:177,186-190): leave the global stream where it
+            # leaves it -- after (w + 1) draws of n -- so that seeded sequences of calls stay in step
+            np.random.set_state(rng_state)
+            np.random.randint(0, mx, (w + 1, self.n))
         # the reference's warning tests the LAST evaluated iteration's count (ransac.py:203-204)
         # (count[0] is the winner's count; if it met the threshold the loop broke there, else it ran to sample set k-1)
         last_cnt = int(count[0]) if count[0] >= (d + self.n) else int(last_count[0])

@@ -396,7 +396,7 @@ def test_device_stitch_compose_matches_host_entry(golden, capsys):
 @pytest.mark.parametrize("sampler", ["nn", "bilinear"])
 def test_layout_hints_do_not_change_results(kind, sampler):
     """b200geo_warp_batch_dev with no layout, the 2-D layout and the 3-D layout (per-image zero fill: edge
-    footprints arrive by tensor copy too) must produce identical bytes, and those match the float64 kernel."""
+    footprints arrive by tensor copy too; full tiles go to the per-warp strip kernel) against the float64 kernel."""
     import torch
     from ransac_with_homography_b200 import _cabi, device
     ctx = _cabi.context()
@@ -413,13 +413,19 @@ def test_layout_hints_do_not_change_results(kind, sampler):
             dst_t = torch.full((B, h, w, 3), 9, dtype=torch.uint8, device="cuda")
             device.warp_resident(src_t, dst_t, jd, B, w, h, 3, sampler, layout=layout)
             outs.append(dst_t.cpu().numpy())
-        assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2]), (kind, h, w)
+        # no layout and the 2-D layout run the same kernel (only the staging differs): identical bytes.  The 3-D layout
+        # routes full tiles to the per-warp strip kernel, whose float32 coordinates are relative to other anchors:
+        # nn stays identical (it is bit-exact by construction), bilinear stays within the same +-1 of the float64 kernel.
+        assert np.array_equal(outs[0], outs[1]), (kind, h, w)
+        if sampler == "nn":
+            assert np.array_equal(outs[0], outs[2]), (kind, h, w)
         ctx.warp_exact(True)
         dst_t = torch.full((B, h, w, 3), 9, dtype=torch.uint8, device="cuda")
         device.warp_resident(src_t, dst_t, jd, B, w, h, 3, sampler)
         ctx.warp_exact(False)
-        d = np.abs(outs[2].astype(np.int16) - dst_t.cpu().numpy().astype(np.int16))
-        assert d.max() <= (0 if sampler == "nn" else U8_TOL), (kind, h, w, int(d.max()))
+        for o in outs:
+            d = np.abs(o.astype(np.int16) - dst_t.cpu().numpy().astype(np.int16))
+            assert d.max() <= (0 if sampler == "nn" else U8_TOL), (kind, h, w, int(d.max()))
 
 
 def test_border_tile_far_from_its_anchor_regression():
