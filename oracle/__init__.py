@@ -224,3 +224,48 @@ def wrapPerspectiveScan(img, H, res, convert="nn"):
     gx, gy = scan_grid(res)
     out = warp(img, np.linalg.inv(np.asarray(H, np.float64)), gx, gy, res, convert)
     return out, 0, 0
+
+
+_ref_mods = None
+
+
+def reference_modules():
+    """(ransac, homography): the modules of the UNMODIFIED reference as copied to oracle/_ref/ by oracle/make_ref.py
+    (digests checked against the manifest), or None when the copy is absent.  They are imported under the private names
+    ``_ref_ransac`` / ``_ref_homography`` so that they never shadow the product's modules.  bench.py's reference arm and
+    cpu_baseline time these; nothing in the product imports them."""
+    global _ref_mods
+    if _ref_mods is not None:
+        return _ref_mods or None
+    import hashlib
+    import importlib
+    import json
+    import sys
+    d = os.path.join(_HERE, "_ref")
+    try:
+        with open(os.path.join(d, "MANIFEST.json")) as f:
+            man = json.load(f)["sha256"]
+        for name in ("ransac.py", "homography.py"):
+            with open(os.path.join(d, name), "rb") as f:
+                if hashlib.sha256(f.read()).hexdigest() != man[name]:
+                    raise ValueError(name + " differs from the manifest")
+    except (OSError, ValueError, KeyError):
+        _ref_mods = ()
+        return None
+    saved = {k: sys.modules.pop(k, None) for k in ("ransac", "homography")}
+    sys.path.insert(0, d)
+    dwb, sys.dont_write_bytecode = sys.dont_write_bytecode, True
+    try:
+        hg = importlib.import_module("homography")
+        rr = importlib.import_module("ransac")           # does `from homography import ...`
+    finally:
+        sys.dont_write_bytecode = dwb
+        sys.path.remove(d)
+        for k in ("ransac", "homography"):
+            sys.modules.pop(k, None)
+            if saved[k] is not None:
+                sys.modules[k] = saved[k]
+    sys.modules["_ref_ransac"], sys.modules["_ref_homography"] = rr, hg
+    _ref_mods = (rr, hg)
+    return _ref_mods
+

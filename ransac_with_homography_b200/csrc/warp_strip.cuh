@@ -40,14 +40,22 @@ constexpr int WS_ROWB = WS_EPR * 8;          // staged row pitch: 384 B
 constexpr int WS_ROWS = 26;                  // staged rows
 constexpr int WS_RAW_W = 160;                // tensor-copy box: bytes per row (multiple of 16) ...
 constexpr int WS_MAXP = 44;                  // ... which holds 4 + 12 + 3 * (44 + 1) <= 160 bytes
-constexpr int WS_WARPS = 16;
+#ifndef B2G_WS_WARPS
+#define B2G_WS_WARPS 12
+#endif
+#ifndef B2G_WS_NRAW
+#define B2G_WS_NRAW 2
+#endif
+constexpr int WS_WARPS = B2G_WS_WARPS;       // warps per CTA (one CTA per SM; shared memory is what limits them)
+constexpr int WS_NRAW = B2G_WS_NRAW;         // raw-row buffers per warp = strips a tensor copy is issued ahead of its use
+constexpr int WS_NREC = WS_NRAW + 1;         // record slots per warp
 constexpr int WS_THREADS = WS_WARPS * 32;
 constexpr int WS_RAW_BYTES = ((WS_RAW_W * WS_ROWS + 127) / 128) * 128;
 constexpr int WS_ENT_BYTES = WS_ROWB * WS_ROWS;
-constexpr int WS_WARP_BYTES = WS_RAW_BYTES + WS_ENT_BYTES;
+constexpr int WS_WARP_BYTES = WS_NRAW * WS_RAW_BYTES + WS_ENT_BYTES;
 static_assert(WS_WARP_BYTES % 128 == 0, "tensor-copy destinations are 128-byte aligned");
 constexpr int WS_REC_BYTES = 80;
-constexpr int WS_SMEM_BYTES = WS_WARPS * (WS_WARP_BYTES + 2 * WS_REC_BYTES + 8) + 16;
+constexpr int WS_SMEM_BYTES = WS_WARPS * (WS_WARP_BYTES + WS_NREC * WS_REC_BYTES + 8 * WS_NRAW) + 16;
 static_assert(WS_SMEM_BYTES <= 227 * 1024, "one CTA per SM");
 constexpr float WS_MAGIC = 12582912.f;       // 1.5 * 2^23: float32(MAGIC + v) has the integer v in its low 23 bits for |v| < 2^22
 constexpr int WS_MAGIC_HI = 0x4B40;          // bits 16.. of MAGIC's pattern: the offset of the 16.16 integer part
@@ -269,28 +277,74 @@ __device__ __forceinline__ void ws_stg32(uint8_t *p, uint32_t v)
 
 #define WS_REC(field) ((uint32_t)offsetof(WsStrip, field))
 
-// raw RGB rows (tensor copy: row pitch WS_RAW_W, entry column 0 at byte `phase`) -> staged entries of this warp
-__device__ __forceinline__ void ws_convert(uint32_t rec, uint32_t s_raw, uint32_t s_ent, int lane)
+// The 80-byte record as the kernel holds it in registers (four / five 16-byte shared-memory loads per strip: the data pipe
+// of the SM is the kernel's limiter, and twenty scalar loads per strip were 8 % of its wavefronts).
+struct WsRegs {
+    uint4 w0, w1, w2, w3, w4;  // (nx0 ny0 ax ay) (bx by gw hw) (tma_x tma_y dst) (dst_pitch img|job ox|oy|rows|chunks mode|phase|b16) (c0|r0 xc yc magic)
+    __device__ __forceinline__ int rows() const { return (int)((w3.z >> 16) & 0xFFu); }
+    __device__ __forceinline__ int chunks() const { return (int)(w3.z >> 24); }
+    __device__ __forceinline__ int ox() const { return (int)(int8_t)(w3.z & 0xFFu); }
+    __device__ __forceinline__ int oy() const { return (int)(int8_t)((w3.z >> 8) & 0xFFu); }
+    __device__ __forceinline__ int mode() const { return (int)(w3.w & 0xFFu); }
+    __device__ __forceinline__ uint32_t phase() const { return (w3.w >> 8) & 0xFFu; }
+    __device__ __forceinline__ uint32_t b16() const { return w3.w >> 16; }
+    __device__ __forceinline__ uint32_t job() const { return w3.y >> 16; }
+    __device__ __forceinline__ uint32_t img() const { return w3.y & 0xFFFFu; }
+};
+static_assert(offsetof(WsStrip, bx) == 16 && offsetof(WsStrip, tma_x) == 32 && offsetof(WsStrip, dst) == 40 && offsetof(WsStrip, dst_pitch) == 48 &&
+              offsetof(WsStrip, img) == 52 && offsetof(WsStrip, job) == 54 && offsetof(WsStrip, ox) == 56 && offsetof(WsStrip, oy) == 57 &&
+              offsetof(WsStrip, rows) == 58 && offsetof(WsStrip, chunks) == 59 && offsetof(WsStrip, mode) == 60 && offsetof(WsStrip, phase) == 61 &&
+              offsetof(WsStrip, b16) == 62 && offsetof(WsStrip, c0) == 64 && offsetof(WsStrip, xc) == 68 && offsetof(WsStrip, magic) == 76,
+              "WsRegs decodes the record by position");
+__device__ __forceinline__ uint4 ws_lds128(uint32_t a)
 {
-    const int rows = (int)ws_ldsu8(rec + WS_REC(rows)), chunks = (int)ws_ldsu8(rec + WS_REC(chunks));
-    const uint32_t magic = ws_lds32(rec + WS_REC(magic)), phase = ws_ldsu8(rec + WS_REC(phase));
-    const int total = rows * chunks;
-    const uint32_t Dr = (uint32_t)WS_RAW_W - 12u * (uint32_t)chunks, De = (uint32_t)WS_ROWB - 16u * (uint32_t)chunks;
-    uint32_t ra = s_raw + phase + 12u * (uint32_t)lane, ea = s_ent + 16u * (uint32_t)lane;
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+
+__device__ __forceinline__ void ws_convert_chunk(uint32_t a, uint32_t d)
+{
+    const uint32_t w0 = ws_lds32(a), w1 = ws_lds32o<4>(a), w2 = ws_lds32o<8>(a), w3 = ws_lds32o<12>(a);
+    uint4 rg, bb;
+    rg.x = __byte_perm(w0, w1, 0x4130); bb.x = __byte_perm(w0, w1, 0x5252);
+    rg.y = __byte_perm(w0, w1, 0x7463); bb.y = __byte_perm(w1, w2, 0x4141);
+    rg.z = __byte_perm(w1, w2, 0x6352); bb.z = __byte_perm(w2, w2, 0x3030);
+    rg.w = __byte_perm(w2, w3, 0x5241); bb.w = __byte_perm(w2, w3, 0x6363);
+    wf_sts128(d, rg);
+    wf_sts128(d + WS_PLANE, bb);
+}
+
+// raw RGB rows (tensor copy: row pitch WS_RAW_W, entry column 0 at byte `phase`) -> staged entries of this warp.
+// A chunk = four entries = 12 raw bytes -> 16 bytes per plane.  Phase A: chunks 0..7 of every row, eight lanes per row (each
+// quarter-warp writes 128 contiguous bytes of one row: no bank conflict; the flattened row-major order, whose quarter-warps
+// straddle rows 384 = 3 x 128 bytes apart, measured 2-way conflicts on every store).  Phase B: the one to three chunks
+// beyond the eighth, flattened over the rows.
+__device__ __forceinline__ void ws_convert(const WsRegs &R, uint32_t s_raw, uint32_t s_ent, int lane)
+{
+    const int rows = R.rows(), chunks = R.chunks();
+    const uint32_t phase = R.phase();
+    {
+        const int k = lane & 7;
+        uint32_t ra = s_raw + phase + (uint32_t)(lane >> 3) * WS_RAW_W + 12u * (uint32_t)k;
+        uint32_t ea = s_ent + (uint32_t)(lane >> 3) * WS_ROWB + 16u * (uint32_t)k;
+        if (k < chunks) {
 #pragma unroll 2
-    for (int t = lane; t < total; t += 32) {
-        const uint32_t i = __umulhi((unsigned)t, magic);
-        const uint32_t a = ra + i * Dr;
-        const uint32_t w0 = ws_lds32(a), w1 = ws_lds32o<4>(a), w2 = ws_lds32o<8>(a), w3 = ws_lds32o<12>(a);
-        const uint32_t d = ea + i * De;
-        uint4 rg, bb;
-        rg.x = __byte_perm(w0, w1, 0x4130); bb.x = __byte_perm(w0, w1, 0x5252);
-        rg.y = __byte_perm(w0, w1, 0x7463); bb.y = __byte_perm(w1, w2, 0x4141);
-        rg.z = __byte_perm(w1, w2, 0x6352); bb.z = __byte_perm(w2, w2, 0x3030);
-        rg.w = __byte_perm(w2, w3, 0x5241); bb.w = __byte_perm(w2, w3, 0x6363);
-        wf_sts128(d, rg);
-        wf_sts128(d + WS_PLANE, bb);
-        ra += 32u * 12u; ea += 32u * 16u;
+            for (int row = lane >> 3; row < rows; row += 4) {
+                ws_convert_chunk(ra, ea);
+                ra += 4u * WS_RAW_W; ea += 4u * WS_ROWB;
+            }
+        }
+    }
+    const int cb = chunks - 8;
+    if (cb > 0) {          // (warp-uniform)
+        const int total = rows * cb;
+#pragma unroll 1
+        for (int t = lane; t < total; t += 32) {
+            const int i = cb == 1 ? t : (cb == 2 ? t >> 1 : (int)(((unsigned)t * 43691u) >> 17));     // t / cb, cb <= 3
+            const int k = 8 + t - i * cb;
+            ws_convert_chunk(s_raw + phase + (uint32_t)i * WS_RAW_W + 12u * (uint32_t)k, s_ent + (uint32_t)i * WS_ROWB + 16u * (uint32_t)k);
+        }
     }
 }
 
@@ -323,35 +377,35 @@ __device__ __forceinline__ void ws_stg32_lh(uint32_t lo, uint32_t hi, uint32_t v
 
 // One strip: 20 pixels per lane (column c0 + lane, rows r0 .. r0+19).
 template <int BILINEAR, int BORDER>
-__device__ __forceinline__ void ws_sample(uint32_t rec, uint32_t s_ent, int lane, const b200geo_warp_job *__restrict__ jobs,
+__device__ __forceinline__ void ws_sample(const WsRegs &R, uint32_t s_ent, int lane, const b200geo_warp_job *__restrict__ jobs,
                                           const uint8_t *__restrict__ src_base, const WfFix &fix0, unsigned &n_exact)
 {
-    const float2 A2 = ws_ldsf2(rec + WS_REC(ax)), B2 = ws_ldsf2(rec + WS_REC(bx));
-    const float gw = ws_ldsf(rec + WS_REC(gw)), hw = ws_ldsf(rec + WS_REC(hw));
+    const float2 A2 = make_float2(__uint_as_float(R.w0.z), __uint_as_float(R.w0.w));
+    const float2 B2 = make_float2(__uint_as_float(R.w1.x), __uint_as_float(R.w1.y));
+    const float gw = __uint_as_float(R.w1.z), hw = __uint_as_float(R.w1.w);
     const float di0 = (float)(lane - WS_W / 2);
-    const float2 nb = __ffma2_rn(A2, make_float2(di0, di0), ws_ldsf2(rec + WS_REC(nx0)));
+    const float2 nb = __ffma2_rn(A2, make_float2(di0, di0), make_float2(__uint_as_float(R.w0.x), __uint_as_float(R.w0.y)));
     const float wb = __fmaf_rn(gw, di0, WF_W0);
-    const int ox = ws_ldss8(rec + WS_REC(ox)), oy = ws_ldss8(rec + WS_REC(oy));
+    const int ox = R.ox(), oy = R.oy();
     // plane-0 word of entry (xi, yi) [bit patterns of the magic-number fixed point, integer parts offset by WS_MAGIC_HI]
     const uint32_t base = s_ent - (uint32_t)((WS_MAGIC_HI + oy) * WS_ROWB + (WS_MAGIC_HI + ox) * 4);
-    unsigned long long dstrip;             // first output byte of the strip
-    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(dstrip) : "r"(rec + WS_REC(dst)));
+    const unsigned long long dstrip = ((unsigned long long)R.w2.w << 32) | R.w2.z;      // first output byte of the strip
     // word (lane & 3) of the 12 bytes of pixels 4 * (lane >> 2) .. + 3:  RGBR | GBRG | BRGB  (three of four lanes store)
     uint32_t g_lo = (uint32_t)dstrip + (uint32_t)(12 * (lane >> 2) + 4 * (lane & 3));
     const uint32_t g_hi = (uint32_t)(dstrip >> 32);
-    const uint32_t pitch = ws_lds32(rec + WS_REC(dst_pitch));
+    const uint32_t pitch = R.w3.x;
     const uint32_t psel = (lane & 3) == 0 ? 0x4210u : ((lane & 3) == 1 ? 0x5421u : 0x6542u);
     const bool st_lane = (lane & 3) != 3;
     float lox = 0.f, hix = 0.f, loy = 0.f, hiy = 0.f, band = 0.f;
     int xlo = 0, xhi = 0, ylo = 0, yhi = 0;
     uint32_t B16 = 0u;
     if (BORDER || !BILINEAR) {
-        B16 = ws_ldsu16(rec + WS_REC(b16));
+        B16 = R.b16();
         band = (float)B16;
     }
     if (BORDER) {
-        const b200geo_warp_job &J = jobs[ws_ldsu16(rec + WS_REC(job))];
-        const int xc = (int)ws_lds32(rec + WS_REC(xc)), yc = (int)ws_lds32(rec + WS_REC(yc));
+        const b200geo_warp_job &J = jobs[R.job()];
+        const int xc = (int)R.w4.y, yc = (int)R.w4.z;
         wf_bounds<BILINEAR>(xc, yc, J.bw, J.bh, lox, hix, loy, hiy);
         xlo = -xc; xhi = J.bw - 1 - xc; ylo = -yc; yhi = J.bh - 1 - yc;
         if (!BILINEAR) {     // the biased coordinate carries + 1/2 px
@@ -434,8 +488,8 @@ __device__ __forceinline__ void ws_sample(uint32_t rec, uint32_t s_ent, int lane
         if (__any_sync(0xffffffffu, amb != 0u)) {
             __syncwarp();                                   // every lane's word stores precede the byte stores below
             if (amb) {
-                const int job = (int)ws_ldsu16(rec + WS_REC(job));
-                const int c = (int)ws_ldsu16(rec + WS_REC(c0)) + lane, r0 = (int)ws_ldsu16(rec + WS_REC(r0));
+                const int job = (int)R.job();
+                const int c = (int)(R.w4.x & 0xFFFFu) + lane, r0 = (int)(R.w4.x >> 16);
                 WfFix fix = fix0;
                 fix.job = job;
 #pragma unroll 1
@@ -454,8 +508,15 @@ __device__ __forceinline__ void ws_sample(uint32_t rec, uint32_t s_ent, int lane
     }
 }
 
-// Grid: min(ceil(n_tiles / 16), SMs) CTAs of 16 warps, dynamic shared memory WS_SMEM_BYTES (one CTA per SM).
+// Grid: min(ceil(n_tiles / WS_WARPS), SMs) CTAs of WS_WARPS warps, dynamic shared memory WS_SMEM_BYTES (one CTA per SM).
 // counts[0] = number of routed tiles (four strip records each); ticket: global tile-ticket counter (zeroed by the host).
+//
+// Per warp, strip n of its sequence (raw buffer n % WS_NRAW, record slot n % WS_NREC):
+//     record -> registers; wait for the tensor copy of strip n; convert raw rows -> entries; the raw buffer is free:
+//     issue the tensor copy of strip n + WS_NRAW into it; fetch the record of strip n + WS_NRAW + 1 (cp.async) into the
+//     slot of strip n; sample strip n from the entries.
+// A tensor copy therefore has WS_NRAW - 1 whole strip periods plus one sampling phase to arrive (measured with one buffer
+// per warp: a strip period of ~6000 cycles of which ~2500 were the wait for the copy -- nn ran no faster than bilinear).
 template <int BILINEAR>
 __global__ void __launch_bounds__(WS_THREADS, 1)
 warp_strip_kernel(const uint8_t *__restrict__ src_base, const b200geo_warp_job *__restrict__ jobs, const WsStrip *__restrict__ strips,
@@ -465,13 +526,14 @@ warp_strip_kernel(const uint8_t *__restrict__ src_base, const b200geo_warp_job *
     extern __shared__ __align__(128) unsigned char ws_smem[];
     const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
     const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(ws_smem);
-    const uint32_t s_raw = s0 + (uint32_t)(wrp * WS_WARP_BYTES), s_ent = s_raw + WS_RAW_BYTES;
-    const uint32_t s_recs = s0 + (uint32_t)(WS_WARPS * WS_WARP_BYTES) + (uint32_t)(wrp * 2 * WS_REC_BYTES);
-    const uint32_t s_bar = s0 + (uint32_t)(WS_WARPS * (WS_WARP_BYTES + 2 * WS_REC_BYTES)) + 8u * (uint32_t)wrp;
-    unsigned *const s_fix_n = reinterpret_cast<unsigned *>(ws_smem + WS_WARPS * (WS_WARP_BYTES + 2 * WS_REC_BYTES + 8));
+    const uint32_t s_raw0 = s0 + (uint32_t)(wrp * WS_WARP_BYTES), s_ent = s_raw0 + WS_NRAW * WS_RAW_BYTES;
+    const uint32_t s_recs = s0 + (uint32_t)(WS_WARPS * WS_WARP_BYTES) + (uint32_t)(wrp * WS_NREC * WS_REC_BYTES);
+    const uint32_t s_bar0 = s0 + (uint32_t)(WS_WARPS * (WS_WARP_BYTES + WS_NREC * WS_REC_BYTES)) + 8u * (uint32_t)(WS_NRAW * wrp);
+    unsigned *const s_fix_n = reinterpret_cast<unsigned *>(ws_smem + WS_WARPS * (WS_WARP_BYTES + WS_NREC * WS_REC_BYTES + 8 * WS_NRAW));
     if (threadIdx.x == 0) *s_fix_n = 0u;
     if (lane == 0) {
-        wp_mbar_init(s_bar, 1);
+#pragma unroll
+        for (int b = 0; b < WS_NRAW; ++b) wp_mbar_init(s_bar0 + 8u * b, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -479,80 +541,105 @@ warp_strip_kernel(const uint8_t *__restrict__ src_base, const b200geo_warp_job *
 
     const unsigned n_tiles = counts[0];
     const unsigned n_warps = gridDim.x * WS_WARPS;
-    unsigned tile = blockIdx.x * WS_WARPS + wrp;
     unsigned n_exact = 0;
     const WfFix fix = {fix_list + (size_t)blockIdx.x * seg_cap, s_fix_n, seg_cap, 0};
 
-    auto fetch_record = [&](uint32_t slot, unsigned strip) {      // asynchronous: lanes 0..7 copy 16 bytes each
-        if (lane < WS_REC_BYTES / 16) {
+    // the warp's strip sequence: four strips per tile, tiles by ticket (the first one is the warp's global index)
+    unsigned g_tile = blockIdx.x * WS_WARPS + wrp;
+    int g_j = -1;
+    unsigned g_tk = 0;                                            // lane 0: ticket of the tile after g_tile
+    constexpr unsigned NONE = 0xFFFFFFFFu;
+    auto next_strip = [&]() -> unsigned {                         // warp-uniform
+        if (g_j < 0) {
+            if (g_tile >= n_tiles) return NONE;
+            g_j = 0;
+            if (lane == 0) g_tk = atomicAdd(ticket, 1u);
+            return g_tile * 4u;
+        }
+        if (g_j < 3) return g_tile * 4u + (unsigned)(++g_j);
+        if (g_tile == NONE) return NONE;
+        g_tile = __shfl_sync(0xffffffffu, g_tk, 0) + n_warps;
+        if (g_tile >= n_tiles) { g_tile = NONE; return NONE; }
+        g_j = 0;
+        if (lane == 0) g_tk = atomicAdd(ticket, 1u);
+        return g_tile * 4u;
+    };
+    auto fetch_record = [&](uint32_t slot, unsigned strip) {      // asynchronous: lanes 0..4 copy 16 bytes each
+        if (strip != NONE && lane < WS_REC_BYTES / 16) {
             const char *g = reinterpret_cast<const char *>(strips + strip) + 16 * lane;
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(slot + 16u * (uint32_t)lane), "l"(g) : "memory");
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    auto issue_copy = [&](uint32_t slot) {                        // lane 0: tensor copy of the strip's footprint into this warp's raw rows
+    auto issue_copy = [&](uint32_t slot, uint32_t raw, uint32_t bar) {   // lane 0: tensor copy of the strip's footprint into a raw buffer of this warp
         if (lane == 0 && (int)ws_ldsu8(slot + WS_REC(mode)) != WF_ZERO) {
-            const int x = (int)ws_lds32(slot + WS_REC(tma_x)), y = (int)ws_lds32(slot + WS_REC(tma_y)), z = (int)ws_ldsu16(slot + WS_REC(img));
+            uint32_t x, y;
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(x), "=r"(y) : "r"(slot + WS_REC(tma_x)));
+            const int z = (int)ws_ldsu16(slot + WS_REC(img));
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // this warp's generic reads of the raw rows precede the overwrite
-            wp_mbar_expect_tx(s_bar, (uint32_t)(WS_RAW_W * WS_ROWS));
+            wp_mbar_expect_tx(bar, (uint32_t)(WS_RAW_W * WS_ROWS));
             asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                         ::"r"(s_raw), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(x), "r"(y), "r"(z), "r"(s_bar) : "memory");
+                         ::"r"(raw), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"((int)x), "r"((int)y), "r"(z), "r"(bar) : "memory");
         }
     };
 
-    if (tile < n_tiles) {
-        uint32_t slot_cur = s_recs, slot_nxt = s_recs + WS_REC_BYTES;
-        unsigned tk = 0;                                          // lane 0: ticket of the tile after `tile`
-        if (lane == 0) tk = atomicAdd(ticket, 1u);
-        fetch_record(slot_cur, tile * 4u);
+    // prologue: records of strips 0 .. WS_NRAW, tensor copies of strips 0 .. WS_NRAW - 1
+    unsigned ids[WS_NREC];                                        // ids[k]: strip n + k (constant indices only: registers)
+#pragma unroll
+    for (int k = 0; k < WS_NREC; ++k) {
+        ids[k] = next_strip();
+        fetch_record(s_recs + (uint32_t)(k * WS_REC_BYTES), ids[k]);
+    }
+    if (ids[0] != NONE) {
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncwarp();
-        issue_copy(slot_cur);
-        uint32_t ph = 0u;
-        int j = 0;
+#pragma unroll
+        for (int k = 0; k < WS_NRAW; ++k)
+            if (ids[k] != NONE) issue_copy(s_recs + (uint32_t)(k * WS_REC_BYTES), s_raw0 + (uint32_t)(k * WS_RAW_BYTES), s_bar0 + 8u * k);
+        uint32_t ph = 0u;                                         // bit b: parity of raw buffer b's mbarrier
+        uint32_t slot = s_recs;                                   // record slot of strip n
+        int buf = 0;                                              // raw buffer of strip n
         for (;;) {
-            unsigned nxt_tile = tile, nxt_strip;
-            bool has_next = true;
-            if (j < 3) nxt_strip = tile * 4u + (unsigned)(j + 1);
-            else {
-                nxt_tile = __shfl_sync(0xffffffffu, tk, 0) + n_warps;
-                has_next = nxt_tile < n_tiles;
-                nxt_strip = nxt_tile * 4u;
-            }
-            if (has_next) fetch_record(slot_nxt, nxt_strip);
-            const int mode = (int)ws_ldsu8(slot_cur + WS_REC(mode));
+            WsRegs R;
+            R.w0 = ws_lds128(slot); R.w1 = ws_lds128(slot + 16u); R.w2 = ws_lds128(slot + 32u); R.w3 = ws_lds128(slot + 48u);
+            R.w4 = ws_lds128(slot + 64u);
+            const int mode = R.mode();
+            const uint32_t raw = s_raw0 + (uint32_t)(buf * WS_RAW_BYTES), bar = s_bar0 + 8u * (uint32_t)buf;
             if (mode != WF_ZERO) {
-                wp_mbar_wait(s_bar, ph);
-                ph ^= 1u;
-                ws_convert(slot_cur, s_raw, s_ent, lane);
+                wp_mbar_wait(bar, (ph >> buf) & 1u);
+                ph ^= 1u << buf;
+                ws_convert(R, raw, s_ent, lane);
             }
-            __syncwarp();                                         // entries written / raw rows read by every lane
-            if (has_next) {
-                asm volatile("cp.async.wait_group 0;" ::: "memory");
-                __syncwarp();
-                issue_copy(slot_nxt);
+            __syncwarp();                                         // entries written, raw rows and the record read by every lane
+            // strip n + WS_NRAW: its record arrived during the previous iteration; its copy goes into the buffer just freed
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncwarp();
+            if (ids[WS_NRAW] != NONE) {
+                uint32_t sl = slot + (uint32_t)(WS_NRAW * WS_REC_BYTES);
+                if (sl >= s_recs + (uint32_t)(WS_NREC * WS_REC_BYTES)) sl -= (uint32_t)(WS_NREC * WS_REC_BYTES);
+                issue_copy(sl, raw, bar);
             }
+            const unsigned id_new = ids[WS_NRAW] != NONE ? next_strip() : NONE;      // strip n + WS_NRAW + 1 -> the slot of strip n
+            fetch_record(slot, id_new);
             // (votes: the branch conditions are warp-uniform by construction, so the shuffles inside need no divergence check)
-            if (__all_sync(0xffffffffu, mode == WF_INTERIOR)) ws_sample<BILINEAR, 0>(slot_cur, s_ent, lane, jobs, src_base, fix, n_exact);
-            else if (__all_sync(0xffffffffu, mode == WF_BORDER)) ws_sample<BILINEAR, 1>(slot_cur, s_ent, lane, jobs, src_base, fix, n_exact);
+            if (__all_sync(0xffffffffu, mode == WF_INTERIOR)) ws_sample<BILINEAR, 0>(R, s_ent, lane, jobs, src_base, fix, n_exact);
+            else if (__all_sync(0xffffffffu, mode == WF_BORDER)) ws_sample<BILINEAR, 1>(R, s_ent, lane, jobs, src_base, fix, n_exact);
             else {
-                unsigned long long d;
-                asm volatile("ld.shared.u64 %0, [%1];" : "=l"(d) : "r"(slot_cur + WS_REC(dst)));
-                uint8_t *gp = reinterpret_cast<uint8_t *>(d) + 4 * lane;
-                const int pitch = (int)ws_lds32(slot_cur + WS_REC(dst_pitch));
+                uint8_t *gp = reinterpret_cast<uint8_t *>(((unsigned long long)R.w2.w << 32) | R.w2.z) + 4 * lane;
+                const int pitch = (int)R.w3.x;
                 if (lane < 24) {
 #pragma unroll 4
                     for (int r = 0; r < WS_H; ++r) ws_stg32(gp + (long long)r * pitch, 0u);
                 }
             }
-            if (!has_next) break;
-            __syncwarp();                                         // every lane is done with the entries and the current record
-            const uint32_t tmp = slot_cur; slot_cur = slot_nxt; slot_nxt = tmp;
-            if (j < 3) ++j;
-            else {
-                tile = nxt_tile; j = 0;
-                if (lane == 0) tk = atomicAdd(ticket, 1u);
-            }
+#pragma unroll
+            for (int k = 0; k < WS_NRAW; ++k) ids[k] = ids[k + 1];
+            ids[WS_NRAW] = id_new;
+            if (ids[0] == NONE) break;
+            __syncwarp();                                         // every lane is done with the entries
+            slot += WS_REC_BYTES;
+            if (slot >= s_recs + (uint32_t)(WS_NREC * WS_REC_BYTES)) slot = s_recs;
+            buf = buf + 1 == WS_NRAW ? 0 : buf + 1;
         }
     }
     if (stats && n_exact) atomicAdd(stats, (unsigned long long)n_exact);

@@ -408,7 +408,9 @@ def test_batched_stitch_pipeline_matches_per_pair_path():
         assert boxes[b, :2].tolist() == [mx, my]
         oh, ow = min(img.shape[0], canvas[0]), min(img.shape[1], canvas[1])
         assert boxes[b, 2:].tolist() == [ow, oh]
-        assert np.array_equal(canv[b, :oh, :ow], img[:oh, :ow])
+        # (the batched launch describes the frames as a 3-D tensor map and may take the per-warp strip kernel, the single
+        # image the tile kernel: same +-1 of the float64 result for bilinear, not necessarily the same bytes)
+        assert np.abs(canv[b, :oh, :ow].astype(np.int16) - img[:oh, :ow].astype(np.int16)).max() <= 1
 
 
 @pytest.mark.parametrize("case,seed,th,d,k", [("E_s1", 1, 5, 60, 1000), ("A_s0", 0, 5, 70, 1000)])
