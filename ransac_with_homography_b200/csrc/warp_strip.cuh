@@ -40,18 +40,22 @@ constexpr int WS_ROWB = WS_EPR * 8;          // staged row pitch: 384 B
 constexpr int WS_ROWS = 26;                  // staged rows
 constexpr int WS_RAW_W = 160;                // tensor-copy box: bytes per row (multiple of 16) ...
 constexpr int WS_MAXP = 44;                  // ... which holds 4 + 12 + 3 * (44 + 1) <= 160 bytes
+#ifndef B2G_WS_DIRECT
+#define B2G_WS_DIRECT 1     // 1: sample straight from the raw rows of the tensor copy (no staged entries, no conversion); 0: staged entries
+#endif
 #ifndef B2G_WS_WARPS
-#define B2G_WS_WARPS 12
+#define B2G_WS_WARPS (B2G_WS_DIRECT ? 20 : 16)
 #endif
 #ifndef B2G_WS_NRAW
-#define B2G_WS_NRAW 2
+#define B2G_WS_NRAW (B2G_WS_DIRECT ? 2 : 1)
 #endif
+static_assert(!B2G_WS_DIRECT || B2G_WS_NRAW >= 2, "direct sampling holds a raw buffer until the strip is sampled: a second one keeps a copy in flight");
 constexpr int WS_WARPS = B2G_WS_WARPS;       // warps per CTA (one CTA per SM; shared memory is what limits them)
 constexpr int WS_NRAW = B2G_WS_NRAW;         // raw-row buffers per warp = strips a tensor copy is issued ahead of its use
 constexpr int WS_NREC = WS_NRAW + 1;         // record slots per warp
 constexpr int WS_THREADS = WS_WARPS * 32;
 constexpr int WS_RAW_BYTES = ((WS_RAW_W * WS_ROWS + 127) / 128) * 128;
-constexpr int WS_ENT_BYTES = WS_ROWB * WS_ROWS;
+constexpr int WS_ENT_BYTES = B2G_WS_DIRECT ? 0 : WS_ROWB * WS_ROWS;
 constexpr int WS_WARP_BYTES = WS_NRAW * WS_RAW_BYTES + WS_ENT_BYTES;
 static_assert(WS_WARP_BYTES % 128 == 0, "tensor-copy destinations are 128-byte aligned");
 constexpr int WS_REC_BYTES = 80;
@@ -387,8 +391,10 @@ __device__ __forceinline__ void ws_sample(const WsRegs &R, uint32_t s_ent, int l
     const float2 nb = __ffma2_rn(A2, make_float2(di0, di0), make_float2(__uint_as_float(R.w0.x), __uint_as_float(R.w0.y)));
     const float wb = __fmaf_rn(gw, di0, WF_W0);
     const int ox = R.ox(), oy = R.oy();
-    // plane-0 word of entry (xi, yi) [bit patterns of the magic-number fixed point, integer parts offset by WS_MAGIC_HI]
-    const uint32_t base = s_ent - (uint32_t)((WS_MAGIC_HI + oy) * WS_ROWB + (WS_MAGIC_HI + ox) * 4);
+    // DIRECT: byte address of R[xi] in raw row yi = yi * 160 + 3 xi + base; else plane-0 word of entry (xi, yi)
+    // [xi, yi: bit patterns of the magic-number fixed point, integer parts offset by WS_MAGIC_HI]
+    const uint32_t base = B2G_WS_DIRECT ? s_ent + R.phase() - (uint32_t)((WS_MAGIC_HI + oy) * WS_RAW_W + (WS_MAGIC_HI + ox) * 3)
+                                        : s_ent - (uint32_t)((WS_MAGIC_HI + oy) * WS_ROWB + (WS_MAGIC_HI + ox) * 4);
     const unsigned long long dstrip = ((unsigned long long)R.w2.w << 32) | R.w2.z;      // first output byte of the strip
     // word (lane & 3) of the 12 bytes of pixels 4 * (lane >> 2) .. + 3:  RGBR | GBRG | BRGB  (three of four lanes store)
     uint32_t g_lo = (uint32_t)dstrip + (uint32_t)(12 * (lane >> 2) + 4 * (lane & 3));
@@ -418,6 +424,7 @@ __device__ __forceinline__ void ws_sample(const WsRegs &R, uint32_t s_ent, int l
     auto group = [&](const int g0, const float2 n2g, const float wg) {
         // n2g, wg: numerators / denominator of row g0 (for the looped form: of row g0, the rows of the group add constants)
         uint32_t t0[G], t1[G], t2[G], t3[G], bx_[G], by_[G];
+        uint32_t u0[G], u1[G], u2[G], v0[G], v1[G], v2[G], sh_[G];     // DIRECT: three raw words per tap row, byte phase * 8
 #pragma unroll
         for (int g = 0; g < G; ++g) {
             const float dj = (float)g;
@@ -449,20 +456,42 @@ __device__ __forceinline__ void ws_sample(const WsRegs &R, uint32_t s_ent, int l
                     yi = (uint32_t)(min(max((int)yi - WS_MAGIC_HI, ylo), yhi) + WS_MAGIC_HI);
                 } else if (near) amb |= 1u << (g0 + g);
             }
-            const uint32_t a = yi * (uint32_t)WS_ROWB + (xi * 4u + base);
-            t0[g] = ws_lds32(a);
-            t1[g] = ws_lds32o<WS_PLANE>(a);
-            if (BILINEAR) {
-                t2[g] = ws_lds32o<WS_ROWB>(a);
-                t3[g] = ws_lds32o<WS_ROWB + WS_PLANE>(a);
+            if (B2G_WS_DIRECT) {
+                // the six bytes of pixels xi, xi+1 start at any byte phase: three aligned words cover them; the funnel shifts
+                // below (shift count taken modulo 32: 8 x the byte phase) bring them to (R0 G0 B0 R1) (G1 B1 . .)
+                const uint32_t a = yi * (uint32_t)WS_RAW_W + (xi * 3u + base);
+                const uint32_t W = a & ~3u;
+                sh_[g] = a << 3;
+                u0[g] = ws_lds32(W); u1[g] = ws_lds32o<4>(W);
+                if (BILINEAR) {
+                    u2[g] = ws_lds32o<8>(W);
+                    v0[g] = ws_lds32o<WS_RAW_W>(W); v1[g] = ws_lds32o<WS_RAW_W + 4>(W); v2[g] = ws_lds32o<WS_RAW_W + 8>(W);
+                }
+            } else {
+                const uint32_t a = yi * (uint32_t)WS_ROWB + (xi * 4u + base);
+                t0[g] = ws_lds32(a);
+                t1[g] = ws_lds32o<WS_PLANE>(a);
+                if (BILINEAR) {
+                    t2[g] = ws_lds32o<WS_ROWB>(a);
+                    t3[g] = ws_lds32o<WS_ROWB + WS_PLANE>(a);
+                }
             }
             bx_[g] = bxv; by_[g] = byv;
         }
 #pragma unroll
         for (int g = 0; g < G; ++g) {
             uint32_t out;
+            if (B2G_WS_DIRECT) {
+                const uint32_t p0 = __funnelshift_r(u0[g], u1[g], sh_[g]);
+                if (BILINEAR) {
+                    const uint32_t p1 = __funnelshift_r(u1[g], u2[g], sh_[g]);
+                    const uint32_t q0 = __funnelshift_r(v0[g], v1[g], sh_[g]), q1 = __funnelshift_r(v1[g], v2[g], sh_[g]);
+                    t0[g] = __byte_perm(p0, p1, 0x4130); t1[g] = __byte_perm(p0, p1, 0x5252);
+                    t2[g] = __byte_perm(q0, q1, 0x4130); t3[g] = __byte_perm(q0, q1, 0x5252);
+                } else out = p0;                                      // (R G B .): byte 3 is never stored
+            }
             if (BILINEAR) out = wf_blend(make_uint2(t0[g], t1[g]), make_uint2(t2[g], t3[g]), bx_[g] & 0xFFFFu, by_[g] & 0xFFFFu);
-            else out = __byte_perm(t0[g], t1[g], 0x4420);
+            else if (!B2G_WS_DIRECT) out = __byte_perm(t0[g], t1[g], 0x4420);
             if (BORDER && !(inmask >> (g0 + g) & 1u)) out = 0u;
             const uint32_t nbr = __shfl_down_sync(0xffffffffu, out, 1);
             const uint32_t word = __byte_perm(out, nbr, psel);
@@ -608,22 +637,27 @@ warp_strip_kernel(const uint8_t *__restrict__ src_base, const b200geo_warp_job *
             if (mode != WF_ZERO) {
                 wp_mbar_wait(bar, (ph >> buf) & 1u);
                 ph ^= 1u << buf;
-                ws_convert(R, raw, s_ent, lane);
+                if (!B2G_WS_DIRECT) ws_convert(R, raw, s_ent, lane);
             }
-            __syncwarp();                                         // entries written, raw rows and the record read by every lane
-            // strip n + WS_NRAW: its record arrived during the previous iteration; its copy goes into the buffer just freed
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-            __syncwarp();
-            if (ids[WS_NRAW] != NONE) {
-                uint32_t sl = slot + (uint32_t)(WS_NRAW * WS_REC_BYTES);
-                if (sl >= s_recs + (uint32_t)(WS_NREC * WS_REC_BYTES)) sl -= (uint32_t)(WS_NREC * WS_REC_BYTES);
-                issue_copy(sl, raw, bar);
+            auto refill = [&]() {
+                // strip n + WS_NRAW: its record arrived during the previous iteration; its copy goes into the buffer just freed;
+                // the record of strip n + WS_NRAW + 1 goes into the slot of strip n (held in registers by now)
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                __syncwarp();
+                if (ids[WS_NRAW] != NONE) {
+                    uint32_t sl = slot + (uint32_t)(WS_NRAW * WS_REC_BYTES);
+                    if (sl >= s_recs + (uint32_t)(WS_NREC * WS_REC_BYTES)) sl -= (uint32_t)(WS_NREC * WS_REC_BYTES);
+                    issue_copy(sl, raw, bar);
+                }
+            };
+            if (!B2G_WS_DIRECT) {
+                __syncwarp();                                     // entries written, raw rows read by every lane
+                refill();
             }
-            const unsigned id_new = ids[WS_NRAW] != NONE ? next_strip() : NONE;      // strip n + WS_NRAW + 1 -> the slot of strip n
-            fetch_record(slot, id_new);
+            const uint32_t s_src = B2G_WS_DIRECT ? raw : s_ent;
             // (votes: the branch conditions are warp-uniform by construction, so the shuffles inside need no divergence check)
-            if (__all_sync(0xffffffffu, mode == WF_INTERIOR)) ws_sample<BILINEAR, 0>(R, s_ent, lane, jobs, src_base, fix, n_exact);
-            else if (__all_sync(0xffffffffu, mode == WF_BORDER)) ws_sample<BILINEAR, 1>(R, s_ent, lane, jobs, src_base, fix, n_exact);
+            if (__all_sync(0xffffffffu, mode == WF_INTERIOR)) ws_sample<BILINEAR, 0>(R, s_src, lane, jobs, src_base, fix, n_exact);
+            else if (__all_sync(0xffffffffu, mode == WF_BORDER)) ws_sample<BILINEAR, 1>(R, s_src, lane, jobs, src_base, fix, n_exact);
             else {
                 uint8_t *gp = reinterpret_cast<uint8_t *>(((unsigned long long)R.w2.w << 32) | R.w2.z) + 4 * lane;
                 const int pitch = (int)R.w3.x;
@@ -632,6 +666,12 @@ warp_strip_kernel(const uint8_t *__restrict__ src_base, const b200geo_warp_job *
                     for (int r = 0; r < WS_H; ++r) ws_stg32(gp + (long long)r * pitch, 0u);
                 }
             }
+            if (B2G_WS_DIRECT) {
+                __syncwarp();                                     // raw rows read by every lane
+                refill();
+            }
+            const unsigned id_new = ids[WS_NRAW] != NONE ? next_strip() : NONE;      // strip n + WS_NRAW + 1 -> the slot of strip n
+            fetch_record(slot, id_new);
 #pragma unroll
             for (int k = 0; k < WS_NRAW; ++k) ids[k] = ids[k + 1];
             ids[WS_NRAW] = id_new;

@@ -1,7 +1,9 @@
 mkdir -p gpurun_out
-export B200GEO_LIB=$PWD/gpurun_variants/lib_w16n1.so
-python tools/prof_strip.py 64 > gpurun_out/plain.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:warp_strip_kernel -s 3 -c 1 -f -o gpurun_out/r02_strip_v2 python tools/prof_strip.py 64 > gpurun_out/ncu.log 2>&1
-python tools/prof_strip.py 64 nn > gpurun_out/plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:warp_strip_kernel -s 3 -c 1 -f -o gpurun_out/r02_strip_v2_nn python tools/prof_strip.py 64 nn > gpurun_out/ncu2.log 2>&1
-tail -2 gpurun_out/ncu.log gpurun_out/ncu2.log
+echo "== default direct w20n2" > gpurun_out/run4.log
+timeout 300 python tools/check_strip.py 256 >> gpurun_out/run4.log 2>&1
+for v in d24 d16 d20n3 d24nu; do
+  echo "== $v" >> gpurun_out/run4.log
+  B200GEO_LIB=$PWD/gpurun_variants/lib_$v.so timeout 300 python tools/check_strip.py 256 2>&1 | grep "variant 0" >> gpurun_out/run4.log
+done
+timeout 600 python tools/fuzz_warp.py 200 8 >> gpurun_out/run4.log 2>&1
+cat gpurun_out/run4.log
