@@ -462,12 +462,17 @@ int launch_warp(b200geo_ctx *ctx, const void *src, void *dst, const b200geo_warp
             // routed: every 64 x 40 tile goes either to warp_strip_kernel (four 32 x 20 strips, one warp each) or, if one of its
             // strips does not qualify, to warp_pipe_kernel; both lists are compact, their lengths stay on the device
             WsStrip *strips;
-            if ((rc = scratch(ctx, S_STRIPS, 4 * sizeof(WsStrip) * (size_t)n_tiles, (void **)&strips))) return rc;
+            cudaEvent_t tev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+            const bool timing = getenv("B200GEO_DEBUG_TIMING") != nullptr;      // debugging: per-kernel times of this call (synchronises)
+            if (timing) for (int i = 0; i < 5; ++i) cudaEventCreate(&tev[i]);
+            if (timing) cudaEventRecord(tev[0], st);
+            if ((rc = scratch(ctx, S_STRIPS, WS_PER_TILE * sizeof(WsStrip) * (size_t)n_tiles, (void **)&strips))) return rc;
             unsigned *route = (unsigned *)(stats + 4), *strip_ticket = (unsigned *)(stats + 5);
             B2G_CUDA(cudaMemsetAsync(route, 0, 16, st));        // both counts and the strip ticket
             if (sampler == B200GEO_BILINEAR) warp_route_setup_kernel<1><<<sgrid, sblock, 0, st>>>(jobs_dev, s8, d8, tma, use_tmap, tiles_x, tiles_y, strips, tiles, route);
             else warp_route_setup_kernel<0><<<sgrid, sblock, 0, st>>>(jobs_dev, s8, d8, tma, use_tmap, tiles_x, tiles_y, strips, tiles, route);
             B2G_CHECK_LAUNCH(ctx);
+            if (timing) cudaEventRecord(tev[1], st);
             long long sctas = (n_tiles + WS_WARPS - 1) / WS_WARPS;
             if (sctas > ctx->sm_count) sctas = ctx->sm_count;
             long long pctas = (long long)ctx->sm_count * WP_OCC;
@@ -479,12 +484,23 @@ int launch_warp(b200geo_ctx *ctx, const void *src, void *dst, const b200geo_warp
             else
                 warp_strip_kernel<0><<<(unsigned)sctas, WS_THREADS, WS_SMEM_BYTES, st>>>(s8, jobs_dev, strips, route, ctx->tmap_strip, fix_list, fix_count, seg_cap, strip_ticket, stats + 2);
             B2G_CHECK_LAUNCH(ctx);
+            if (timing) cudaEventRecord(tev[2], st);
             WfFixEntry *fl = fix_list + (size_t)sctas * seg_cap;
             unsigned *fc = fix_count + sctas;
             if (sampler == B200GEO_BILINEAR)
                 warp_pipe_kernel<1><<<(unsigned)pctas, WP_THREADS, sizeof(WpSmem), st>>>(s8, d8, jobs_dev, tiles, 0, route + 1, tiles_x, tiles_y, stats + 2, ctx->tmap, use_tmap, tma.image_rows, fl, fc, seg_cap, tile_counter);
             else
                 warp_pipe_kernel<0><<<(unsigned)pctas, WP_THREADS, sizeof(WpSmem), st>>>(s8, d8, jobs_dev, tiles, 0, route + 1, tiles_x, tiles_y, stats + 2, ctx->tmap, use_tmap, tma.image_rows, fl, fc, seg_cap, tile_counter);
+            if (timing) {
+                cudaEventRecord(tev[3], st);
+                cudaEventSynchronize(tev[3]);
+                float a = 0, b = 0, c = 0;
+                cudaEventElapsedTime(&a, tev[0], tev[1]); cudaEventElapsedTime(&b, tev[1], tev[2]); cudaEventElapsedTime(&c, tev[2], tev[3]);
+                unsigned rc2[2] = {0, 0};
+                cudaMemcpy(rc2, route, 8, cudaMemcpyDeviceToHost);
+                fprintf(stderr, "[b200geo] warp timing: set-up %.3f ms, strip kernel %.3f ms (%u tiles), tile kernel %.3f ms (%u tiles)\n", a, b, rc2[0], c, rc2[1]);
+                for (int i = 0; i < 5; ++i) cudaEventDestroy(tev[i]);
+            }
         } else {
             // persistent CTAs, TMA bulk copies one tile ahead
             if (sampler == B200GEO_BILINEAR) warp_tile_setup_kernel<1><<<sgrid, sblock, 0, st>>>(jobs_dev, s8, d8, tma, use_tmap, tiles_x, tiles_y, tiles);

@@ -32,19 +32,24 @@
 
 namespace b200geo {
 
-constexpr int WS_W = 32, WS_H = 20;          // strip size (a 64 x 40 tile = 2 x 2 strips)
-static_assert(WF_TW == 2 * WS_W && WF_TH == 2 * WS_H, "a tile is four strips");
+#ifndef B2G_WS_H
+#define B2G_WS_H 40
+#endif
+constexpr int WS_W = 32, WS_H = B2G_WS_H;    // strip size: a 64 x 40 tile = two strips side by side (WS_H = 40) or 2 x 2 strips (20)
+static_assert(WF_TW == 2 * WS_W && (WF_TH == WS_H || WF_TH == 2 * WS_H), "a tile is two or four strips");
+constexpr int WS_PER_TILE = 2 * (WF_TH / WS_H);
+constexpr int WS_HALF = 20;                  // rows sampled per pass of the unrolled loop
 constexpr int WS_EPR = 48;                   // entries per staged row
 constexpr int WS_PLANE = WS_EPR * 4;         // byte offset of the B-pair words inside a staged row
 constexpr int WS_ROWB = WS_EPR * 8;          // staged row pitch: 384 B
-constexpr int WS_ROWS = 26;                  // staged rows
+constexpr int WS_ROWS = WS_H == 40 ? 50 : 26; // rows of the tensor-copy box
 constexpr int WS_RAW_W = 160;                // tensor-copy box: bytes per row (multiple of 16) ...
 constexpr int WS_MAXP = 44;                  // ... which holds 4 + 12 + 3 * (44 + 1) <= 160 bytes
 #ifndef B2G_WS_DIRECT
 #define B2G_WS_DIRECT 1     // 1: sample straight from the raw rows of the tensor copy (no staged entries, no conversion); 0: staged entries
 #endif
 #ifndef B2G_WS_WARPS
-#define B2G_WS_WARPS (B2G_WS_DIRECT ? 20 : 16)
+#define B2G_WS_WARPS (B2G_WS_DIRECT ? (B2G_WS_H == 40 ? 14 : 20) : 16)
 #endif
 #ifndef B2G_WS_NRAW
 #define B2G_WS_NRAW (B2G_WS_DIRECT ? 2 : 1)
@@ -206,11 +211,11 @@ warp_route_setup_kernel(const b200geo_warp_job *__restrict__ jobs, const uint8_t
     const b200geo_warp_job &J = jobs[blockIdx.z];
     const int c0 = tx * WF_TW, r0 = ty * WF_TH;
     if (live && (c0 >= J.ow || r0 >= J.oh)) live = false;
-    WsStrip S[4];
+    WsStrip S[WS_PER_TILE];
     bool fast = live;
     if (fast) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
+        for (int k = 0; k < WS_PER_TILE; ++k)
             if (fast) fast = ws_setup<BILINEAR>(J, (int)blockIdx.z, c0 + (k & 1) * WS_W, r0 + (k >> 1) * WS_H, tma, dst_base, S[k]);
     }
     const unsigned m_fast = __ballot_sync(0xffffffffu, fast), m_old = __ballot_sync(0xffffffffu, live && !fast);
@@ -223,10 +228,10 @@ warp_route_setup_kernel(const b200geo_warp_job *__restrict__ jobs, const uint8_t
     b_old = __shfl_sync(0xffffffffu, b_old, 0);
     const unsigned below = (1u << lane) - 1u;
     if (fast) {
-        uint4 *d = reinterpret_cast<uint4 *>(strips + 4 * (size_t)(b_fast + __popc(m_fast & below)));
+        uint4 *d = reinterpret_cast<uint4 *>(strips + WS_PER_TILE * (size_t)(b_fast + __popc(m_fast & below)));
         const uint4 *sv = reinterpret_cast<const uint4 *>(S);
 #pragma unroll
-        for (int i = 0; i < 4 * WS_REC_BYTES / 16; ++i) d[i] = sv[i];
+        for (int i = 0; i < WS_PER_TILE * WS_REC_BYTES / 16; ++i) d[i] = sv[i];
     } else if (live) {
         WpTile W;
         wp_build_tile<BILINEAR>(J, (int)blockIdx.z, c0, r0, src_base, dst_base, tma, use_tmap, W);
@@ -353,7 +358,7 @@ __device__ __forceinline__ void ws_convert(const WsRegs &R, uint32_t s_raw, uint
 }
 
 #ifndef B2G_WS_GROUP
-#define B2G_WS_GROUP 4      // rows of a lane whose taps are in flight together
+#define B2G_WS_GROUP 2      // rows of a lane whose taps are in flight together (2 measured best: 576 vs 569 (4), 556 (5) Gpix/s)
 #endif
 #ifndef B2G_WS_UNROLL
 #define B2G_WS_UNROLL 1     // 1: the 20 rows of an INTERIOR strip fully unrolled (row index = immediate operand)
@@ -419,7 +424,12 @@ __device__ __forceinline__ void ws_sample(const WsRegs &R, uint32_t s_ent, int l
         }
     }
     constexpr int G = B2G_WS_GROUP;
-    static_assert(WS_H % G == 0, "row groups");
+    static_assert(WS_HALF % G == 0 && WS_H % WS_HALF == 0, "row groups");
+#pragma unroll 1
+    for (int hf = 0; hf < WS_H / WS_HALF; ++hf) {             // (the 'g0' below count rows inside this pass)
+    const float djh = (float)(hf * WS_HALF - WS_H / 2);
+    const float2 nbh = __ffma2_rn(B2, make_float2(djh, djh), nb);
+    const float wbh = __fmaf_rn(hw, djh, wb);
     uint32_t amb = 0u, inmask = 0u;
     auto group = [&](const int g0, const float2 n2g, const float wg) {
         // n2g, wg: numerators / denominator of row g0 (for the looped form: of row g0, the rows of the group add constants)
@@ -446,7 +456,8 @@ __device__ __forceinline__ void ws_sample(const WsRegs &R, uint32_t s_ent, int l
                 const float2 f = __ffma2_rn(n2, make_float2(rw, rw), make_float2(WS_MAGIC, WS_MAGIC));
                 bxv = __float_as_uint(f.x); byv = __float_as_uint(f.y);
             }
-            uint32_t xi = ws_hi16(bxv), yi = ws_hi16(byv);
+            uint32_t xi = 0u, yi = 0u;
+            if (!(B2G_WS_DIRECT && !BORDER)) { xi = ws_hi16(bxv); yi = ws_hi16(byv); }
             if (!BILINEAR) {
                 const uint32_t fx = bxv & 0xFFFFu, fy = byv & 0xFFFFu;
                 const bool near = fx - B16 > 65535u - 2u * B16 || fy - B16 > 65535u - 2u * B16;
@@ -459,7 +470,11 @@ __device__ __forceinline__ void ws_sample(const WsRegs &R, uint32_t s_ent, int l
             if (B2G_WS_DIRECT) {
                 // the six bytes of pixels xi, xi+1 start at any byte phase: three aligned words cover them; the funnel shifts
                 // below (shift count taken modulo 32: 8 x the byte phase) bring them to (R0 G0 B0 R1) (G1 B1 . .)
-                const uint32_t a = yi * (uint32_t)WS_RAW_W + (xi * 3u + base);
+                // byte address of R[xi] in row yi: yi * 160 + xi * 3 + base -- one two-way dot product on the packed integer
+                // parts (IDP.2A: u16 x u8) when they come straight from the fixed-point patterns
+                uint32_t a;
+                if (!BORDER) a = __dp2a_lo(__byte_perm(bxv, byv, 0x7632), (uint32_t)(3 | (WS_RAW_W << 8)), base);
+                else a = yi * (uint32_t)WS_RAW_W + (xi * 3u + base);
                 const uint32_t W = a & ~3u;
                 sh_[g] = a << 3;
                 u0[g] = ws_lds32(W); u1[g] = ws_lds32o<4>(W);
@@ -501,15 +516,15 @@ __device__ __forceinline__ void ws_sample(const WsRegs &R, uint32_t s_ent, int l
     };
     if (B2G_WS_UNROLL && !BORDER) {
 #pragma unroll
-        for (int g0 = 0; g0 < WS_H; g0 += G) {
-            const float dj = (float)(g0 - WS_H / 2);
-            group(g0, __ffma2_rn(B2, make_float2(dj, dj), nb), __fmaf_rn(hw, dj, wb));
+        for (int g0 = 0; g0 < WS_HALF; g0 += G) {
+            const float dj = (float)g0;
+            group(g0, g0 ? __ffma2_rn(B2, make_float2(dj, dj), nbh) : nbh, g0 ? __fmaf_rn(hw, dj, wbh) : wbh);
         }
     } else {
-        float dj = (float)(-WS_H / 2);
+        float dj = 0.f;
 #pragma unroll 1
-        for (int g0 = 0; g0 < WS_H; g0 += G) {
-            group(g0, __ffma2_rn(B2, make_float2(dj, dj), nb), __fmaf_rn(hw, dj, wb));
+        for (int g0 = 0; g0 < WS_HALF; g0 += G) {
+            group(g0, __ffma2_rn(B2, make_float2(dj, dj), nbh), __fmaf_rn(hw, dj, wbh));
             dj += (float)G;
         }
     }
@@ -523,7 +538,7 @@ __device__ __forceinline__ void ws_sample(const WsRegs &R, uint32_t s_ent, int l
                 fix.job = job;
 #pragma unroll 1
                 for (uint32_t rest = amb; rest; rest &= rest - 1u) {
-                    const int k = __ffs((int)rest) - 1;
+                    const int k = __ffs((int)rest) - 1 + hf * WS_HALF;
                     if (!wf_defer(fix, c, r0 + k)) {
                         const b200geo_warp_job &J = jobs[job];
                         const uint32_t v = wf_exact_px<BILINEAR>(J, src_base + J.src_offset, c, r0 + k);
@@ -535,6 +550,7 @@ __device__ __forceinline__ void ws_sample(const WsRegs &R, uint32_t s_ent, int l
             }
         }
     }
+    }   // hf
 }
 
 // Grid: min(ceil(n_tiles / WS_WARPS), SMs) CTAs of WS_WARPS warps, dynamic shared memory WS_SMEM_BYTES (one CTA per SM).
@@ -583,15 +599,15 @@ warp_strip_kernel(const uint8_t *__restrict__ src_base, const b200geo_warp_job *
             if (g_tile >= n_tiles) return NONE;
             g_j = 0;
             if (lane == 0) g_tk = atomicAdd(ticket, 1u);
-            return g_tile * 4u;
+            return g_tile * (unsigned)WS_PER_TILE;
         }
-        if (g_j < 3) return g_tile * 4u + (unsigned)(++g_j);
+        if (g_j < WS_PER_TILE - 1) return g_tile * (unsigned)WS_PER_TILE + (unsigned)(++g_j);
         if (g_tile == NONE) return NONE;
         g_tile = __shfl_sync(0xffffffffu, g_tk, 0) + n_warps;
         if (g_tile >= n_tiles) { g_tile = NONE; return NONE; }
         g_j = 0;
         if (lane == 0) g_tk = atomicAdd(ticket, 1u);
-        return g_tile * 4u;
+        return g_tile * (unsigned)WS_PER_TILE;
     };
     auto fetch_record = [&](uint32_t slot, unsigned strip) {      // asynchronous: lanes 0..4 copy 16 bytes each
         if (strip != NONE && lane < WS_REC_BYTES / 16) {

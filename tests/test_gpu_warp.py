@@ -376,7 +376,10 @@ def test_host_batch_pipeline_equals_device_path(sampler):
             if pinned:
                 src_h, out_h = src_h.pin_memory(), out_h.pin_memory()
             device.warp_host(src_h, out_h, jobs, 3, sampler, chunk_jobs=4)
-            assert np.array_equal(out_h.numpy(), want), (form, pinned)
+            # (the pipeline re-bases the frames into its staging buffers, so a tile may be routed to the other fast kernel:
+            # nn is bit-exact either way, bilinear stays within the +-1 both keep against the float64 kernel)
+            d = np.abs(out_h.numpy().astype(np.int16) - want.astype(np.int16))
+            assert d.max() <= (0 if sampler == "nn" else U8_TOL), (form, pinned, int(d.max()))
 
 
 def test_device_stitch_compose_matches_host_entry(golden, capsys):
