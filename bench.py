@@ -409,21 +409,29 @@ def bench_ransac(torch, dist, rank, world, args, ctx, peaks, local_gpu):
         e2e_s = (time.perf_counter() - t0) / n_e2e
         e2e_how = "ransac.RANSAC.run([X, Y], 'fwd', idx=...) on numpy arrays (b200geo_ransac_host: the sample sets past the first scoring wave are uploaded under that wave's scoring)"
     else:
-        pin_p, pin_i = torch.from_numpy(pts_h).pin_memory(), torch.from_numpy(idx_h).pin_memory()
+        # every rank uploads the correspondences and ONLY ITS OWN shard of the sample sets; the winner's four indices reach the
+        # other ranks inside the 48-byte record that is all-gathered instead of the 16-byte max all-reduce (device.ransac_sharded)
+        pin_p, pin_i = torch.from_numpy(pts_h).pin_memory(), torch.from_numpy(np.ascontiguousarray(idx_h[lo:hi])).pin_memory()
         out_h = torch.empty(32, dtype=torch.float64).pin_memory()
         mask_h = torch.empty(M, dtype=torch.uint8).pin_memory()
+        rec = torch.empty(device.WINREC_BYTES, dtype=torch.uint8, device="cuda")
+        recs = torch.empty(world * device.WINREC_BYTES, dtype=torch.uint8, device="cuda")
 
         def e2e_step():
             p = pin_p.cuda(non_blocking=True)
             i = pin_i.cuda(non_blocking=True)
-            r, m = device.ransac(p, i, th, d, 4, "fwd", group=group, keys=keys, result=result, mask=mask)
+            r, m = device.ransac_sharded(p, i, lo, th, d, 4, "fwd", group=group, rec=rec, recs=recs, result=result, mask=mask)
             out_h.copy_(r, non_blocking=True)
             mask_h.copy_(m, non_blocking=True)
             torch.cuda.synchronize()
         n_e2e = max(2, min(args.steps, 5))
         ems = timed_steps(torch, dist, world, e2e_step, n_e2e, 1)
         e2e_s = ems / n_e2e / 1e3
-        e2e_how = "pinned host -> device.ransac (sharded, NCCL max) -> pinned host, per rank"
+        assert int(out_h[0]) == int(res[0]) and int(out_h[1]) == int(res[1]), "sharded e2e run disagrees with the device-resident run"
+        h2d = world * pts_h.nbytes + idx_h.nbytes
+        d2h = world * (32 * 8 + M)
+        e2e_how = ("per rank: pinned host correspondences + this rank's shard of the sample sets -> device.ransac_sharded (48-byte all-gather "
+                   "of the per-rank winner records) -> pinned host; bytes are the whole job's")
     e2e = {"value": K * M / e2e_s, "unit": "hyp*pts/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
            "ms_per_step": e2e_s * 1e3, "how": e2e_how}
     rec = {"metric": "ransac_hyp_pts_per_s", "value": value, "unit": "hyp*pts/s", "ms_per_step": ms / args.steps,

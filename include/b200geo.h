@@ -144,6 +144,16 @@ int b200geo_ransac_finish_dev(b200geo_ctx *ctx, const float *pts, int M, const i
                               const unsigned long long *keys, float th, int method,
                               double *result, uint8_t *mask, void *stream);
 
+/* (2b', 2c') the same search when every GPU holds only ITS OWN shard of the sample sets (rows k_offset .. k_offset + n_local - 1
+ *      of the K x 4 index array, at idx_shard): the 48-byte record `rec` (device) receives this shard's two keys and the four
+ *      correspondence indices of the sample sets they name.  The ranks exchange their records (an all-gather of 48 bytes each);
+ *      b200geo_ransac_finish_recs_dev then takes the n_recs records, reduces the keys (MAX) and finishes as
+ *      b200geo_ransac_finish_dev does -- on every rank, no broadcast.  counts_shard (optional): n_local int32. */
+int b200geo_ransac_search_shard_dev(b200geo_ctx *ctx, const float *pts, int M, const int32_t *idx_shard, int k_offset, int n_local,
+                                    float th, double thr, int method, void *rec, int32_t *counts_shard, void *stream);
+int b200geo_ransac_finish_recs_dev(b200geo_ctx *ctx, const float *pts, int M, const void *recs, int n_recs, float th, int method,
+                                   double *result, uint8_t *mask, void *stream);
+
 /* Whole RANSAC.run (ransac.py:159-213) on host buffers: H2D, search, finish, D2H.  The sample sets are uploaded
  * in chunks on a second stream while earlier chunks are being solved and scored.
  *   thr = M*d/100 + n as the reference computes it (ransac.py:169,186).

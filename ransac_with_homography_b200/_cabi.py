@@ -87,6 +87,8 @@ SIGNATURES = {
     "b200geo_dist_host": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "b200geo_ransac_search_dev": (_i, [_vp, _vp, _i, _vp, _i, _i, _f, _d, _i, _vp, _i, _vp, _vp]),
     "b200geo_ransac_finish_dev": (_i, [_vp, _vp, _i, _vp, _vp, _f, _i, _vp, _vp, _vp]),
+    "b200geo_ransac_search_shard_dev": (_i, [_vp, _vp, _i, _vp, _i, _i, _f, _d, _i, _vp, _vp, _vp]),
+    "b200geo_ransac_finish_recs_dev": (_i, [_vp, _vp, _i, _vp, _i, _f, _i, _vp, _vp, _vp]),
     "b200geo_ransac_host": (_i, [_vp, _vp, _i, _vp, _i, _f, _d, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200geo_ransac_batched_dev": (_i, [_vp, _vp, _i, _vp, _i, _i, _f, _d, _i, _vp, _vp, _vp]),
     "b200geo_refit_host": (_i, [_vp, _vp, _i, _vp, _vp]),

@@ -61,6 +61,7 @@ int b200geo_destroy(b200geo_ctx *ctx)
         for (int i = 0; i < S_NUM; ++i)
             if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
         if (ctx->pinned) cudaFreeHost(ctx->pinned);
+        if (ctx->order_event) cudaEventDestroy(ctx->order_event);
         if (ctx->pipe_ready) {
             for (int i = 0; i < 3; ++i) cudaStreamDestroy(ctx->pipe_stream[i]);
             for (int i = 0; i < 3; ++i)
@@ -198,6 +199,43 @@ int launch_score_exact(b200geo_ctx *ctx, const float *pts, int M, const float *H
     return B200GEO_OK;
 }
 
+int launch_cmax(b200geo_ctx *ctx, const float *pts, int M, int B, float **cmax_out, cudaStream_t st)
+{
+    float *cmax;
+    int rc;
+    if ((rc = scratch(ctx, S_CMAX, sizeof(float) * (size_t)B, (void **)&cmax))) return rc;
+    B2G_CUDA(cudaMemsetAsync(cmax, 0, sizeof(float) * (size_t)B, st));
+    cmax_kernel<<<dim3((M + 2047) / 2048, B), 256, 0, st>>>((const float4 *)pts, M, cmax);
+    B2G_CHECK_LAUNCH(ctx);
+    *cmax_out = cmax;
+    ctx->cmax_pts = (const void *)pts; ctx->cmax_M = M; ctx->cmax_B = B;
+    return B200GEO_OK;
+}
+
+// Point-range splits of a scoring launch: `blocks` CTAs per split, `slots` CTAs resident on the GPU.  A CTA's time grows with the
+// correspondences it streams, the launch's with the number of waves: minimise waves x points-per-split (+ a CTA's prologue) over
+// the split count.  (Round 1 took "at least 16 waves" and whole 1024-point tiles: 8.3 waves -> 9 at K/8 = 125k sample sets, one
+// tenth of the kernel's time lost to the last wave; the same search also serves the unsharded launch.)
+int choose_splits(long long blocks, int M, int slots, int granule, int min_pts, int *per_out)
+{
+    int best_s = 1, best_per = (M + granule - 1) / granule * granule;
+    double best_cost = 1e300;
+    int max_s = M / min_pts;
+    if (max_s < 1) max_s = 1;
+    if (max_s > 512) max_s = 512;
+    for (int s = 1; s <= max_s; ++s) {
+        int per = ((M + s - 1) / s + granule - 1) / granule * granule;
+        if (per < 1) per = granule;
+        const int s_eff = (M + per - 1) / per;
+        const long long ctas = blocks * s_eff;
+        const long long waves = (ctas + slots - 1) / slots;
+        const double cost = (double)waves * (per + 40.0);
+        if (cost < best_cost * 0.9999) { best_cost = cost; best_s = s_eff; best_per = per; }
+    }
+    *per_out = best_per;
+    return best_s;
+}
+
 // K2.  fwd / backward with a positive finite threshold take the division-free FFMA2 kernel (exact
 // chain only inside the ambiguity shell); everything else takes the exact kernel.
 int launch_score(b200geo_ctx *ctx, const float *pts, int M, const float *H, const float *Hinv, const uint8_t *flags,
@@ -211,25 +249,15 @@ int launch_score(b200geo_ctx *ctx, const float *pts, int M, const float *H, cons
     float *cmax;
     unsigned long long *stats;
     int rc;
-    if ((rc = scratch(ctx, S_CMAX, sizeof(float) * (size_t)B, (void **)&cmax))) return rc;
     if ((rc = ensure_stats(ctx, st, &stats))) return rc;
-    B2G_CUDA(cudaMemsetAsync(cmax, 0, sizeof(float) * (size_t)B, st));
-    cmax_kernel<<<dim3((M + 2047) / 2048, B), 256, 0, st>>>((const float4 *)pts, M, cmax);
-    B2G_CHECK_LAUNCH(ctx);
+    if ((rc = launch_cmax(ctx, pts, M, B, &cmax, st))) return rc;
 
     if (method == B200GEO_REPROJ) {
         // two-sided bracket of the sum of the two errors (score_fast2_kernel), same deferred exact list
         const int per_cta2 = FAST2_THREADS * 2;
         int gx2 = (nk + per_cta2 - 1) / per_cta2;
-        long long blocks2 = (long long)gx2 * B, want2 = 16LL * 2 * ctx->sm_count;
-        int max_splits2 = (M + FAST2_TILE - 1) / FAST2_TILE, splits2 = 1;
-        if (blocks2 < want2) {
-            splits2 = (int)((want2 + blocks2 - 1) / blocks2);
-            if (splits2 > max_splits2) splits2 = max_splits2;
-        }
-        int per2 = (M + splits2 - 1) / splits2;
-        per2 = ((per2 + FAST2_TILE - 1) / FAST2_TILE) * FAST2_TILE;
-        splits2 = (M + per2 - 1) / per2;
+        int per2 = M;
+        int splits2 = choose_splits((long long)gx2 * B, M, 2 * ctx->sm_count, FAST_CHUNK, 256, &per2);
         if (splits2 > 1)
             for (int b = 0; b < B; ++b)
                 B2G_CUDA(cudaMemsetAsync(counts + (size_t)b * K_stride + k_begin, 0, sizeof(int32_t) * (size_t)nk, st));
@@ -252,17 +280,8 @@ int launch_score(b200geo_ctx *ctx, const float *pts, int M, const float *H, cons
 
     const int per_cta = FAST_THREADS * FAST_T;
     int gx = (nk + per_cta - 1) / per_cta;
-    long long blocks = (long long)gx * B;
-    long long want = 16LL * 2 * ctx->sm_count;                      // >= 16 waves at 2 CTAs per SM
-    int max_splits = (M + FAST_TILE - 1) / FAST_TILE;
-    int splits = 1;
-    if (blocks < want) {
-        splits = (int)((want + blocks - 1) / blocks);
-        if (splits > max_splits) splits = max_splits;
-    }
-    int per = (M + splits - 1) / splits;
-    per = ((per + FAST_TILE - 1) / FAST_TILE) * FAST_TILE;
-    splits = (M + per - 1) / per;
+    int per = M;
+    int splits = choose_splits((long long)gx * B, M, 2 * ctx->sm_count, FAST_CHUNK, 256, &per);
     if (splits > 1) {
         for (int b = 0; b < B; ++b)
             B2G_CUDA(cudaMemsetAsync(counts + (size_t)b * K_stride + k_begin, 0, sizeof(int32_t) * (size_t)nk, st));
@@ -322,10 +341,34 @@ int search(b200geo_ctx *ctx, const float *pts, int M, const int32_t *idx, int k_
     return launch_select(ctx, counts, k_begin, k_end, K_stride, B, thr, keys, st);
 }
 
+// K3 over B pairs: G CTAs per pair (mask slice + Gram partials), the last one solves.  S_CMAX is reused when it holds the largest
+// coordinate magnitudes of exactly these B sets (left there by the search that produced `keys`).
 int launch_finish(b200geo_ctx *ctx, const float *pts, int M, const int32_t *idx, int K_stride, int B,
-                  const unsigned long long *keys, float th, int method, double *result, uint8_t *mask, cudaStream_t st)
+                  const unsigned long long *keys, float th, int method, double *result, uint8_t *mask, cudaStream_t st,
+                  const WinRec *recs = nullptr, int n_recs = 0)
 {
-    finish_kernel<solve_t><<<B, REFIT_THREADS, 0, st>>>((const float4 *)pts, M, (const int4 *)idx, K_stride, keys, th, method, result, mask);
+    float *cmax = (float *)ctx->scratch[S_CMAX];
+    int rc;
+    const bool cmax_valid = cmax && ctx->cmax_pts == (const void *)pts && ctx->cmax_M == M && ctx->cmax_B == B;
+    if (!cmax_valid) {
+        if ((rc = launch_cmax(ctx, pts, M, B, &cmax, st))) return rc;
+    }
+    int G = (M + 1023) / 1024;                     // ~4 correspondences per thread
+    if (G > 64) G = 64;
+    if ((long long)G * B > 8LL * ctx->sm_count && B > 1) { G = (int)(8LL * ctx->sm_count / B); if (G < 1) G = 1; }
+    int per = (M + G - 1) / G;
+    G = (M + per - 1) / per;
+    double *partial;
+    unsigned *done;
+    if ((rc = scratch(ctx, S_FINISH, sizeof(double) * FINISH_NSUM * (size_t)G * B + sizeof(unsigned) * (size_t)B + 64, (void **)&partial))) return rc;
+    done = (unsigned *)(partial + (size_t)FINISH_NSUM * G * B);
+    if (ctx->finish_done_zeroed != (void *)done || ctx->finish_done_n < B) {      // the kernel leaves the counters at zero
+        B2G_CUDA(cudaMemsetAsync(done, 0, sizeof(unsigned) * (size_t)B, st));
+        ctx->finish_done_zeroed = (void *)done;
+        ctx->finish_done_n = B;
+    }
+    finish_kernel<solve_t><<<dim3(G, B), FINISH_THREADS, 0, st>>>((const float4 *)pts, M, (const int4 *)idx, K_stride, keys, recs, n_recs, th, method,
+                                                                 cmax, per, partial, done, result, mask);
     B2G_CHECK_LAUNCH(ctx);
     return B200GEO_OK;
 }
@@ -565,6 +608,7 @@ int b200geo_dlt4_dev(b200geo_ctx *ctx, const float *pts, int M, const int32_t *i
                      uint8_t *flags, void *stream)
 {
     B2G_ENTER(ctx);
+    stream_order(ctx, (cudaStream_t)stream);
     B2G_ARG(pts && idx && H && M > 0 && K >= 0);
     return launch_dlt4(ctx, pts, M, idx, 0, K, K, 1, H, Hinv, flags, (cudaStream_t)stream);
 }
@@ -573,6 +617,7 @@ int b200geo_dlt4_host(b200geo_ctx *ctx, const float *pts, int M, const int32_t *
                       uint8_t *flags)
 {
     B2G_ENTER(ctx);
+    stream_order(ctx, 0);
     B2G_ARG(pts && idx && H && M > 0 && K >= 0);
     if (K == 0) return B200GEO_OK;
     float *dp, *dH, *dHi = nullptr;
@@ -597,6 +642,7 @@ int b200geo_dlt4_host(b200geo_ctx *ctx, const float *pts, int M, const int32_t *
 int b200geo_homography4_host(b200geo_ctx *ctx, const double *u, const double *v, double *H)
 {
     B2G_ENTER(ctx);
+    stream_order(ctx, 0);
     B2G_ARG(u && v && H);
     double *d;
     int rc;
@@ -618,6 +664,7 @@ int b200geo_score_dev(b200geo_ctx *ctx, const float *pts, int M, const float *H,
                       int K, float th, int method, int32_t *counts, void *stream)
 {
     B2G_ENTER(ctx);
+    stream_order(ctx, (cudaStream_t)stream);
     B2G_ARG(pts && H && counts && M >= 0 && K >= 0);
     B2G_ARG(method == B200GEO_FWD || method == B200GEO_BACKWARD || method == B200GEO_REPROJ);
     B2G_ARG(method == B200GEO_FWD || Hinv != nullptr);
@@ -628,6 +675,7 @@ int b200geo_score_host(b200geo_ctx *ctx, const float *pts, int M, const float *H
                        int method, int32_t *counts)
 {
     B2G_ENTER(ctx);
+    stream_order(ctx, 0);
     B2G_ARG(pts && H && counts && M >= 0 && K >= 0);
     B2G_ARG(method == B200GEO_FWD || method == B200GEO_BACKWARD || method == B200GEO_REPROJ);
     B2G_ARG(method == B200GEO_FWD || Hinv != nullptr);
@@ -651,6 +699,7 @@ int b200geo_score_host(b200geo_ctx *ctx, const float *pts, int M, const float *H
 int b200geo_loss_host(b200geo_ctx *ctx, const float *pts, int M, const float *H, const float *Hinv, int method, float *err)
 {
     B2G_ENTER(ctx);
+    stream_order(ctx, 0);
     B2G_ARG(pts && H && err && M >= 0);
     B2G_ARG(method == B200GEO_FWD || Hinv != nullptr);
     if (M == 0) return B200GEO_OK;
@@ -673,6 +722,7 @@ int b200geo_loss_host(b200geo_ctx *ctx, const float *pts, int M, const float *H,
 int b200geo_project_host(b200geo_ctx *ctx, const float *Hm, const float *P, int M, float *out)
 {
     B2G_ENTER(ctx);
+    stream_order(ctx, 0);
     B2G_ARG(Hm && P && out && M >= 0);
     if (M == 0) return B200GEO_OK;
     float *dp, *dh, *dout;
@@ -693,6 +743,7 @@ int b200geo_project_host(b200geo_ctx *ctx, const float *Hm, const float *P, int 
 int b200geo_dist_host(b200geo_ctx *ctx, const float *a, const float *b, int rows, int M, float *out)
 {
     B2G_ENTER(ctx);
+    stream_order(ctx, 0);
     B2G_ARG(a && b && out && rows > 0 && M >= 0);
     if (M == 0) return B200GEO_OK;
     float *da, *dout;
@@ -715,6 +766,7 @@ int b200geo_ransac_search_dev(b200geo_ctx *ctx, const float *pts, int M, const i
                               void *stream)
 {
     B2G_ENTER(ctx);
+    stream_order(ctx, (cudaStream_t)stream);
     B2G_ARG(pts && idx && keys && M > 0 && k_begin >= 0 && k_end >= k_begin);
     B2G_ARG(method == B200GEO_FWD || method == B200GEO_BACKWARD || method == B200GEO_REPROJ);
     cudaStream_t st = (cudaStream_t)stream;
@@ -727,8 +779,40 @@ int b200geo_ransac_finish_dev(b200geo_ctx *ctx, const float *pts, int M, const i
                               float th, int method, double *result, uint8_t *mask, void *stream)
 {
     B2G_ENTER(ctx);
+    stream_order(ctx, (cudaStream_t)stream);
     B2G_ARG(pts && idx && keys && result && mask && M > 0);
     return launch_finish(ctx, pts, M, idx, 0, 1, keys, th, method, result, mask, (cudaStream_t)stream);
+}
+
+int b200geo_ransac_search_shard_dev(b200geo_ctx *ctx, const float *pts, int M, const int32_t *idx_shard, int k_offset, int n_local,
+                                    float th, double thr, int method, void *rec, int32_t *counts_shard, void *stream)
+{
+    B2G_ENTER(ctx);
+    stream_order(ctx, (cudaStream_t)stream);
+    B2G_ARG(pts && idx_shard && rec && M > 0 && k_offset >= 0 && n_local >= 0 && (long long)k_offset + n_local <= 0x7fffffffLL);
+    B2G_ARG(method == B200GEO_FWD || method == B200GEO_BACKWARD || method == B200GEO_REPROJ);
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long *dk;
+    int rc;
+    if ((rc = scratch(ctx, S_KEYS, 16, (void **)&dk))) return rc;
+    B2G_CUDA(cudaMemsetAsync(dk, 0, 16, st));
+    // the kernels address sample set k as idx[k]: a base pointer k_offset rows before the shard makes the shard rows
+    // k_offset .. k_offset + n_local - 1 (nothing outside them is dereferenced)
+    const int32_t *idx_virtual = idx_shard - 4 * (ptrdiff_t)k_offset;
+    int32_t *counts_virtual = counts_shard ? counts_shard - (ptrdiff_t)k_offset : nullptr;
+    if ((rc = search(ctx, pts, M, idx_virtual, k_offset, k_offset + n_local, k_offset + n_local, 1, th, thr, method, dk, counts_virtual, st))) return rc;
+    pack_winner_kernel<<<1, 32, 0, st>>>(dk, (const int4 *)idx_virtual, (WinRec *)rec);
+    B2G_CHECK_LAUNCH(ctx);
+    return B200GEO_OK;
+}
+
+int b200geo_ransac_finish_recs_dev(b200geo_ctx *ctx, const float *pts, int M, const void *recs, int n_recs, float th, int method,
+                                   double *result, uint8_t *mask, void *stream)
+{
+    B2G_ENTER(ctx);
+    stream_order(ctx, (cudaStream_t)stream);
+    B2G_ARG(pts && recs && n_recs > 0 && n_recs <= 4096 && result && mask && M > 0);
+    return launch_finish(ctx, pts, M, nullptr, 0, 1, nullptr, th, method, result, mask, (cudaStream_t)stream, (const WinRec *)recs, n_recs);
 }
 
 namespace {
@@ -750,6 +834,7 @@ int b200geo_ransac_host(b200geo_ctx *ctx, const float *pts, int M, const int32_t
                         int32_t *out_count, int32_t *out_counts, int32_t *out_last_count)
 {
     B2G_ENTER(ctx);
+    stream_order(ctx, 0);
     B2G_ARG(pts && idx && M > 0 && K > 0);
     B2G_ARG(method == B200GEO_FWD || method == B200GEO_BACKWARD || method == B200GEO_REPROJ);
     float *dp;
@@ -805,6 +890,7 @@ int b200geo_ransac_batched_dev(b200geo_ctx *ctx, const float *pts, int M, const 
                                double thr, int method, double *results, uint8_t *masks, void *stream)
 {
     B2G_ENTER(ctx);
+    stream_order(ctx, (cudaStream_t)stream);
     B2G_ARG(pts && idx && results && masks && M > 0 && K > 0 && B > 0 && B <= 65535);
     B2G_ARG(method == B200GEO_FWD || method == B200GEO_BACKWARD || method == B200GEO_REPROJ);
     cudaStream_t st = (cudaStream_t)stream;
@@ -819,6 +905,7 @@ int b200geo_ransac_batched_dev(b200geo_ctx *ctx, const float *pts, int M, const 
 int b200geo_refit_host(b200geo_ctx *ctx, const float *pts, int M, const uint8_t *mask, double *H)
 {
     B2G_ENTER(ctx);
+    stream_order(ctx, 0);
     B2G_ARG(pts && H && M > 0);
     float *dp;
     uint8_t *dm = nullptr;
@@ -842,6 +929,7 @@ int b200geo_warp_jobs_dev(b200geo_ctx *ctx, const void *src, void *dst, const b2
                           int max_ow, int max_oh, int channels, int src_type, int dst_type, int sampler, void *stream)
 {
     B2G_ENTER(ctx);
+    stream_order(ctx, (cudaStream_t)stream);
     B2G_ARG(src && dst && jobs_dev && n_jobs >= 0);
     B2G_ARG(sampler == B200GEO_NN || sampler == B200GEO_BILINEAR);
     B2G_ARG(dst_type == B200GEO_U8 || dst_type == B200GEO_F32 || dst_type == B200GEO_F64);
@@ -853,6 +941,7 @@ int b200geo_warp_batch_dev(b200geo_ctx *ctx, const void *src, void *dst, const b
                            const b200geo_src_layout *layout, void *stream)
 {
     B2G_ENTER(ctx);
+    stream_order(ctx, (cudaStream_t)stream);
     B2G_ARG(src && dst && jobs_dev && n_jobs >= 0);
     B2G_ARG(sampler == B200GEO_NN || sampler == B200GEO_BILINEAR);
     B2G_ARG(dst_type == B200GEO_U8 || dst_type == B200GEO_F32 || dst_type == B200GEO_F64);
@@ -863,6 +952,7 @@ int b200geo_warp_dev(b200geo_ctx *ctx, const void *src, void *dst, const b200geo
                      int src_type, int dst_type, int sampler, void *stream)
 {
     B2G_ENTER(ctx);
+    stream_order(ctx, (cudaStream_t)stream);
     B2G_ARG(src && dst && jobs && n_jobs >= 0);
     B2G_ARG(sampler == B200GEO_NN || sampler == B200GEO_BILINEAR);
     B2G_ARG(dst_type == B200GEO_U8 || dst_type == B200GEO_F32 || dst_type == B200GEO_F64);
@@ -901,6 +991,7 @@ int b200geo_warp_batch_host(b200geo_ctx *ctx, const void *src_host, void *dst_ho
                             int channels, int src_type, int dst_type, int sampler, int chunk_jobs)
 {
     B2G_ENTER(ctx);
+    stream_order(ctx, 0);
     B2G_ARG(src_host && dst_host && jobs && n_jobs >= 0);
     B2G_ARG(sampler == B200GEO_NN || sampler == B200GEO_BILINEAR);
     B2G_ARG(dst_type == B200GEO_U8 || dst_type == B200GEO_F32 || dst_type == B200GEO_F64);
@@ -909,6 +1000,7 @@ int b200geo_warp_batch_host(b200geo_ctx *ctx, const void *src_host, void *dst_ho
     if (chunk_jobs > n_jobs) chunk_jobs = n_jobs;
     int prc;
     if ((prc = ensure_pipe(ctx))) return prc;
+    B2G_CUDA(cudaStreamSynchronize(0));      // earlier work of this context (ordered onto the legacy stream above) shares the scratch blocks
     cudaStream_t s_in = ctx->pipe_stream[0], s_k = ctx->pipe_stream[1], s_out = ctx->pipe_stream[2];
     // device images of one chunk are packed back to back (256-byte aligned); jobs are rebased onto them
     const int n_chunks = (n_jobs + chunk_jobs - 1) / chunk_jobs;
@@ -988,6 +1080,7 @@ int b200geo_warp_host(b200geo_ctx *ctx, const void *src, void *dst, const b200ge
                       int src_type, int dst_type, int sampler)
 {
     B2G_ENTER(ctx);
+    stream_order(ctx, 0);
     B2G_ARG(src && dst && job);
     B2G_ARG(job->ow > 0 && job->oh > 0 && job->iw > 0 && job->ih > 0);
     size_t sbytes = (size_t)job->src_pitch * (size_t)job->ih;
@@ -1012,6 +1105,7 @@ int b200geo_match_hamming_host(b200geo_ctx *ctx, const uint8_t *descA, int nA, c
                                int cross_check, int32_t *train_idx, int32_t *dist)
 {
     B2G_ENTER(ctx);
+    stream_order(ctx, 0);
     B2G_ARG(nA >= 0 && nB >= 0 && desc_bytes > 0 && desc_bytes % 4 == 0 && desc_bytes <= 4 * HM_MAX_WORDS);
     B2G_ARG((nA == 0 || (descA && train_idx && dist)) && (nB == 0 || descB));
     if (nA == 0) return B200GEO_OK;
@@ -1052,6 +1146,7 @@ int b200geo_stitch_compose_dev(b200geo_ctx *ctx, const void *imgT, const void *i
                                const b200geo_compose *p, void *stream)
 {
     B2G_ENTER(ctx);
+    stream_order(ctx, (cudaStream_t)stream);
     B2G_ARG(imgT && imgQ && canvas && job && p);
     B2G_ARG(p->fw > 0 && p->fh > 0 && p->qw > 0 && p->qh > 0 && job->iw > 0 && job->ih > 0 && job->ow >= 0 && job->oh >= 0);
     B2G_ARG(p->blend == 0 || p->blend == 1);
@@ -1069,6 +1164,7 @@ int b200geo_stitch_compose_host(b200geo_ctx *ctx, const void *imgT, const void *
                                 const b200geo_compose *p)
 {
     B2G_ENTER(ctx);
+    stream_order(ctx, 0);
     B2G_ARG(imgT && imgQ && canvas && job && p && p->fh > 0 && p->qh > 0 && job->ih > 0);
     const size_t tbytes = (size_t)job->src_pitch * (size_t)job->ih, qbytes = (size_t)p->q_pitch * (size_t)p->qh;
     const size_t cbytes = (size_t)p->canvas_pitch * (size_t)p->fh;
@@ -1091,6 +1187,7 @@ int b200geo_sample_host(b200geo_ctx *ctx, const void *src, int ih, int iw, int c
                         const double *zy, long long N, int bh, int bw, int sampler, int dst_type, void *dst)
 {
     B2G_ENTER(ctx);
+    stream_order(ctx, 0);
     B2G_ARG(src && zx && zy && dst && ih > 0 && iw > 0 && N >= 0);
     B2G_ARG(sampler == B200GEO_NN || sampler == B200GEO_BILINEAR);
     B2G_ARG(dst_type == B200GEO_U8 || dst_type == B200GEO_F32 || dst_type == B200GEO_F64);

@@ -47,7 +47,7 @@ inline int fail(int code, const char *fmt, const char *a = "", const char *b = "
     } while (0)
 
 enum ScratchSlot {
-    S_PTS = 0, S_IDX, S_H, S_HINV, S_FLAGS, S_COUNTS, S_KEYS, S_RESULT, S_MASK, S_JOBS, S_SRC, S_DST, S_MISC, S_CMAX, S_STATS, S_WORKLIST, S_TILES, S_PIPE_SRC, S_PIPE_DST, S_PIPE_JOBS, S_WARPFIX, S_STRIPS,
+    S_PTS = 0, S_IDX, S_H, S_HINV, S_FLAGS, S_COUNTS, S_KEYS, S_RESULT, S_MASK, S_JOBS, S_SRC, S_DST, S_MISC, S_CMAX, S_STATS, S_WORKLIST, S_TILES, S_PIPE_SRC, S_PIPE_DST, S_PIPE_JOBS, S_WARPFIX, S_STRIPS, S_FINISH,
     S_NUM
 };
 
@@ -76,6 +76,13 @@ struct b200geo_ctx {
     long long tmap_pitch, tmap_rows, tmap_image_rows, tmap_row_bytes;
     void *scratch[b200geo::S_NUM];
     size_t scratch_cap[b200geo::S_NUM];
+    const void *cmax_pts;  // S_CMAX holds the largest |coordinate| of these cmax_B sets of cmax_M correspondences
+    int cmax_M, cmax_B;
+    cudaStream_t order_stream;  // stream of the latest _dev call (the scratch buffers are shared: see stream_order)
+    int order_valid;
+    cudaEvent_t order_event;
+    void *finish_done_zeroed;   // finish_kernel's per-pair arrival counters: where they are, and how many are known to be zero
+    int finish_done_n;
     void *pinned;          // small pinned staging block for scalar results
     size_t pinned_cap;
 };
@@ -128,6 +135,22 @@ struct DeviceGuard {
         if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
     }
 };
+
+// A context's scratch buffers, counters and cached tensor maps are shared by all its calls.  Calls issued on ONE stream are
+// ordered by the stream; when a _dev call arrives on a different stream than the previous one, it is made to wait for
+// everything queued on that previous stream so far (an event recorded there now), so that two streams never run two calls
+// of one context concurrently.  No cost while the stream does not change.
+inline void stream_order(b200geo_ctx *ctx, cudaStream_t st)
+{
+    if (ctx->order_valid && ctx->order_stream != st) {
+        if (!ctx->order_event) cudaEventCreateWithFlags(&ctx->order_event, cudaEventDisableTiming);
+        if (ctx->order_event && cudaEventRecord(ctx->order_event, ctx->order_stream) == cudaSuccess)
+            cudaStreamWaitEvent(st, ctx->order_event, 0);
+        cudaGetLastError();          // (the previous stream may have been destroyed by its owner: nothing left to wait for)
+    }
+    ctx->order_stream = st;
+    ctx->order_valid = 1;
+}
 
 #define B2G_ENTER(ctx)                                                                          \
     B2G_ARG((ctx) != nullptr);                                                                  \

@@ -110,6 +110,64 @@ __device__ __forceinline__ void block_reduce_sums(double (&v)[REFIT_NSUM], int n
     __syncthreads();
 }
 
+// The constrained 8x8 solve from the 24 Gram sums v[] (P, PX, PY, PR blocks of 6: xx, xy, x, yy, y, 1) accumulated in the
+// normalised coordinates x = (x - cx) ss, X = (X - cX) sd ...  One thread; the 9x9 / 8x9 matrices live in shared memory
+// (in registers they spilled 748 bytes of finish_kernel's frame).  Returns false for a singular system.
+struct RefitSolveMem { double G[9][9]; double A[8][9]; };
+__device__ __noinline__ bool refit_solve(const double *v, double cx, double cy, double cX, double cY, double ss, double sd,
+                                         RefitSolveMem &m_, double *out_H)
+{
+    double (&G)[9][9] = m_.G;
+    double (&A)[8][9] = m_.A;
+    auto blk = [&](int base, int r, int c) -> double {
+        const int map[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
+        return v[base + map[r][c]];
+    };
+    // G (9x9) = [[P,0,-PX],[0,P,-PY],[-PX,-PY,PR]]
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) {
+            double P = blk(0, r, c), PX = blk(6, r, c), PY = blk(12, r, c), PR = blk(18, r, c);
+            G[r][c] = P;          G[r][3 + c] = 0.0;      G[r][6 + c] = -PX;
+            G[3 + r][c] = 0.0;    G[3 + r][3 + c] = P;    G[3 + r][6 + c] = -PY;
+            G[6 + r][c] = -PX;    G[6 + r][3 + c] = -PY;  G[6 + r][6 + c] = PR;
+        }
+    // constraint h22 = 1 in normalised coordinates:  g8 = 1 + a*g6 + b*g7,  a = ss*cx, b = ss*cy
+    // g = e8 + E y,  E = [I8 ; (0..0, a, b)]  ->  (E^T G E) y = -E^T G e8
+    const double ea6 = ss * cx, ea7 = ss * cy;
+    for (int r = 0; r < 8; ++r) {
+        const double er = r == 6 ? ea6 : (r == 7 ? ea7 : 0.0);
+        for (int c = 0; c < 8; ++c) {
+            const double ec = c == 6 ? ea6 : (c == 7 ? ea7 : 0.0);
+            A[r][c] = G[r][c] + er * G[8][c] + G[r][8] * ec + er * G[8][8] * ec;
+        }
+        A[r][8] = -(G[r][8] + er * G[8][8]);
+    }
+    double yv[8];
+    bool ok = gauss_solve<double, 8>(A, yv);
+    double g[9];
+    for (int i = 0; i < 8; ++i) g[i] = yv[i];
+    g[8] = 1.0 + ea6 * yv[6] + ea7 * yv[7];
+    // H = Td^-1 * G * Ts
+    const double dd = 1.0 / sd;
+    double m[9];
+    for (int r = 0; r < 3; ++r) {
+        m[3 * r + 0] = g[3 * r + 0] * ss;
+        m[3 * r + 1] = g[3 * r + 1] * ss;
+        m[3 * r + 2] = g[3 * r + 2] - (g[3 * r + 0] * cx + g[3 * r + 1] * cy) * ss;
+    }
+    double h[9];
+    for (int c = 0; c < 3; ++c) {
+        h[c] = m[c] * dd + cX * m[6 + c];
+        h[3 + c] = m[3 + c] * dd + cY * m[6 + c];
+        h[6 + c] = m[6 + c];
+    }
+    const double inv = 1.0 / h[8];
+    for (int i = 0; i < 8; ++i) { h[i] *= inv; ok = ok && (fabs(h[i]) <= 1.0e300); }
+    h[8] = 1.0;
+    for (int i = 0; i < 9; ++i) out_H[i] = h[i];
+    return ok;
+}
+
 // mask-driven least squares; returns status in out[0..9] = {status, H[9]}; all threads call.
 __device__ void refit_block(const float4 *__restrict__ pts, int M, const uint8_t *__restrict__ mask,
                             RefitShared &sh, double *out_H, int *out_status, int *out_count)
@@ -188,116 +246,188 @@ __device__ void refit_block(const float4 *__restrict__ pts, int M, const uint8_t
     block_reduce_sums(v, REFIT_NSUM, sh);
 
     if (threadIdx.x == 0) {
-        // symmetric 3x3 blocks from the 6 packed sums (xx, xy, x, yy, y, 1)
-        auto blk = [&](int base, int r, int c) -> double {
-            const int map[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
-            return v[base + map[r][c]];
-        };
-        // G (9x9) = [[P,0,-PX],[0,P,-PY],[-PX,-PY,PR]]
-        double G[9][9];
-        for (int r = 0; r < 3; ++r)
-            for (int c = 0; c < 3; ++c) {
-                double P = blk(0, r, c), PX = blk(6, r, c), PY = blk(12, r, c), PR = blk(18, r, c);
-                G[r][c] = P;          G[r][3 + c] = 0.0;      G[r][6 + c] = -PX;
-                G[3 + r][c] = 0.0;    G[3 + r][3 + c] = P;    G[3 + r][6 + c] = -PY;
-                G[6 + r][c] = -PX;    G[6 + r][3 + c] = -PY;  G[6 + r][6 + c] = PR;
-            }
-        // constraint h22 = 1 in normalised coordinates:  g8 = 1 + a*g6 + b*g7,  a = ss*cx, b = ss*cy
-        // g = e8 + E y,  E = [I8 ; (0..0, a, b)]  ->  (E^T G E) y = -E^T G e8
-        const double ea[8] = {0, 0, 0, 0, 0, 0, ss * cx, ss * cy};
-        double A[8][9];
-        for (int r = 0; r < 8; ++r) {
-            for (int c = 0; c < 8; ++c)
-                A[r][c] = G[r][c] + ea[r] * G[8][c] + G[r][8] * ea[c] + ea[r] * G[8][8] * ea[c];
-            A[r][8] = -(G[r][8] + ea[r] * G[8][8]);
-        }
-        double yv[8];
-        bool ok = gauss_solve<double, 8>(A, yv);
-        double g[9];
-        for (int i = 0; i < 8; ++i) g[i] = yv[i];
-        g[8] = 1.0 + ea[6] * yv[6] + ea[7] * yv[7];
-        // H = Td^-1 * G * Ts
-        const double dd = 1.0 / sd;
-        double m[9];
-        for (int r = 0; r < 3; ++r) {
-            m[3 * r + 0] = g[3 * r + 0] * ss;
-            m[3 * r + 1] = g[3 * r + 1] * ss;
-            m[3 * r + 2] = g[3 * r + 2] - (g[3 * r + 0] * cx + g[3 * r + 1] * cy) * ss;
-        }
-        double h[9];
-        for (int c = 0; c < 3; ++c) {
-            h[c] = m[c] * dd + cX * m[6 + c];
-            h[3 + c] = m[3 + c] * dd + cY * m[6 + c];
-            h[6 + c] = m[6 + c];
-        }
-        const double inv = 1.0 / h[8];
-        for (int i = 0; i < 8; ++i) { h[i] *= inv; ok = ok && (fabs(h[i]) <= 1.0e300); }
-        h[8] = 1.0;
-        for (int i = 0; i < 9; ++i) out_H[i] = h[i];
+        __shared__ RefitSolveMem sm_solve;
+        const bool ok = refit_solve(v, cx, cy, cX, cY, ss, sd, sm_solve, out_H);
         *out_status = ok ? 0 : B200GEO_ERR_SINGULAR;
     }
 }
 
-// K3.  Grid (B); block REFIT_THREADS.  result: B x 32 doubles (layout in b200geo.h).
-template <typename T>
-__global__ void __launch_bounds__(REFIT_THREADS)
-finish_kernel(const float4 *__restrict__ pts, int M, const int4 *__restrict__ idx, int K_stride,
-              const unsigned long long *__restrict__ keys, float th, int method, double *__restrict__ result,
-              uint8_t *__restrict__ mask)
+// K3.  Grid (G, B), block FINISH_THREADS: CTA (g, b) takes the correspondences [g * per, (g + 1) * per) of pair b.
+// Every CTA decodes the winner and re-solves its four points (one thread, ~200 float64 operations), writes its slice of the
+// inlier mask with the reference-order chain and accumulates the Gram sums of its inliers; the last CTA of a pair to finish
+// (a counter in global memory, reset for the next launch) adds the G partial sums in index order -- the result does not depend
+// on the arrival order -- and solves.  The normalisation (centre and scale of the coordinates the sums are taken in) must be
+// known before the inliers are: the centroid of the winning sample's four points and the largest coordinate magnitude of
+// the set (`cmax`, already computed for the scoring band); the least-squares minimiser does not depend on it, only the
+// conditioning of its float64 evaluation does.  (Round 1: one 1024-thread CTA, two passes, 67 us at M = 20000 and 748 bytes
+// of spills -- the non-sharded part of the multi-GPU step.)
+// result: B x 32 doubles (layout in b200geo.h); entries 3..20 are NaN whenever the status is not 0.
+// What a rank contributes to the choice of the winner when the sample sets are sharded AND each rank holds only its own shard of
+// them: its two keys and the four correspondence indices of the sample sets they name (the other ranks cannot look those up).
+struct __align__(16) WinRec {
+    unsigned long long best, early;      // keys[0], keys[1] of this rank's hypothesis block
+    int4 ibest, iearly;                  // idx[k] of the sample set each key names (unused when the key is 0)
+};
+static_assert(sizeof(WinRec) == 48, "WinRec is exchanged as 48 bytes per rank");
+
+// Grid (1), block (32): keys (2 x u64, this rank's block reduced) + idx -> rec.  idx is indexed by absolute k.
+__global__ void pack_winner_kernel(const unsigned long long *__restrict__ keys, const int4 *__restrict__ idx, WinRec *__restrict__ rec)
 {
-    __shared__ RefitShared sh;
+    if (threadIdx.x != 0) return;
+    WinRec r;
+    r.best = keys[0]; r.early = keys[1];
+    r.ibest = make_int4(0, 0, 0, 0); r.iearly = make_int4(0, 0, 0, 0);
+    if ((r.best >> 32) != 0ull) r.ibest = __ldg(idx + (0xFFFFFFFFu - (unsigned)(r.best & 0xFFFFFFFFull)));
+    if (r.early != 0ull) r.iearly = __ldg(idx + (unsigned)(0x100000000ull - r.early));
+    *rec = r;
+}
+
+constexpr int FINISH_THREADS = 256;
+constexpr int FINISH_NSUM = 25;      // inlier count + the 24 Gram sums
+
+template <typename T>
+__global__ void __launch_bounds__(FINISH_THREADS)
+finish_kernel(const float4 *__restrict__ pts, int M, const int4 *__restrict__ idx, int K_stride,
+              const unsigned long long *__restrict__ keys, const WinRec *__restrict__ recs, int n_recs, float th, int method,
+              const float *__restrict__ cmax, int per, double *__restrict__ partial, unsigned *__restrict__ done,
+              double *__restrict__ result, uint8_t *__restrict__ mask)
+{
+    __shared__ double red[FINISH_THREADS / 32][FINISH_NSUM];
     __shared__ float sH[9], sHi[9];
-    __shared__ int sWin, sStatus, sCount;
-    const int b = blockIdx.x;
+    __shared__ double sC[4];
+    __shared__ int sWin, sStatus, sLast;
+    __shared__ RefitSolveMem sm_solve;
+    const int b = blockIdx.y, G = gridDim.x;
     pts += (size_t)b * M;
     mask += (size_t)b * M;
     result += (size_t)b * 32;
+    partial += ((size_t)b * G + blockIdx.x) * FINISH_NSUM;
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
 
     if (threadIdx.x == 0) {
-        int w = decode_winner(keys[2 * b], keys[2 * b + 1]);
+        int w;
+        int4 id = make_int4(0, 0, 0, 0);
+        if (recs) {          // (B = 1) the per-rank records of a sharded search: the max of the keys, and the indices that came with it
+            unsigned long long kb = 0ull, ke = 0ull;
+            int4 ib = id, ie = id;
+            for (int r = 0; r < n_recs; ++r) {
+                const WinRec q = recs[r];
+                if (q.best > kb) { kb = q.best; ib = q.ibest; }
+                if (q.early > ke) { ke = q.early; ie = q.iearly; }
+            }
+            w = decode_winner(kb, ke);
+            id = ke != 0ull ? ie : ib;
+        } else {
+            w = decode_winner(keys[2 * b], keys[2 * b + 1]);
+            if (w >= 0) id = __ldg(idx + (size_t)b * K_stride + w);
+        }
         sWin = w;
         sStatus = 0;
         if (w >= 0) {
             float Hf[9], Hif[9];
-            int4 id = __ldg(idx + (size_t)b * K_stride + w);
+            if (((unsigned)id.x >= (unsigned)M) | ((unsigned)id.y >= (unsigned)M) | ((unsigned)id.z >= (unsigned)M) | ((unsigned)id.w >= (unsigned)M))
+                id = make_int4(0, 0, 0, 0);        // (cannot win: such a sample set is flagged and scores 0)
             bool deg = solve_sample<T>(pts, id, Hf, Hif, true);
             for (int j = 0; j < 9; ++j) { sH[j] = Hf[j]; sHi[j] = Hif[j]; }
             if (deg) sStatus = B200GEO_ERR_SINGULAR;
+            const float4 p0 = __ldg(pts + id.x), p1 = __ldg(pts + id.y), p2 = __ldg(pts + id.z), p3 = __ldg(pts + id.w);
+            sC[0] = 0.25 * ((double)p0.x + p1.x + p2.x + p3.x); sC[1] = 0.25 * ((double)p0.y + p1.y + p2.y + p3.y);
+            sC[2] = 0.25 * ((double)p0.z + p1.z + p2.z + p3.z); sC[3] = 0.25 * ((double)p0.w + p1.w + p2.w + p3.w);
         } else {
             sStatus = B200GEO_ERR_NOMODEL;
         }
     }
     __syncthreads();
     const int win = sWin;
+    const int j0 = blockIdx.x * per, j1 = min(M, j0 + per);
     if (win < 0 || sStatus != 0) {
-        for (int j = threadIdx.x; j < M; j += blockDim.x) mask[j] = 0;
-        if (threadIdx.x == 0) {
+        for (int j = j0 + threadIdx.x; j < j1; j += blockDim.x) mask[j] = 0;
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
             result[0] = (double)win; result[1] = 0.0; result[2] = (double)sStatus;
-            for (int j = 3; j < 32; ++j) result[j] = 0.0;
+            for (int j = 3; j < 21; ++j) result[j] = qnan;
+            for (int j = 21; j < 32; ++j) result[j] = 0.0;
         }
         return;
     }
     float h[9], hi[9];
 #pragma unroll
     for (int j = 0; j < 9; ++j) { h[j] = sH[j]; hi[j] = sHi[j]; }
-    // inliers_pos = err_total < th   (ransac.py:183)
-    for (int j = threadIdx.x; j < M; j += blockDim.x) {
-        float4 p = __ldg(pts + j);
+    const double cx = sC[0], cy = sC[1], cX = sC[2], cY = sC[3];
+    const double C = (double)cmax[b];
+    const double ss = (C > 0.0 && C < 1.0e300) ? 1.0 / C : 1.0, sd = ss;
+    double v[FINISH_NSUM];
+#pragma unroll
+    for (int i = 0; i < FINISH_NSUM; ++i) v[i] = 0.0;
+    // inliers_pos = err_total < th (ransac.py:183); P = sum p p^T, PX = sum X p p^T, PY = sum Y p p^T, PR = sum (X^2+Y^2) p p^T, p = (x, y, 1)
+    for (int j = j0 + threadIdx.x; j < j1; j += blockDim.x) {
+        const float4 q = __ldg(pts + j);
         float e;
-        if (method == B200GEO_FWD) e = exact_loss<B200GEO_FWD>(h, hi, p);
-        else if (method == B200GEO_BACKWARD) e = exact_loss<B200GEO_BACKWARD>(h, hi, p);
-        else e = exact_loss<B200GEO_REPROJ>(h, hi, p);
-        mask[j] = (uint8_t)(e < th);
+        if (method == B200GEO_FWD) e = exact_loss<B200GEO_FWD>(h, hi, q);
+        else if (method == B200GEO_BACKWARD) e = exact_loss<B200GEO_BACKWARD>(h, hi, q);
+        else e = exact_loss<B200GEO_REPROJ>(h, hi, q);
+        const bool in = e < th;
+        mask[j] = (uint8_t)in;
+        if (in) {
+            const double x = ((double)q.x - cx) * ss, y = ((double)q.y - cy) * ss;
+            const double X = ((double)q.z - cX) * sd, Y = ((double)q.w - cY) * sd;
+            const double pp[6] = {x * x, x * y, x, y * y, y, 1.0};
+            const double R = X * X + Y * Y;
+            v[24] += 1.0;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                v[i] += pp[i];
+                v[6 + i] += X * pp[i];
+                v[12 + i] += Y * pp[i];
+                v[18 + i] += R * pp[i];
+            }
+        }
     }
-    __syncthreads();   // mask[] written by this block is read below (global, same block)
-    __threadfence_block();
-    refit_block(pts, M, mask, sh, result + 12, &sStatus, &sCount);
+    {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+        for (int i = 0; i < FINISH_NSUM; ++i) {
+            const double sacc = warp_sum(v[i]);
+            if (lane == 0) red[warp][i] = sacc;
+        }
+        __syncthreads();
+        if (threadIdx.x < FINISH_NSUM) {
+            double sacc = 0.0;
+            for (int w = 0; w < FINISH_THREADS / 32; ++w) sacc += red[w][threadIdx.x];
+            partial[threadIdx.x] = sacc;
+        }
+    }
+    __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(done + b, 1u);
+        sLast = (t == (unsigned)G - 1u);
+        if (sLast) done[b] = 0u;               // ready for the next launch (stream order)
+    }
+    __syncthreads();
+    if (!sLast) return;
+    __threadfence();
+    // last CTA of the pair: add the partial sums in index order, solve
+    if (threadIdx.x < FINISH_NSUM) {
+        const double *p = partial - (size_t)blockIdx.x * FINISH_NSUM + threadIdx.x;
+        double sacc = 0.0;
+        for (int g = 0; g < G; ++g) sacc += __ldcg(p + (size_t)g * FINISH_NSUM);
+        red[0][threadIdx.x] = sacc;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const double n = red[0][24];
+        int status = 0;
+        double Hout[9];
+        for (int j = 0; j < 9; ++j) Hout[j] = qnan;
+        // the reference's fit(collective=True) needs more than n = 4 columns (ransac.py:38); 4 exact inliers still have a
+        // unique solution here, fewer do not
+        if (n < 4.0) status = B200GEO_ERR_SINGULAR;
+        else if (!refit_solve(red[0], cx, cy, cX, cY, ss, sd, sm_solve, Hout)) status = B200GEO_ERR_SINGULAR;
         result[0] = (double)win;
-        result[1] = (double)sCount;
-        result[2] = (double)sStatus;
+        result[1] = n;
+        result[2] = (double)status;
         for (int j = 0; j < 9; ++j) result[3 + j] = (double)sH[j];
+        for (int j = 0; j < 9; ++j) result[12 + j] = status == 0 ? Hout[j] : qnan;
         for (int j = 21; j < 32; ++j) result[j] = 0.0;
     }
 }

@@ -114,6 +114,45 @@ def ransac(pts, idx, th, d, n=4, method="fwd", group=None, keys=None, result=Non
     return ransac_finish(pts, idx, keys, th, method, result=result, mask=mask)
 
 
+WINREC_BYTES = 48      # struct WinRec (csrc/select_refit.cuh): keys[2] + the sample indices each key names
+
+
+def ransac_sharded(pts, idx_shard, k_offset, th, d, n=4, method="fwd", group=None, rec=None, recs=None, result=None, mask=None,
+                   counts=None):
+    """RANSAC.run over K sample sets of which THIS rank holds only rows k_offset .. k_offset + len(idx_shard) - 1 (its own
+    hypothesis block; `pts` is replicated).  Each rank reduces its block to a 48-byte record -- its two keys and the four
+    correspondence indices of the sample sets they name --, ONE all-gather of those records (48 bytes per rank over NVLink)
+    replaces the max all-reduce of `ransac`, and every rank finishes from the gathered records (no broadcast: the winner's
+    indices travel in the record).  Same result as `ransac` on the full index array.  Returns (result, mask)."""
+    import torch.distributed as dist
+    _chk_pts(pts)
+    assert idx_shard.dtype == torch.int32 and idx_shard.is_contiguous() and idx_shard.shape[-1] == 4
+    ctx = _ctx(pts)
+    M = pts.shape[0]
+    thr = M * d / 100 + n
+    world = 1
+    if dist.is_available() and dist.is_initialized():
+        world = dist.get_world_size(group)
+    if rec is None:
+        rec = torch.empty((WINREC_BYTES,), dtype=torch.uint8, device=pts.device)
+    _cabi.check(ctx.lib.b200geo_ransac_search_shard_dev(ctx.handle, _p(pts), M, _p(idx_shard), int(k_offset), int(idx_shard.shape[0]),
+                                                        float(np.float32(th)), float(thr), _cabi.METHODS[method], _p(rec), _p(counts),
+                                                        _stream(pts)))
+    if world > 1:
+        if recs is None:
+            recs = torch.empty((world * WINREC_BYTES,), dtype=torch.uint8, device=pts.device)
+        dist.all_gather_into_tensor(recs, rec, group=group)
+    else:
+        recs = rec
+    if result is None:
+        result = torch.empty((32,), dtype=torch.float64, device=pts.device)
+    if mask is None:
+        mask = torch.empty((M,), dtype=torch.uint8, device=pts.device)
+    _cabi.check(ctx.lib.b200geo_ransac_finish_recs_dev(ctx.handle, _p(pts), M, _p(recs), world, float(np.float32(th)),
+                                                       _cabi.METHODS[method], _p(result), _p(mask), _stream(pts)))
+    return result, mask
+
+
 def ransac_batched(pts, idx, th, d, n=4, method="fwd", results=None, masks=None):
     """B independent pairs: pts (B,M,4), idx (B,K,4) -> results (B,32) float64, masks (B,M) uint8."""
     _chk_pts(pts)

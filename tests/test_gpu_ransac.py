@@ -425,3 +425,49 @@ def test_global_rng_position_after_run_equals_reference(golden, case, seed, th, 
     with redirect_stdout(io.StringIO()):
         RANSAC(HomoModel(th=th, d=d, n=4), k=k).run([A.T, B.T], method="fwd")
     assert np.array_equal(np.random.randint(0, 1 << 30, 8), golden.file("api")[f"rng_after_{case}"])
+
+
+def test_sharded_sample_sets_with_winner_records(ctx):
+    """Multi-GPU e2e protocol on one GPU: four 'ranks' each search only their own shard of the sample sets
+    (b200geo_ransac_search_shard_dev: idx rows k_offset ..), their 48-byte winner records are concatenated (what the
+    all-gather does) and b200geo_ransac_finish_recs_dev finishes from them -- identical to the unsharded run, with and
+    without an early exit."""
+    import torch
+    from ransac_with_homography_b200 import _cabi, device
+    X, Y = synth_pair(3, 2000)
+    pts = oracle.pack_points(X, Y)
+    K = 8192
+    idx = np.random.RandomState(9).randint(0, 2000, (K, 4)).astype(np.int32)
+    tp, ti = torch.from_numpy(pts).cuda(), torch.from_numpy(idx).cuda()
+    for d in (95.0, 40.0):
+        want, wmask = device.ransac(tp, ti, 4.0, d)
+        thr = 2000 * d / 100 + 4
+        recs = torch.zeros(4 * device.WINREC_BYTES, dtype=torch.uint8, device="cuda")
+        for r in range(4):
+            lo, hi = device.shard_range(K, r, 4)
+            shard = ti[lo:hi].contiguous()
+            rec = recs[r * device.WINREC_BYTES:(r + 1) * device.WINREC_BYTES]
+            _cabi.check(ctx.lib.b200geo_ransac_search_shard_dev(ctx.handle, _cabi._vp(tp.data_ptr()), 2000, _cabi._vp(shard.data_ptr()), lo, hi - lo,
+                                                                4.0, float(thr), 0, _cabi._vp(rec.data_ptr()), None, None))
+        res = torch.empty(32, dtype=torch.float64, device="cuda")
+        mask = torch.empty(2000, dtype=torch.uint8, device="cuda")
+        _cabi.check(ctx.lib.b200geo_ransac_finish_recs_dev(ctx.handle, _cabi._vp(tp.data_ptr()), 2000, _cabi._vp(recs.data_ptr()), 4, 4.0, 0,
+                                                           _cabi._vp(res.data_ptr()), _cabi._vp(mask.data_ptr()), None))
+        assert np.array_equal(res.cpu().numpy()[:21], want.cpu().numpy()[:21])
+        assert torch.equal(mask, wmask)
+    # single-rank form of the Python wrapper
+    r1, m1 = device.ransac_sharded(tp, ti, 0, 4.0, 95.0)
+    assert np.array_equal(r1.cpu().numpy()[:21], device.ransac(tp, ti, 4.0, 95.0)[0].cpu().numpy()[:21])
+
+
+def test_failed_runs_leave_nan_in_the_result(ctx):
+    """status != 0 (no model / singular refit): result[3..20] is NaN, never uninitialised memory."""
+    import torch
+    from ransac_with_homography_b200 import device
+    rs = np.random.RandomState(0)
+    pts = torch.from_numpy((rs.rand(50, 4) * 1000).astype(np.float32)).cuda()
+    idx = torch.zeros((8, 4), dtype=torch.int32, device="cuda")            # every sample degenerate -> all counts 0
+    res = torch.full((32,), 7.0, dtype=torch.float64, device="cuda")
+    res, mask = device.ransac(pts, idx, 1e-3, 50, result=res)
+    r = res.cpu().numpy()
+    assert int(r[2]) == -5 and int(r[0]) == -1 and np.isnan(r[3:21]).all() and int(mask.sum()) == 0
