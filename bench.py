@@ -173,6 +173,59 @@ def merge_clocks(a, b):
     return out
 
 
+def numa_bind(local_gpu):
+    """Run this rank on the CPUs NVML names as local to its GPU, so that pinned host buffers allocated afterwards are
+    NUMA-local to the GPU's PCIe root.  Returns a short description for the record."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_gpu)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = [64 * i + b for i, wd in enumerate(words) for b in range(64) if (wd >> b) & 1]
+        cpus = [c for c in cpus if c in os.sched_getaffinity(0)]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"{len(cpus)} cpus local to gpu {local_gpu} (nvml)"
+    except Exception as e:          # noqa: BLE001 -- a missing NVML call must not stop the benchmark
+        return f"not bound ({type(e).__name__})"
+    return "not bound"
+
+
+def measure_link(torch, dist, world, mb=256, reps=3):
+    """Host link of this box as the e2e paths use it: pinned host <-> device copies of `mb` MB, each direction alone and
+    both at once (two streams), on all ranks at the same time.  GB/s per rank: the MIN over the ranks (what the slowest rank
+    sees while the others copy too); `sum_*` adds the ranks up."""
+    n = mb << 20
+    hin, hout = torch.empty(n, dtype=torch.uint8).pin_memory(), torch.empty(n, dtype=torch.uint8).pin_memory()
+    din, dout = torch.empty(n, dtype=torch.uint8, device="cuda"), torch.empty(n, dtype=torch.uint8, device="cuda")
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def run(up, down):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            if up:
+                with torch.cuda.stream(s1):
+                    din.copy_(hin, non_blocking=True)
+            if down:
+                with torch.cuda.stream(s2):
+                    hout.copy_(dout, non_blocking=True)
+        torch.cuda.synchronize()
+        return n * reps / (time.perf_counter() - t0) / 1e9
+    run(True, True)
+    vals = [run(True, False), run(False, True), run(True, True)]
+    t = torch.tensor(vals, dtype=torch.float64, device="cuda")
+    tmin, tsum = t.clone(), t.clone()
+    if world > 1:
+        dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+    a, b = tmin.cpu().tolist(), tsum.cpu().tolist()
+    return {"h2d_alone_gbs": a[0], "d2h_alone_gbs": a[1], "each_direction_concurrent_gbs": a[2], "sum_ranks_each_direction_concurrent_gbs": b[2],
+            "how": f"{mb} MB pinned <-> device copies, all {world} rank(s) at once; per-rank figures are the minimum over ranks"}
+
+
 # ------------------------------------------------------------------------------------------------
 # CPU arms
 # ------------------------------------------------------------------------------------------------
@@ -507,7 +560,7 @@ def bench_warp(torch, dist, rank, world, args, ctx, peaks, local_gpu):
                       "sharding": f"frames over {world} rank(s), no communication",
                       "l2": "inputs (25.5 GB per 4096 frames) are larger than L2"},
            "roofline": roof,
-           "e2e": {"value": e2e_v, "unit": "Gpix/s", "h2d_bytes_per_step": int(nb * per_frame), "d2h_bytes_per_step": int(nb * per_frame),
+           "e2e": {"value": e2e_v, "unit": "Gpix/s", "h2d_bytes_per_step": int(world * nb * per_frame), "d2h_bytes_per_step": int(world * nb * per_frame),
                    "ms_per_step": ems / n_e2e, "how": f"{nb} frames per rank per step: pinned host -> device.warp_host (b200geo_warp_batch_host: 16-frame chunks, "
                                                         "copies and kernels overlapped on three streams) -> pinned host"},
            "gpu_launches": int(launches), "clocks": cs.summary()}
@@ -531,15 +584,19 @@ def bench_stitch(torch, dist, rank, world, args, ctx, peaks, local_gpu):
         m = min(64, n - i)
         frames[i:i + m] = torch.randint(0, 256, (m, h, w, 3), dtype=torch.uint8, device="cuda", generator=g)
     canv = torch.zeros((n, ch, cw, 3), dtype=torch.uint8, device="cuda")
+    from ransac_with_homography_b200 import _cabi as _c
+    jobs_buf = torch.empty((n * _c.WARP_JOB_DTYPE.itemsize,), dtype=torch.uint8, device="cuda")
+    boxes_buf = torch.empty((n, 5), dtype=torch.int32, device="cuda")
     out = {}
 
     def step():
-        out["r"] = device.stitch_batched(pts, idx, frames, C5["th"], C5["d"], (ch, cw), canvases=canv)
+        out["r"] = device.stitch_batched(pts, idx, frames, C5["th"], C5["d"], (ch, cw), canvases=canv, jobs=jobs_buf, boxes=boxes_buf)
     l0 = ctx.launch_count()
     ms = timed_steps(torch, dist, world, step, args.steps, args.warmup, None)
     launches = (ctx.launch_count() - l0) * args.steps // (args.steps + args.warmup)
     _, boxes, results, _ = out["r"]
     res = results.cpu().numpy()
+    boxes = boxes.cpu().numpy()
     pix = int((boxes[:, 2].astype(np.int64) * boxes[:, 3]).sum())
     if world > 1:
         t = torch.tensor([pix], dtype=torch.int64, device="cuda")
@@ -555,6 +612,45 @@ def bench_stitch(torch, dist, rank, world, args, ctx, peaks, local_gpu):
             "gpu_launches": int(launches), "pairs_ok": int((res[:, 2] == 0).sum()), "median_inliers": float(np.median(res[:, 1]))}
 
 
+def bench_aux(torch, ctx):
+    """The two kernels beside the hot path that the driver's line did not show so far: K5 stitch
+    compose (stitchPanorama as one kernel, device-resident 1080p pair) and K6 Hamming matcher (500 x 500 ORB descriptors with
+    cross-check, host API: copies inside).  Latency-bound single calls: milliseconds, not rooflines."""
+    from ransac_with_homography_b200 import device
+    from ransac_with_homography_b200.ransac import match_hamming
+    h, w = C4["h"], C4["w"]
+    g = torch.Generator(device="cuda"); g.manual_seed(5)
+    q = torch.randint(0, 256, (h, w, 3), dtype=torch.uint8, device="cuda", generator=g)
+    t = torch.randint(0, 256, (h, w, 3), dtype=torch.uint8, device="cuda", generator=g)
+    H = frame_homographies(1, h, w, 0.1, seed=3)[0]
+    H[0, 2] += 400.0
+    out = {}
+    for name, blend in (("paste", False), ("blend_rate", "Rate")):
+        canvas = device.stitch_compose(q, t, H, blend, 0.2)
+        for _ in range(3):
+            device.stitch_compose(q, t, H, blend, 0.2, canvas=canvas)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(20):
+            device.stitch_compose(q, t, H, blend, 0.2, canvas=canvas)
+        b.record(); torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / 20
+        out["compose_" + name] = {"ms_per_call": ms, "canvas": list(canvas.shape[:2]), "gpix_per_s": canvas.shape[0] * canvas.shape[1] / ms / 1e6,
+                                  "what": "K5 stitch_compose_kernel: warp of a 1080p image + placement + " + name + " + uint8, device-resident"}
+    rs = np.random.RandomState(2)
+    A = rs.randint(0, 256, (500, 32)).astype(np.uint8)
+    Bd = rs.randint(0, 256, (500, 32)).astype(np.uint8)
+    for _ in range(3):
+        m = match_hamming(A, Bd, True)
+    t0 = time.perf_counter()
+    for _ in range(20):
+        m = match_hamming(A, Bd, True)
+    out["match_hamming"] = {"ms_per_call": (time.perf_counter() - t0) / 20 * 1e3, "matches": len(m),
+                            "what": "K6 hamming_best_kernel + cross-check, 500 x 500 descriptors of 256 bits, host API (copies and Match list inside)"}
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -566,9 +662,12 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    numa = numa_bind(local)
     from ransac_with_homography_b200 import _cabi
     ctx = _cabi.context(local)
     peaks = measured_peaks()
+    link = measure_link(torch, dist, world)
+    link["numa"] = numa
     line = None
     warp_rec = None
     if args.workload in ("all", "ransac"):
@@ -584,6 +683,16 @@ def run_ours(args):
         line.setdefault("clocks", {"sm_mhz": None, "sm_max_mhz": None, "reasons": []})
     if line is None:
         line, warp_rec = warp_rec, None
+    # e2e roofline: the copies of a step against the measured host link (both directions at once)
+    for rec in (line, warp_rec):
+        if rec is not None and "e2e" in rec:
+            e = rec["e2e"]
+            e["link"] = link
+            ms = e.get("ms_per_step")
+            if ms:
+                gbs = (e["h2d_bytes_per_step"] + e["d2h_bytes_per_step"]) / (ms / 1e3) / 1e9
+                e["copy_gbs"] = gbs              # whole job, both directions
+                e["link_frac"] = gbs / (2.0 * link["sum_ranks_each_direction_concurrent_gbs"])
     line.update({"n_gpus": world, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "strong",
                  "vs_baseline": None, "data": "synthetic"})
     line.setdefault("dtype", "f32")
@@ -614,6 +723,8 @@ def run_ours(args):
             tgt["cpu_baseline"] = {"value": v, "unit": "Gpix/s", "cores": 1, "kind": kind, "seconds": dt,
                                    "sample": "16 of 4096 frames 1080p bilinear, " +
                                              ("wrapPerspectiveScan of the unmodified reference (oracle/_ref)" if kind == "reference" else "numpy port of homography.py:186-209,123-138")}
+    if rank == 0 and world == 1 and args.workload == "all":
+        line["aux"] = bench_aux(torch, ctx)
     if rank == 0:
         order = ["metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
                  "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"]

@@ -178,6 +178,11 @@ int b200geo_ransac_batched_dev(b200geo_ctx *ctx, const float *pts, int M, const 
  * over the rows with mask[j] != 0 (mask NULL = all rows).  H: 9 doubles. */
 int b200geo_refit_host(b200geo_ctx *ctx, const float *pts, int M, const uint8_t *mask, double *H);
 
+/* The homogeneous least-squares homography over M correspondences: calcHomography(u, v, collective=True) (homography.py:71-88
+ * with the 2M x 9 matrix of calc_correspCollective, :30-46) -- the right singular vector of the smallest singular value,
+ * scaled to h22 = 1.  H: 9 doubles. */
+int b200geo_homography_svd_host(b200geo_ctx *ctx, const float *pts, int M, double *H);
+
 /* ------------------------------------------------------------------------------------------------
  * (3) backward warp -- replaces wrapPerspective / wrapPerspectiveScan + the samplers
  *     nearestNeighbor / bilinear (homography.py:108-209) and the astype(uint8) of
@@ -268,6 +273,14 @@ typedef struct b200geo_compose {
 /* device buffers (uint8 RGB), asynchronous on `stream` */
 int b200geo_stitch_compose_dev(b200geo_ctx *ctx, const void *imgT, const void *imgQ, void *canvas,
                                const b200geo_warp_job *job, const b200geo_compose *p, void *stream);
+/* Batched stitch pipeline: the warp jobs of B pairs from their RANSAC results, on the device (no host round trip between
+ * b200geo_ransac_batched_dev and b200geo_warp_batch_dev).  Pair b: transformImageH(frame_b, H_b) (homography.py:230-242) with
+ * wrapPerspective's output rectangle (:143-163) and inv(H) (:172), frame b at src offset b * ih * iw * 3, output into canvas
+ * slot b (canvas_h x canvas_w x 3, back to back), clipped to the slot.  results: B x 32 doubles (b200geo_ransac_finish_dev
+ * layout); jobs_dev: B jobs; boxes_dev: B x 5 int32 = (min_x, min_y, out_w, out_h, ok); ok = 0: the search failed or the
+ * projected corners are not finite -- the job is the identity warp. */
+int b200geo_stitch_jobs_dev(b200geo_ctx *ctx, const double *results, int B, int ih, int iw, int canvas_h, int canvas_w,
+                            b200geo_warp_job *jobs_dev, int32_t *boxes_dev, void *stream);
 /* host buffers: H2D of both images, one kernel, D2H of the canvas */
 int b200geo_stitch_compose_host(b200geo_ctx *ctx, const void *imgT, const void *imgQ, void *canvas,
                                 const b200geo_warp_job *job, const b200geo_compose *p);

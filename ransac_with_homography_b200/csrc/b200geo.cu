@@ -133,6 +133,8 @@ int b200geo_sync(b200geo_ctx *ctx, void *stream)
 // ------------------------------------------------------------------------------------------------
 namespace {
 
+size_t type_size(int t) { return t == B200GEO_U8 ? 1 : (t == B200GEO_F32 ? 4 : 8); }
+
 // 128-byte statistics / counter block (8-byte words): [0] score pairs taken by the exact chain, [1] deferred-work counter,
 // [2] warp pixels evaluated in float64 by the fast warp kernel, [3] tile tickets of warp_pipe_kernel,
 // [4] routed launch: number of strip tiles, number of old-kernel tiles (2 x u32), [5] tile tickets of warp_strip_kernel
@@ -572,7 +574,6 @@ int launch_warp(b200geo_ctx *ctx, const void *src, void *dst, const b200geo_warp
     return fail(B200GEO_ERR_ARG, "unsupported source type / channel count%s%s");
 }
 
-size_t type_size(int t) { return t == B200GEO_U8 ? 1 : (t == B200GEO_F32 ? 4 : 8); }
 
 template <typename SrcT, int C>
 int launch_sample_t(b200geo_ctx *ctx, const void *src, int ih, int iw, int bh, int bw, const double *zx, const double *zy,
@@ -925,6 +926,26 @@ int b200geo_refit_host(b200geo_ctx *ctx, const float *pts, int M, const uint8_t 
     return B200GEO_OK;
 }
 
+int b200geo_homography_svd_host(b200geo_ctx *ctx, const float *pts, int M, double *H)
+{
+    B2G_ENTER(ctx);
+    stream_order(ctx, 0);
+    B2G_ARG(pts && H && M > 0);
+    float *dp;
+    double *dr;
+    int rc;
+    if ((rc = scratch(ctx, S_PTS, (size_t)M * 16, (void **)&dp))) return rc;
+    if ((rc = scratch(ctx, S_RESULT, 32 * 8, (void **)&dr))) return rc;
+    B2G_CUDA(cudaMemcpyAsync(dp, pts, (size_t)M * 16, cudaMemcpyHostToDevice, 0));
+    homography_svd_kernel<<<1, REFIT_THREADS, 0, 0>>>((const float4 *)dp, M, dr);
+    B2G_CHECK_LAUNCH(ctx);
+    double res[10];
+    B2G_CUDA(cudaMemcpy(res, dr, sizeof res, cudaMemcpyDeviceToHost));
+    for (int j = 0; j < 9; ++j) H[j] = res[1 + j];
+    if ((int)res[0] != 0) return fail(B200GEO_ERR_SINGULAR, "degenerate homogeneous system%s%s");
+    return B200GEO_OK;
+}
+
 int b200geo_warp_jobs_dev(b200geo_ctx *ctx, const void *src, void *dst, const b200geo_warp_job *jobs_dev, int n_jobs,
                           int max_ow, int max_oh, int channels, int src_type, int dst_type, int sampler, void *stream)
 {
@@ -972,6 +993,9 @@ int b200geo_warp_dev(b200geo_ctx *ctx, const void *src, void *dst, const b200geo
     b200geo_src_layout lay = {jobs[0].src_pitch, 0, 0, 0};
     bool uniform = true, same = channels == 3 && src_type == B200GEO_U8;     // same: equal images at multiples of their size -> 3-D tensor map
     for (int i = 0; i < n_jobs; ++i) {
+        B2G_ARG(jobs[i].iw > 0 && jobs[i].ih > 0 && jobs[i].ow >= 0 && jobs[i].oh >= 0);
+        B2G_ARG((size_t)jobs[i].src_pitch >= (size_t)jobs[i].iw * channels * type_size(src_type));
+        B2G_ARG((size_t)jobs[i].dst_pitch >= (size_t)jobs[i].ow * channels * type_size(dst_type));
         if (jobs[i].ow > max_ow) max_ow = jobs[i].ow;
         if (jobs[i].oh > max_oh) max_oh = jobs[i].oh;
         if (jobs[i].src_pitch != lay.pitch || lay.pitch <= 0 || jobs[i].src_offset < 0 || jobs[i].src_offset % lay.pitch) uniform = false;
@@ -1019,6 +1043,8 @@ int b200geo_warp_batch_host(b200geo_ctx *ctx, const void *src_host, void *dst_ho
         size_t so = 0, dofs = 0;
         for (int j = c * chunk_jobs; j < n_jobs && j < (c + 1) * chunk_jobs; ++j) {
             B2G_ARG(jobs[j].ow > 0 && jobs[j].oh > 0 && jobs[j].iw > 0 && jobs[j].ih > 0 && jobs[j].src_pitch > 0 && jobs[j].dst_pitch > 0);
+            B2G_ARG((size_t)jobs[j].src_pitch >= (size_t)jobs[j].iw * channels * type_size(src_type));
+            B2G_ARG((size_t)jobs[j].dst_pitch >= (size_t)jobs[j].ow * channels * type_size(dst_type));
             dj[j].src_offset = (int64_t)so;
             dj[j].dst_offset = (int64_t)dofs;
             if (jobs[j].src_pitch != lay.pitch || (so % (size_t)lay.pitch)) uniform = false;
@@ -1156,6 +1182,19 @@ int b200geo_stitch_compose_dev(b200geo_ctx *ctx, const void *imgT, const void *i
     B2G_ARG(grid.y <= 65535);
     if (p->blend) stitch_compose_kernel<1><<<grid, block, 0, st>>>((const uint8_t *)imgT, (const uint8_t *)imgQ, (uint8_t *)canvas, *job, *p);
     else stitch_compose_kernel<0><<<grid, block, 0, st>>>((const uint8_t *)imgT, (const uint8_t *)imgQ, (uint8_t *)canvas, *job, *p);
+    B2G_CHECK_LAUNCH(ctx);
+    return B200GEO_OK;
+}
+
+int b200geo_stitch_jobs_dev(b200geo_ctx *ctx, const double *results, int B, int ih, int iw, int canvas_h, int canvas_w,
+                            b200geo_warp_job *jobs_dev, int32_t *boxes_dev, void *stream)
+{
+    B2G_ENTER(ctx);
+    stream_order(ctx, (cudaStream_t)stream);
+    B2G_ARG(results && jobs_dev && boxes_dev && B > 0 && ih > 0 && iw > 0 && canvas_h > 0 && canvas_w > 0);
+    const long long sp = 3LL * iw, dp = 3LL * canvas_w;
+    stitch_jobs_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(results, B, ih, iw, canvas_h, canvas_w, sp, sp * ih, dp, dp * canvas_h,
+                                                                      jobs_dev, boxes_dev);
     B2G_CHECK_LAUNCH(ctx);
     return B200GEO_OK;
 }

@@ -15,6 +15,7 @@
 //                             canvas = uint8(float32(v)) inside the T rect, uint8(q) elsewhere               (:330-334)
 #pragma once
 
+#include "solve.cuh"
 #include "warp.cuh"
 
 namespace b200geo {
@@ -76,6 +77,71 @@ stitch_compose_kernel(const uint8_t *__restrict__ imgT, const uint8_t *__restric
         const double v = __dadd_rn(__dmul_rn(wq, (double)q8[ch]), __dmul_rn(wt, t[ch]));
         o[ch] = (uint8_t)(int)__double2float_rn(v);                         // float32 canvas, then astype(np.uint8)
     }
+}
+
+// Batched stitch pipeline (config 5): the warp jobs of B pairs built ON THE DEVICE from the RANSAC results, so that no host
+// round trip separates the refit from the warp.  Per pair: transformImageH(frame_b, H_b) -> wrapPerspective's output rectangle
+// (homography.py:143-163): the four corners (0,0), (w-1,0), (w-1,h-1), (0,h-1) through H in float64, int() truncation of the
+// extremes, and inv(H) (homography.py:172) by the adjugate.  The output goes to canvas slot b, clipped to the slot.
+// Pairs whose search failed (status != 0), whose H or projected corners are not finite, or whose rectangle is absurd get the
+// identity warp and ok = 0.  results: B x 32 doubles (b200geo_ransac_finish_dev layout); boxes: B x 5 int32
+// (min_x, min_y, out_w, out_h, ok).  One thread per pair.
+__global__ void __launch_bounds__(128)
+stitch_jobs_kernel(const double *__restrict__ results, int B, int ih, int iw, int canvas_h, int canvas_w, long long src_pitch,
+                   long long src_stride, long long dst_pitch, long long dst_stride, b200geo_warp_job *__restrict__ jobs,
+                   int *__restrict__ boxes)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const double *r = results + (size_t)b * 32;
+    double H[9];
+    bool ok = r[2] == 0.0;
+#pragma unroll
+    for (int j = 0; j < 9; ++j) { H[j] = r[12 + j]; ok = ok && fabs(H[j]) < 1.0e300; }
+    double mnx = 0, mxx = 0, mny = 0, mxy = 0;
+    if (ok) {
+        const double cxs[4] = {0.0, (double)(iw - 1), (double)(iw - 1), 0.0}, cys[4] = {0.0, 0.0, (double)(ih - 1), (double)(ih - 1)};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            // (numpy: H @ bnd with float64 dgemm, then the division by row 2)
+            const double zx = fma(H[2], 1.0, fma(H[1], cys[k], H[0] * cxs[k]));
+            const double zy = fma(H[5], 1.0, fma(H[4], cys[k], H[3] * cxs[k]));
+            const double zw = fma(H[8], 1.0, fma(H[7], cys[k], H[6] * cxs[k]));
+            const double px = zx / zw, py = zy / zw;
+            ok = ok && fabs(px) < 1.0e9 && fabs(py) < 1.0e9;        // also NaN
+            if (k == 0) { mnx = mxx = px; mny = mxy = py; }
+            else { mnx = fmin(mnx, px); mxx = fmax(mxx, px); mny = fmin(mny, py); mxy = fmax(mxy, py); }
+        }
+    }
+    double Hi[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    if (ok) {
+        invert3<double>(H, Hi);
+#pragma unroll
+        for (int j = 0; j < 9; ++j) ok = ok && fabs(Hi[j]) < 1.0e300;
+    }
+    long long min_x = 0, min_y = 0, ow = iw, oh = ih;
+    if (ok) {
+        min_x = (long long)mnx; min_y = (long long)mny;             // int(): toward zero
+        ow = (long long)mxx - min_x + 1; oh = (long long)mxy - min_y + 1;
+    } else {
+        Hi[0] = Hi[4] = Hi[8] = 1.0; Hi[1] = Hi[2] = Hi[3] = Hi[5] = Hi[6] = Hi[7] = 0.0;
+    }
+    if (ow > canvas_w) ow = canvas_w;
+    if (oh > canvas_h) oh = canvas_h;
+    if (ow < 0) ow = 0;
+    if (oh < 0) oh = 0;
+    b200geo_warp_job J;
+#pragma unroll
+    for (int j = 0; j < 9; ++j) J.invH[j] = Hi[j];
+    J.x0 = (double)min_x; J.dx = 1.0; J.x_last = (double)(min_x + ow - 1);
+    J.y0 = (double)min_y; J.dy = 1.0; J.y_last = (double)(min_y + oh - 1);
+    J.ow = (int)ow; J.oh = (int)oh; J.bw = iw; J.bh = ih; J.iw = iw; J.ih = ih;
+    J.reserved0 = 0; J.reserved1 = 0;
+    J.src_offset = (long long)b * src_stride; J.src_pitch = src_pitch;
+    J.dst_offset = (long long)b * dst_stride; J.dst_pitch = dst_pitch;
+    jobs[b] = J;
+    int *bx = boxes + (size_t)b * 5;
+    bx[0] = (int)min_x; bx[1] = (int)min_y; bx[2] = (int)ow; bx[3] = (int)oh; bx[4] = ok ? 1 : 0;
 }
 
 }  // namespace b200geo

@@ -432,6 +432,94 @@ finish_kernel(const float4 *__restrict__ pts, int M, const int4 *__restrict__ id
     }
 }
 
+// S6: calcHomography(u, v, collective=True) (homography.py:30-46, 71-88): the unit-norm minimiser of |A h| over the 2M x 9
+// matrix of calc_correspCollective -- the last right singular vector of A, scaled to h22 = 1.  The reference takes a float32 SVD
+// of A; here the 9 x 9 Gram matrix A^T A is accumulated in float64 from the same float32 rows (products x x', ... rounded to
+// float32 as the reference's matrix holds them) and its smallest eigenvector is found by cyclic Jacobi rotations, which
+// resolve small eigenvalues of a graded matrix to high relative accuracy (measured against a float64 SVD of A: 5e-11 on the
+// fixture, where LAPACK's tridiagonal eigensolver on the same Gram matrix loses 3e-4).  One CTA; result: [status, H[9]].
+__global__ void __launch_bounds__(REFIT_THREADS)
+homography_svd_kernel(const float4 *__restrict__ pts, int M, double *__restrict__ result)
+{
+    __shared__ RefitShared sh;
+    __shared__ double G[9][9], V[9][9];
+    // 30 sums: a a^T (6: xx xy x yy y 1), a (x) cx (9), a (x) cy (9), cx cx^T + cy cy^T (6), with a = (x, y, 1),
+    // cx = (x X, y X, X), cy = (x Y, y Y, Y)
+    double v[REFIT_NSUM], v2[6];
+#pragma unroll
+    for (int i = 0; i < REFIT_NSUM; ++i) v[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) v2[i] = 0.0;
+    for (int j = threadIdx.x; j < M; j += blockDim.x) {
+        const float4 q = __ldg(pts + j);
+        const double a[3] = {(double)q.x, (double)q.y, 1.0};
+        const double cx[3] = {(double)__fmul_rn(q.x, q.z), (double)__fmul_rn(q.y, q.z), (double)q.z};
+        const double cy[3] = {(double)__fmul_rn(q.x, q.w), (double)__fmul_rn(q.y, q.w), (double)q.w};
+        v[0] += a[0] * a[0]; v[1] += a[0] * a[1]; v[2] += a[0]; v[3] += a[1] * a[1]; v[4] += a[1]; v[5] += 1.0;
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { v[6 + 3 * r + c] += a[r] * cx[c]; v[15 + 3 * r + c] += a[r] * cy[c]; }
+        v2[0] += cx[0] * cx[0] + cy[0] * cy[0]; v2[1] += cx[0] * cx[1] + cy[0] * cy[1]; v2[2] += cx[0] * cx[2] + cy[0] * cy[2];
+        v2[3] += cx[1] * cx[1] + cy[1] * cy[1]; v2[4] += cx[1] * cx[2] + cy[1] * cy[2]; v2[5] += cx[2] * cx[2] + cy[2] * cy[2];
+    }
+    block_reduce_sums(v, REFIT_NSUM, sh);
+    double w6[REFIT_NSUM];
+#pragma unroll
+    for (int i = 0; i < REFIT_NSUM; ++i) w6[i] = i < 6 ? v2[i] : 0.0;
+    block_reduce_sums(w6, 6, sh);
+    if (threadIdx.x != 0) return;
+    const int map[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) {
+            // rows of A: (-a, 0, cx) and (0, -a, cy)
+            G[r][c] = v[map[r][c]];       G[r][3 + c] = 0.0;                G[r][6 + c] = -v[6 + 3 * r + c];
+            G[3 + r][c] = 0.0;            G[3 + r][3 + c] = v[map[r][c]];   G[3 + r][6 + c] = -v[15 + 3 * r + c];
+            G[6 + r][c] = -v[6 + 3 * c + r]; G[6 + r][3 + c] = -v[15 + 3 * c + r]; G[6 + r][6 + c] = w6[map[r][c]];
+        }
+    for (int r = 0; r < 9; ++r)
+        for (int c = 0; c < 9; ++c) V[r][c] = r == c ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        double off = 0.0, diag = 0.0;
+        for (int p = 0; p < 9; ++p) {
+            diag += G[p][p] * G[p][p];
+            for (int q = p + 1; q < 9; ++q) off += G[p][q] * G[p][q];
+        }
+        if (!(off > 1e-60 * diag)) break;
+        for (int p = 0; p < 8; ++p)
+            for (int q = p + 1; q < 9; ++q) {
+                const double apq = G[p][q];
+                if (fabs(apq) < 1e-300 || fabs(apq) <= 1e-19 * sqrt(fabs(G[p][p] * G[q][q]))) continue;
+                const double theta = (G[q][q] - G[p][p]) / (2.0 * apq);
+                const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+                for (int k = 0; k < 9; ++k) {       // columns p, q
+                    const double gkp = G[k][p], gkq = G[k][q];
+                    G[k][p] = c * gkp - sn * gkq; G[k][q] = sn * gkp + c * gkq;
+                }
+                for (int k = 0; k < 9; ++k) {       // rows p, q
+                    const double gpk = G[p][k], gqk = G[q][k];
+                    G[p][k] = c * gpk - sn * gqk; G[q][k] = sn * gpk + c * gqk;
+                }
+                for (int k = 0; k < 9; ++k) {
+                    const double vkp = V[k][p], vkq = V[k][q];
+                    V[k][p] = c * vkp - sn * vkq; V[k][q] = sn * vkp + c * vkq;
+                }
+            }
+    }
+    int kmin = 0;
+    for (int k = 1; k < 9; ++k)
+        if (G[k][k] < G[kmin][kmin]) kmin = k;
+    const double h8 = V[8][kmin];
+    bool ok = fabs(h8) > 1e-300 && M >= 4;
+    for (int i = 0; i < 9; ++i) {
+        const double hv = V[i][kmin] / h8;         // h / h[2,2] (homography.py:83-84)
+        result[1 + i] = hv;
+        ok = ok && fabs(hv) <= 1.0e300;
+    }
+    result[0] = ok ? 0.0 : (double)B200GEO_ERR_SINGULAR;
+}
+
 __global__ void __launch_bounds__(REFIT_THREADS)
 refit_kernel(const float4 *__restrict__ pts, int M, const uint8_t *__restrict__ mask, double *__restrict__ result)
 {

@@ -72,6 +72,8 @@ warp_generic_kernel(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ 
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     const int r = blockIdx.y * blockDim.y + threadIdx.y;
     if (c >= J.ow || r >= J.oh) return;
+    // a job whose rows overlap (pitch smaller than a row) is not executed: the in-bounds arguments below assume iw / ow columns per row
+    if (J.src_pitch < (long long)J.iw * C * (long long)sizeof(SrcT) || J.dst_pitch < (long long)J.ow * C * (long long)sizeof(DstT)) return;
     const SrcT *src = reinterpret_cast<const SrcT *>(src_base + J.src_offset);
     const size_t spitch = (size_t)J.src_pitch / sizeof(SrcT);
     DstT *dst = reinterpret_cast<DstT *>(dst_base + J.dst_offset + (size_t)r * (size_t)J.dst_pitch) + (size_t)c * C;

@@ -145,6 +145,12 @@ struct WfTma {
     int image_rows, row_bytes;
 };
 
+// jobs that arrive in device memory cannot be checked by the host: a job whose pitches are smaller than its rows is skipped
+__device__ __forceinline__ bool wf_job_ok(const b200geo_warp_job &J)
+{
+    return J.src_pitch >= 3LL * J.iw && J.dst_pitch >= 3LL * J.ow && J.iw > 0 && J.ih > 0;
+}
+
 template <int BILINEAR>
 __device__ void wf_setup(const b200geo_warp_job &J, int c0, int r0, int tw, int th, const WfTma &tma, WfDesc &T)
 {
@@ -281,7 +287,7 @@ warp_setup_kernel(const b200geo_warp_job *__restrict__ jobs, const uint8_t *__re
     const b200geo_warp_job &J = jobs[blockIdx.z];
     WfDesc T;
     const int c0 = tx * WF_TW, r0 = ty * WF_TH;
-    if (c0 >= J.ow || r0 >= J.oh) {
+    if (c0 >= J.ow || r0 >= J.oh || !wf_job_ok(J)) {
         T.mode = WF_EMPTY;
         T.P = 0; T.rows = 0; T.ox = 0; T.oy = 0; T.xc = 0; T.yc = 0; T.band = 0.f; T.magic = 0u;
         T.nx0 = T.ax = T.bx = T.ny0 = T.ay = T.by = T.gw = T.hw = 0.f; T.srow = 0;
@@ -1204,7 +1210,7 @@ warp_tile_setup_kernel(const b200geo_warp_job *__restrict__ jobs, const uint8_t 
     const b200geo_warp_job &J = jobs[blockIdx.z];
     WpTile W;
     const int c0 = tx * WF_TW, r0 = ty * WF_TH;
-    if (c0 >= J.ow || r0 >= J.oh) {
+    if (c0 >= J.ow || r0 >= J.oh || !wf_job_ok(J)) {
         uint4 *z = reinterpret_cast<uint4 *>(&W);
 #pragma unroll
         for (int i = 0; i < WP_TILE_WORDS; ++i) z[i] = make_uint4(0u, 0u, 0u, 0u);

@@ -210,7 +210,7 @@ warp_route_setup_kernel(const b200geo_warp_job *__restrict__ jobs, const uint8_t
     bool live = tx < tiles_x && ty < tiles_y;
     const b200geo_warp_job &J = jobs[blockIdx.z];
     const int c0 = tx * WF_TW, r0 = ty * WF_TH;
-    if (live && (c0 >= J.ow || r0 >= J.oh)) live = false;
+    if (live && (c0 >= J.ow || r0 >= J.oh || !wf_job_ok(J))) live = false;
     WsStrip S[WS_PER_TILE];
     bool fast = live;
     if (fast) {

@@ -204,6 +204,9 @@ def bbox_jobs(H: np.ndarray, src_hw, channels=3, src_itemsize=1, dst_itemsize=1,
     bnd = np.array([[0, iw - 1, iw - 1, 0], [0, 0, ih - 1, ih - 1], [1.0, 1, 1, 1]])
     q = H @ bnd
     q = q / q[:, 2:3, :]
+    bad = ~np.isfinite(q[:, :2]).all(axis=(1, 2)) | (np.abs(q[:, :2]) > 1e9).any(axis=(1, 2))
+    if bad.any():                                     # H finite but a corner at w ~ 0: the reference's int() raises here
+        raise ValueError(f"bbox_jobs: projected corners are not finite for frames {np.nonzero(bad)[0].tolist()}")
     trunc = lambda a: np.trunc(a).astype(np.int64)   # int(): toward zero
     min_x, max_x = trunc(q[:, 0].min(1)), trunc(q[:, 0].max(1))
     min_y, max_y = trunc(q[:, 1].min(1)), trunc(q[:, 1].max(1))
@@ -267,28 +270,40 @@ def warp_host(src, dst, jobs: np.ndarray, channels: int = 3, sampler: str = "bil
     return dst
 
 
-def stitch_batched(pts, idx, frames, th, d, canvas_hw, n=4, method="fwd", sampler="bilinear", canvases=None):
+def stitch_jobs(results: torch.Tensor, src_hw, canvas_hw, jobs: torch.Tensor | None = None, boxes: torch.Tensor | None = None):
+    """Warp jobs of B pairs from their RANSAC results, built on the device (b200geo_stitch_jobs_dev): wrapPerspective's
+    output rectangle (reference homography.py:143-163) and inv(H) per pair, outputs clipped to canvas slots.
+    Returns (jobs (B*184,) uint8 device, boxes (B,5) int32 device = min_x, min_y, out_w, out_h, ok)."""
+    B = results.shape[0]
+    ctx = _ctx(results)
+    assert results.dtype == torch.float64 and results.is_contiguous() and results.shape[1] == 32
+    if jobs is None:
+        jobs = torch.empty((B * _cabi.WARP_JOB_DTYPE.itemsize,), dtype=torch.uint8, device=results.device)
+    if boxes is None:
+        boxes = torch.empty((B, 5), dtype=torch.int32, device=results.device)
+    _cabi.check(ctx.lib.b200geo_stitch_jobs_dev(ctx.handle, _p(results), B, int(src_hw[0]), int(src_hw[1]), int(canvas_hw[0]), int(canvas_hw[1]),
+                                                _p(jobs), _p(boxes), _stream(results)))
+    return jobs, boxes
+
+
+def stitch_batched(pts, idx, frames, th, d, canvas_hw, n=4, method="fwd", sampler="bilinear", canvases=None, jobs=None, boxes=None):
     """Batched stitch pipeline (config "1024 pairs x 2k correspondences x 8192 hypotheses + warp to a
     4K canvas"): for every pair b, RANSAC.run over pts[b] with the sample sets idx[b] (reference
     ransac.py:159-213), then transformImageH(frames[b], H_b) (reference homography.py:230-242) into
     canvas slot b, clipped to canvas_hw.  pts (B,M,4) f32, idx (B,K,4) i32, frames (B,h,w,3) u8, all
-    on the device.  One host round trip in the middle: the B refit homographies (72 B each) come
-    back so that the host can lay out the output rectangles exactly as the reference does
-    (bounding box of the warped corners, int() truncation).  Returns (canvases (B,H,W,3) u8,
-    boxes (B,4) = min_x, min_y, out_w, out_h, results (B,32) f64, masks (B,M) u8)."""
+    on the device.  Nothing returns to the host in between: the output rectangles (bounding box of the
+    warped corners, int() truncation) and inv(H) are computed by a kernel from the refit results.
+    Returns (canvases (B,H,W,3) u8, boxes (B,5) int32 device = min_x, min_y, out_w, out_h, ok,
+    results (B,32) f64, masks (B,M) u8).  Pairs with ok = 0 (failed search / degenerate H) get the identity warp."""
     B, h, w, c = frames.shape
     assert c == 3 and frames.dtype == torch.uint8 and frames.is_contiguous()
     results, masks = ransac_batched(pts, idx, th, d, n, method)
-    res = results.cpu().numpy()
-    H = res[:, 12:21].reshape(B, 3, 3)
-    ok = (res[:, 2] == 0) & np.isfinite(H).all(axis=(1, 2))
-    H = np.where(ok[:, None, None], H, np.eye(3)[None])          # failed pairs: identity warp, flagged in results[:, 2]
-    jobs, boxes = bbox_jobs(H, (h, w), canvas_hw=canvas_hw)
+    jobs, boxes = stitch_jobs(results, (h, w), canvas_hw, jobs, boxes)
     if canvases is None:
         canvases = torch.zeros((B, canvas_hw[0], canvas_hw[1], 3), dtype=torch.uint8, device=frames.device)
-    # the frames are one 2-D byte array (rows = B * h): each tile's footprint arrives by one tensor copy
-    warp_resident(frames, canvases, upload_jobs(jobs, frames.device), B, int(boxes[:, 2].max()), int(boxes[:, 3].max()), 3, sampler,
-                  layout=(w * 3, B * h, h, w * 3))
+    # the frames are one 3-D byte array (row bytes x rows x frames): each strip's / tile's footprint arrives by one tensor copy.
+    # The launch is sized for the largest rectangle a job can have: the canvas slot.
+    warp_resident(frames, canvases, jobs, B, min(canvas_hw[1], 1 << 16), min(canvas_hw[0], 1 << 16), 3, sampler, layout=(w * 3, B * h, h, w * 3))
     return canvases, boxes, results, masks
 
 

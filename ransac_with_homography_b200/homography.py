@@ -94,13 +94,14 @@ def calcHomography(u, v, collective=False):
     """DLT homography u -> v as a (3,3) float32 with h22 = 1 (reference homography.py:71-88).
 
     4 points: the kernel solves the same system the reference's SVD null vector satisfies
-    (b200geo_dlt4).  collective=True (M points; unused by RANSAC.run) returns the least-squares
-    homography of the inhomogeneous system instead of the SVD's unit-norm minimiser."""
+    (b200geo_dlt4).  collective=True (M points; unused by RANSAC.run): the unit-norm minimiser of
+    |A h| over the 2M x 9 matrix of calc_correspCollective, i.e. the reference's last right singular
+    vector, from the float64 Gram matrix by Jacobi rotations (b200geo_homography_svd_host)."""
     ctx = _cabi.context()
     if collective:
         H = np.empty(9, np.float64)
         rows = _rows_f32(u, v)
-        _cabi.check(ctx.lib.b200geo_refit_host(ctx.handle, _cabi.ptr(rows), rows.shape[0], None, _cabi.ptr(H)))
+        _cabi.check(ctx.lib.b200geo_homography_svd_host(ctx.handle, _cabi.ptr(rows), rows.shape[0], _cabi.ptr(H)))
         return H.reshape(3, 3).astype(_F32)
     uu, vv = _pack_uv(u, v)
     assert uu.shape[0] == 4, "calcHomography needs 4 correspondences"

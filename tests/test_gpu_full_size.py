@@ -216,7 +216,8 @@ def test_config5_stitch_batched_full_size():
     canv, boxes, results, masks = device.stitch_batched(torch.from_numpy(pts).cuda(), torch.from_numpy(idx).cuda(),
                                                         torch.from_numpy(frames).cuda(), C5["th"], C5["d"], canvas)
     canv, res, masks = canv.cpu().numpy(), results.cpu().numpy(), masks.cpu().numpy()
-    boxes = np.asarray(boxes.cpu().numpy() if hasattr(boxes, "cpu") else boxes)
+    boxes = boxes.cpu().numpy()
+    assert boxes[:, 4].all()
     worst = 0
     for b in range(B):
         with redirect_stdout(io.StringIO()):
@@ -227,7 +228,7 @@ def test_config5_stitch_batched_full_size():
         want = oracle.to_u8(o)
         assert boxes[b, :2].tolist() == [mx, my]
         oh, ow = min(want.shape[0], canvas[0]), min(want.shape[1], canvas[1])
-        assert boxes[b, 2:].tolist() == [ow, oh]
+        assert boxes[b, 2:4].tolist() == [ow, oh]
         st = _diff_stats(canv[b, :oh, :ow], want[:oh, :ow])
         assert st["max_abs"] <= U8_TOL, (b, st)
         worst = max(worst, st["off_by_one_share"])
@@ -291,3 +292,43 @@ def test_c3_band_hit_census():
     r = res.cpu().numpy()
     REPORT["c3_20k_x_1M"] = {"pairs": K * M, "exact_chain_pairs": int(hits), "share": hits / (K * M), "winner": int(r[0]), "inliers": int(r[1])}
     assert hits / (K * M) < 1e-3
+
+
+def test_device_built_stitch_jobs_equal_the_numpy_rectangles():
+    """b200geo_stitch_jobs_dev (the output rectangle of wrapPerspective and inv(H), computed by a kernel from the refit
+    results) against device.bbox_jobs (numpy, the reference's expressions): census over 4096 random homographies of the C5
+    family -- rectangles equal, inverse homographies equal to 1e-12 relative; failed / degenerate pairs flagged."""
+    import torch
+    from ransac_with_homography_b200 import _cabi, device
+    rs = np.random.RandomState(17)
+    B, h, w, canvas = 4096, 1080, 1920, (2160, 3840)
+    src = np.array([[0, 0], [w, 0], [w, h], [0, h]], np.float64)
+    Hs = np.empty((B, 3, 3))
+    for i in range(B):
+        dst = src + rs.uniform(-0.1, 0.1, (4, 2)) * [w, h] + rs.uniform(-1, 1, 2) * [900, 500]
+        A = np.zeros((8, 8)); b = np.zeros(8)
+        for j, ((x, y), (X, Y)) in enumerate(zip(src, dst)):
+            A[2 * j] = [x, y, 1, 0, 0, 0, -x * X, -y * X]; A[2 * j + 1] = [0, 0, 0, x, y, 1, -x * Y, -y * Y]
+            b[2 * j], b[2 * j + 1] = X, Y
+        Hs[i] = np.append(np.linalg.solve(A, b), 1).reshape(3, 3)
+    res = np.zeros((B, 32))
+    res[:, 12:21] = Hs.reshape(B, 9)
+    res[5, 2] = -4                                   # a failed search
+    res[6, 12:21] = np.nan                           # a non-finite H
+    res[7, 12:21] = [1, 0, 0, 0, 1, 0, -1.0 / (w - 1), 0, 1]   # a corner at w = 0
+    jobs_t, boxes_t = device.stitch_jobs(torch.from_numpy(res).cuda(), (h, w), canvas)
+    boxes = boxes_t.cpu().numpy()
+    jobs = jobs_t.cpu().numpy().view(_cabi.WARP_JOB_DTYPE)
+    good = np.ones(B, bool); good[[5, 6, 7]] = False
+    assert not boxes[~good, 4].any() and boxes[good, 4].all()
+    want_jobs, want_boxes = device.bbox_jobs(Hs[good], (h, w), canvas_hw=canvas)
+    diff = (boxes[good, :4] != want_boxes).any(axis=1)
+    REPORT["c5_device_built_rectangles"] = {"pairs": int(good.sum()), "rectangles_differing_from_numpy": int(diff.sum())}
+    assert not diff.any()
+    rel = np.abs(jobs["invH"][good] - want_jobs["invH"]).max(axis=1) / np.abs(want_jobs["invH"]).max(axis=1)
+    assert rel.max() < 1e-12
+    for f in ("x0", "dx", "x_last", "y0", "dy", "y_last", "ow", "oh", "bw", "bh", "iw", "ih", "src_pitch", "dst_pitch"):
+        assert np.array_equal(jobs[f][good], want_jobs[f]), f
+    assert np.array_equal(jobs["src_offset"], np.arange(B, dtype=np.int64) * (w * 3 * h))
+    assert np.array_equal(jobs["dst_offset"], np.arange(B, dtype=np.int64) * (canvas[1] * 3 * canvas[0]))
+    assert np.array_equal(jobs["invH"][~good], np.tile(np.eye(3).reshape(9), (3, 1)))

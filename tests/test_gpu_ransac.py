@@ -398,7 +398,8 @@ def test_batched_stitch_pipeline_matches_per_pair_path():
     frames = rs.randint(0, 256, (B, h, w, 3)).astype(np.uint8)
     canv, boxes, results, masks = device.stitch_batched(torch.from_numpy(pts).cuda(), torch.from_numpy(idx).cuda(),
                                                         torch.from_numpy(frames).cuda(), 4.0, 95.0, canvas)
-    canv, res, masks = canv.cpu().numpy(), results.cpu().numpy(), masks.cpu().numpy()
+    canv, res, masks, boxes = canv.cpu().numpy(), results.cpu().numpy(), masks.cpu().numpy(), boxes.cpu().numpy()
+    assert boxes[:, 4].all()
     for b in range(B):
         with redirect_stdout(io.StringIO()):
             H, inl, cnt = RANSAC(HomoModel(th=4, d=95, n=4), k=K).run([pts[b, :, :2].T, pts[b, :, 2:].T], method="fwd", idx=idx[b])
@@ -407,7 +408,7 @@ def test_batched_stitch_pipeline_matches_per_pair_path():
         img, mx, my = transformImageH(frames[b].copy(), H)
         assert boxes[b, :2].tolist() == [mx, my]
         oh, ow = min(img.shape[0], canvas[0]), min(img.shape[1], canvas[1])
-        assert boxes[b, 2:].tolist() == [ow, oh]
+        assert boxes[b, 2:4].tolist() == [ow, oh]
         # (the batched launch describes the frames as a 3-D tensor map and may take the per-warp strip kernel, the single
         # image the tile kernel: same +-1 of the float64 result for bilinear, not necessarily the same bytes)
         assert np.abs(canv[b, :oh, :ow].astype(np.int16) - img[:oh, :ow].astype(np.int16)).max() <= 1

@@ -491,3 +491,27 @@ def test_calls_on_two_streams_do_not_interleave():
     torch.cuda.synchronize()
     for o in outs:
         assert torch.equal(o, want)
+
+
+def test_malformed_jobs_are_rejected_or_skipped():
+    """Pitches smaller than a row: host-visible job arrays are refused with an argument error; jobs that are
+    already on the device are skipped by the kernels (nothing is read or written out of bounds)."""
+    import torch
+    from ransac_with_homography_b200 import _cabi, device
+    h, w = 96, 128
+    frames = torch.randint(0, 256, (2, h, w, 3), dtype=torch.uint8, device="cuda")
+    jobs = device.scan_jobs(np.stack([np.eye(3), np.eye(3)]), (h, w), (h, w))
+    bad = jobs.copy()
+    bad["dst_pitch"][1] = w * 3 - 4
+    out = torch.full((2, h, w, 3), 9, dtype=torch.uint8, device="cuda")
+    with pytest.raises(_cabi.B200GeoError):
+        device.warp(frames, out, bad, 3, "bilinear")
+    bad2 = jobs.copy()
+    bad2["src_pitch"][0] = w * 3 - 1
+    with pytest.raises(_cabi.B200GeoError):
+        device.warp_host(frames.cpu().numpy(), np.empty((2, h, w, 3), np.uint8), bad2, 3, "nn")
+    for layout in (None, (w * 3, 2 * h, h, w * 3)):
+        out.fill_(9)
+        device.warp_resident(frames, out, device.upload_jobs(bad, "cuda"), 2, w, h, 3, "bilinear", layout=layout)
+        torch.cuda.synchronize()
+        assert bool((out[1] == 9).all()) and not bool((out[0] == 9).all())      # job 1 skipped, job 0 done
