@@ -238,6 +238,26 @@ int choose_splits(long long blocks, int M, int slots, int granule, int min_pts, 
     return best_s;
 }
 
+// The deferred exact-work list of a scoring launch: one segment of seg_cap entries per CTA (counts[cta] entries used, written
+// by the CTA itself -- no initialisation needed).  `want` = entries the whole launch may need (1M .. 64M in total).
+int worklist(b200geo_ctx *ctx, unsigned long long want, unsigned long long n_ctas, FastDeferred **wl, unsigned **counts, unsigned *n_seg,
+             unsigned *seg_cap)
+{
+    if (want < (1ull << 20)) want = 1ull << 20;
+    if (want > (1ull << 26)) want = 1ull << 26;
+    if (n_ctas < 1) n_ctas = 1;
+    unsigned long long per = want / n_ctas;
+    if (per < 64) per = 64;                          // (a full segment falls back to settling the chunk inside the kernel)
+    if (per * n_ctas > (1ull << 27)) per = (1ull << 27) / n_ctas;
+    if (per < 1) per = 1;
+    int rc;
+    if ((rc = scratch(ctx, S_WORKLIST, per * n_ctas * sizeof(FastDeferred), (void **)wl))) return rc;
+    if ((rc = scratch(ctx, S_WLCOUNT, n_ctas * sizeof(unsigned), (void **)counts))) return rc;
+    *n_seg = (unsigned)n_ctas;
+    *seg_cap = (unsigned)per;
+    return B200GEO_OK;
+}
+
 // K2.  fwd / backward with a positive finite threshold take the division-free FFMA2 kernel (exact
 // chain only inside the ambiguity shell); everything else takes the exact kernel.
 int launch_score(b200geo_ctx *ctx, const float *pts, int M, const float *H, const float *Hinv, const uint8_t *flags,
@@ -264,17 +284,13 @@ int launch_score(b200geo_ctx *ctx, const float *pts, int M, const float *H, cons
             for (int b = 0; b < B; ++b)
                 B2G_CUDA(cudaMemsetAsync(counts + (size_t)b * K_stride + k_begin, 0, sizeof(int32_t) * (size_t)nk, st));
         unsigned long long cap2 = (unsigned long long)nk * B * (unsigned long long)((M + FAST_CHUNK - 1) / FAST_CHUNK) / 32;
-        if (cap2 < (1ull << 20)) cap2 = 1ull << 20;
-        if (cap2 > (1ull << 26)) cap2 = 1ull << 26;
         FastDeferred *wl2;
-        unsigned *wl2_count = (unsigned *)(stats + 1);
-        if ((rc = scratch(ctx, S_WORKLIST, cap2 * sizeof(FastDeferred), (void **)&wl2))) return rc;
-        unsigned wl2_cap = (unsigned)(ctx->scratch_cap[S_WORKLIST] / sizeof(FastDeferred));
-        B2G_CUDA(cudaMemsetAsync(wl2_count, 0, sizeof(unsigned), st));
+        unsigned *wl2_count, n_seg2, seg_cap2;
+        if ((rc = worklist(ctx, cap2, (unsigned long long)gx2 * splits2 * B, &wl2, &wl2_count, &n_seg2, &seg_cap2))) return rc;
         score_fast2_kernel<<<dim3(gx2, splits2, B), FAST2_THREADS, 0, st>>>((const float4 *)pts, M, H, Hinv, flags, k_begin, k_end, K_stride, th,
-                                                                            cmax, per2, counts, wl2, wl2_count, wl2_cap);
+                                                                            cmax, per2, counts, wl2, wl2_count, seg_cap2);
         B2G_CHECK_LAUNCH(ctx);
-        score_fixup2_kernel<<<8 * ctx->sm_count, 256, 0, st>>>((const float4 *)pts, M, H, Hinv, K_stride, th, cmax, wl2, wl2_count, wl2_cap,
+        score_fixup2_kernel<<<8 * ctx->sm_count, 256, 0, st>>>((const float4 *)pts, M, H, Hinv, K_stride, th, cmax, wl2, wl2_count, n_seg2, seg_cap2,
                                                                counts, stats);
         B2G_CHECK_LAUNCH(ctx);
         return B200GEO_OK;
@@ -290,24 +306,20 @@ int launch_score(b200geo_ctx *ctx, const float *pts, int M, const float *H, cons
     }
     // deferred exact work: capacity for a 1/64 trigger rate per (hypothesis, chunk), 1M .. 64M entries
     unsigned long long want_cap = (unsigned long long)nk * B * (unsigned long long)((M + FAST_CHUNK - 1) / FAST_CHUNK) / 64;
-    if (want_cap < (1ull << 20)) want_cap = 1ull << 20;
-    if (want_cap > (1ull << 26)) want_cap = 1ull << 26;
     FastDeferred *wl;
-    unsigned *wl_count = (unsigned *)(stats + 1);
-    if ((rc = scratch(ctx, S_WORKLIST, want_cap * sizeof(FastDeferred), (void **)&wl))) return rc;
-    unsigned wl_cap = (unsigned)(ctx->scratch_cap[S_WORKLIST] / sizeof(FastDeferred));
-    B2G_CUDA(cudaMemsetAsync(wl_count, 0, sizeof(unsigned), st));
+    unsigned *wl_count, n_seg, wl_cap;
+    if ((rc = worklist(ctx, want_cap, (unsigned long long)gx * splits * B, &wl, &wl_count, &n_seg, &wl_cap))) return rc;
     dim3 grid(gx, splits, B);
     const float4 *p4 = (const float4 *)pts;
     int fix_blocks = 8 * ctx->sm_count;
     if (method == B200GEO_FWD) {
         score_fast_kernel<B200GEO_FWD><<<grid, FAST_THREADS, 0, st>>>(p4, M, H, flags, k_begin, k_end, K_stride, th, cmax, per, counts, stats, wl, wl_count, wl_cap);
         B2G_CHECK_LAUNCH(ctx);
-        score_fixup_kernel<B200GEO_FWD><<<fix_blocks, 256, 0, st>>>(p4, M, H, K_stride, th, cmax, wl, wl_count, wl_cap, counts, stats);
+        score_fixup_kernel<B200GEO_FWD><<<fix_blocks, 256, 0, st>>>(p4, M, H, K_stride, th, cmax, wl, wl_count, n_seg, wl_cap, counts, stats);
     } else {
         score_fast_kernel<B200GEO_BACKWARD><<<grid, FAST_THREADS, 0, st>>>(p4, M, Hinv, flags, k_begin, k_end, K_stride, th, cmax, per, counts, stats, wl, wl_count, wl_cap);
         B2G_CHECK_LAUNCH(ctx);
-        score_fixup_kernel<B200GEO_BACKWARD><<<fix_blocks, 256, 0, st>>>(p4, M, Hinv, K_stride, th, cmax, wl, wl_count, wl_cap, counts, stats);
+        score_fixup_kernel<B200GEO_BACKWARD><<<fix_blocks, 256, 0, st>>>(p4, M, Hinv, K_stride, th, cmax, wl, wl_count, n_seg, wl_cap, counts, stats);
     }
     B2G_CHECK_LAUNCH(ctx);
     return B200GEO_OK;

@@ -192,6 +192,14 @@ score_fast_kernel(const float4 *__restrict__ pts, int M, const float *__restrict
 {
     __shared__ float4 tile[2 * FAST_TILE];
     const int b = blockIdx.z;
+    // deferred exact work goes to THIS CTA's segment of the list (wl_cap entries, counted in shared memory): one global
+    // counter for all CTAs was an atomic per deferred chunk on a single address -- about one per nanosecond on the batched
+    // configuration, i.e. the L2's serialisation rate (score_fast_kernel ran at 79 % of its single-pair rate there)
+    __shared__ unsigned s_wl;
+    const unsigned cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    FastDeferred *const wl_seg = wl + (size_t)cta * wl_cap;
+    if (threadIdx.x == 0) s_wl = 0u;
+    __syncthreads();
     pts += (size_t)b * M;
     const float C = cmax[b];
     const float invT = 1.0f / T;       // only to scale x', y' in the tile; its rounding is inside `band`
@@ -282,10 +290,10 @@ score_fast_kernel(const float4 *__restrict__ pts, int M, const float *__restrict
                     mq[t] = 3.0e38f;
                     if (dead[t]) continue;
                     const size_t o = (size_t)b * K_stride + base + t * FAST_THREADS;
-                    const unsigned w = atomicAdd(wl_count, 1u);
+                    const unsigned w = atomicAdd(&s_wl, 1u);
                     if (w < wl_cap) {
-                        wl[w].slot = (unsigned)o;
-                        wl[w].j0 = (unsigned)(t0 + i);
+                        wl_seg[w].slot = (unsigned)o;
+                        wl_seg[w].j0 = (unsigned)(t0 + i);
                         continue;
                     }
                     float hx[9], hq[9];
@@ -319,6 +327,8 @@ score_fast_kernel(const float4 *__restrict__ pts, int M, const float *__restrict
         else counts[o] = c;
     }
     if (stat_ambiguous && n_amb) atomicAdd(stat_ambiguous, (unsigned long long)n_amb);
+    __syncthreads();
+    if (threadIdx.x == 0) wl_count[cta] = min(s_wl, wl_cap);
 }
 
 // Exact re-evaluation of the deferred chunks: one thread per (deferred chunk, correspondence).
@@ -328,15 +338,14 @@ template <int METHOD>
 __global__ void __launch_bounds__(256)
 score_fixup_kernel(const float4 *__restrict__ pts, int M, const float *__restrict__ H, int K_stride, float T,
                    const float *__restrict__ cmax, const FastDeferred *__restrict__ wl, const unsigned *__restrict__ wl_count,
-                   unsigned wl_cap, int32_t *__restrict__ counts, unsigned long long *__restrict__ stat_ambiguous)
+                   unsigned n_seg, unsigned wl_cap, int32_t *__restrict__ counts, unsigned long long *__restrict__ stat_ambiguous)
 {
-    const unsigned n = min(*wl_count, wl_cap);
-    const unsigned long long total = (unsigned long long)n * FAST_CHUNK;
     const float invT = 1.0f / T;
     unsigned local = 0;
-    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < total;
-         i += (unsigned long long)gridDim.x * blockDim.x) {
-        const FastDeferred e = wl[i / FAST_CHUNK];
+    // segment `sgm` of the list holds wl_count[sgm] entries of the CTA that filled it; a block takes whole segments
+    for (unsigned sgm = blockIdx.x; sgm < n_seg; sgm += gridDim.x)
+    for (unsigned i = threadIdx.x, total = min(wl_count[sgm], wl_cap) * FAST_CHUNK; i < total; i += blockDim.x) {
+        const FastDeferred e = wl[(size_t)sgm * wl_cap + i / FAST_CHUNK];
         const unsigned j = e.j0 + (unsigned)(i % FAST_CHUNK);
         if (j >= (unsigned)M) continue;
         const unsigned b = e.slot / (unsigned)K_stride;
@@ -448,6 +457,14 @@ score_fast2_kernel(const float4 *__restrict__ pts, int M, const float *__restric
 {
     __shared__ float4 tile[4 * FAST2_TILE];
     const int b = blockIdx.z;
+    // deferred exact work goes to THIS CTA's segment of the list (wl_cap entries, counted in shared memory): one global
+    // counter for all CTAs was an atomic per deferred chunk on a single address -- about one per nanosecond on the batched
+    // configuration, i.e. the L2's serialisation rate (score_fast_kernel ran at 79 % of its single-pair rate there)
+    __shared__ unsigned s_wl;
+    const unsigned cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    FastDeferred *const wl_seg = wl + (size_t)cta * wl_cap;
+    if (threadIdx.x == 0) s_wl = 0u;
+    __syncthreads();
     pts += (size_t)b * M;
     const float C = cmax[b];
     const float Th = 0.5f * T, invTh = 1.0f / Th;
@@ -518,10 +535,10 @@ score_fast2_kernel(const float4 *__restrict__ pts, int M, const float *__restric
                 if (!und[t] || dead[t]) continue;
                 // some correspondence of this chunk is undecided: defer the chunk to score_fixup2_kernel
                 const size_t o = (size_t)b * K_stride + base + t * FAST2_THREADS;
-                const unsigned w = atomicAdd(wl_count, 1u);
+                const unsigned w = atomicAdd(&s_wl, 1u);
                 if (w < wl_cap) {
-                    wl[w].slot = (unsigned)o;
-                    wl[w].j0 = (unsigned)(t0 + i);
+                    wl_seg[w].slot = (unsigned)o;
+                    wl_seg[w].j0 = (unsigned)(t0 + i);
                     continue;
                 }
                 // list full: settle the chunk here
@@ -548,21 +565,21 @@ score_fast2_kernel(const float4 *__restrict__ pts, int M, const float *__restric
         if (gridDim.y > 1) { if (c) atomicAdd(counts + o, c); }
         else counts[o] = c;
     }
+    __syncthreads();
+    if (threadIdx.x == 0) wl_count[cta] = min(s_wl, wl_cap);
 }
 
 // Exact settlement of the deferred reproj chunks: one thread per (deferred chunk, correspondence).
 __global__ void __launch_bounds__(256)
 score_fixup2_kernel(const float4 *__restrict__ pts, int M, const float *__restrict__ H, const float *__restrict__ Hinv, int K_stride,
                     float T, const float *__restrict__ cmax, const FastDeferred *__restrict__ wl, const unsigned *__restrict__ wl_count,
-                    unsigned wl_cap, int32_t *__restrict__ counts, unsigned long long *__restrict__ stat_ambiguous)
+                    unsigned n_seg, unsigned wl_cap, int32_t *__restrict__ counts, unsigned long long *__restrict__ stat_ambiguous)
 {
-    const unsigned n = min(*wl_count, wl_cap);
-    const unsigned long long total = (unsigned long long)n * FAST_CHUNK;
     const float Th = 0.5f * T, invTh = 1.0f / Th;
     unsigned local = 0;
-    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < total;
-         i += (unsigned long long)gridDim.x * blockDim.x) {
-        const FastDeferred e = wl[i / FAST_CHUNK];
+    for (unsigned sgm = blockIdx.x; sgm < n_seg; sgm += gridDim.x)
+    for (unsigned i = threadIdx.x, total = min(wl_count[sgm], wl_cap) * FAST_CHUNK; i < total; i += blockDim.x) {
+        const FastDeferred e = wl[(size_t)sgm * wl_cap + i / FAST_CHUNK];
         const unsigned j = e.j0 + (unsigned)(i % FAST_CHUNK);
         if (j >= (unsigned)M) continue;
         const unsigned b = e.slot / (unsigned)K_stride;

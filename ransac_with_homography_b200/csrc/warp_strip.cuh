@@ -82,7 +82,7 @@ struct __align__(16) WsStrip {
     uint16_t b16;                            // ambiguity half-width in units of 2^-16 px, rounded up (+2)
     uint16_t c0, r0;                         // first output pixel of the strip
     int xc, yc;                              // anchor (absolute source pixel)
-    uint32_t magic;                          // ceil(2^32 / chunks)
+    uint32_t magic;                          // tw | th << 8: the strip's extent (32, 40 unless cut by the output's edge)
 };
 static_assert(sizeof(WsStrip) == WS_REC_BYTES, "strip records are fetched as five 16-byte words");
 
@@ -90,8 +90,13 @@ static_assert(sizeof(WsStrip) == WS_REC_BYTES, "strip records are fetched as fiv
 template <int BILINEAR>
 __device__ bool ws_setup(const b200geo_warp_job &J, int job, int c0, int r0, const WfTma &tma, uint8_t *__restrict__ dst_base, WsStrip &S)
 {
-    if (c0 + WS_W > J.ow || r0 + WS_H > J.oh) return false;                   // full strips only
     if (tma.image_rows <= 0) return false;                                    // needs the 3-D tensor map
+    const int tw = min(WS_W, J.ow - c0), th = min(WS_H, J.oh - r0);           // < 32 / < 40: cut by the output's right / bottom edge
+    if (tw <= 0 || th <= 0) {                                                 // the tile's second strip lies outside the output
+        memset(&S, 0, sizeof S);
+        S.mode = (uint8_t)WF_EMPTY;
+        return true;
+    }
     const int cm = c0 + WS_W / 2, rm = r0 + WS_H / 2;
     const double Xm = (double)cm * J.dx + J.x0, Ym = (double)rm * J.dy + J.y0;
     const double exl = (double)(J.ow - 1) * J.dx + J.x0, eyl = (double)(J.oh - 1) * J.dy + J.y0;
@@ -124,7 +129,7 @@ __device__ bool ws_setup(const b200geo_warp_job &J, int job, int c0, int r0, con
     float rxmin = 3.0e38f, rxmax = -3.0e38f, rymin = 3.0e38f, rymax = -3.0e38f;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const float di = (float)(((k & 1) ? WS_W - 1 : 0) - WS_W / 2), dj = (float)(((k & 2) ? WS_H - 1 : 0) - WS_H / 2);
+        const float di = (float)(((k & 1) ? tw - 1 : 0) - WS_W / 2), dj = (float)(((k & 2) ? th - 1 : 0) - WS_H / 2);
         float rx, ry;
         wf_rel16(T, di, dj, rx, ry);
         rxmin = fminf(rxmin, rx); rxmax = fmaxf(rxmax, rx);
@@ -145,11 +150,11 @@ __device__ bool ws_setup(const b200geo_warp_job &J, int job, int c0, int r0, con
     if (J.dst_pitch <= 0 || J.dst_pitch >= (1LL << 31)) return false;
     uint8_t *const dt = dst_base + J.dst_offset + (long long)r0 * J.dst_pitch + 3LL * c0;
     if ((((size_t)dt) | (size_t)J.dst_pitch) & 3) return false;
-    if ((((size_t)dt) >> 32) != (((size_t)dt + (size_t)(WS_H - 1) * (size_t)J.dst_pitch + 3 * WS_W) >> 32)) return false;   // row steps add to the low word only
+    if ((((size_t)dt) >> 32) != (((size_t)dt + (size_t)(th - 1) * (size_t)J.dst_pitch + 3 * tw) >> 32)) return false;   // row steps add to the low word only
     if (c0 > 65535 || r0 > 65535 || job > 65535) return false;
     S.dst = dt; S.dst_pitch = (int)J.dst_pitch; S.job = (uint16_t)job; S.c0 = (uint16_t)c0; S.r0 = (uint16_t)r0;
     S.xc = T.xc; S.yc = T.yc; S.b16 = (uint16_t)((int)B + 2);
-    S.tma_x = S.tma_y = 0; S.img = 0; S.phase = 0; S.ox = S.oy = 0; S.rows = 0; S.chunks = 2; S.magic = 0x80000000u;
+    S.tma_x = S.tma_y = 0; S.img = 0; S.phase = 0; S.ox = S.oy = 0; S.rows = 0; S.chunks = 2; S.magic = (uint32_t)(tw | (th << 8));
     S.nx0 = S.ax = S.bx = S.ny0 = S.ay = S.by = S.gw = S.hw = 0.f;
     if (all_out) { S.mode = (uint8_t)WF_ZERO; return true; }
     int x_lo, x_hi, y_lo, y_hi;
@@ -185,7 +190,6 @@ __device__ bool ws_setup(const b200geo_warp_job &J, int job, int c0, int r0, con
     if (ox < -128 || y_lo < -128 || ox > 127 || y_lo > 127 || img > 65535) return false;
     S.mode = all_in ? WF_INTERIOR : WF_BORDER;
     S.ox = (int8_t)ox; S.oy = (int8_t)y_lo; S.rows = (uint8_t)rows; S.chunks = (uint8_t)(P >> 2);
-    S.magic = (unsigned)((0x100000000ULL + (unsigned)S.chunks - 1) / (unsigned)S.chunks);
     S.tma_x = (3 * ax0) & ~15; S.phase = (uint8_t)((3 * ax0) & 15); S.tma_y = ay0;
     S.img = (uint16_t)img;
     // biased coefficients: n' = n + bias * w, so that  round(n' / w) = floor(n / w [+ 1/2 px for nn])  up to a quarter unit
@@ -384,7 +388,10 @@ __device__ __forceinline__ void ws_stg32_lh(uint32_t lo, uint32_t hi, uint32_t v
     asm volatile("{\n\t.reg .b64 a;\n\tmov.b64 a, {%0, %1};\n\tst.global.u32 [a], %2;\n\t}" ::"r"(lo), "r"(hi), "r"(v) : "memory");
 }
 
-// One strip: 20 pixels per lane (column c0 + lane, rows r0 .. r0+19).
+// One strip: 40 pixels per lane (column c0 + lane, rows r0 .. r0+39), in two passes of 20 rows.
+// BORDER = 0: wholly unmasked full strip (rows unrolled); 1: per-pixel mask (the strip crosses the sampler's bounds);
+// 2: as 1 for a strip cut by the output's right / bottom edge: lanes >= tw and rows >= th repeat the last valid position
+// (every address stays inside the footprint) and store nothing; the valid pixels are stored byte by byte.
 template <int BILINEAR, int BORDER>
 __device__ __forceinline__ void ws_sample(const WsRegs &R, uint32_t s_ent, int lane, const b200geo_warp_job *__restrict__ jobs,
                                           const uint8_t *__restrict__ src_base, const WfFix &fix0, unsigned &n_exact)
@@ -392,7 +399,8 @@ __device__ __forceinline__ void ws_sample(const WsRegs &R, uint32_t s_ent, int l
     const float2 A2 = make_float2(__uint_as_float(R.w0.z), __uint_as_float(R.w0.w));
     const float2 B2 = make_float2(__uint_as_float(R.w1.x), __uint_as_float(R.w1.y));
     const float gw = __uint_as_float(R.w1.z), hw = __uint_as_float(R.w1.w);
-    const float di0 = (float)(lane - WS_W / 2);
+    const int tw = BORDER == 2 ? (int)(R.w4.w & 0xFFu) : WS_W, th = BORDER == 2 ? (int)((R.w4.w >> 8) & 0xFFu) : WS_H;
+    const float di0 = (float)(min(lane, tw - 1) - WS_W / 2);
     const float2 nb = __ffma2_rn(A2, make_float2(di0, di0), make_float2(__uint_as_float(R.w0.x), __uint_as_float(R.w0.y)));
     const float wb = __fmaf_rn(gw, di0, WF_W0);
     const int ox = R.ox(), oy = R.oy();
@@ -427,6 +435,7 @@ __device__ __forceinline__ void ws_sample(const WsRegs &R, uint32_t s_ent, int l
     static_assert(WS_HALF % G == 0 && WS_H % WS_HALF == 0, "row groups");
 #pragma unroll 1
     for (int hf = 0; hf < WS_H / WS_HALF; ++hf) {             // (the 'g0' below count rows inside this pass)
+    if (BORDER == 2 && hf * WS_HALF >= th) break;
     const float djh = (float)(hf * WS_HALF - WS_H / 2);
     const float2 nbh = __ffma2_rn(B2, make_float2(djh, djh), nb);
     const float wbh = __fmaf_rn(hw, djh, wb);
@@ -438,16 +447,24 @@ __device__ __forceinline__ void ws_sample(const WsRegs &R, uint32_t s_ent, int l
 #pragma unroll
         for (int g = 0; g < G; ++g) {
             const float dj = (float)g;
-            const float2 n2 = g ? __ffma2_rn(B2, make_float2(dj, dj), n2g) : n2g;
-            const float w = g ? __fmaf_rn(hw, dj, wg) : wg;
+            float2 n2 = g ? __ffma2_rn(B2, make_float2(dj, dj), n2g) : n2g;
+            float w = g ? __fmaf_rn(hw, dj, wg) : wg;
+            bool valid = true;
+            if (BORDER == 2) {          // rows past the strip's last one repeat it
+                const int row = hf * WS_HALF + g0 + g;
+                valid = row < th && lane < tw;
+                const float rj = (float)(min(row, th - 1) - hf * WS_HALF);
+                n2 = __ffma2_rn(B2, make_float2(rj, rj), nbh);
+                w = __fmaf_rn(hw, rj, wbh);
+            }
             const float rw = wf_rcp(w);
             uint32_t bxv, byv;
             if (BORDER) {
                 float2 r = __fmul2_rn(n2, make_float2(rw, rw));
                 const bool in = r.x >= lox + band && r.x <= hix - band && r.y >= loy + band && r.y <= hiy - band;
                 const bool outp = r.x < lox - band || r.x > hix + band || r.y < loy - band || r.y > hiy + band;
-                if (in) inmask |= 1u << (g0 + g);
-                else if (!outp) amb |= 1u << (g0 + g);                 // also NaN coordinates
+                if (in && valid) inmask |= 1u << (g0 + g);
+                else if (!outp && valid) amb |= 1u << (g0 + g);        // also NaN coordinates
                 r.x = fminf(fmaxf(r.x, lox), hix);                     // (NaN -> lox)
                 r.y = fminf(fmaxf(r.y, loy), hiy);
                 const float2 f = __fadd2_rn(r, make_float2(WS_MAGIC, WS_MAGIC));
@@ -462,7 +479,7 @@ __device__ __forceinline__ void ws_sample(const WsRegs &R, uint32_t s_ent, int l
                 const uint32_t fx = bxv & 0xFFFFu, fy = byv & 0xFFFFu;
                 const bool near = fx - B16 > 65535u - 2u * B16 || fy - B16 > 65535u - 2u * B16;
                 if (BORDER) {
-                    if (near && (inmask >> (g0 + g) & 1u)) amb |= 1u << (g0 + g);
+                    if (near && (inmask >> (g0 + g) & 1u)) amb |= 1u << (g0 + g);      // (inmask is only set for valid pixels)
                     xi = (uint32_t)(min(max((int)xi - WS_MAGIC_HI, xlo), xhi) + WS_MAGIC_HI);
                     yi = (uint32_t)(min(max((int)yi - WS_MAGIC_HI, ylo), yhi) + WS_MAGIC_HI);
                 } else if (near) amb |= 1u << (g0 + g);
@@ -508,10 +525,17 @@ __device__ __forceinline__ void ws_sample(const WsRegs &R, uint32_t s_ent, int l
             if (BILINEAR) out = wf_blend(make_uint2(t0[g], t1[g]), make_uint2(t2[g], t3[g]), bx_[g] & 0xFFFFu, by_[g] & 0xFFFFu);
             else if (!B2G_WS_DIRECT) out = __byte_perm(t0[g], t1[g], 0x4420);
             if (BORDER && !(inmask >> (g0 + g) & 1u)) out = 0u;
-            const uint32_t nbr = __shfl_down_sync(0xffffffffu, out, 1);
-            const uint32_t word = __byte_perm(out, nbr, psel);
-            if (st_lane) ws_stg32_lh(g_lo, g_hi, word);
-            g_lo += pitch;
+            if (BORDER == 2) {
+                if (lane < tw && hf * WS_HALF + g0 + g < th) {
+                    uint8_t *p = reinterpret_cast<uint8_t *>(dstrip) + (long long)(hf * WS_HALF + g0 + g) * (int)pitch + 3 * lane;
+                    p[0] = (uint8_t)out; p[1] = (uint8_t)(out >> 8); p[2] = (uint8_t)(out >> 16);
+                }
+            } else {
+                const uint32_t nbr = __shfl_down_sync(0xffffffffu, out, 1);
+                const uint32_t word = __byte_perm(out, nbr, psel);
+                if (st_lane) ws_stg32_lh(g_lo, g_hi, word);
+                g_lo += pitch;
+            }
         }
     };
     if (B2G_WS_UNROLL && !BORDER) {
@@ -617,7 +641,8 @@ warp_strip_kernel(const uint8_t *__restrict__ src_base, const b200geo_warp_job *
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
     auto issue_copy = [&](uint32_t slot, uint32_t raw, uint32_t bar) {   // lane 0: tensor copy of the strip's footprint into a raw buffer of this warp
-        if (lane == 0 && (int)ws_ldsu8(slot + WS_REC(mode)) != WF_ZERO) {
+        const int m_ = (int)ws_ldsu8(slot + WS_REC(mode));
+        if (lane == 0 && (m_ == WF_INTERIOR || m_ == WF_BORDER)) {
             uint32_t x, y;
             asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(x), "=r"(y) : "r"(slot + WS_REC(tma_x)));
             const int z = (int)ws_ldsu16(slot + WS_REC(img));
@@ -650,7 +675,7 @@ warp_strip_kernel(const uint8_t *__restrict__ src_base, const b200geo_warp_job *
             R.w4 = ws_lds128(slot + 64u);
             const int mode = R.mode();
             const uint32_t raw = s_raw0 + (uint32_t)(buf * WS_RAW_BYTES), bar = s_bar0 + 8u * (uint32_t)buf;
-            if (mode != WF_ZERO) {
+            if (mode == WF_INTERIOR || mode == WF_BORDER) {
                 wp_mbar_wait(bar, (ph >> buf) & 1u);
                 ph ^= 1u << buf;
                 if (!B2G_WS_DIRECT) ws_convert(R, raw, s_ent, lane);
@@ -672,14 +697,21 @@ warp_strip_kernel(const uint8_t *__restrict__ src_base, const b200geo_warp_job *
             }
             const uint32_t s_src = B2G_WS_DIRECT ? raw : s_ent;
             // (votes: the branch conditions are warp-uniform by construction, so the shuffles inside need no divergence check)
-            if (__all_sync(0xffffffffu, mode == WF_INTERIOR)) ws_sample<BILINEAR, 0>(R, s_src, lane, jobs, src_base, fix, n_exact);
+            const bool partial = (R.w4.w & 0xFFFFu) != (uint32_t)(WS_W | (WS_H << 8));
+            if (__all_sync(0xffffffffu, (mode == WF_INTERIOR || mode == WF_BORDER) && partial)) ws_sample<BILINEAR, 2>(R, s_src, lane, jobs, src_base, fix, n_exact);
+            else if (__all_sync(0xffffffffu, mode == WF_INTERIOR)) ws_sample<BILINEAR, 0>(R, s_src, lane, jobs, src_base, fix, n_exact);
             else if (__all_sync(0xffffffffu, mode == WF_BORDER)) ws_sample<BILINEAR, 1>(R, s_src, lane, jobs, src_base, fix, n_exact);
-            else {
-                uint8_t *gp = reinterpret_cast<uint8_t *>(((unsigned long long)R.w2.w << 32) | R.w2.z) + 4 * lane;
-                const int pitch = (int)R.w3.x;
-                if (lane < 24) {
+            else if (mode == WF_ZERO) {
+                uint8_t *gp = reinterpret_cast<uint8_t *>(((unsigned long long)R.w2.w << 32) | R.w2.z);
+                const int pitch = (int)R.w3.x, tw = (int)(R.w4.w & 0xFFu), th = (int)((R.w4.w >> 8) & 0xFFu);
+                if (!partial) {
+                    if (lane < 24) {
 #pragma unroll 4
-                    for (int r = 0; r < WS_H; ++r) ws_stg32(gp + (long long)r * pitch, 0u);
+                        for (int r = 0; r < WS_H; ++r) ws_stg32(gp + 4 * lane + (long long)r * pitch, 0u);
+                    }
+                } else {
+                    for (int r = 0; r < th; ++r)
+                        for (int i = lane; i < 3 * tw; i += 32) gp[(long long)r * pitch + i] = 0;
                 }
             }
             if (B2G_WS_DIRECT) {
