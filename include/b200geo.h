@@ -303,6 +303,16 @@ int b200geo_sample_host(b200geo_ctx *ctx, const void *src, int ih, int iw, int c
                         const double *zx, const double *zy, long long N, int bh, int bw, int sampler,
                         int dst_type, void *dst);
 
+/* ------------------------------------------------------------------------------------------------
+ * (6) cv2.remap(img, map_x, map_y, INTER_LINEAR, borderMode=BORDER_TRANSPARENT) for uint8 images of 1, 2 or 4
+ *     channels -- the resampling step of cylindricalWarp (homography.py:391-410: BGRA image, float32 maps,
+ *     INTER_AREA which cv::remap executes as INTER_LINEAR).  OpenCV's fixed-point algorithm (1/32 px coordinates,
+ *     15-bit weights, round half up), bit-exact; destination pixels whose integer source position is outside
+ *     the source are left untouched (dst is read and written).  Host buffers; maps and dst are oh x ow.
+ * ---------------------------------------------------------------------------------------------- */
+int b200geo_remap_linear_host(b200geo_ctx *ctx, const uint8_t *src, int ih, int iw, int channels,
+                              const float *map_x, const float *map_y, int oh, int ow, uint8_t *dst);
+
 #ifdef __cplusplus
 }
 #endif

@@ -244,3 +244,47 @@ def bf_match_hamming(A, B, cross_check=True):
         ib = D.argmin(axis=0)
         keep = ib[ja] == q
     return q[keep], ja[keep], D[q, ja][keep]
+
+
+def remap_linear_transparent(src, map_x, map_y, dst):
+    """cv2.remap(src, map_x, map_y, cv2.INTER_LINEAR, dst=dst, borderMode=cv2.BORDER_TRANSPARENT) for uint8 images with
+    1, 2 or 4 channels (OpenCV 4.13 imgwarp.cpp: float32 maps -> 1/32 px fixed point with round-half-even, 15-bit weights,
+    (sum + 2^14) >> 15; pixels whose integer source position lies outside the image keep dst, taps
+    beyond the last column / row repeat it).  The resampling step of the
+    reference's cylindricalWarp (homography.py:410).  Pinned to cv2.remap in tests/test_oracle_golden.py."""
+    src = np.asarray(src)
+    ih, iw = src.shape[:2]
+    s = src.reshape(ih, iw, -1).astype(np.int64)
+    out = np.array(dst, copy=True)
+    o = out.reshape(out.shape[0], out.shape[1], -1)
+    fx = np.rint(np.asarray(map_x, np.float32) * np.float32(32)).astype(np.int64)       # rint: half to even, like cvRound
+    fy = np.rint(np.asarray(map_y, np.float32) * np.float32(32)).astype(np.int64)
+    ix, iy, ax, ay = fx >> 5, fy >> 5, fx & 31, fy & 31
+    ok = (ix >= 0) & (ix < iw) & (iy >= 0) & (iy < ih)          # (observed on 4.13: written iff the integer position is inside; ...
+    r, c = np.nonzero(ok)
+    x, y, a, b = ix[r, c], iy[r, c], ax[r, c][:, None], ay[r, c][:, None]
+    x1, y1 = np.minimum(x + 1, iw - 1), np.minimum(y + 1, ih - 1)  # ... the taps beyond the last column / row repeat it)
+    t = (32 - a) * (32 - b) * 32 * s[y, x] + a * (32 - b) * 32 * s[y, x1] + (32 - a) * b * 32 * s[y1, x] + a * b * 32 * s[y1, x1]
+    o[r, c] = np.clip((t + (1 << 14)) >> 15, 0, 255).astype(np.uint8)
+    return out
+
+
+def cylindrical_maps(h, w, K):
+    """The float32 coordinate maps of the reference's cylindricalWarp (homography.py:393-406), same numpy expressions."""
+    y_i, x_i = np.indices((h, w))
+    X = np.stack([x_i, y_i, np.ones_like(x_i)], axis=-1).reshape(h * w, 3)
+    X = np.linalg.inv(K).dot(X.T).T
+    A = np.stack([np.sin(X[:, 0]), X[:, 1], np.cos(X[:, 0])], axis=-1).reshape(w * h, 3)
+    B = K.dot(A.T).T
+    B = B[:, :-1] / B[:, [-1]]
+    B[(B[:, 0] < 0) | (B[:, 0] >= w) | (B[:, 1] < 0) | (B[:, 1] >= h)] = -1
+    B = B.reshape(h, w, -1)
+    return B[:, :, 0].astype(np.float32), B[:, :, 1].astype(np.float32)
+
+
+def cylindrical_warp(img, K):
+    """cylindricalWarp (homography.py:391-410) with zero-initialised transparent pixels."""
+    h, w = img.shape[:2]
+    mx, my = cylindrical_maps(h, w, K)
+    rgba = np.dstack([img, np.full((h, w), 255, np.uint8)])
+    return remap_linear_transparent(rgba, mx, my, np.zeros((h, w, 4), np.uint8))

@@ -9,6 +9,7 @@
 #include "warp_strip.cuh"
 #include "compose.cuh"
 #include "match.cuh"
+#include "remap.cuh"
 
 #include <new>
 #include <stdlib.h>
@@ -1260,6 +1261,37 @@ int b200geo_sample_host(b200geo_ctx *ctx, const void *src, int ih, int iw, int c
     else if (channels == 3) rc = launch_sample_t<float, 3>(ctx, ds, ih, iw, bh, bw, dz, dz + N, N, sampler, dst_type, dd, 0);
     else rc = launch_sample_t<float, 4>(ctx, ds, ih, iw, bh, bw, dz, dz + N, N, sampler, dst_type, dd, 0);
     if (rc) return rc;
+    B2G_CUDA(cudaMemcpyAsync(dst, dd, dbytes, cudaMemcpyDeviceToHost, 0));
+    B2G_CUDA(cudaStreamSynchronize(0));
+    return B200GEO_OK;
+}
+
+int b200geo_remap_linear_host(b200geo_ctx *ctx, const uint8_t *src, int ih, int iw, int channels, const float *map_x, const float *map_y,
+                              int oh, int ow, uint8_t *dst)
+{
+    B2G_ENTER(ctx);
+    stream_order(ctx, 0);
+    B2G_ARG(ih > 0 && iw > 0 && oh >= 0 && ow >= 0 && (channels == 1 || channels == 2 || channels == 4));
+    if (oh == 0 || ow == 0) return B200GEO_OK;
+    B2G_ARG(src && map_x && map_y && dst);
+    const size_t sbytes = (size_t)ih * iw * channels, dbytes = (size_t)oh * ow * channels, mbytes = (size_t)oh * ow * sizeof(float);
+    uint8_t *ds, *dd;
+    float *dm;
+    int rc;
+    if ((rc = scratch(ctx, S_SRC, sbytes, (void **)&ds))) return rc;
+    if ((rc = scratch(ctx, S_DST, dbytes, (void **)&dd))) return rc;
+    if ((rc = scratch(ctx, S_MISC, 2 * mbytes, (void **)&dm))) return rc;
+    B2G_CUDA(cudaMemcpyAsync(ds, src, sbytes, cudaMemcpyHostToDevice, 0));
+    B2G_CUDA(cudaMemcpyAsync(dd, dst, dbytes, cudaMemcpyHostToDevice, 0));          // transparent pixels keep the caller's bytes
+    B2G_CUDA(cudaMemcpyAsync(dm, map_x, mbytes, cudaMemcpyHostToDevice, 0));
+    B2G_CUDA(cudaMemcpyAsync(dm + (size_t)oh * ow, map_y, mbytes, cudaMemcpyHostToDevice, 0));
+    const dim3 grid((ow + 255) / 256, oh);
+    B2G_ARG(oh <= 65535);
+    const long long sp = (long long)iw * channels, dp = (long long)ow * channels;
+    if (channels == 4) remap_linear_kernel<4><<<grid, 256, 0, 0>>>(ds, ih, iw, sp, dm, dm + (size_t)oh * ow, oh, ow, dd, dp);
+    else if (channels == 2) remap_linear_kernel<2><<<grid, 256, 0, 0>>>(ds, ih, iw, sp, dm, dm + (size_t)oh * ow, oh, ow, dd, dp);
+    else remap_linear_kernel<1><<<grid, 256, 0, 0>>>(ds, ih, iw, sp, dm, dm + (size_t)oh * ow, oh, ow, dd, dp);
+    B2G_CHECK_LAUNCH(ctx);
     B2G_CUDA(cudaMemcpyAsync(dst, dd, dbytes, cudaMemcpyDeviceToHost, 0));
     B2G_CUDA(cudaStreamSynchronize(0));
     return B200GEO_OK;

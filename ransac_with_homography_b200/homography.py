@@ -428,17 +428,91 @@ def stitchPanorama(imgQ, imgT, H, method='bilinear', blending=False, blendrate=0
 
 
 # ------------------------------------------------------------------------------------------------
-# cylindrical projections (reference homography.py:340-416) are outside this framework's scope
-# (component 10: unreachable from the app).  The names exist so that
-# `from homography import ... cylindericlMap` (reference ransac.py:3) keeps importing.
+# cylindrical projections (reference homography.py:340-416).  Dead code for the app
+# (ransac.py:249-251 is commented out), kept because `from homography import ... cylindericlMap` (ransac.py:3)
+# and homography.example1 name them.
 # ------------------------------------------------------------------------------------------------
-def _out_of_scope(name):
-    def f(*a, **k):
-        raise NotImplementedError(f"{name} is outside the B200 hot path (cylindrical warps; SURVEY.md section 2 #10)")
-    f.__name__ = name
-    return f
+def cylindericalTransform(img, f, xc=0.5, yc=0.5, method='bilinear', wrap="fwd"):
+    """Reference homography.py:340-389, statement for statement around the GPU sampler.
+
+    What the reference computes here is narrower than its docstring: `z` is (3, N) and the reference indexes its
+    COLUMNS (`z[:,0]`, `_z[:,1]`), so only output pixels 0 and 1 receive cylindrical coordinates and every other
+    pixel is sampled at its own position; the bounding box (min_x, min_y) likewise comes from the first two
+    columns of `bnd`.  That is reproduced as is (the same numpy expressions build `_z`; the sampler runs on the
+    GPU).  Two branches of the reference do not produce a defined result and raise here instead:
+      * method='bilinear' (the default): the grid holds x = w-1 exactly, which the sampler's mask lets through,
+        so the reference dies with IndexError at homography.py:135 for every image -- same exception here;
+      * wrap='backward': `_z = np.empty(z.shape)` is sampled with all but two columns uninitialised
+        (homography.py:373-378) -- the output is whatever the allocator left: ValueError here."""
+    h, w, c = img.shape
+    _xc = int(xc * w) - 1
+    _yc = int(yc * h) - 1
+    __xc = int((1 - xc) * w) - 1
+    __yc = int((1 - yc) * h) - 1
+    bnd = np.array([[0, 0, _xc, w - 1, w - 1, __xc, w - 1, 0],
+                    [0, _yc, 0, __yc, 0, h - 1, h - 1, h - 1],
+                    [1., 1, 1, 1, 1, 1, 1, 1]])
+    bnd_n = bnd.copy()
+    tmp = (bnd[:, 0] - _xc) / f
+    bnd_n[:, 0] = f * np.tan(tmp) + _xc
+    bnd_n[:, 1] = (bnd[:, 1] - _yc) / np.cos(tmp) + _yc
+    max_x = int(np.max(bnd_n[0, :]))
+    min_x = int(np.min(bnd_n[0, :]))
+    max_y = int(np.max(bnd_n[1, :]))
+    min_y = int(np.min(bnd_n[1, :]))
+    if wrap == "backward":
+        raise ValueError("cylindericalTransform(wrap='backward') samples an uninitialised coordinate array in the reference "
+                         "(homography.py:373-378): there is no defined output to reproduce")
+    sampler = convertfunc[method]
+    if method == 'bilinear':
+        raise IndexError(f"index {w} is out of bounds for axis 1 with size {w}")      # homography.py:135, always (x = w-1 is sampled)
+    x = np.linspace(0, w - 1, w)
+    y = np.linspace(0, h - 1, h)
+    xv, yv = np.meshgrid(x, y)
+    z = np.dstack([xv, yv, np.ones((h, w))]).reshape([w * h, 3]).T
+    _z = z.copy()
+    tmp = (z[:, 0] - _xc) / f
+    _z[:, 0] = f * np.tan(tmp) + _xc
+    _z[:, 1] = (z[:, 1] - _yc) / np.cos(tmp) + _yc
+    img_n = sampler(_z, img, h, w, h, w).astype(np.uint8)
+    return img_n, min_x, min_y
 
 
-cylindericalTransform = _out_of_scope("cylindericalTransform")
-cylindricalWarp = _out_of_scope("cylindricalWarp")
-cylindericlMap = _out_of_scope("cylindericlMap")
+def cylindricalWarp(img, K):
+    """Reference homography.py:391-410: cylindrical warp of a BGR uint8 image for intrinsics K; returns BGRA with
+    transparent (alpha 0) pixels where the cylinder leaves the image.
+
+    The coordinate maps are the reference's own numpy expressions (float64 sin / cos, then float32); the resampling
+    -- cv2.cvtColor(BGR2BGRA) + cv2.remap(..., INTER_AREA, BORDER_TRANSPARENT) in the reference -- runs on the GPU
+    (b200geo_remap_linear_host: OpenCV's fixed-point bilinear remap, bit-exact).  cv2.remap leaves the pixels it
+    does not write (taps outside the image) as its freshly allocated output had them, which is zero-filled memory in
+    practice; here they are zero by construction."""
+    h_, w_ = img.shape[:2]
+    y_i, x_i = np.indices((h_, w_))
+    X = np.stack([x_i, y_i, np.ones_like(x_i)], axis=-1).reshape(h_ * w_, 3)
+    Kinv = np.linalg.inv(K)
+    X = Kinv.dot(X.T).T
+    A = np.stack([np.sin(X[:, 0]), X[:, 1], np.cos(X[:, 0])], axis=-1).reshape(w_ * h_, 3)
+    B = K.dot(A.T).T
+    B = B[:, :-1] / B[:, [-1]]
+    B[(B[:, 0] < 0) | (B[:, 0] >= w_) | (B[:, 1] < 0) | (B[:, 1] >= h_)] = -1
+    B = B.reshape(h_, w_, -1)
+    assert img.ndim == 3 and img.shape[2] == 3 and img.dtype == np.uint8       # cv2.cvtColor(BGR2BGRA) accepts nothing else here
+    img_rgba = np.empty((h_, w_, 4), np.uint8)
+    img_rgba[:, :, :3] = img
+    img_rgba[:, :, 3] = 255
+    mx = np.ascontiguousarray(B[:, :, 0].astype(np.float32))
+    my = np.ascontiguousarray(B[:, :, 1].astype(np.float32))
+    out = np.zeros((h_, w_, 4), np.uint8)
+    ctx = _cabi.context()
+    _cabi.check(ctx.lib.b200geo_remap_linear_host(ctx.handle, _cabi.ptr(img_rgba), h_, w_, 4, _cabi.ptr(mx), _cabi.ptr(my), h_, w_,
+                                                  _cabi.ptr(out)))
+    return out
+
+
+def cylindericlMap(img, f=1600):
+    """Reference homography.py:412-416."""
+    h, w, c = img.shape
+    K = np.array([[f, 0, w / 2], [0, f, h / 2], [0, 0, 1]])
+    img_cyl = cylindricalWarp(img, K)
+    return img_cyl

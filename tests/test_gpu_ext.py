@@ -1,0 +1,72 @@
+"""GPU: components either side of the hot path: the cylindrical warps (homography.py:340-416) and the
+cv2.remap kernel behind them, against the live reference's outputs (tests/golden/ext.npz) and the oracle."""
+import numpy as np
+import pytest
+
+from oracle import ref_numpy as R
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("ch", [1, 2, 4])
+def test_remap_kernel_is_bit_exact(golden, ch):
+    from ransac_with_homography_b200 import _cabi
+    z = golden.file("ext")
+    src, mx, my, dst = z[f"remap_src{ch}"], z[f"remap_mx{ch}"], z[f"remap_my{ch}"], z[f"remap_dst{ch}"]
+    out = np.ascontiguousarray(dst.copy())
+    ctx = _cabi.context()
+    _cabi.check(ctx.lib.b200geo_remap_linear_host(ctx.handle, _cabi.ptr(np.ascontiguousarray(src)), src.shape[0], src.shape[1], ch,
+                                                  _cabi.ptr(np.ascontiguousarray(mx)), _cabi.ptr(np.ascontiguousarray(my)), mx.shape[0], mx.shape[1],
+                                                  _cabi.ptr(out)))
+    assert np.array_equal(out, z[f"remap_ref{ch}"])              # cv2.remap of OpenCV 4.13, NaN / inf / huge coordinates included
+
+
+def test_remap_kernel_random_against_oracle():
+    from ransac_with_homography_b200 import _cabi
+    rs = np.random.RandomState(3)
+    ctx = _cabi.context()
+    for _ in range(6):
+        ih, iw, oh, ow = rs.randint(1, 90), rs.randint(1, 120), rs.randint(1, 70), rs.randint(1, 300)
+        src = rs.randint(0, 256, (ih, iw, 4)).astype(np.uint8)
+        mx = (rs.rand(oh, ow) * (iw + 8) - 4).astype(np.float32)
+        my = (rs.rand(oh, ow) * (ih + 8) - 4).astype(np.float32)
+        dst = rs.randint(0, 256, (oh, ow, 4)).astype(np.uint8)
+        out = dst.copy()
+        _cabi.check(ctx.lib.b200geo_remap_linear_host(ctx.handle, _cabi.ptr(src), ih, iw, 4, _cabi.ptr(mx), _cabi.ptr(my), oh, ow, _cabi.ptr(out)))
+        assert np.array_equal(out, R.remap_linear_transparent(src, mx, my, dst))
+
+
+@pytest.mark.parametrize("f", [100, 300, 1600])
+def test_cylindericl_map_equals_reference(golden, f):
+    from ransac_with_homography_b200 import homography as hg
+    z = golden.file("ext")
+    img = z["cyl_img"]
+    o = hg.cylindericlMap(img.copy(), f=f)
+    ref = z[f"cyl_map_f{f}"]
+    h, w = img.shape[:2]
+    assert o.shape == ref.shape and o.dtype == np.uint8
+    assert np.array_equal(o, R.cylindrical_warp(img, np.array([[f, 0, w / 2], [0, f, h / 2], [0, 0, 1]])))
+    t = o[..., 3] == 255
+    assert np.array_equal(o[t], ref[t]) and not o[~t].any()       # the reference leaves the unwritten pixels uninitialised
+
+
+def test_cylindrical_warp_general_intrinsics(golden):
+    from ransac_with_homography_b200 import homography as hg
+    z = golden.file("ext")
+    o = hg.cylindricalWarp(z["cyl_img"].copy(), z["cyl_K"])
+    t = o[..., 3] == 255
+    assert t.mean() > 0.5 and np.array_equal(o[t], z["cyl_warp_K"][t]) and not o[~t].any()
+
+
+def test_cylinderical_transform(golden):
+    from ransac_with_homography_b200 import homography as hg
+    z = golden.file("ext")
+    img = z["cyl_img"]
+    o, mx, my = hg.cylindericalTransform(img.copy(), 100, method="nn")
+    assert np.array_equal(o, z["cyl_transform_nn"]) and [mx, my] == z["cyl_transform_nn_off"].tolist()
+    o, mx, my = hg.cylindericalTransform(img.copy(), 37.5, xc=0.3, yc=0.8, method="nn")
+    assert np.array_equal(o, z["cyl_transform_nn2"]) and [mx, my] == z["cyl_transform_nn2_off"].tolist()
+    with pytest.raises(IndexError):                               # the reference's default method dies at homography.py:135
+        hg.cylindericalTransform(img.copy(), 100)
+    with pytest.raises(ValueError):                               # samples np.empty in the reference
+        hg.cylindericalTransform(img.copy(), 100, method="nn", wrap="backward")
