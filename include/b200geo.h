@@ -313,6 +313,26 @@ int b200geo_sample_host(b200geo_ctx *ctx, const void *src, int ih, int iw, int c
 int b200geo_remap_linear_host(b200geo_ctx *ctx, const uint8_t *src, int ih, int iw, int channels,
                               const float *map_x, const float *map_y, int oh, int ow, uint8_t *dst);
 
+/* ------------------------------------------------------------------------------------------------
+ * (7) device-side JPEG decode / encode -- the GPU counterparts of cv2.imread (app.py:122,154,158;
+ *     ransac.py:291-294) and cv2.imwrite (app.py:193-195; ransac.py:301): file bytes <-> interleaved 8-bit
+ *     pixels in HBM, so that decoded frames never cross the host link.  Codec: nvJPEG, loaded on first use
+ *     (B200GEO_ERR_NODEVICE if libnvjpeg.so.12 is absent).  order: B200GEO_BGR (cv2's) or B200GEO_RGB.
+ *     Grayscale files decode to three equal channels (cv2.IMREAD_COLOR).  Decoded values may differ from
+ *     libjpeg-turbo's (cv2) by a few grey levels: different IDCT and chroma up-sampling; censused in the tests.
+ *     decode: dst holds height rows of dst_pitch >= 3*width bytes, on the device (asynchronous on `stream`)
+ *     or on the host (dst_on_device = 0: synchronous).  encode: cv2.imwrite's defaults (pass quality 95;
+ *     4:2:0 chroma, baseline Huffman); out = NULL queries *nbytes (the encode is then already done and a
+ *     second call with a buffer retrieves nothing new -- call once with a buffer of height*width*3 + 4096).
+ * ---------------------------------------------------------------------------------------------- */
+#define B200GEO_BGR 0
+#define B200GEO_RGB 1
+int b200geo_jpeg_info(b200geo_ctx *ctx, const uint8_t *data, size_t nbytes, int *height, int *width, int *components);
+int b200geo_jpeg_decode(b200geo_ctx *ctx, const uint8_t *data, size_t nbytes, int order, void *dst,
+                        long long dst_pitch, int dst_on_device, void *stream);
+int b200geo_jpeg_encode(b200geo_ctx *ctx, const void *src, int height, int width, long long src_pitch, int order,
+                        int src_on_device, int quality, uint8_t *out, size_t capacity, size_t *nbytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -10,6 +10,7 @@
 #include "compose.cuh"
 #include "match.cuh"
 #include "remap.cuh"
+#include "jpeg_io.cuh"
 
 #include <new>
 #include <stdlib.h>
@@ -63,6 +64,7 @@ int b200geo_destroy(b200geo_ctx *ctx)
             if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
         if (ctx->pinned) cudaFreeHost(ctx->pinned);
         if (ctx->order_event) cudaEventDestroy(ctx->order_event);
+        jpeg_release(ctx);
         if (ctx->pipe_ready) {
             for (int i = 0; i < 3; ++i) cudaStreamDestroy(ctx->pipe_stream[i]);
             for (int i = 0; i < 3; ++i)
@@ -1294,6 +1296,95 @@ int b200geo_remap_linear_host(b200geo_ctx *ctx, const uint8_t *src, int ih, int 
     B2G_CHECK_LAUNCH(ctx);
     B2G_CUDA(cudaMemcpyAsync(dst, dd, dbytes, cudaMemcpyDeviceToHost, 0));
     B2G_CUDA(cudaStreamSynchronize(0));
+    return B200GEO_OK;
+}
+
+int b200geo_jpeg_info(b200geo_ctx *ctx, const uint8_t *data, size_t nbytes, int *height, int *width, int *components)
+{
+    B2G_ENTER(ctx);
+    B2G_ARG(data && nbytes > 0);
+    JpegState *st;
+    int rc;
+    if ((rc = jpeg_state(ctx, &st))) return rc;
+    int nc = 0, ws[NVJPEG_MAX_COMPONENT] = {0}, hs[NVJPEG_MAX_COMPONENT] = {0};
+    nvjpegChromaSubsampling_t sub;
+    B2G_JPEG(st, GetImageInfo, st->handle, data, nbytes, &nc, &sub, ws, hs);
+    if (height) *height = hs[0];
+    if (width) *width = ws[0];
+    if (components) *components = nc;
+    return B200GEO_OK;
+}
+
+int b200geo_jpeg_decode(b200geo_ctx *ctx, const uint8_t *data, size_t nbytes, int order, void *dst, long long dst_pitch, int dst_on_device,
+                        void *stream)
+{
+    B2G_ENTER(ctx);
+    cudaStream_t cs = (cudaStream_t)stream;
+    stream_order(ctx, cs);
+    B2G_ARG(data && nbytes > 0 && dst && (order == B200GEO_BGR || order == B200GEO_RGB));
+    JpegState *st;
+    int rc;
+    if ((rc = jpeg_state(ctx, &st))) return rc;
+    int nc = 0, ws[NVJPEG_MAX_COMPONENT] = {0}, hs[NVJPEG_MAX_COMPONENT] = {0};
+    nvjpegChromaSubsampling_t sub;
+    B2G_JPEG(st, GetImageInfo, st->handle, data, nbytes, &nc, &sub, ws, hs);
+    const int h = hs[0], w = ws[0];
+    B2G_ARG(h > 0 && w > 0 && dst_pitch >= 3LL * w);
+    nvjpegImage_t im;
+    memset(&im, 0, sizeof im);
+    if (dst_on_device) {
+        im.channel[0] = static_cast<unsigned char *>(dst);
+        im.pitch[0] = (size_t)dst_pitch;
+    } else {
+        void *d;
+        if ((rc = scratch(ctx, S_DST, (size_t)h * w * 3, &d))) return rc;
+        im.channel[0] = static_cast<unsigned char *>(d);
+        im.pitch[0] = (size_t)w * 3;
+    }
+    B2G_JPEG(st, Decode, st->handle, st->dec, data, nbytes, order == B200GEO_BGR ? NVJPEG_OUTPUT_BGRI : NVJPEG_OUTPUT_RGBI, &im, cs);
+    if (!dst_on_device) {
+        B2G_CUDA(cudaMemcpy2DAsync(dst, (size_t)dst_pitch, im.channel[0], im.pitch[0], (size_t)w * 3, (size_t)h, cudaMemcpyDeviceToHost, cs));
+        B2G_CUDA(cudaStreamSynchronize(cs));
+    }
+    return B200GEO_OK;
+}
+
+int b200geo_jpeg_encode(b200geo_ctx *ctx, const void *src, int height, int width, long long src_pitch, int order, int src_on_device, int quality,
+                        uint8_t *out, size_t capacity, size_t *nbytes, void *stream)
+{
+    B2G_ENTER(ctx);
+    cudaStream_t cs = (cudaStream_t)stream;
+    stream_order(ctx, cs);
+    B2G_ARG(src && nbytes && height > 0 && width > 0 && src_pitch >= 3LL * width && quality >= 1 && quality <= 100);
+    B2G_ARG(order == B200GEO_BGR || order == B200GEO_RGB);
+    JpegState *st;
+    int rc;
+    if ((rc = jpeg_state(ctx, &st))) return rc;
+    nvjpegImage_t im;
+    memset(&im, 0, sizeof im);
+    if (src_on_device) {
+        im.channel[0] = const_cast<unsigned char *>(static_cast<const unsigned char *>(src));
+        im.pitch[0] = (size_t)src_pitch;
+    } else {
+        void *d;
+        if ((rc = scratch(ctx, S_SRC, (size_t)height * width * 3, &d))) return rc;
+        B2G_CUDA(cudaMemcpy2DAsync(d, (size_t)width * 3, src, (size_t)src_pitch, (size_t)width * 3, (size_t)height, cudaMemcpyHostToDevice, cs));
+        im.channel[0] = static_cast<unsigned char *>(d);
+        im.pitch[0] = (size_t)width * 3;
+    }
+    // cv2.imwrite's defaults: quality 95 unless given, 4:2:0 chroma, baseline Huffman tables
+    B2G_JPEG(st, EncoderParamsSetQuality, st->params, quality, cs);
+    B2G_JPEG(st, EncoderParamsSetOptimizedHuffman, st->params, 0, cs);
+    B2G_JPEG(st, EncoderParamsSetSamplingFactors, st->params, NVJPEG_CSS_420, cs);
+    B2G_JPEG(st, EncodeImage, st->handle, st->enc, st->params, &im, order == B200GEO_BGR ? NVJPEG_INPUT_BGRI : NVJPEG_INPUT_RGBI, width, height, cs);
+    size_t len = 0;
+    B2G_JPEG(st, EncodeRetrieveBitstream, st->handle, st->enc, nullptr, &len, cs);
+    *nbytes = len;
+    if (!out) return B200GEO_OK;                       // size query
+    if (capacity < len) return fail(B200GEO_ERR_ARG, "jpeg_encode: output buffer too small%s%s");
+    B2G_JPEG(st, EncodeRetrieveBitstream, st->handle, st->enc, out, &len, cs);
+    B2G_CUDA(cudaStreamSynchronize(cs));
+    *nbytes = len;
     return B200GEO_OK;
 }
 

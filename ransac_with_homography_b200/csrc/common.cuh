@@ -85,6 +85,7 @@ struct b200geo_ctx {
     int finish_done_n;
     void *pinned;          // small pinned staging block for scalar results
     size_t pinned_cap;
+    void *jpeg;            // b200geo::JpegState (nvJPEG handle and codec states), created by the first JPEG call
 };
 
 namespace b200geo {

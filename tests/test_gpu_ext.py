@@ -70,3 +70,58 @@ def test_cylinderical_transform(golden):
         hg.cylindericalTransform(img.copy(), 100)
     with pytest.raises(ValueError):                               # samples np.empty in the reference
         hg.cylindericalTransform(img.copy(), 100, method="nn", wrap="backward")
+
+
+# ---- device-side JPEG I/O (b200geo_jpeg_*, nvJPEG): cv2.imread / cv2.imwrite of the reference's own fixtures ----
+def _psnr(a, b):
+    d = a.astype(np.float64) - b.astype(np.float64)
+    return 10 * np.log10(255.0 ** 2 / max(float((d * d).mean()), 1e-12))
+
+
+@pytest.mark.parametrize("name", ["foto1A.jpg", "cv.jpg"])
+def test_jpeg_decode_against_cv2(name):
+    """cv2.imread decodes with libjpeg-turbo (integer IDCT, 'fancy' chroma up-sampling); nvJPEG's IDCT and up-sampling
+    differ, so the comparison is a census: same shape, and the decoded pixels within a few grey levels of cv2's."""
+    import os
+    cv2 = pytest.importorskip("cv2")
+    import torch
+    from ransac_with_homography_b200 import imgio
+    from conftest import GOLDEN
+    path = os.path.join(GOLDEN, name)
+    ref = cv2.imread(path)
+    got = imgio.imread(path)
+    assert got.shape == ref.shape and got.dtype == np.uint8
+    d = np.abs(got.astype(np.int16) - ref.astype(np.int16))
+    census = {"max": int(d.max()), "mean": float(d.mean()), "p99": float(np.percentile(d, 99)), "equal": float((d == 0).mean())}
+    print("jpeg decode census", name, census)
+    assert census["mean"] < 1.5 and census["p99"] <= 12 and _psnr(got, ref) > 35, census
+    # device-resident form, RGB order (what ransac.example1 makes of cv2.imread with [:, :, ::-1])
+    with open(path, "rb") as f:
+        data = f.read()
+    t = imgio.decode(data, order="rgb")
+    torch.cuda.synchronize()
+    assert t.is_cuda and np.array_equal(t.cpu().numpy(), got[:, :, ::-1])
+    assert imgio.info(data)[:2] == ref.shape[:2]
+
+
+def test_jpeg_encode_round_trip():
+    import os
+    cv2 = pytest.importorskip("cv2")
+    import torch
+    from ransac_with_homography_b200 import imgio
+    from conftest import GOLDEN
+    img = cv2.imread(os.path.join(GOLDEN, "foto1B.jpg"))
+    data = imgio.imencode(img)                                    # quality 95, 4:2:0: cv2.imwrite's defaults
+    assert data[:2] == b"\xff\xd8" and data[-2:] == b"\xff\xd9"
+    back = cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_COLOR)        # an independent decoder reads our file
+    ok, ref_bytes = cv2.imencode(".jpg", img)
+    ref_back = cv2.imdecode(ref_bytes, cv2.IMREAD_COLOR)
+    assert back.shape == img.shape
+    p_ours, p_cv = _psnr(back, img), _psnr(ref_back, img)
+    print("jpeg encode: psnr ours", p_ours, "cv2", p_cv, "bytes ours", len(data), "cv2", len(ref_bytes))
+    assert p_ours > p_cv - 1.0 and 0.5 < len(data) / len(ref_bytes) < 2.0
+    t = torch.from_numpy(np.ascontiguousarray(img[:, :, ::-1])).cuda()
+    data2 = imgio.encode(t, order="rgb")
+    assert data2 == data                                          # same pixels, device-resident source
+    with pytest.raises(ValueError):
+        imgio.imwrite("/tmp/x.png", img)
