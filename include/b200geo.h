@@ -333,6 +333,22 @@ int b200geo_jpeg_decode(b200geo_ctx *ctx, const uint8_t *data, size_t nbytes, in
 int b200geo_jpeg_encode(b200geo_ctx *ctx, const void *src, int height, int width, long long src_pitch, int order,
                         int src_on_device, int quality, uint8_t *out, size_t capacity, size_t *nbytes, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * (8) ORB feature front-end -- replaces cv2.ORB_create().detectAndCompute(gray, None) in stitching()
+ *     (ransac.py:255-257), the step before the Hamming matcher (5).  OpenCV's defaults as the reference uses
+ *     them (8 levels, scale 1.2f, edge threshold 31, patch 31, FAST threshold 20, Harris score, WTA_K 2);
+ *     nfeatures is cv2.ORB_create's first argument (500).  img: height x width uint8 with `pitch` bytes per row,
+ *     host memory; channels = 1 (grey) or 3 (interleaved RGB: cv2.cvtColor(img, COLOR_RGB2GRAY) of ransac.py:252-253
+ *     is then done on the device, bit-exact).  keypoints: capacity x 6 float32 (x, y, size, angle in degrees, Harris response, octave);
+ *     descriptors: capacity x 32 bytes; *n_out = number found (a few more than nfeatures when responses tie,
+ *     as in OpenCV).  Positions, sizes, angles, responses, octaves, the ORDER of the keypoints and the
+ *     descriptors are bit-identical to OpenCV 4.13's (x86-64 build with AVX2 dispatch).  Pyramid, FAST, Harris,
+ *     orientation, blur and the 256 pair tests run on the GPU; the two retainBest selections
+ *     (std::nth_element order) and cosf / sinf of the angles run on the host.
+ * ---------------------------------------------------------------------------------------------- */
+int b200geo_orb_host(b200geo_ctx *ctx, const uint8_t *img, int height, int width, long long pitch, int channels, int nfeatures,
+                     float *keypoints, uint8_t *descriptors, int capacity, int *n_out);
+
 #ifdef __cplusplus
 }
 #endif

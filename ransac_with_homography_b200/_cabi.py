@@ -101,6 +101,7 @@ SIGNATURES = {
     "b200geo_sample_host": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, C.c_longlong, _i, _i, _i, _i, _vp]),
     "b200geo_match_hamming_host": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp]),
     "b200geo_remap_linear_host": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _i, _vp]),
+    "b200geo_orb_host": (_i, [_vp, _vp, _i, _i, C.c_longlong, _i, _i, _vp, _vp, _i, _vp]),
     "b200geo_jpeg_info": (_i, [_vp, _vp, C.c_size_t, _vp, _vp, _vp]),
     "b200geo_jpeg_decode": (_i, [_vp, _vp, C.c_size_t, _i, _vp, C.c_longlong, _i, _vp]),
     "b200geo_jpeg_encode": (_i, [_vp, _vp, _i, _i, C.c_longlong, _i, _i, _i, _vp, C.c_size_t, _vp, _vp]),

@@ -11,10 +11,14 @@
 #include "match.cuh"
 #include "remap.cuh"
 #include "jpeg_io.cuh"
+#include "orb.cuh"
 
 #include <new>
 #include <stdlib.h>
 #include <vector>
+#include <algorithm>
+#include <cmath>
+#define CV_PI_F64 3.1415926535897932384626433832795
 
 using namespace b200geo;
 
@@ -1385,6 +1389,187 @@ int b200geo_jpeg_encode(b200geo_ctx *ctx, const void *src, int height, int width
     B2G_JPEG(st, EncodeRetrieveBitstream, st->handle, st->enc, out, &len, cs);
     B2G_CUDA(cudaStreamSynchronize(cs));
     *nbytes = len;
+    return B200GEO_OK;
+}
+
+// KeyPointsFilter::retainBest (features2d/src/keypoint.cpp): the n best by response plus every point tied with the n-th,
+// in the element order std::nth_element and std::partition of libstdc++ leave behind (OpenCV's output order inherits it).
+namespace {
+struct OrbKp { int x, y; float response; float harris; };
+void orb_retain_best(std::vector<OrbKp> &kps, int n)
+{
+    if (n >= 0 && kps.size() > (size_t)n) {
+        if (n == 0) { kps.clear(); return; }
+        std::nth_element(kps.begin(), kps.begin() + n - 1, kps.end(), [](const OrbKp &a, const OrbKp &b) { return a.response > b.response; });
+        const float ambiguous = kps[n - 1].response;
+        auto new_end = std::partition(kps.begin() + n, kps.end(), [ambiguous](const OrbKp &k) { return k.response >= ambiguous; });
+        kps.resize(new_end - kps.begin());
+    }
+}
+}  // namespace
+
+int b200geo_orb_host(b200geo_ctx *ctx, const uint8_t *gray, int height, int width, long long pitch, int channels, int nfeatures, float *keypoints,
+                     uint8_t *descriptors, int capacity, int *n_out)
+{
+    B2G_ENTER(ctx);
+    stream_order(ctx, 0);
+    B2G_ARG(gray && n_out && height > 0 && width > 0 && height < 32768 && width < 32768 && (channels == 1 || channels == 3) && pitch >= (long long)width * channels &&
+            nfeatures >= 0 && capacity >= 0);
+    B2G_ARG(capacity == 0 || (keypoints && descriptors));
+    *n_out = 0;
+    // ---- level geometry: ORB_Impl::detectAndCompute / computeKeyPoints (orb.cpp), default parameters ----
+    const double scale_factor = (double)1.2f;                      // ORB::create(float scaleFactor = 1.2f) stored as double
+    float scales[ORB_LEVELS];
+    OrbLevels L;
+    memset(&L, 0, sizeof L);
+    L.n = ORB_LEVELS;
+    long long bytes = 0;
+    unsigned cand_total = 0;
+    int max_w = 0, max_h = 0;
+    for (int lv = 0; lv < ORB_LEVELS; ++lv) {
+        scales[lv] = (float)std::pow(scale_factor, (double)lv);
+        const float inv = 1.0f / scales[lv];
+        OrbLevel &o = L.lv[lv];
+        o.w = (int)lrintf((float)width * inv);
+        o.h = (int)lrintf((float)height * inv);
+        B2G_ARG(o.w >= 1 && o.h >= 1);
+        o.pitch = (o.w + 2 * ORB_BORDER + 15) & ~15;
+        o.pw = lv ? L.lv[lv - 1].w : width;
+        o.ph = lv ? L.lv[lv - 1].h : height;
+        o.ofs = bytes;
+        bytes += (long long)o.pitch * (o.h + 2 * ORB_BORDER);
+        o.cand_ofs = cand_total;
+        o.cand_cap = (unsigned)(((o.w + 1) / 2) * ((o.h + 1) / 2));    // strict 3 x 3 maxima: at most one per 2 x 2 block
+        cand_total += o.cand_cap;
+        max_w = std::max(max_w, o.w);
+        max_h = std::max(max_h, o.h);
+    }
+    int per_level[ORB_LEVELS];
+    {
+        const float factor = (float)(1.0 / scale_factor);
+        float nd = nfeatures * (1 - factor) / (1 - (float)std::pow((double)factor, (double)ORB_LEVELS));
+        int sum = 0;
+        for (int lv = 0; lv < ORB_LEVELS - 1; ++lv) {
+            per_level[lv] = (int)lrintf(nd);
+            sum += per_level[lv];
+            nd *= factor;
+        }
+        per_level[ORB_LEVELS - 1] = std::max(nfeatures - sum, 0);
+    }
+    OrbUmax um;
+    {
+        // the end of each row of the circular patch (computeKeyPoints)
+        const int hp = ORB_HALF_PATCH;
+        const int vmax = (int)std::floor(hp * std::sqrt(2.f) / 2 + 1), vmin = (int)std::ceil(hp * std::sqrt(2.f) / 2);
+        for (int v = 0; v <= hp + 1; ++v) um.u[v] = 0;
+        for (int v = 0; v <= vmax; ++v) um.u[v] = (int)lrint(std::sqrt((double)hp * hp - v * v));
+        for (int v = hp, v0 = 0; v >= vmin; --v) {
+            while (um.u[v0] == um.u[v0 + 1]) ++v0;
+            um.u[v] = v0;
+            ++v0;
+        }
+    }
+    // ---- device buffers ----
+    uint8_t *d_in, *d_pyr, *d_score, *d_blur;
+    OrbCandidate *d_cand;
+    unsigned *d_counts;
+    int rc;
+    if ((rc = scratch(ctx, S_SRC, (size_t)height * width * channels, (void **)&d_in))) return rc;
+    if ((rc = scratch(ctx, S_ORB_PYR, (size_t)bytes, (void **)&d_pyr))) return rc;
+    if ((rc = scratch(ctx, S_ORB_SCORE, (size_t)bytes, (void **)&d_score))) return rc;
+    if ((rc = scratch(ctx, S_ORB_BLUR, (size_t)bytes, (void **)&d_blur))) return rc;
+    if ((rc = scratch(ctx, S_ORB_CAND, (size_t)cand_total * sizeof(OrbCandidate), (void **)&d_cand))) return rc;
+    if ((rc = scratch(ctx, S_MISC, 64, (void **)&d_counts))) return rc;
+    B2G_CUDA(cudaMemcpy2DAsync(d_in, (size_t)width * channels, gray, (size_t)pitch, (size_t)width * channels, (size_t)height, cudaMemcpyHostToDevice, 0));
+    B2G_CUDA(cudaMemsetAsync(d_score, 0, (size_t)bytes, 0));
+    B2G_CUDA(cudaMemsetAsync(d_counts, 0, sizeof(unsigned) * ORB_LEVELS, 0));
+    for (int lv = 0; lv < ORB_LEVELS; ++lv) {
+        const OrbLevel &o = L.lv[lv];
+        const dim3 grid((o.w + 2 * ORB_BORDER + 255) / 256, o.h + 2 * ORB_BORDER);
+        if (lv == 0) orb_level_kernel<<<grid, 256, 0, 0>>>(d_in, (long long)width * channels, width, height, d_pyr + o.ofs, o.pitch, o.w, o.h, channels);
+        else {
+            const OrbLevel &q = L.lv[lv - 1];
+            orb_level_kernel<<<grid, 256, 0, 0>>>(d_pyr + q.ofs + (long long)ORB_BORDER * q.pitch + ORB_BORDER, (long long)q.pitch, q.w, q.h, d_pyr + o.ofs, o.pitch,
+                                                  o.w, o.h, 0);
+        }
+        B2G_CHECK_LAUNCH(ctx);
+    }
+    if (max_w > 6 && max_h > 6) {
+        orb_fast_kernel<<<dim3((max_w - 6 + 255) / 256, max_h - 6, ORB_LEVELS), 256, 0, 0>>>(d_pyr, d_score, L);
+        B2G_CHECK_LAUNCH(ctx);
+    }
+    if (max_w > 2 * ORB_EDGE && max_h > 2 * ORB_EDGE) {
+        orb_candidates_kernel<<<dim3((max_w - 2 * ORB_EDGE + 255) / 256, max_h - 2 * ORB_EDGE, ORB_LEVELS), 256, 0, 0>>>(d_pyr, d_score, L, d_cand, d_counts);
+        B2G_CHECK_LAUNCH(ctx);
+    }
+    unsigned counts[ORB_LEVELS];
+    B2G_CUDA(cudaMemcpyAsync(counts, d_counts, sizeof counts, cudaMemcpyDeviceToHost, 0));
+    orb_blur_kernel<<<dim3((max_w + 255) / 256, max_h, ORB_LEVELS), 256, 0, 0>>>(d_pyr, d_blur, L);      // runs under the host's selection below
+    B2G_CHECK_LAUNCH(ctx);
+    B2G_CUDA(cudaStreamSynchronize(0));
+    // ---- selection on the host, level by level, exactly as computeKeyPoints orders it ----
+    std::vector<OrbCandidate> recs;
+    std::vector<OrbKp> level_kps[ORB_LEVELS];
+    for (int lv = 0; lv < ORB_LEVELS; ++lv) {
+        const OrbLevel &o = L.lv[lv];
+        const unsigned n = std::min(counts[lv], o.cand_cap);
+        if (!n) continue;
+        recs.resize(n);
+        B2G_CUDA(cudaMemcpy(recs.data(), d_cand + o.cand_ofs, sizeof(OrbCandidate) * n, cudaMemcpyDeviceToHost));
+        std::sort(recs.begin(), recs.end(), [](const OrbCandidate &a, const OrbCandidate &b) { return a.pos < b.pos; });      // FAST's row-major order
+        std::vector<OrbKp> &kps = level_kps[lv];
+        kps.resize(n);
+        for (unsigned i = 0; i < n; ++i) kps[i] = OrbKp{(int)(recs[i].pos & 0xFFFFu), (int)(recs[i].pos >> 16), (float)recs[i].score, recs[i].harris};
+        orb_retain_best(kps, 2 * per_level[lv]);             // by FAST score (HARRIS_SCORE keeps twice the level's share first)
+        for (OrbKp &k : kps) k.response = k.harris;
+        orb_retain_best(kps, per_level[lv]);                 // by Harris response
+    }
+    std::vector<OrbPoint> pts;
+    for (int lv = 0; lv < ORB_LEVELS; ++lv)
+        for (const OrbKp &k : level_kps[lv]) pts.push_back(OrbPoint{lv, k.x, k.y, 0.f, 0.f});
+    const int n = (int)pts.size();
+    *n_out = n;
+    if (n == 0) return B200GEO_OK;
+    if (n > capacity) return fail(B200GEO_ERR_ARG, "orb: more keypoints than the output buffers hold%s%s");
+    OrbPoint *d_pts;
+    float *d_angle;
+    uint8_t *d_desc;
+    if ((rc = scratch(ctx, S_ORB_PTS, (size_t)n * (sizeof(OrbPoint) + sizeof(float) + 32), (void **)&d_pts))) return rc;
+    d_angle = reinterpret_cast<float *>(d_pts + n);
+    d_desc = reinterpret_cast<uint8_t *>(d_angle + n);
+    B2G_CUDA(cudaMemcpyAsync(d_pts, pts.data(), sizeof(OrbPoint) * n, cudaMemcpyHostToDevice, 0));
+    orb_angle_kernel<<<(n * 32 + 127) / 128, 128, 0, 0>>>(d_pyr, L, d_pts, n, um, d_angle);
+    B2G_CHECK_LAUNCH(ctx);
+    std::vector<float> angle(n);
+    B2G_CUDA(cudaMemcpyAsync(angle.data(), d_angle, sizeof(float) * n, cudaMemcpyDeviceToHost, 0));
+    B2G_CUDA(cudaStreamSynchronize(0));
+    {
+        int i = 0;
+        for (int lv = 0; lv < ORB_LEVELS; ++lv)
+            for (const OrbKp &k : level_kps[lv]) {
+                const float sf = scales[lv];
+                float *o = keypoints + 6 * (size_t)i;
+                o[0] = (float)k.x * sf; o[1] = (float)k.y * sf;          // pt *= scale
+                o[2] = ORB_PATCH * sf;                                   // size
+                o[3] = angle[i];
+                o[4] = k.response;                                       // Harris response
+                o[5] = (float)lv;                                        // octave
+                // computeOrbDescriptors: position back on the level, cos / sin of the angle in float (libm's cosf / sinf)
+                const float inv = 1.f / sf;
+                float ang = angle[i];
+                ang *= (float)(CV_PI_F64 / 180.f);
+                pts[i].x = (int)lrintf(o[0] * inv);
+                pts[i].y = (int)lrintf(o[1] * inv);
+                pts[i].a = cosf(ang);
+                pts[i].b = sinf(ang);
+                ++i;
+            }
+    }
+    B2G_CUDA(cudaMemcpyAsync(d_pts, pts.data(), sizeof(OrbPoint) * n, cudaMemcpyHostToDevice, 0));
+    orb_describe_kernel<<<(n * 32 + 127) / 128, 128, 0, 0>>>(d_blur, L, d_pts, n, d_desc);
+    B2G_CHECK_LAUNCH(ctx);
+    B2G_CUDA(cudaMemcpyAsync(descriptors, d_desc, (size_t)n * 32, cudaMemcpyDeviceToHost, 0));
+    B2G_CUDA(cudaStreamSynchronize(0));
     return B200GEO_OK;
 }
 

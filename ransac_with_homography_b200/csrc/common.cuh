@@ -47,7 +47,7 @@ inline int fail(int code, const char *fmt, const char *a = "", const char *b = "
     } while (0)
 
 enum ScratchSlot {
-    S_PTS = 0, S_IDX, S_H, S_HINV, S_FLAGS, S_COUNTS, S_KEYS, S_RESULT, S_MASK, S_JOBS, S_SRC, S_DST, S_MISC, S_CMAX, S_STATS, S_WORKLIST, S_TILES, S_PIPE_SRC, S_PIPE_DST, S_PIPE_JOBS, S_WARPFIX, S_STRIPS, S_FINISH, S_WLCOUNT,
+    S_PTS = 0, S_IDX, S_H, S_HINV, S_FLAGS, S_COUNTS, S_KEYS, S_RESULT, S_MASK, S_JOBS, S_SRC, S_DST, S_MISC, S_CMAX, S_STATS, S_WORKLIST, S_TILES, S_PIPE_SRC, S_PIPE_DST, S_PIPE_JOBS, S_WARPFIX, S_STRIPS, S_FINISH, S_WLCOUNT, S_ORB_PYR, S_ORB_SCORE, S_ORB_BLUR, S_ORB_CAND, S_ORB_PTS,
     S_NUM
 };
 

@@ -12,6 +12,8 @@ reference's ``break``), else the lowest-index maximum (the reference's strict ``
 """
 from __future__ import annotations
 
+import ctypes as C
+
 import numpy as np
 
 from . import _cabi
@@ -243,6 +245,44 @@ def match_hamming(featuresA, featuresB, crossCheck=True):
     return [Match(i, tr[i], ds[i]) for i in np.nonzero(tr >= 0)[0]]
 
 
+class KeyPoint:
+    """The fields of cv2.KeyPoint the reference and OpenCV's ORB fill (ransac.py:261-262 reads .pt)."""
+    __slots__ = ("pt", "size", "angle", "response", "octave", "class_id")
+
+    def __init__(self, x, y, size, angle, response, octave):
+        self.pt = (float(x), float(y))
+        self.size, self.angle, self.response, self.octave, self.class_id = float(size), float(angle), float(response), int(octave), -1
+
+    def __repr__(self):
+        return f"KeyPoint(pt={self.pt}, size={self.size}, angle={self.angle}, response={self.response}, octave={self.octave})"
+
+
+def orb_detect_and_compute(img, nfeatures=500, as_arrays=False):
+    """cv2.ORB_create(nfeatures).detectAndCompute(gray, None) (reference ransac.py:255-257) on the GPU (K7,
+    b200geo_orb_host): same keypoints in the same order, same 32-byte descriptors as OpenCV 4.13.
+
+    img: (h, w) uint8 grey image, or (h, w, 3) uint8 RGB -- the cv2.cvtColor(img, cv2.COLOR_RGB2GRAY) of
+    ransac.py:252-253 is then done on the device (bit-exact).  Returns (keypoints, descriptors) like OpenCV: a list of
+    KeyPoint and an (n, 32) uint8 array, or ((), None) when nothing is found; as_arrays=True returns the keypoints as an
+    (n, 6) float32 array (x, y, size, angle, response, octave) instead."""
+    a = np.ascontiguousarray(img)
+    assert a.dtype == np.uint8 and (a.ndim == 2 or (a.ndim == 3 and a.shape[2] == 3))
+    h, w = a.shape[:2]
+    ch = 1 if a.ndim == 2 else 3
+    cap = 2 * int(nfeatures) + 256
+    kp = np.empty((cap, 6), np.float32)
+    ds = np.empty((cap, 32), np.uint8)
+    n = C.c_int()
+    ctx = _cabi.context()
+    _cabi.check(ctx.lib.b200geo_orb_host(ctx.handle, _cabi.ptr(a), h, w, w * ch, ch, int(nfeatures), _cabi.ptr(kp), _cabi.ptr(ds), cap, C.byref(n)))
+    kp, ds = kp[:n.value].copy(), ds[:n.value].copy()
+    if as_arrays:
+        return kp, (ds if n.value else None)
+    if n.value == 0:
+        return (), None
+    return [KeyPoint(*r) for r in kp], ds
+
+
 def stitching(trainImg, queryImg,
               ransacMet="fwd",
               th=5,
@@ -255,16 +295,12 @@ def stitching(trainImg, queryImg,
               override=0,
               cylinderT=1):
     """Stitch trainImg into queryImg's frame (reference ransac.py:235-283; called from app.py:364).
-    ORB detection stays on OpenCV as in the reference (third-party); the brute-force
-    Hamming matcher with cross-check, RANSAC, the backward warp and the compose run on the GPU."""
-    import cv2
+    Grey conversion + ORB detection and description (K7), the brute-force Hamming matcher with cross-check (K6), RANSAC
+    (K1-K3), the backward warp and the compose (K4 / K5) all run on the GPU; only the alternates the reference itself
+    delegates to OpenCV (mode != None: cv2.findHomography; override: cv2.Stitcher) stay there."""
     if override == 0:
-        trainImg_gray = cv2.cvtColor(trainImg, cv2.COLOR_RGB2GRAY)
-        queryImg_gray = cv2.cvtColor(queryImg, cv2.COLOR_RGB2GRAY)
-
-        descriptor = cv2.ORB_create()
-        (kpsA, featuresA) = descriptor.detectAndCompute(trainImg_gray, None)
-        (kpsB, featuresB) = descriptor.detectAndCompute(queryImg_gray, None)
+        (kpsA, featuresA) = orb_detect_and_compute(trainImg)            # cvtColor(RGB2GRAY) + ORB_create().detectAndCompute
+        (kpsB, featuresB) = orb_detect_and_compute(queryImg)
 
         matches = sorted(match_hamming(featuresA, featuresB, crossCheck=True), key=lambda m: m.distance)
 
@@ -278,11 +314,13 @@ def stitching(trainImg, queryImg,
             ransac = RANSAC(model, k=k)
             H, inliers, _len = ransac.run([ptsA.T, ptsB.T], method=ransacMet)
         else:
+            import cv2
             reprojThresh = 4
             (H, status) = cv2.findHomography(ptsA, ptsB, cv2.RANSAC, reprojThresh)
 
         imgn = stitchPanorama(queryImg, trainImg, H=H, blending=blending, blendrate=blendrate)
     else:
+        import cv2
         stitcher = cv2.Stitcher_create()
         (status, imgn) = stitcher.stitch([trainImg, queryImg])
     return imgn

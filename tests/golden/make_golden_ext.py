@@ -4,7 +4,8 @@ reference and from OpenCV itself (build container only):
 
     PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden_ext.py
 
-Writes tests/golden/ext.npz: cylindericlMap / cylindricalWarp and cylindericalTransform('nn', 'fwd') of the
+Writes tests/golden/orb.npz (cv2.ORB_create().detectAndCompute on the reference's images, a noise image and a small
+image, and the matched point lists stitching() feeds to RANSAC) and tests/golden/ext.npz: cylindericlMap / cylindricalWarp and cylindericalTransform('nn', 'fwd') of the
 unmodified reference (homography.py:340-416) on the 114 x 171 fixture crop, and cv2.remap on random maps.
 """
 import os
@@ -53,6 +54,37 @@ def main():
         Z[f"remap_ref{ch}"] = ref.reshape(41, 47, ch)
     np.savez_compressed(os.path.join(OUT, "ext.npz"), **Z)
     print("wrote ext.npz:", sorted(Z))
+
+    # ---- ORB: cv2.ORB_create().detectAndCompute exactly as stitching() calls it (ransac.py:252-257), and the matcher after it ----
+    Q = {}
+
+    def kparr(kps):
+        return np.array([[k.pt[0], k.pt[1], k.size, k.angle, k.response, k.octave] for k in kps], np.float32).reshape(-1, 6)
+
+    rs = np.random.RandomState(9)
+    noise = rs.randint(0, 256, (211, 317, 3)).astype(np.uint8)
+    small = cv2.resize(cv2.imread(os.path.join(OUT, "cv.jpg")), (163, 121))[:, :, ::-1].copy()
+    cases = {f.split(".")[0]: np.ascontiguousarray(cv2.imread(os.path.join(OUT, f))[:, :, ::-1]) for f in ("foto1A.jpg", "foto1B.jpg", "cv.jpg", "notebook.jpg")}
+    cases["noise"], cases["small"] = noise, small
+    Q["noise_rgb"], Q["small_rgb"] = noise, small
+    for name, rgb in cases.items():
+        gray = cv2.cvtColor(rgb, cv2.COLOR_RGB2GRAY)
+        for nf in ((500, 60) if name in ("foto1A", "noise") else (500,)):
+            kps, des = cv2.ORB_create(nf).detectAndCompute(gray, None) if nf != 500 else cv2.ORB_create().detectAndCompute(gray, None)
+            tag = name if nf == 500 else f"{name}_n{nf}"
+            Q[f"{tag}__kp"] = kparr(kps)
+            Q[f"{tag}__desc"] = des if des is not None else np.zeros((0, 32), np.uint8)
+            print("orb", tag, gray.shape, len(kps))
+    # the correspondences stitching() hands to RANSAC for the reference's own pair (ransac.example1)
+    ga, gb = (cv2.cvtColor(cases[n], cv2.COLOR_RGB2GRAY) for n in ("foto1A", "foto1B"))
+    ka, fa = cv2.ORB_create().detectAndCompute(ga, None)
+    kb, fb = cv2.ORB_create().detectAndCompute(gb, None)
+    m = sorted(cv2.BFMatcher(cv2.NORM_HAMMING, crossCheck=True).match(fa, fb), key=lambda x: x.distance)
+    pa, pb = np.float32([k.pt for k in ka]), np.float32([k.pt for k in kb])
+    Q["pair_ptsA"] = np.float32([pa[x.queryIdx] for x in m])
+    Q["pair_ptsB"] = np.float32([pb[x.trainIdx] for x in m])
+    np.savez_compressed(os.path.join(OUT, "orb.npz"), **Q)
+    print("wrote orb.npz:", len(Q), "arrays;", len(m), "matches on the reference's pair")
 
 
 if __name__ == "__main__":
