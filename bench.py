@@ -648,6 +648,32 @@ def bench_aux(torch, ctx):
         m = match_hamming(A, Bd, True)
     out["match_hamming"] = {"ms_per_call": (time.perf_counter() - t0) / 20 * 1e3, "matches": len(m),
                             "what": "K6 hamming_best_kernel + cross-check, 500 x 500 descriptors of 256 bits, host API (copies and Match list inside)"}
+    # K7: ORB detect + describe of one 1080p grey frame through the host API (upload, 8 pyramid levels, FAST, Harris, the host's
+    # two retainBest selections, orientation, blur, 256 pair tests, download); OpenCV on one host core beside it when importable
+    from ransac_with_homography_b200.ransac import orb_detect_and_compute
+    base = rs.randint(0, 256, (h // 8 + 1, w // 8 + 1)).astype(np.float32)
+    gray = np.clip(np.kron(base, np.ones((8, 8), np.float32))[:h, :w] + rs.randn(h, w).astype(np.float32) * 4, 0, 255).astype(np.uint8)
+    for _ in range(3):
+        kp, ds = orb_detect_and_compute(gray, 500, as_arrays=True)
+    t0 = time.perf_counter()
+    for _ in range(10):
+        kp, ds = orb_detect_and_compute(gray, 500, as_arrays=True)
+    rec = {"ms_per_call": (time.perf_counter() - t0) / 10 * 1e3, "keypoints": int(len(kp)), "frame": [h, w],
+           "what": "K7 ORB (cv2.ORB_create().detectAndCompute), 1080p grey frame, host API"}
+    try:
+        import cv2
+        cv2.setNumThreads(1)
+        orb = cv2.ORB_create()
+        orb.detectAndCompute(gray, None)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            k2, d2 = orb.detectAndCompute(gray, None)
+        rec["opencv_cpu_ms_per_call"] = (time.perf_counter() - t0) / 3 * 1e3
+        rec["identical_to_opencv"] = bool(len(k2) == len(kp) and np.array_equal(d2, ds) and
+                                          np.array_equal(np.float32([[k.pt[0], k.pt[1], k.angle, k.response] for k in k2]), kp[:, [0, 1, 3, 4]]))
+    except ImportError:
+        pass
+    out["orb"] = rec
     return out
 
 

@@ -1507,6 +1507,18 @@ int b200geo_orb_host(b200geo_ctx *ctx, const uint8_t *gray, int height, int widt
     orb_blur_kernel<<<dim3((max_w + 255) / 256, max_h, ORB_LEVELS), 256, 0, 0>>>(d_pyr, d_blur, L);      // runs under the host's selection below
     B2G_CHECK_LAUNCH(ctx);
     B2G_CUDA(cudaStreamSynchronize(0));
+    if (const char *dump = getenv("B200GEO_ORB_DUMP")) {           // debugging aid: pyramid, scores and level table to a file
+        std::vector<uint8_t> hp((size_t)bytes), hs((size_t)bytes);
+        B2G_CUDA(cudaMemcpy(hp.data(), d_pyr, (size_t)bytes, cudaMemcpyDeviceToHost));
+        B2G_CUDA(cudaMemcpy(hs.data(), d_score, (size_t)bytes, cudaMemcpyDeviceToHost));
+        if (FILE *f = fopen(dump, "wb")) {
+            fwrite(&bytes, sizeof bytes, 1, f);
+            fwrite(&L, sizeof L, 1, f);
+            fwrite(hp.data(), 1, hp.size(), f);
+            fwrite(hs.data(), 1, hs.size(), f);
+            fclose(f);
+        }
+    }
     // ---- selection on the host, level by level, exactly as computeKeyPoints orders it ----
     std::vector<OrbCandidate> recs;
     std::vector<OrbKp> level_kps[ORB_LEVELS];

@@ -99,17 +99,24 @@ orb_fast_kernel(const uint8_t *__restrict__ pyr, uint8_t *__restrict__ score, co
     d[4] = c[3] - v;           d[5] = c[-p + 3] - v;      d[6] = c[-2 * p + 2] - v;  d[7] = c[-3 * p + 1] - v;
     d[8] = c[-3 * p] - v;      d[9] = c[-3 * p - 1] - v;  d[10] = c[-2 * p - 2] - v; d[11] = c[-p - 3] - v;
     d[12] = c[-3] - v;         d[13] = c[p - 3] - v;      d[14] = c[2 * p - 2] - v;  d[15] = c[3 * p - 1] - v;
-    int best = -256;
+    // min / max over the 16 windows of 9 consecutive ring pixels by doubling (windows of 2, 4, 8, then one more element).
+    // (The direct form -- for every start k a running min and max over d[(k + j) & 15] -- is miscompiled by nvcc 12.9 for
+    // sm_100a: the min / max chains are fused into 3-input VIMNMX3 with the two roles exchanged, and the kernel returned the
+    // largest ring difference instead; isolated reproducer and this form checked on the device against the host on 2e5 rings.)
+    int m2[16], M2[16], m4[16], M4[16], m8[16], M8[16];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        int lo = d[k], hi = d[k];
+    for (int i = 0; i < 16; ++i) { m2[i] = min(d[i], d[(i + 1) & 15]); M2[i] = max(d[i], d[(i + 1) & 15]); }
 #pragma unroll
-        for (int j = 1; j < 9; ++j) {
-            lo = min(lo, d[(k + j) & 15]);
-            hi = max(hi, d[(k + j) & 15]);
-        }
-        best = max(best, max(lo, -hi));
+    for (int i = 0; i < 16; ++i) { m4[i] = min(m2[i], m2[(i + 2) & 15]); M4[i] = max(M2[i], M2[(i + 2) & 15]); }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { m8[i] = min(m4[i], m4[(i + 4) & 15]); M8[i] = max(M4[i], M4[(i + 4) & 15]); }
+    int bright = -256, dark = 256;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        bright = max(bright, min(m8[i], d[(i + 8) & 15]));
+        dark = min(dark, max(M8[i], d[(i + 8) & 15]));
     }
+    const int best = max(bright, -dark);
     score[lv.ofs + (long long)(y + ORB_BORDER) * lv.pitch + (x + ORB_BORDER)] = best > ORB_FAST_T ? (uint8_t)(best - 1) : (uint8_t)0;
 }
 
