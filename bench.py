@@ -37,10 +37,11 @@ sys.path.insert(0, ROOT)
 
 FLOP_PER_PAIR = 25.0          # algorithmic FLOP per hypothesis x correspondence, fwd loss
 # DRAM traffic of the dominant kernels from the committed ncu --set full captures (dram__bytes_read + write):
-#   warp_pipe_kernel, profiles/r01_warp_pipe_v15.ncu-rep: 400.0 MB + 364.6 MB for 64 frames 1080p = 5.76 B per output pixel
-#   score_fast_kernel, profiles/r01_score_fast_K200k.ncu-rep: 8.6 MB for 200k x 20k pairs (FP32-bound: traffic is incidental)
-WARP_TRAFFIC_B_PER_PIXEL = (399.999232e6 + 364.638208e6) / (64 * 1080 * 1920)
-SCORE_TRAFFIC_B_PER_PAIR = 8.584448e6 / (200000 * 20000)
+#   warp_strip_kernel, profiles/r02_strip_v6.ncu-rep: 442.2 MB + 361.0 MB for 64 frames 1080p = 6.05 B per output pixel
+#   score_fast_kernel, profiles/r02_score_fast.ncu-rep: 41.5 MB + 3.9 MB for 1M x 20k pairs (FP32-bound: traffic is incidental)
+# (constants of those captures scaled by the launch's units, not per-run measurements: re-captured whenever a kernel changes)
+WARP_TRAFFIC_B_PER_PIXEL = (442.207744e6 + 361.041408e6) / (64 * 1080 * 1920)
+SCORE_TRAFFIC_B_PER_PAIR = (41.497088e6 + 3.899392e6) / (1000000 * 20000)
 C3 = dict(M=20000, K=1_000_000, th=3.0, d=99.0, seed=1, idx_seed=0)
 C4 = dict(frames=4096, h=1080, w=1920, jitter=0.05)
 
@@ -369,7 +370,7 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
-def timed_steps(torch, dist, world, fn, steps, warmup, flush=None):
+def timed_steps(torch, dist, world, fn, steps, warmup, flush=None, per_step=None):
     """W warm-up steps, then K timed steps (CUDA events on the current stream; optional L2 flush
     between steps, outside the events); barrier + synchronize on both sides; max over ranks.
     Returns (total ms over the K steps as max over ranks)."""
@@ -391,6 +392,8 @@ def timed_steps(torch, dist, world, fn, steps, warmup, flush=None):
         dist.barrier()
     torch.cuda.synchronize()
     ms = sum(a.elapsed_time(b) for a, b in ev)
+    if per_step is not None:
+        per_step.extend(a.elapsed_time(b) for a, b in ev)
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -435,7 +438,7 @@ def bench_ransac(torch, dist, rank, world, args, ctx, peaks, local_gpu):
     clocks = cs.summary()
     roof = {"bound": "fp32", "kernel": "score (K2)", "achieved": flops / k_avg_s / 1e12, "peak": peak_tflops, "unit": "TFLOP/s",
             "frac": flops / k_avg_s / 1e12 / peak_tflops, "traffic": SCORE_TRAFFIC_B_PER_PAIR * (hi - lo) * M,
-            "traffic_source": "ncu dram bytes per pair (profiles/r01_score_fast_K200k.ncu-rep) x pairs of this launch",
+            "traffic_source": "ncu dram bytes per pair (profiles/r02_score_fast.ncu-rep) x pairs of this launch",
             "peak_source": f"148 SM x 128 FP32 lanes x 2 x sm_max_mhz ({peaks['sm_max_mhz']:.0f} MHz, MEASURED_PEAKS.json: {peaks['source']})",
             "algorithmic_flop_per_hyp_pt": FLOP_PER_PAIR, "kernel_ms": k_avg_s * 1e3,
             "kernel_share_of_step": (k_avg_s * 1e3) / (ms / args.steps)}
@@ -522,19 +525,30 @@ def bench_warp(torch, dist, rank, world, args, ctx, peaks, local_gpu):
     def step():
         device.warp_resident(src, dst, jobs_dev, n, w, h, 3, "bilinear", layout=layout)
 
+    # one cold call after a pause, timed alone: the rate before the power cap pulls the SM clock down (burst); the timed steps
+    # below run back to back at the clock the 1000 W cap allows (sustained: tools/loop_strip.py shows 1965 -> ~1670 MHz from the
+    # second call on), and `value` is the sustained figure
+    step(); torch.cuda.synchronize(); time.sleep(1.0)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); step(); e1.record(); torch.cuda.synchronize()
+    burst_ms = e0.elapsed_time(e1)
     l0 = ctx.launch_count()
+    steps_ms = []
     with ClockSampler(local_gpu) as cs:
-        ms = timed_steps(torch, dist, world, step, args.steps, args.warmup, None)
+        ms = timed_steps(torch, dist, world, step, args.steps, args.warmup, None, per_step=steps_ms)
     launches = (ctx.launch_count() - l0) * args.steps // (args.steps + args.warmup)
     pix = total * h * w
     value = pix * args.steps / (ms / 1e3) / 1e9
     bytes_per_launch = 2.0 * n * per_frame                      # each source byte once + each output byte once
     k_avg_s = ms / args.steps / 1e3
-    roof = {"bound": "hbm", "kernel": "warp_pipe_kernel (K4, bilinear u8 RGB; + warp_setup_kernel, <1% of the step)", "achieved": bytes_per_launch / k_avg_s / 1e9, "peak": peaks["hbm_gbs"],
+    roof = {"bound": "hbm", "kernel": "warp_strip_kernel (K4, bilinear u8 RGB; + warp_route_setup_kernel 2.7 %, warp_pipe_kernel for the tiles the strips leave, warp_fixup_kernel)", "achieved": bytes_per_launch / k_avg_s / 1e9, "peak": peaks["hbm_gbs"],
             "unit": "GB/s", "frac": bytes_per_launch / k_avg_s / 1e9 / peaks["hbm_gbs"], "traffic": WARP_TRAFFIC_B_PER_PIXEL * n * h * w,
-            "traffic_source": "ncu dram bytes per output pixel (profiles/r01_warp_pipe_v15.ncu-rep, 64 frames) x pixels of this launch",
+            "traffic_source": "ncu dram bytes per output pixel (profiles/r02_strip_v6.ncu-rep, 64 frames) x pixels of this launch",
             "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peaks['source']})", "algorithmic_bytes_per_pixel": 6.0,
-            "kernel_ms": k_avg_s * 1e3, "kernel_share_of_step": 1.0}
+            "kernel_ms": k_avg_s * 1e3, "kernel_share_of_step": 1.0,
+            "burst": {"ms": burst_ms, "achieved": bytes_per_launch / burst_ms / 1e6, "frac": bytes_per_launch / burst_ms / 1e6 / peaks["hbm_gbs"],
+                      "what": "one launch sequence after a 1 s pause (SM clock at its maximum); the timed steps run under sw_power_cap"},
+            "step_ms": [round(v, 3) for v in steps_ms]}
 
     # end to end on a bounded batch: pinned host frames in, pinned host frames out, through the host-buffer entry
     # point b200geo_warp_batch_host (chunked host->device / warp / device->host pipeline inside the library)
@@ -648,32 +662,42 @@ def bench_aux(torch, ctx):
         m = match_hamming(A, Bd, True)
     out["match_hamming"] = {"ms_per_call": (time.perf_counter() - t0) / 20 * 1e3, "matches": len(m),
                             "what": "K6 hamming_best_kernel + cross-check, 500 x 500 descriptors of 256 bits, host API (copies and Match list inside)"}
-    # K7: ORB detect + describe of one 1080p grey frame through the host API (upload, 8 pyramid levels, FAST, Harris, the host's
-    # two retainBest selections, orientation, blur, 256 pair tests, download); OpenCV on one host core beside it when importable
+    # K7: ORB detect + describe through the host API (upload, grey conversion, 8 pyramid levels, FAST, Harris, the host's two
+    # retainBest selections, orientation, blur, 256 pair tests, download) on the reference's own C1 image (tests/golden/foto1A.jpg,
+    # 683 x 1024) and on a synthetic 1080p frame of 8 x 8 blocks + noise (~20x the FAST candidates of a photograph: the host's
+    # ordering of the candidates dominates there); OpenCV on one host core beside it when importable
+    from ransac_with_homography_b200 import imgio
     from ransac_with_homography_b200.ransac import orb_detect_and_compute
     base = rs.randint(0, 256, (h // 8 + 1, w // 8 + 1)).astype(np.float32)
-    gray = np.clip(np.kron(base, np.ones((8, 8), np.float32))[:h, :w] + rs.randn(h, w).astype(np.float32) * 4, 0, 255).astype(np.uint8)
-    for _ in range(3):
-        kp, ds = orb_detect_and_compute(gray, 500, as_arrays=True)
-    t0 = time.perf_counter()
-    for _ in range(10):
-        kp, ds = orb_detect_and_compute(gray, 500, as_arrays=True)
-    rec = {"ms_per_call": (time.perf_counter() - t0) / 10 * 1e3, "keypoints": int(len(kp)), "frame": [h, w],
-           "what": "K7 ORB (cv2.ORB_create().detectAndCompute), 1080p grey frame, host API"}
+    blocky = np.clip(np.kron(base, np.ones((8, 8), np.float32))[:h, :w] + rs.randn(h, w).astype(np.float32) * 4, 0, 255).astype(np.uint8)
     try:
         import cv2
         cv2.setNumThreads(1)
-        orb = cv2.ORB_create()
-        orb.detectAndCompute(gray, None)
-        t0 = time.perf_counter()
-        for _ in range(3):
-            k2, d2 = orb.detectAndCompute(gray, None)
-        rec["opencv_cpu_ms_per_call"] = (time.perf_counter() - t0) / 3 * 1e3
-        rec["identical_to_opencv"] = bool(len(k2) == len(kp) and np.array_equal(d2, ds) and
-                                          np.array_equal(np.float32([[k.pt[0], k.pt[1], k.angle, k.response] for k in k2]), kp[:, [0, 1, 3, 4]]))
     except ImportError:
-        pass
-    out["orb"] = rec
+        cv2 = None
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tests", "golden", "foto1A.jpg")
+    photo = np.ascontiguousarray(cv2.imread(path)[:, :, ::-1]) if cv2 is not None else imgio.imread(path, order="rgb")
+    for key, img, what in (("orb", photo, "C1 image foto1A.jpg 683 x 1024 RGB (grey conversion on the device)"), ("orb_1080p_blocks", blocky, "synthetic 1080p grey frame, 8 x 8 blocks + noise")):
+        for _ in range(3):
+            kp, ds = orb_detect_and_compute(img, 500, as_arrays=True)
+        t0 = time.perf_counter()
+        for _ in range(10):
+            kp, ds = orb_detect_and_compute(img, 500, as_arrays=True)
+        rec = {"ms_per_call": (time.perf_counter() - t0) / 10 * 1e3, "keypoints": int(len(kp)), "frame": list(img.shape[:2]),
+               "what": "K7 ORB (cv2.cvtColor + cv2.ORB_create().detectAndCompute), host API: " + what}
+        if cv2 is not None:
+            orb = cv2.ORB_create()
+            g = cv2.cvtColor(img, cv2.COLOR_RGB2GRAY) if img.ndim == 3 else img
+            orb.detectAndCompute(g, None)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                g = cv2.cvtColor(img, cv2.COLOR_RGB2GRAY) if img.ndim == 3 else img
+                k2, d2 = orb.detectAndCompute(g, None)
+            rec["opencv_cpu_ms_per_call"] = (time.perf_counter() - t0) / 3 * 1e3
+            rec["opencv_threads"] = 1
+            rec["identical_to_opencv"] = bool(len(k2) == len(kp) and np.array_equal(d2, ds) and
+                                              np.array_equal(np.float32([[k.pt[0], k.pt[1], k.angle, k.response] for k in k2]), kp[:, [0, 1, 3, 4]]))
+        out[key] = rec
     return out
 
 

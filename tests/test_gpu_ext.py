@@ -6,6 +6,19 @@ import pytest
 from oracle import ref_numpy as R
 
 pytestmark = pytest.mark.gpu
+REPORT = {}
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _write_report():
+    """Census of what these tests measured -> gpurun_out/PARITY_r02_ext.json (copied to profiles/ by hand)."""
+    yield
+    import json
+    import os
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    with open(os.path.join(out, "PARITY_r02_ext.json"), "w") as f:
+        json.dump(REPORT, f, indent=1, sort_keys=True)
 
 
 @pytest.mark.parametrize("ch", [1, 2, 4])
@@ -48,6 +61,7 @@ def test_cylindericl_map_equals_reference(golden, f):
     assert np.array_equal(o, R.cylindrical_warp(img, np.array([[f, 0, w / 2], [0, f, h / 2], [0, 0, 1]])))
     t = o[..., 3] == 255
     assert np.array_equal(o[t], ref[t]) and not o[~t].any()       # the reference leaves the unwritten pixels uninitialised
+    REPORT[f"cylindericlMap_f{f}"] = {"written_pixel_share": float(t.mean()), "written_pixels_differing_from_reference": int((o[t] != ref[t]).any(-1).sum())}
 
 
 def test_cylindrical_warp_general_intrinsics(golden):
@@ -94,6 +108,7 @@ def test_jpeg_decode_against_cv2(name):
     d = np.abs(got.astype(np.int16) - ref.astype(np.int16))
     census = {"max": int(d.max()), "mean": float(d.mean()), "p99": float(np.percentile(d, 99)), "equal": float((d == 0).mean())}
     print("jpeg decode census", name, census)
+    REPORT["jpeg_decode_vs_cv2_" + name] = dict(census, psnr_db=float(_psnr(got, ref)))
     assert census["mean"] < 1.5 and census["p99"] <= 12 and _psnr(got, ref) > 35, census
     # device-resident form, RGB order (what ransac.example1 makes of cv2.imread with [:, :, ::-1])
     with open(path, "rb") as f:
@@ -119,6 +134,7 @@ def test_jpeg_encode_round_trip():
     assert back.shape == img.shape
     p_ours, p_cv = _psnr(back, img), _psnr(ref_back, img)
     print("jpeg encode: psnr ours", p_ours, "cv2", p_cv, "bytes ours", len(data), "cv2", len(ref_bytes))
+    REPORT["jpeg_encode_q95_foto1B"] = {"psnr_db": float(p_ours), "cv2_psnr_db": float(p_cv), "bytes": len(data), "cv2_bytes": len(ref_bytes)}
     # nvJPEG's quantisation / colour conversion give 43.7 dB where libjpeg-turbo gives 49.0 dB at the same size on this image (B200, r02)
     assert p_ours > 40.0 and p_ours > p_cv - 7.0 and 0.5 < len(data) / len(ref_bytes) < 2.0
     t = torch.from_numpy(np.ascontiguousarray(img[:, :, ::-1])).cuda()

@@ -12,6 +12,19 @@ from conftest import GOLDEN
 from oracle import orb_numpy as O
 
 pytestmark = pytest.mark.gpu
+REPORT = {}
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _write_report():
+    """Census of what these tests measured -> gpurun_out/PARITY_r02_orb.json (copied to profiles/ by hand)."""
+    yield
+    import json
+    import os
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    with open(os.path.join(out, "PARITY_r02_orb.json"), "w") as f:
+        json.dump(REPORT, f, indent=1, sort_keys=True)
 PATTERN = np.load(os.path.join(GOLDEN, "orb_pattern.npy")).astype(np.int64)
 
 
@@ -50,6 +63,9 @@ def test_orb_equals_opencv_on_the_reference_images(golden, name, nf):
     kps, ds = orb_detect_and_compute(_jpeg_rgb(name), nf)
     ref = z[tag + "__kp"]
     got = np.array([[k.pt[0], k.pt[1], k.size, k.angle, k.response, k.octave] for k in kps], np.float32)
+    REPORT[tag] = {"keypoints": int(len(got)), "opencv_keypoints": int(len(ref)),
+                   "keypoint_fields_differing": int((got.view(np.uint32) != ref.view(np.uint32)).sum()) if got.shape == ref.shape else -1,
+                   "descriptor_bits_differing": int(np.unpackbits(ds ^ z[tag + "__desc"]).sum()) if ds.shape == z[tag + "__desc"].shape else -1}
     assert got.shape == ref.shape and np.array_equal(got.view(np.uint32), ref.view(np.uint32))
     assert np.array_equal(ds, z[tag + "__desc"])
     assert kps[0].class_id == -1 and isinstance(kps[0].pt, tuple)
@@ -81,6 +97,7 @@ def test_stitching_front_end_feeds_ransac_the_reference_points(golden):
     pa, pb = np.float32([k.pt for k in ka]), np.float32([k.pt for k in kb])
     assert np.array_equal(np.float32([pa[x.queryIdx] for x in m]), z["pair_ptsA"])
     assert np.array_equal(np.float32([pb[x.trainIdx] for x in m]), z["pair_ptsB"])
+    REPORT["stitching_front_end_foto1A_foto1B"] = {"matches": len(m), "point_lists_equal_to_opencv_pipeline": True}
 
 
 def test_stitching_end_to_end_on_the_reference_pair():
