@@ -1528,7 +1528,19 @@ int b200geo_orb_host(b200geo_ctx *ctx, const uint8_t *gray, int height, int widt
         if (!n) continue;
         recs.resize(n);
         B2G_CUDA(cudaMemcpy(recs.data(), d_cand + o.cand_ofs, sizeof(OrbCandidate) * n, cudaMemcpyDeviceToHost));
-        std::sort(recs.begin(), recs.end(), [](const OrbCandidate &a, const OrbCandidate &b) { return a.pos < b.pos; });      // FAST's row-major order
+        // FAST's row-major order (the kernel appends in whatever order its blocks run): rows by counting, then each row by x
+        if (n < 4096) std::sort(recs.begin(), recs.end(), [](const OrbCandidate &a, const OrbCandidate &b) { return a.pos < b.pos; });
+        else {
+            std::vector<unsigned> start((size_t)o.h + 1, 0u);
+            for (const OrbCandidate &r : recs) ++start[(r.pos >> 16) + 1];
+            for (int y = 0; y < o.h; ++y) start[y + 1] += start[y];
+            std::vector<OrbCandidate> byrow(n);
+            std::vector<unsigned> fill(start.begin(), start.end() - 1);
+            for (const OrbCandidate &r : recs) byrow[fill[r.pos >> 16]++] = r;
+            for (int y = 0; y < o.h; ++y)
+                std::sort(byrow.begin() + start[y], byrow.begin() + start[y + 1], [](const OrbCandidate &a, const OrbCandidate &b) { return a.pos < b.pos; });
+            recs.swap(byrow);
+        }
         std::vector<OrbKp> &kps = level_kps[lv];
         kps.resize(n);
         for (unsigned i = 0; i < n; ++i) kps[i] = OrbKp{(int)(recs[i].pos & 0xFFFFu), (int)(recs[i].pos >> 16), (float)recs[i].score, recs[i].harris};

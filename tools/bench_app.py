@@ -77,5 +77,37 @@ out["C2_scanner_2480x3508_ms"] = {"ours": best(lambda: hg.transformImage(img.cop
 v2 = np.array([[0, 840, 840, 0], [0, 0, 1188, 1188], [1, 1, 1, 1]], np.float64)
 hg.transformImage(img.copy(), u, v2, box=[1188, 840])
 out["C2_scanner_840x1188_ms"] = {"ours": best(lambda: hg.transformImage(img.copy(), u, v2, box=[1188, 840]))}
+# the whole Stitch button (ransac.example1 / app.py:364): stitching(foto1A, foto1B, "fwd", blending="Rate") on the reference's own pair,
+# ours (no OpenCV on the path) against the unmodified reference (oracle/_ref: cv2 ORB + BFMatcher, numpy RANSAC, numpy warp + blend)
+try:
+    import cv2
+    from ransac_with_homography_b200.ransac import stitching
+    imA = np.ascontiguousarray(cv2.imread(os.path.join(ROOT, "tests", "golden", "foto1A.jpg"))[:, :, ::-1])
+    imB = np.ascontiguousarray(cv2.imread(os.path.join(ROOT, "tests", "golden", "foto1B.jpg"))[:, :, ::-1])
+
+    def ours_stitch():
+        np.random.seed(0)
+        with redirect_stdout(io.StringIO()):
+            return stitching(imA.copy(), imB.copy(), "fwd", blending="Rate", blendrate=0.2)
+    ours_stitch()
+    rec = {"ours": best(ours_stitch)}
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    if os.path.exists(os.path.join(ref_dir, "ransac.py")):
+        sys.path.insert(0, ref_dir)
+        cwd = os.getcwd()
+        os.chdir(ref_dir)
+        try:
+            import ransac as ref_ransac              # the unmodified reference
+
+            def ref_stitch():
+                np.random.seed(0)
+                with redirect_stdout(io.StringIO()):
+                    return ref_ransac.stitching(imA.copy(), imB.copy(), "fwd", blending="Rate", blendrate=0.2)
+            rec["reference"] = best(ref_stitch, 2)
+        finally:
+            os.chdir(cwd)
+    out["C1_stitching_foto1A_foto1B_ms"] = rec
+except ImportError:
+    pass
 out["host_cores"] = os.cpu_count()
 print(json.dumps(out))
