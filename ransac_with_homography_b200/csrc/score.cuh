@@ -393,9 +393,10 @@ score_fast_kernel(const float4 *__restrict__ pts, int M, const float *__restrict
     if (threadIdx.x == 0) wl_count[cta] = min(s_wl, wl_cap);
 }
 
-// Exact re-evaluation of the deferred chunks: one thread per (deferred chunk, correspondence).
-// Recomputes q with the scalar twin of fast_q2 (bit-identical), and for |q| <= band replaces the
-// fast decision by the reference-order chain's:  counts[slot] += exact - fast.
+// Exact re-evaluation of the deferred chunks: one thread per deferred chunk (its hypothesis, band and scaled rows are set up
+// once and its FAST_CHUNK correspondences walked in a loop -- one thread per (chunk, correspondence) repeated that set-up eight
+// times and was 7 % of the batched step).  Recomputes q with the scalar twin of fast_q2 (bit-identical), and for |q| <= band
+// replaces the fast decision by the reference-order chain's:  counts[slot] += exact - fast.
 template <int METHOD>
 __global__ void __launch_bounds__(256)
 score_fixup_kernel(const float4 *__restrict__ pts, int M, const float *__restrict__ H, int K_stride, float T,
@@ -406,10 +407,8 @@ score_fixup_kernel(const float4 *__restrict__ pts, int M, const float *__restric
     unsigned local = 0;
     // segment `sgm` of the list holds wl_count[sgm] entries of the CTA that filled it; a block takes whole segments
     for (unsigned sgm = blockIdx.x; sgm < n_seg; sgm += gridDim.x)
-    for (unsigned i = threadIdx.x, total = min(wl_count[sgm], wl_cap) * FAST_CHUNK; i < total; i += blockDim.x) {
-        const FastDeferred e = wl[(size_t)sgm * wl_cap + i / FAST_CHUNK];
-        const unsigned j = e.j0 + (unsigned)(i % FAST_CHUNK);
-        if (j >= (unsigned)M) continue;
+    for (unsigned i = threadIdx.x, total = min(wl_count[sgm], wl_cap); i < total; i += blockDim.x) {
+        const FastDeferred e = wl[(size_t)sgm * wl_cap + i];
         const unsigned b = e.slot / (unsigned)K_stride;
         float hx[9], hq[9];
 #pragma unroll
@@ -418,14 +417,19 @@ score_fixup_kernel(const float4 *__restrict__ pts, int M, const float *__restric
         hq[6] = __fmul_rn(T, hq[6]);
         hq[7] = __fmul_rn(T, hq[7]);
         hq[8] = __fmul_rn(T, hq[8]);
-        float4 p = __ldg(pts + (size_t)b * M + j);
-        if (METHOD == B200GEO_BACKWARD) p = make_float4(p.z, p.w, p.x, p.y);
-        const float q = fast_q1(hq, p.x, p.y, -__fmul_rn(p.z, invT), -__fmul_rn(p.w, invT));
-        if (fabsf(q) > band) continue;
-        const int exact_in = exact_err(hx, p.x, p.y, p.z, p.w) < T ? 1 : 0;
-        const int d = exact_in - (int)(__float_as_uint(q) >> 31);
+        const float4 *pp = pts + (size_t)b * M + e.j0;
+        const int n = min(FAST_CHUNK, M - (int)e.j0);
+        int d = 0;
+        for (int u = 0; u < n; ++u) {
+            float4 p = __ldg(pp + u);
+            if (METHOD == B200GEO_BACKWARD) p = make_float4(p.z, p.w, p.x, p.y);
+            const float q = fast_q1(hq, p.x, p.y, -__fmul_rn(p.z, invT), -__fmul_rn(p.w, invT));
+            if (fabsf(q) > band) continue;
+            const int exact_in = exact_err(hx, p.x, p.y, p.z, p.w) < T ? 1 : 0;
+            d += exact_in - (int)(__float_as_uint(q) >> 31);
+            ++local;
+        }
         if (d) atomicAdd(counts + e.slot, d);
-        ++local;
     }
     // one atomic per block: 300k threads adding to one word serialise at the L2 (measured: 188 us for a 125k-hypothesis shard,
     // more than the work of the kernel)
@@ -631,7 +635,7 @@ score_fast2_kernel(const float4 *__restrict__ pts, int M, const float *__restric
     if (threadIdx.x == 0) wl_count[cta] = min(s_wl, wl_cap);
 }
 
-// Exact settlement of the deferred reproj chunks: one thread per (deferred chunk, correspondence).
+// Exact settlement of the deferred reproj chunks: one thread per deferred chunk (see score_fixup_kernel).
 __global__ void __launch_bounds__(256)
 score_fixup2_kernel(const float4 *__restrict__ pts, int M, const float *__restrict__ H, const float *__restrict__ Hinv, int K_stride,
                     float T, const float *__restrict__ cmax, const FastDeferred *__restrict__ wl, const unsigned *__restrict__ wl_count,
@@ -640,10 +644,8 @@ score_fixup2_kernel(const float4 *__restrict__ pts, int M, const float *__restri
     const float Th = 0.5f * T, invTh = 1.0f / Th;
     unsigned local = 0;
     for (unsigned sgm = blockIdx.x; sgm < n_seg; sgm += gridDim.x)
-    for (unsigned i = threadIdx.x, total = min(wl_count[sgm], wl_cap) * FAST_CHUNK; i < total; i += blockDim.x) {
-        const FastDeferred e = wl[(size_t)sgm * wl_cap + i / FAST_CHUNK];
-        const unsigned j = e.j0 + (unsigned)(i % FAST_CHUNK);
-        if (j >= (unsigned)M) continue;
+    for (unsigned i = threadIdx.x, total = min(wl_count[sgm], wl_cap); i < total; i += blockDim.x) {
+        const FastDeferred e = wl[(size_t)sgm * wl_cap + i];
         const unsigned b = e.slot / (unsigned)K_stride;
         float hx[9], hix[9], f[9], g[9];
 #pragma unroll
@@ -653,13 +655,19 @@ score_fixup2_kernel(const float4 *__restrict__ pts, int M, const float *__restri
         fast2_bands(hix, cmax[b], T, a2, r2b);
 #pragma unroll
         for (int c = 6; c < 9; ++c) { f[c] = __fmul_rn(Th, f[c]); g[c] = __fmul_rn(Th, g[c]); }
-        const float4 p = __ldg(pts + (size_t)b * M + j);
-        float q1, r1, q2, r2;
-        fast2_q1(f, p.x, p.y, -__fmul_rn(p.z, invTh), -__fmul_rn(p.w, invTh), q1, r1);
-        fast2_q1(g, p.z, p.w, -__fmul_rn(p.x, invTh), -__fmul_rn(p.y, invTh), q2, r2);
-        if (fast2_decide(q1, r1, q2, r2, a1, r1b, a2, r2b) != 2) continue;
-        if (exact_loss<B200GEO_REPROJ>(hx, hix, p) < T) atomicAdd(counts + e.slot, 1);
-        ++local;
+        const float4 *pp = pts + (size_t)b * M + e.j0;
+        const int n = min(FAST_CHUNK, M - (int)e.j0);
+        int d = 0;
+        for (int u = 0; u < n; ++u) {
+            const float4 p = __ldg(pp + u);
+            float q1, r1, q2, r2;
+            fast2_q1(f, p.x, p.y, -__fmul_rn(p.z, invTh), -__fmul_rn(p.w, invTh), q1, r1);
+            fast2_q1(g, p.z, p.w, -__fmul_rn(p.x, invTh), -__fmul_rn(p.y, invTh), q2, r2);
+            if (fast2_decide(q1, r1, q2, r2, a1, r1b, a2, r2b) != 2) continue;
+            if (exact_loss<B200GEO_REPROJ>(hx, hix, p) < T) ++d;
+            ++local;
+        }
+        if (d) atomicAdd(counts + e.slot, d);
     }
     // one atomic per block: 300k threads adding to one word serialise at the L2 (measured: 188 us for a 125k-hypothesis shard,
     // more than the work of the kernel)
