@@ -110,3 +110,14 @@ def test_stitching_end_to_end_on_the_reference_pair():
     assert out.dtype == np.uint8 and out.ndim == 3 and out.shape[2] == 3
     assert out.shape[0] >= B.shape[0] and out.shape[1] > B.shape[1] and out.shape[1] < 3 * B.shape[1]
     assert (out.reshape(-1, 3).any(1)).mean() > 0.5
+
+
+def test_orb_short_fuzz_against_live_opencv():
+    """tools/fuzz_orb.py (random sizes, contents, feature budgets, grey / RGB input against OpenCV on this machine): a short run."""
+    pytest.importorskip("cv2")
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_orb.py"), "40", "3"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "0 failures" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    REPORT["fuzz_orb_short"] = r.stdout.strip().splitlines()[-1]
