@@ -175,11 +175,19 @@ __device__ bool ws_setup(const b200geo_warp_job &J, int job, int c0, int r0, con
         else { y_lo = max(y_lo, iy_lo); y_hi = min(y_hi, iy_hi + ytap); }
     }
     if (x_hi < x_lo || y_hi < y_lo) { x_hi = x_lo; y_hi = y_lo; }
-    const int ax0 = (T.xc + x_lo) & ~3;
+    // staged origin: sampling straight from the raw rows works at any byte phase, so the footprint starts at its first pixel
+    // (the staged-entries form converts in chunks of four pixels and needs a 4-pixel-aligned origin)
+    const int ax0 = B2G_WS_DIRECT ? T.xc + x_lo : (T.xc + x_lo) & ~3;
     const int ox = ax0 - T.xc;
     const long long width = (long long)x_hi - ox + 1, rows = (long long)y_hi - y_lo + 1;
-    const long long P = max(8LL, (width + 3) & ~3LL);
-    if (P > WS_MAXP || rows > WS_ROWS) return false;
+    const long long P = B2G_WS_DIRECT ? max(2LL, width) : max(8LL, (width + 3) & ~3LL);
+    if (rows > WS_ROWS) return false;
+    if (B2G_WS_DIRECT) {
+        // the bytes of pixels ax0 .. ax0 + P (the right tap of the last pixel included) must lie inside the 160-byte box,
+        // whose first byte is the 16-byte-aligned one at or before pixel ax0 (reads past them return bytes nobody uses)
+        const long long ph = (3LL * ax0) & 15;
+        if (ph + 3 * (P + 1) > WS_RAW_W) return false;
+    } else if (P > WS_MAXP) return false;
     const int ay0 = T.yc + y_lo;
     // the one footprint per image that holds source pixel (0,0) (it must read as 0) stays with the old kernel
     const bool has00 = ax0 <= 0 && (long long)ax0 + P + 1 > 0 && ay0 <= 0 && (long long)ay0 + rows > 0;
@@ -189,7 +197,7 @@ __device__ bool ws_setup(const b200geo_warp_job &J, int job, int c0, int r0, con
     const long long img = J.src_offset / (tma.pitch * tma.image_rows);
     if (ox < -128 || y_lo < -128 || ox > 127 || y_lo > 127 || img > 65535) return false;
     S.mode = all_in ? WF_INTERIOR : WF_BORDER;
-    S.ox = (int8_t)ox; S.oy = (int8_t)y_lo; S.rows = (uint8_t)rows; S.chunks = (uint8_t)(P >> 2);
+    S.ox = (int8_t)ox; S.oy = (int8_t)y_lo; S.rows = (uint8_t)rows; S.chunks = (uint8_t)((P + 3) >> 2);
     S.tma_x = (3 * ax0) & ~15; S.phase = (uint8_t)((3 * ax0) & 15); S.tma_y = ay0;
     S.img = (uint16_t)img;
     // biased coefficients: n' = n + bias * w, so that  round(n' / w) = floor(n / w [+ 1/2 px for nn])  up to a quarter unit
