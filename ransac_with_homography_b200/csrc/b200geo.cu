@@ -188,8 +188,8 @@ int launch_score_exact(b200geo_ctx *ctx, const float *pts, int M, const float *H
     splits = M > 0 ? (M + per - 1) / per : 1;
     if (splits < 1) splits = 1;
     if (splits > 1) {
-        for (int b = 0; b < B; ++b)
-            B2G_CUDA(cudaMemsetAsync(counts + (size_t)b * K_stride + k_begin, 0, sizeof(int32_t) * (size_t)nk, st));
+        // (one 2-D memset for all pairs: a memset per pair was 0.3 ms of a 128-pair step)
+        B2G_CUDA(cudaMemset2DAsync(counts + k_begin, sizeof(int32_t) * (size_t)K_stride, 0, sizeof(int32_t) * (size_t)nk, (size_t)B, st));
     }
     dim3 grid(gx, splits, B);
     const float4 *p4 = (const float4 *)pts;
@@ -288,8 +288,7 @@ int launch_score(b200geo_ctx *ctx, const float *pts, int M, const float *H, cons
         int per2 = M;
         int splits2 = choose_splits((long long)gx2 * B, M, 2 * ctx->sm_count, FAST_CHUNK, 256, &per2);
         if (splits2 > 1)
-            for (int b = 0; b < B; ++b)
-                B2G_CUDA(cudaMemsetAsync(counts + (size_t)b * K_stride + k_begin, 0, sizeof(int32_t) * (size_t)nk, st));
+            B2G_CUDA(cudaMemset2DAsync(counts + k_begin, sizeof(int32_t) * (size_t)K_stride, 0, sizeof(int32_t) * (size_t)nk, (size_t)B, st));
         unsigned long long cap2 = (unsigned long long)nk * B * (unsigned long long)((M + FAST_CHUNK - 1) / FAST_CHUNK) / 32;
         FastDeferred *wl2;
         unsigned *wl2_count, n_seg2, seg_cap2;
@@ -308,8 +307,8 @@ int launch_score(b200geo_ctx *ctx, const float *pts, int M, const float *H, cons
     int per = M;
     int splits = choose_splits((long long)gx * B, M, 2 * ctx->sm_count, FAST_CHUNK, 256, &per);
     if (splits > 1) {
-        for (int b = 0; b < B; ++b)
-            B2G_CUDA(cudaMemsetAsync(counts + (size_t)b * K_stride + k_begin, 0, sizeof(int32_t) * (size_t)nk, st));
+        // (one 2-D memset for all pairs: a memset per pair was 0.3 ms of a 128-pair step)
+        B2G_CUDA(cudaMemset2DAsync(counts + k_begin, sizeof(int32_t) * (size_t)K_stride, 0, sizeof(int32_t) * (size_t)nk, (size_t)B, st));
     }
     // deferred exact work: capacity for a 1/64 trigger rate per (hypothesis, chunk), 1M .. 64M entries
     unsigned long long want_cap = (unsigned long long)nk * B * (unsigned long long)((M + FAST_CHUNK - 1) / FAST_CHUNK) / 64;
