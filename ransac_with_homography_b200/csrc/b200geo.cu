@@ -1443,6 +1443,17 @@ int b200geo_orb_host(b200geo_ctx *ctx, const uint8_t *gray, int height, int widt
         max_w = std::max(max_w, o.w);
         max_h = std::max(max_h, o.h);
     }
+    OrbRows R;
+    memset(&R, 0, sizeof R);
+    unsigned rows_total = 0, words_total = 0;
+    for (int lv = 0; lv < ORB_LEVELS; ++lv) {
+        const int rows = std::max(L.lv[lv].h - 2 * ORB_EDGE, 0), cols = std::max(L.lv[lv].w - 2 * ORB_EDGE, 0);
+        R.row_ofs[lv] = rows_total;
+        R.word_ofs[lv] = words_total;
+        R.words_per_row[lv] = (cols + 31) / 32;
+        rows_total += (unsigned)rows;
+        words_total += (unsigned)rows * (unsigned)R.words_per_row[lv];
+    }
     int per_level[ORB_LEVELS];
     {
         const float factor = (float)(1.0 / scale_factor);
@@ -1478,7 +1489,10 @@ int b200geo_orb_host(b200geo_ctx *ctx, const uint8_t *gray, int height, int widt
     if ((rc = scratch(ctx, S_ORB_SCORE, (size_t)bytes, (void **)&d_score))) return rc;
     if ((rc = scratch(ctx, S_ORB_BLUR, (size_t)bytes, (void **)&d_blur))) return rc;
     if ((rc = scratch(ctx, S_ORB_CAND, (size_t)cand_total * sizeof(OrbCandidate), (void **)&d_cand))) return rc;
-    if ((rc = scratch(ctx, S_MISC, 64, (void **)&d_counts))) return rc;
+    unsigned *d_rows, *d_masks;
+    if ((rc = scratch(ctx, S_MISC, 64 + sizeof(unsigned) * ((size_t)rows_total + words_total + 2), (void **)&d_counts))) return rc;
+    d_rows = d_counts + 16;
+    d_masks = d_rows + rows_total + 1;
     B2G_CUDA(cudaMemcpy2DAsync(d_in, (size_t)width * channels, gray, (size_t)pitch, (size_t)width * channels, (size_t)height, cudaMemcpyHostToDevice, 0));
     B2G_CUDA(cudaMemsetAsync(d_score, 0, (size_t)bytes, 0));
     B2G_CUDA(cudaMemsetAsync(d_counts, 0, sizeof(unsigned) * ORB_LEVELS, 0));
@@ -1498,7 +1512,14 @@ int b200geo_orb_host(b200geo_ctx *ctx, const uint8_t *gray, int height, int widt
         B2G_CHECK_LAUNCH(ctx);
     }
     if (max_w > 2 * ORB_EDGE && max_h > 2 * ORB_EDGE) {
-        orb_candidates_kernel<<<dim3((max_w - 2 * ORB_EDGE + 255) / 256, max_h - 2 * ORB_EDGE, ORB_LEVELS), 256, 0, 0>>>(d_pyr, d_score, L, d_cand, d_counts);
+        const int max_rows = max_h - 2 * ORB_EDGE;
+        orb_rowflags_kernel<<<dim3((max_rows + 3) / 4, ORB_LEVELS), 128, 0, 0>>>(d_score, L, R, d_masks, d_rows);
+        B2G_CHECK_LAUNCH(ctx);
+        orb_rowscan_kernel<<<ORB_LEVELS, 1024, 0, 0>>>(L, R, d_rows, d_counts);
+        B2G_CHECK_LAUNCH(ctx);
+        orb_rowwrite_kernel<<<dim3((max_rows + 3) / 4, ORB_LEVELS), 128, 0, 0>>>(d_score, L, R, d_masks, d_rows, d_cand);
+        B2G_CHECK_LAUNCH(ctx);
+        orb_harris_kernel<<<dim3((L.lv[0].cand_cap + 255) / 256, ORB_LEVELS), 256, 0, 0>>>(d_pyr, L, d_counts, d_cand);
         B2G_CHECK_LAUNCH(ctx);
     }
     unsigned counts[ORB_LEVELS];
@@ -1527,19 +1548,7 @@ int b200geo_orb_host(b200geo_ctx *ctx, const uint8_t *gray, int height, int widt
         if (!n) continue;
         recs.resize(n);
         B2G_CUDA(cudaMemcpy(recs.data(), d_cand + o.cand_ofs, sizeof(OrbCandidate) * n, cudaMemcpyDeviceToHost));
-        // FAST's row-major order (the kernel appends in whatever order its blocks run): rows by counting, then each row by x
-        if (n < 4096) std::sort(recs.begin(), recs.end(), [](const OrbCandidate &a, const OrbCandidate &b) { return a.pos < b.pos; });
-        else {
-            std::vector<unsigned> start((size_t)o.h + 1, 0u);
-            for (const OrbCandidate &r : recs) ++start[(r.pos >> 16) + 1];
-            for (int y = 0; y < o.h; ++y) start[y + 1] += start[y];
-            std::vector<OrbCandidate> byrow(n);
-            std::vector<unsigned> fill(start.begin(), start.end() - 1);
-            for (const OrbCandidate &r : recs) byrow[fill[r.pos >> 16]++] = r;
-            for (int y = 0; y < o.h; ++y)
-                std::sort(byrow.begin() + start[y], byrow.begin() + start[y + 1], [](const OrbCandidate &a, const OrbCandidate &b) { return a.pos < b.pos; });
-            recs.swap(byrow);
-        }
+        // (the records arrive in FAST's row-major order)
         std::vector<OrbKp> &kps = level_kps[lv];
         kps.resize(n);
         for (unsigned i = 0; i < n; ++i) kps[i] = OrbKp{(int)(recs[i].pos & 0xFFFFu), (int)(recs[i].pos >> 16), (float)recs[i].score, recs[i].harris};

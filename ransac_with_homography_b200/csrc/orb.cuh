@@ -9,9 +9,9 @@
 //   orb_level_kernel      level L (with its 32 px BORDER_REFLECT_101 frame) from level L-1: INTER_LINEAR_EXACT resize,
 //                         8.8 fixed-point coefficients from float64 coordinates, (sum + 2^15) >> 16
 //   orb_fast_kernel       FAST-9/16 corner score of every pixel of every level (0 = no corner)
-//   orb_candidates_kernel 3 x 3 non-maximum suppression + border filter + Harris response (7 x 7 block) -> candidate
-//                         records per level (unordered; the host sorts them into OpenCV's row-major order and runs
-//                         retainBest = std::nth_element + std::partition twice, as KeyPointsFilter does)
+//   orb_rowflags / rowscan / rowwrite / harris kernels: 3 x 3 non-maximum suppression + border filter -> candidate records per
+//                         level in FAST's row-major order (ballot words + row scan, no atomics, no sort) + Harris response;
+//                         the host runs retainBest = std::nth_element + std::partition twice on them, as KeyPointsFilter does
 //   orb_angle_kernel      intensity-centroid orientation, one warp per keypoint, cv::fastAtan2 in float32
 //   orb_blur_kernel       7 x 7 Gaussian, sigma 2: sepFilter2D's float32 path in the operation order of OpenCV's AVX2 build
 //   orb_describe_kernel   256 rotated pair tests per keypoint, one warp per keypoint (cos / sin come from the host's libm,
@@ -120,22 +120,103 @@ orb_fast_kernel(const uint8_t *__restrict__ pyr, uint8_t *__restrict__ score, co
     score[lv.ofs + (long long)(y + ORB_BORDER) * lv.pitch + (x + ORB_BORDER)] = best > ORB_FAST_T ? (uint8_t)(best - 1) : (uint8_t)0;
 }
 
-// Non-maximum suppression (strict, 8 neighbours), KeyPointsFilter::runByImageBorder(31) and HarrisResponses (orb.cpp:
-// 7 x 7 block, Sobel-like integer gradients, float32 score) of the survivors.
-__global__ void __launch_bounds__(256)
-orb_candidates_kernel(const uint8_t *__restrict__ pyr, const uint8_t *__restrict__ score, const OrbLevels L, OrbCandidate *__restrict__ cand,
-                      unsigned *__restrict__ counts)
+// Candidates in OpenCV's order without a sort.  FAST emits its keypoints row by row, left to right, and the two retainBest
+// selections that follow inherit that order (std::nth_element's result depends on the input sequence), so the candidate list
+// must be row-major.  Three small kernels instead of an atomic append + a host sort:
+//   orb_rowflags_kernel   one warp per row of the level's interior (31 px margin: KeyPointsFilter::runByImageBorder): strict
+//                         3 x 3 non-maximum suppression of the FAST scores, one ballot word per 32 columns, the row's count
+//   orb_rowscan_kernel    exclusive scan of the row counts (one block per level) -> first record of every row, level totals
+//   orb_rowwrite_kernel   the same walk: position and FAST score of every flagged pixel to its slot (row offset + rank in the row)
+//   orb_harris_kernel     HarrisResponses (orb.cpp: 7 x 7 block, Sobel-like integer gradients, float32 score in OpenCV's
+//                         operation order), one thread per candidate
+struct OrbRows { unsigned row_ofs[ORB_LEVELS]; unsigned word_ofs[ORB_LEVELS]; int words_per_row[ORB_LEVELS]; };
+
+__global__ void __launch_bounds__(128)
+orb_rowflags_kernel(const uint8_t *__restrict__ score, const OrbLevels L, const OrbRows R, unsigned *__restrict__ masks, unsigned *__restrict__ row_count)
 {
-    const OrbLevel &lv = L.lv[blockIdx.z];
-    const int x = blockIdx.x * blockDim.x + threadIdx.x + ORB_EDGE, y = blockIdx.y + ORB_EDGE;
-    if (x >= lv.w - ORB_EDGE || y >= lv.h - ORB_EDGE) return;
-    const int p = lv.pitch;
-    const long long o = lv.ofs + (long long)(y + ORB_BORDER) * p + (x + ORB_BORDER);
-    const uint8_t *s = score + o;
-    const int v = s[0];
-    if (v == 0) return;
-    if (!(v > s[-1] && v > s[1] && v > s[-p - 1] && v > s[-p] && v > s[-p + 1] && v > s[p - 1] && v > s[p] && v > s[p + 1])) return;
-    const uint8_t *c = pyr + o;
+    const OrbLevel &lv = L.lv[blockIdx.y];
+    const int row = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    const int rows = lv.h - 2 * ORB_EDGE;
+    if (row >= rows) return;
+    const int y = row + ORB_EDGE, p = lv.pitch;
+    const uint8_t *srow = score + lv.ofs + (long long)(y + ORB_BORDER) * p + ORB_BORDER;
+    unsigned *mrow = masks + R.word_ofs[blockIdx.y] + (size_t)row * R.words_per_row[blockIdx.y];
+    unsigned n = 0;
+    for (int c = 0; c < R.words_per_row[blockIdx.y]; ++c) {
+        const int x = ORB_EDGE + 32 * c + lane;
+        bool f = false;
+        if (x < lv.w - ORB_EDGE) {
+            const uint8_t *s = srow + x;
+            const int v = s[0];
+            f = v != 0 && v > s[-1] && v > s[1] && v > s[-p - 1] && v > s[-p] && v > s[-p + 1] && v > s[p - 1] && v > s[p] && v > s[p + 1];
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, f);
+        if (lane == 0) mrow[c] = m;
+        n += __popc(m);
+    }
+    if (lane == 0) row_count[R.row_ofs[blockIdx.y] + row] = n;
+}
+
+// one block of 1024 threads per level; row_count -> exclusive offsets in place, counts[level] = total (clipped to the capacity)
+__global__ void __launch_bounds__(1024)
+orb_rowscan_kernel(const OrbLevels L, const OrbRows R, unsigned *__restrict__ row_count, unsigned *__restrict__ counts)
+{
+    __shared__ unsigned part[1024];
+    const OrbLevel &lv = L.lv[blockIdx.x];
+    const int rows = max(lv.h - 2 * ORB_EDGE, 0);
+    unsigned *rc = row_count + R.row_ofs[blockIdx.x];
+    const int per = (rows + 1023) / 1024, r0 = threadIdx.x * per, r1 = min(rows, r0 + per);
+    unsigned sum = 0;
+    for (int r = r0; r < r1; ++r) sum += rc[r];
+    part[threadIdx.x] = sum;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {                       // inclusive scan of the per-thread sums
+        const unsigned v = threadIdx.x >= d ? part[threadIdx.x - d] : 0u;
+        __syncthreads();
+        part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    unsigned run = part[threadIdx.x] - sum;
+    for (int r = r0; r < r1; ++r) { const unsigned c = rc[r]; rc[r] = run; run += c; }
+    if (threadIdx.x == 1023) counts[blockIdx.x] = min(part[1023], lv.cand_cap);
+}
+
+__global__ void __launch_bounds__(128)
+orb_rowwrite_kernel(const uint8_t *__restrict__ score, const OrbLevels L, const OrbRows R, const unsigned *__restrict__ masks,
+                    const unsigned *__restrict__ row_first, OrbCandidate *__restrict__ cand)
+{
+    const OrbLevel &lv = L.lv[blockIdx.y];
+    const int row = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= lv.h - 2 * ORB_EDGE) return;
+    const int y = row + ORB_EDGE;
+    const uint8_t *srow = score + lv.ofs + (long long)(y + ORB_BORDER) * lv.pitch + ORB_BORDER;
+    const unsigned *mrow = masks + R.word_ofs[blockIdx.y] + (size_t)row * R.words_per_row[blockIdx.y];
+    unsigned at = row_first[R.row_ofs[blockIdx.y] + row];
+    for (int c = 0; c < R.words_per_row[blockIdx.y]; ++c) {
+        const unsigned m = mrow[c];
+        if (m >> lane & 1u) {
+            const unsigned k = at + __popc(m & ((1u << lane) - 1u));
+            if (k < lv.cand_cap) {
+                const int x = ORB_EDGE + 32 * c + lane;
+                OrbCandidate rec;
+                rec.pos = ((unsigned)y << 16) | (unsigned)x; rec.score = srow[x]; rec.harris = 0.f;
+                cand[lv.cand_ofs + k] = rec;
+            }
+        }
+        at += __popc(m);
+    }
+}
+
+// Grid: (ceil(max candidates of a level / 256), levels)
+__global__ void __launch_bounds__(256)
+orb_harris_kernel(const uint8_t *__restrict__ pyr, const OrbLevels L, const unsigned *__restrict__ counts, OrbCandidate *__restrict__ cand)
+{
+    const OrbLevel &lv = L.lv[blockIdx.y];
+    const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= counts[blockIdx.y]) return;
+    OrbCandidate &rec = cand[lv.cand_ofs + k];
+    const int x = (int)(rec.pos & 0xFFFFu), y = (int)(rec.pos >> 16), p = lv.pitch;
+    const uint8_t *c = pyr + lv.ofs + (long long)(y + ORB_BORDER) * p + (x + ORB_BORDER);
     int a = 0, b = 0, cc = 0;
     for (int i = -3; i <= 3; ++i)
         for (int j = -3; j <= 3; ++j) {
@@ -147,13 +228,7 @@ orb_candidates_kernel(const uint8_t *__restrict__ pyr, const uint8_t *__restrict
     const float scale = __fdiv_rn(1.f, __fmul_rn(28.f, 255.f));                       // 1.f / ((1 << 2) * blockSize * 255.f)
     const float s4 = __fmul_rn(__fmul_rn(__fmul_rn(scale, scale), scale), scale);
     const float af = (float)a, bf = (float)b, cf = (float)cc, sum = __fadd_rn(af, bf);
-    const float r = __fmul_rn(__fsub_rn(__fsub_rn(__fmul_rn(af, bf), __fmul_rn(cf, cf)), __fmul_rn(__fmul_rn(0.04f, sum), sum)), s4);
-    const unsigned n = atomicAdd(counts + blockIdx.z, 1u);
-    if (n < lv.cand_cap) {
-        OrbCandidate rec;
-        rec.pos = ((unsigned)y << 16) | (unsigned)x; rec.score = (unsigned)v; rec.harris = r;
-        cand[lv.cand_ofs + n] = rec;
-    }
+    rec.harris = __fmul_rn(__fsub_rn(__fsub_rn(__fmul_rn(af, bf), __fmul_rn(cf, cf)), __fmul_rn(__fmul_rn(0.04f, sum), sum)), s4);
 }
 
 struct OrbUmax { int u[ORB_HALF_PATCH + 2]; };
