@@ -142,3 +142,21 @@ def test_jpeg_encode_round_trip():
     assert data2 == data                                          # same pixels, device-resident source
     with pytest.raises(ValueError):
         imgio.imwrite("/tmp/x.png", img)
+
+
+def test_jpeg_gray_file_and_bad_input():
+    """A single-component JPEG decodes to three equal channels (cv2.IMREAD_COLOR); garbage is an error, not a crash."""
+    cv2 = pytest.importorskip("cv2")
+    from ransac_with_homography_b200 import _cabi, imgio
+    rs = np.random.RandomState(1)
+    gray = cv2.GaussianBlur(rs.randint(0, 256, (75, 101)).astype(np.uint8), (0, 0), 2.0)
+    ok, data = cv2.imencode(".jpg", gray)
+    ref = cv2.imdecode(data, cv2.IMREAD_COLOR)
+    got = imgio.imdecode(data.tobytes())
+    assert got.shape == ref.shape == (75, 101, 3)
+    assert np.array_equal(got[..., 0], got[..., 1]) and np.array_equal(got[..., 1], got[..., 2])
+    assert np.abs(got.astype(np.int16) - ref.astype(np.int16)).max() <= 2
+    assert imgio.info(data.tobytes()) == (75, 101, 1)
+    with pytest.raises(_cabi.B200GeoError):
+        imgio.imdecode(b"not a jpeg at all" * 10)
+    assert imgio.imread("/nonexistent/file.jpg") is None

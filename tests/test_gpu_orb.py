@@ -121,3 +121,24 @@ def test_orb_short_fuzz_against_live_opencv():
     r = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_orb.py"), "40", "3"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "0 failures" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
     REPORT["fuzz_orb_short"] = r.stdout.strip().splitlines()[-1]
+
+
+def test_orb_edge_cases():
+    """Sizes with empty pyramid levels, tiny feature budgets, a constant image, and the capacity of the output buffers."""
+    cv2 = pytest.importorskip("cv2")
+    from ransac_with_homography_b200.ransac import orb_detect_and_compute
+    rs = np.random.RandomState(8)
+    for (h, w, nf) in ((30, 30, 500), (63, 200, 500), (200, 63, 500), (64, 65, 500), (120, 160, 1), (120, 160, 2), (120, 160, 0), (97, 1300, 37)):
+        img = cv2.GaussianBlur(rs.randint(0, 256, (h, w)).astype(np.uint8), (0, 0), 1.0)
+        kps, des = cv2.ORB_create(nf).detectAndCompute(img, None)
+        ref = np.array([[k.pt[0], k.pt[1], k.size, k.angle, k.response, k.octave] for k in kps], np.float32).reshape(-1, 6)
+        kp, ds = orb_detect_and_compute(img, nf, as_arrays=True)
+        assert kp.shape == ref.shape and np.array_equal(kp.view(np.uint32), ref.view(np.uint32)), (h, w, nf)
+        if len(ref):
+            assert np.array_equal(ds, des), (h, w, nf)
+        else:
+            assert ds is None
+    with pytest.raises(AssertionError):
+        orb_detect_and_compute(np.zeros((40, 40, 4), np.uint8))
+    with pytest.raises(AssertionError):
+        orb_detect_and_compute(np.zeros((40, 40), np.float32))
