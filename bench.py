@@ -416,6 +416,9 @@ def bench_ransac(torch, dist, rank, world, args, ctx, peaks, local_gpu):
     l2 = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")        # > 126 MB L2
     flush = lambda: l2.fill_(1)
     group = None
+    # N > 1: the per-rank winner records are exchanged by peer stores over NVLink / NVSwitch + a flag wait inside two single-block
+    # kernels (device.peer_setup: CUDA IPC inboxes); if the inboxes cannot be mapped the NCCL collectives stay in place
+    peer = device.peer_setup(group) if world > 1 and not os.environ.get("B200GEO_NO_PEER") else False
 
     def step():
         device.ransac(pts, idx, th, d, 4, "fwd", group=group, keys=keys, result=result, mask=mask)
@@ -486,13 +489,14 @@ def bench_ransac(torch, dist, rank, world, args, ctx, peaks, local_gpu):
         assert int(out_h[0]) == int(res[0]) and int(out_h[1]) == int(res[1]), "sharded e2e run disagrees with the device-resident run"
         h2d = world * pts_h.nbytes + idx_h.nbytes
         d2h = world * (32 * 8 + M)
-        e2e_how = ("per rank: pinned host correspondences + this rank's shard of the sample sets -> device.ransac_sharded (48-byte all-gather "
-                   "of the per-rank winner records) -> pinned host; bytes are the whole job's")
+        e2e_how = ("per rank: pinned host correspondences + this rank's shard of the sample sets -> device.ransac_sharded (48-byte winner records "
+                   + ("over peer memory" if peer else "by one NCCL all-gather") + ") -> pinned host; bytes are the whole job's")
     e2e = {"value": K * M / e2e_s, "unit": "hyp*pts/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
            "ms_per_step": e2e_s * 1e3, "how": e2e_how}
     rec = {"metric": "ransac_hyp_pts_per_s", "value": value, "unit": "hyp*pts/s", "ms_per_step": ms / args.steps,
            "config": {"workload": C3_WORKLOAD,
-                      "sharding": f"hypothesis blocks over {world} rank(s), one 16-byte all-reduce(MAX) per step",
+                      "sharding": f"hypothesis blocks over {world} rank(s), " + ("none" if world == 1 else ("48-byte winner records exchanged over peer memory (NVLink stores + flag wait), no collective"
+                                                                                         if peer else "one 16-byte all-reduce(MAX) per step (NCCL)")),
                       "l2": "256 MB buffer written between timed steps (inputs are 16.3 MB and L2-resident by nature)"},
            "roofline": roof, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
            "result": {"winner": int(res[0]), "inliers": int(res[1])}}

@@ -349,6 +349,22 @@ int b200geo_jpeg_encode(b200geo_ctx *ctx, const void *src, int height, int width
 int b200geo_orb_host(b200geo_ctx *ctx, const uint8_t *img, int height, int width, long long pitch, int channels, int nfeatures,
                      float *keypoints, uint8_t *descriptors, int capacity, int *n_out);
 
+/* ------------------------------------------------------------------------------------------------
+ * (9) The record exchange of a sharded search over peer memory (NVLink / NVSwitch) instead of a collective: one
+ *     process per GPU of one node.  b200geo_peer_export allocates this rank's inbox and returns its 64-byte CUDA
+ *     IPC handle; the caller gathers the handles of all ranks (any transport: they are host bytes) and passes the
+ *     array to b200geo_peer_open, which maps every other rank's inbox; after a barrier,
+ *     b200geo_ransac_exchange_peer_dev replaces the all-gather between b200geo_ransac_search_shard_dev and
+ *     b200geo_ransac_finish_recs_dev: it stores `rec` (48 bytes, device) into every rank's inbox and fills `recs`
+ *     (world x 48 bytes, device) with the records of all ranks -- two single-block kernels on `stream`, no host
+ *     synchronisation.  All ranks must call it the same number of times.  A rank that does not answer within about
+ *     two seconds contributes an empty record (the search then reports B200GEO_ERR_NOMODEL if no other rank has one).
+ * ---------------------------------------------------------------------------------------------- */
+int b200geo_peer_export(b200geo_ctx *ctx, int world, void *handle_out);
+int b200geo_peer_open(b200geo_ctx *ctx, int rank, int world, const void *handles);
+int b200geo_peer_close(b200geo_ctx *ctx);
+int b200geo_ransac_exchange_peer_dev(b200geo_ctx *ctx, const void *rec, void *recs, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -102,6 +102,10 @@ SIGNATURES = {
     "b200geo_match_hamming_host": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp]),
     "b200geo_remap_linear_host": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _i, _vp]),
     "b200geo_orb_host": (_i, [_vp, _vp, _i, _i, C.c_longlong, _i, _i, _vp, _vp, _i, _vp]),
+    "b200geo_peer_export": (_i, [_vp, _i, _vp]),
+    "b200geo_peer_open": (_i, [_vp, _i, _i, _vp]),
+    "b200geo_peer_close": (_i, [_vp]),
+    "b200geo_ransac_exchange_peer_dev": (_i, [_vp, _vp, _vp, _vp]),
     "b200geo_jpeg_info": (_i, [_vp, _vp, C.c_size_t, _vp, _vp, _vp]),
     "b200geo_jpeg_decode": (_i, [_vp, _vp, C.c_size_t, _i, _vp, C.c_longlong, _i, _vp]),
     "b200geo_jpeg_encode": (_i, [_vp, _vp, _i, _i, C.c_longlong, _i, _i, _i, _vp, C.c_size_t, _vp, _vp]),

@@ -69,6 +69,11 @@ int b200geo_destroy(b200geo_ctx *ctx)
         if (ctx->pinned) cudaFreeHost(ctx->pinned);
         if (ctx->order_event) cudaEventDestroy(ctx->order_event);
         jpeg_release(ctx);
+        if (ctx->peer_box) {
+            for (int r = 0; r < ctx->peer_world; ++r)
+                if (ctx->peer_map[r] && ctx->peer_map[r] != ctx->peer_box) cudaIpcCloseMemHandle(ctx->peer_map[r]);
+            cudaFree(ctx->peer_box);
+        }
         if (ctx->pipe_ready) {
             for (int i = 0; i < 3; ++i) cudaStreamDestroy(ctx->pipe_stream[i]);
             for (int i = 0; i < 3; ++i)
@@ -1602,6 +1607,81 @@ int b200geo_orb_host(b200geo_ctx *ctx, const uint8_t *gray, int height, int widt
     B2G_CHECK_LAUNCH(ctx);
     B2G_CUDA(cudaMemcpyAsync(descriptors, d_desc, (size_t)n * 32, cudaMemcpyDeviceToHost, 0));
     B2G_CUDA(cudaStreamSynchronize(0));
+    return B200GEO_OK;
+}
+
+int b200geo_peer_export(b200geo_ctx *ctx, int world, void *handle_out)
+{
+    B2G_ENTER(ctx);
+    B2G_ARG(world >= 1 && world <= PEER_MAX && handle_out);
+    if (ctx->peer_box) return fail(B200GEO_ERR_ARG, "peer exchange already set up on this context (b200geo_peer_close first)%s%s");
+    const size_t bytes = (size_t)2 * world * 64;
+    B2G_CUDA(cudaMalloc(&ctx->peer_box, bytes));
+    B2G_CUDA(cudaMemset(ctx->peer_box, 0, bytes));
+    B2G_CUDA(cudaDeviceSynchronize());
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "the handle travels as 64 bytes");
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, ctx->peer_box);
+    if (e != cudaSuccess) {
+        cudaFree(ctx->peer_box);
+        ctx->peer_box = nullptr;
+        return fail(B200GEO_ERR_CUDA, "cudaIpcGetMemHandle: %s%s", cudaGetErrorString(e));
+    }
+    memcpy(handle_out, &h, 64);
+    ctx->peer_world = world;
+    return B200GEO_OK;
+}
+
+int b200geo_peer_open(b200geo_ctx *ctx, int rank, int world, const void *handles)
+{
+    B2G_ENTER(ctx);
+    B2G_ARG(ctx->peer_box && world == ctx->peer_world && rank >= 0 && rank < world && handles);
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) { ctx->peer_map[r] = ctx->peer_box; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, static_cast<const char *>(handles) + 64 * (size_t)r, 64);
+        cudaError_t e = cudaIpcOpenMemHandle(&ctx->peer_map[r], h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            for (int q = 0; q < r; ++q)
+                if (q != rank && ctx->peer_map[q]) { cudaIpcCloseMemHandle(ctx->peer_map[q]); ctx->peer_map[q] = nullptr; }
+            return fail(B200GEO_ERR_CUDA, "cudaIpcOpenMemHandle: %s%s", cudaGetErrorString(e));
+        }
+    }
+    ctx->peer_rank = rank;
+    ctx->peer_epoch = 0ull;
+    return B200GEO_OK;
+}
+
+int b200geo_peer_close(b200geo_ctx *ctx)
+{
+    B2G_ENTER(ctx);
+    if (!ctx->peer_box) return B200GEO_OK;
+    cudaDeviceSynchronize();
+    for (int r = 0; r < ctx->peer_world; ++r)
+        if (ctx->peer_map[r] && ctx->peer_map[r] != ctx->peer_box) cudaIpcCloseMemHandle(ctx->peer_map[r]);
+    memset(ctx->peer_map, 0, sizeof ctx->peer_map);
+    cudaFree(ctx->peer_box);
+    ctx->peer_box = nullptr;
+    ctx->peer_world = 0;
+    return B200GEO_OK;
+}
+
+int b200geo_ransac_exchange_peer_dev(b200geo_ctx *ctx, const void *rec, void *recs, void *stream)
+{
+    B2G_ENTER(ctx);
+    cudaStream_t st = (cudaStream_t)stream;
+    stream_order(ctx, st);
+    B2G_ARG(rec && recs);
+    if (!ctx->peer_box || !ctx->peer_map[ctx->peer_rank]) return fail(B200GEO_ERR_ARG, "peer exchange is not set up (b200geo_peer_export / _open)%s%s");
+    PeerBoxes P;
+    memset(&P, 0, sizeof P);
+    for (int r = 0; r < ctx->peer_world; ++r) P.box[r] = static_cast<unsigned long long *>(ctx->peer_map[r]);
+    const unsigned long long epoch = ++ctx->peer_epoch;
+    peer_publish_kernel<<<1, PEER_MAX, 0, st>>>(static_cast<const WinRec *>(rec), P, ctx->peer_world, ctx->peer_rank, epoch);
+    B2G_CHECK_LAUNCH(ctx);
+    peer_gather_kernel<<<1, PEER_MAX, 0, st>>>(static_cast<unsigned long long *>(ctx->peer_box), ctx->peer_world, epoch, static_cast<WinRec *>(recs),
+                                               20000000ull);          // ~ 2 s of polling at 64 ns + the load's round trip
+    B2G_CHECK_LAUNCH(ctx);
     return B200GEO_OK;
 }
 

@@ -85,6 +85,10 @@ struct b200geo_ctx {
     int finish_done_n;
     void *pinned;          // small pinned staging block for scalar results
     size_t pinned_cap;
+    void *peer_box;        // this rank's inbox of the peer-memory record exchange (cudaMalloc, exported by CUDA IPC), or NULL
+    void *peer_map[64];    // every rank's inbox as mapped into this process (own rank: peer_box)
+    int peer_world, peer_rank;
+    unsigned long long peer_epoch;
     void *jpeg;            // b200geo::JpegState (nvJPEG handle and codec states), created by the first JPEG call
 };
 

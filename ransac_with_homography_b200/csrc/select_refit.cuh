@@ -282,6 +282,47 @@ __global__ void pack_winner_kernel(const unsigned long long *__restrict__ keys, 
     *rec = r;
 }
 
+// ---- the 48-byte winner records of a sharded search exchanged over peer memory (NVLink / NVSwitch) instead of a collective ----
+// Every rank owns an inbox in its own HBM: 2 parities x world slots of 64 bytes (record + epoch flag), mapped into every other
+// rank's address space (CUDA IPC).  peer_publish_kernel: thread r writes this rank's record into rank r's inbox (six 8-byte
+// peer stores, a system-scope fence, then the epoch as the flag).  peer_gather_kernel: thread r waits for rank r's flag in the
+// local inbox and copies the record into the contiguous array finish_kernel reads.  The parity alternates per exchange: a
+// rank can be at most one exchange ahead of the slowest one (it needs that rank's next record to get further), so a slot is
+// never overwritten before its reader has consumed it.
+constexpr int PEER_MAX = 64;
+struct PeerBoxes { unsigned long long *box[PEER_MAX]; };
+
+__global__ void peer_publish_kernel(const WinRec *__restrict__ rec, const PeerBoxes P, int world, int rank, unsigned long long epoch)
+{
+    const int r = threadIdx.x;
+    if (r >= world) return;
+    unsigned long long *slot = P.box[r] + ((size_t)(epoch & 1ull) * world + rank) * 8;
+    const unsigned long long *s = reinterpret_cast<const unsigned long long *>(rec);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) slot[i] = s[i];
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(slot + 7), "l"(epoch) : "memory");
+}
+
+// budget: spin iterations before giving up (a rank that never publishes must not hang this GPU): the record is then zero,
+// which finish_kernel reports as "no model"
+__global__ void peer_gather_kernel(unsigned long long *__restrict__ inbox, int world, unsigned long long epoch, WinRec *__restrict__ recs,
+                                   unsigned long long budget)
+{
+    const int r = threadIdx.x;
+    if (r >= world) return;
+    unsigned long long *slot = inbox + ((size_t)(epoch & 1ull) * world + r) * 8;
+    unsigned long long f = 0ull, spins = 0ull;
+    for (;;) {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(f) : "l"(slot + 7) : "memory");
+        if (f == epoch || ++spins > budget) break;
+        __nanosleep(64);
+    }
+    unsigned long long *d = reinterpret_cast<unsigned long long *>(recs) + (size_t)r * 6;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) d[i] = f == epoch ? slot[i] : 0ull;
+}
+
 constexpr int FINISH_THREADS = 256;
 constexpr int FINISH_NSUM = 25;      // inlier count + the 24 Gram sums
 

@@ -20,6 +20,9 @@ import torch
 from . import _cabi
 
 
+_peer_ready = {}      # device index -> world size the peer-memory inboxes were opened for (peer_setup)
+
+
 def _ctx(t: torch.Tensor) -> _cabi.Context:
     assert t.is_cuda, "device tensors required (no CPU fallback)"
     return _cabi.context(t.device.index if t.device.index is not None else torch.cuda.current_device())
@@ -108,6 +111,9 @@ def ransac(pts, idx, th, d, n=4, method="fwd", group=None, keys=None, result=Non
     if dist.is_available() and dist.is_initialized():
         world, rank = dist.get_world_size(group), dist.get_rank(group)
     lo, hi = shard_range(K, rank, world)
+    if world > 1 and _peer_ready.get(pts.device.index) == world and counts is None:
+        # peer-memory exchange set up (peer_setup): the winner records travel by peer stores, no collective at all
+        return ransac_sharded(pts, idx[lo:hi], lo, th, d, n, method, group=group, result=result, mask=mask)
     keys = ransac_search(pts, idx, lo, hi, th, thr, method, keys=keys, counts=counts)
     if world > 1:
         dist.all_reduce(keys, op=dist.ReduceOp.MAX, group=group)     # 16 bytes over NVLink
@@ -117,12 +123,53 @@ def ransac(pts, idx, th, d, n=4, method="fwd", group=None, keys=None, result=Non
 WINREC_BYTES = 48      # struct WinRec (csrc/select_refit.cuh): keys[2] + the sample indices each key names
 
 
+def peer_setup(group=None, device=None) -> bool:
+    """Open the peer-memory record exchange among the ranks of `group` (one process per GPU of ONE node): every rank allocates
+    an inbox in its HBM, the 64-byte CUDA IPC handles are all-gathered once, and every rank maps the others' inboxes
+    (b200geo_peer_export / _open).  `ransac_sharded` then exchanges its 48-byte winner records by peer stores over NVLink and a
+    flag wait instead of an NCCL all-gather.  Returns False (and leaves the collective path in place) if any rank cannot
+    export or map -- e.g. GPUs without peer access."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return False
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    dev = torch.cuda.current_device() if device is None else device
+    if world < 2 or world > 64:
+        return False
+    ctx = _cabi.context(dev)
+    h = np.zeros(64, np.uint8)
+    ok = ctx.lib.b200geo_peer_export(ctx.handle, world, _cabi.ptr(h)) == _cabi.OK
+    mine = torch.from_numpy(np.concatenate([h, np.array([1 if ok else 0], np.uint8)])).to(f"cuda:{dev}")
+    allh = torch.empty((world, 65), dtype=torch.uint8, device=f"cuda:{dev}")
+    dist.all_gather_into_tensor(allh, mine.view(1, 65), group=group)
+    allh = allh.cpu().numpy()
+    ok = bool(allh[:, 64].all())
+    if ok:
+        ok = ctx.lib.b200geo_peer_open(ctx.handle, rank, world, _cabi.ptr(np.ascontiguousarray(allh[:, :64]))) == _cabi.OK
+    flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=f"cuda:{dev}")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)          # also the barrier before the first peer store
+    ok = bool(flag.item())
+    if not ok:
+        ctx.lib.b200geo_peer_close(ctx.handle)
+        _peer_ready.pop(dev, None)
+    else:
+        _peer_ready[dev] = world
+    return ok
+
+
+def peer_close(device=None):
+    dev = torch.cuda.current_device() if device is None else device
+    if _peer_ready.pop(dev, None) is not None:
+        ctx = _cabi.context(dev)
+        ctx.lib.b200geo_peer_close(ctx.handle)
+
+
 def ransac_sharded(pts, idx_shard, k_offset, th, d, n=4, method="fwd", group=None, rec=None, recs=None, result=None, mask=None,
                    counts=None):
     """RANSAC.run over K sample sets of which THIS rank holds only rows k_offset .. k_offset + len(idx_shard) - 1 (its own
     hypothesis block; `pts` is replicated).  Each rank reduces its block to a 48-byte record -- its two keys and the four
-    correspondence indices of the sample sets they name --, ONE all-gather of those records (48 bytes per rank over NVLink)
-    replaces the max all-reduce of `ransac`, and every rank finishes from the gathered records (no broadcast: the winner's
+    correspondence indices of the sample sets they name --, ONE exchange of those records (48 bytes per rank over NVLink: peer
+    stores + flag wait after `peer_setup`, else an NCCL all-gather) replaces the max all-reduce of `ransac`, and every rank finishes from the gathered records (no broadcast: the winner's
     indices travel in the record).  Same result as `ransac` on the full index array.  Returns (result, mask)."""
     import torch.distributed as dist
     _chk_pts(pts)
@@ -141,7 +188,11 @@ def ransac_sharded(pts, idx_shard, k_offset, th, d, n=4, method="fwd", group=Non
     if world > 1:
         if recs is None:
             recs = torch.empty((world * WINREC_BYTES,), dtype=torch.uint8, device=pts.device)
-        dist.all_gather_into_tensor(recs, rec, group=group)
+        if _peer_ready.get(pts.device.index) == world:
+            # records by peer stores into every rank's inbox + a flag wait (two single-block kernels), no collective
+            _cabi.check(ctx.lib.b200geo_ransac_exchange_peer_dev(ctx.handle, _p(rec), _p(recs), _stream(pts)))
+        else:
+            dist.all_gather_into_tensor(recs, rec, group=group)
     else:
         recs = rec
     if result is None:
