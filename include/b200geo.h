@@ -357,8 +357,8 @@ int b200geo_orb_host(b200geo_ctx *ctx, const uint8_t *img, int height, int width
  *     b200geo_ransac_exchange_peer_dev replaces the all-gather between b200geo_ransac_search_shard_dev and
  *     b200geo_ransac_finish_recs_dev: it stores `rec` (48 bytes, device) into every rank's inbox and fills `recs`
  *     (world x 48 bytes, device) with the records of all ranks -- two single-block kernels on `stream`, no host
- *     synchronisation.  All ranks must call it the same number of times.  A rank that does not answer within about
- *     two seconds contributes an empty record (the search then reports B200GEO_ERR_NOMODEL if no other rank has one).
+ *     synchronisation.  All ranks must call it the same number of times.  A rank that does not answer within a few
+ *     seconds contributes an empty record (the search then reports B200GEO_ERR_NOMODEL if no other rank has one).
  * ---------------------------------------------------------------------------------------------- */
 int b200geo_peer_export(b200geo_ctx *ctx, int world, void *handle_out);
 int b200geo_peer_open(b200geo_ctx *ctx, int rank, int world, const void *handles);

@@ -1680,7 +1680,7 @@ int b200geo_ransac_exchange_peer_dev(b200geo_ctx *ctx, const void *rec, void *re
     peer_publish_kernel<<<1, PEER_MAX, 0, st>>>(static_cast<const WinRec *>(rec), P, ctx->peer_world, ctx->peer_rank, epoch);
     B2G_CHECK_LAUNCH(ctx);
     peer_gather_kernel<<<1, PEER_MAX, 0, st>>>(static_cast<unsigned long long *>(ctx->peer_box), ctx->peer_world, epoch, static_cast<WinRec *>(recs),
-                                               20000000ull);          // ~ 2 s of polling at 64 ns + the load's round trip
+                                               4000000ull);           // a few seconds of polling (64 ns sleep + the load per iteration)
     B2G_CHECK_LAUNCH(ctx);
     return B200GEO_OK;
 }
