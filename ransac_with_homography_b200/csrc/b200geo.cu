@@ -1415,199 +1415,204 @@ void orb_retain_best(std::vector<OrbKp> &kps, int n)
 int b200geo_orb_host(b200geo_ctx *ctx, const uint8_t *gray, int height, int width, long long pitch, int channels, int nfeatures, float *keypoints,
                      uint8_t *descriptors, int capacity, int *n_out)
 {
-    B2G_ENTER(ctx);
-    stream_order(ctx, 0);
-    B2G_ARG(gray && n_out && height > 0 && width > 0 && height < 32768 && width < 32768 && (channels == 1 || channels == 3) && pitch >= (long long)width * channels &&
-            nfeatures >= 0 && capacity >= 0);
-    B2G_ARG(capacity == 0 || (keypoints && descriptors));
-    *n_out = 0;
-    // ---- level geometry: ORB_Impl::detectAndCompute / computeKeyPoints (orb.cpp), default parameters ----
-    const double scale_factor = (double)1.2f;                      // ORB::create(float scaleFactor = 1.2f) stored as double
-    float scales[ORB_LEVELS];
-    OrbLevels L;
-    memset(&L, 0, sizeof L);
-    L.n = ORB_LEVELS;
-    long long bytes = 0;
-    unsigned cand_total = 0;
-    int max_w = 0, max_h = 0;
-    for (int lv = 0; lv < ORB_LEVELS; ++lv) {
-        scales[lv] = (float)std::pow(scale_factor, (double)lv);
-        const float inv = 1.0f / scales[lv];
-        OrbLevel &o = L.lv[lv];
-        o.w = (int)lrintf((float)width * inv);
-        o.h = (int)lrintf((float)height * inv);
-        B2G_ARG(o.w >= 1 && o.h >= 1);
-        o.pitch = (o.w + 2 * ORB_BORDER + 15) & ~15;
-        o.pw = lv ? L.lv[lv - 1].w : width;
-        o.ph = lv ? L.lv[lv - 1].h : height;
-        o.ofs = bytes;
-        bytes += (long long)o.pitch * (o.h + 2 * ORB_BORDER);
-        o.cand_ofs = cand_total;
-        o.cand_cap = (unsigned)(((o.w + 1) / 2) * ((o.h + 1) / 2));    // strict 3 x 3 maxima: at most one per 2 x 2 block
-        cand_total += o.cand_cap;
-        max_w = std::max(max_w, o.w);
-        max_h = std::max(max_h, o.h);
-    }
-    OrbRows R;
-    memset(&R, 0, sizeof R);
-    unsigned rows_total = 0, words_total = 0;
-    for (int lv = 0; lv < ORB_LEVELS; ++lv) {
-        const int rows = std::max(L.lv[lv].h - 2 * ORB_EDGE, 0), cols = std::max(L.lv[lv].w - 2 * ORB_EDGE, 0);
-        R.row_ofs[lv] = rows_total;
-        R.word_ofs[lv] = words_total;
-        R.words_per_row[lv] = (cols + 31) / 32;
-        rows_total += (unsigned)rows;
-        words_total += (unsigned)rows * (unsigned)R.words_per_row[lv];
-    }
-    int per_level[ORB_LEVELS];
-    {
-        const float factor = (float)(1.0 / scale_factor);
-        float nd = nfeatures * (1 - factor) / (1 - (float)std::pow((double)factor, (double)ORB_LEVELS));
-        int sum = 0;
-        for (int lv = 0; lv < ORB_LEVELS - 1; ++lv) {
-            per_level[lv] = (int)lrintf(nd);
-            sum += per_level[lv];
-            nd *= factor;
+    try {
+        B2G_ENTER(ctx);
+        stream_order(ctx, 0);
+        B2G_ARG(gray && n_out && height > 0 && width > 0 && height < 32768 && width < 32768 && (channels == 1 || channels == 3) && pitch >= (long long)width * channels &&
+                nfeatures >= 0 && capacity >= 0);
+        B2G_ARG(capacity == 0 || (keypoints && descriptors));
+        *n_out = 0;
+        // ---- level geometry: ORB_Impl::detectAndCompute / computeKeyPoints (orb.cpp), default parameters ----
+        const double scale_factor = (double)1.2f;                      // ORB::create(float scaleFactor = 1.2f) stored as double
+        float scales[ORB_LEVELS];
+        OrbLevels L;
+        memset(&L, 0, sizeof L);
+        L.n = ORB_LEVELS;
+        long long bytes = 0;
+        unsigned cand_total = 0;
+        int max_w = 0, max_h = 0;
+        for (int lv = 0; lv < ORB_LEVELS; ++lv) {
+            scales[lv] = (float)std::pow(scale_factor, (double)lv);
+            const float inv = 1.0f / scales[lv];
+            OrbLevel &o = L.lv[lv];
+            o.w = (int)lrintf((float)width * inv);
+            o.h = (int)lrintf((float)height * inv);
+            B2G_ARG(o.w >= 1 && o.h >= 1);
+            o.pitch = (o.w + 2 * ORB_BORDER + 15) & ~15;
+            o.pw = lv ? L.lv[lv - 1].w : width;
+            o.ph = lv ? L.lv[lv - 1].h : height;
+            o.ofs = bytes;
+            bytes += (long long)o.pitch * (o.h + 2 * ORB_BORDER);
+            o.cand_ofs = cand_total;
+            o.cand_cap = (unsigned)(((o.w + 1) / 2) * ((o.h + 1) / 2));    // strict 3 x 3 maxima: at most one per 2 x 2 block
+            cand_total += o.cand_cap;
+            max_w = std::max(max_w, o.w);
+            max_h = std::max(max_h, o.h);
         }
-        per_level[ORB_LEVELS - 1] = std::max(nfeatures - sum, 0);
-    }
-    OrbUmax um;
-    {
-        // the end of each row of the circular patch (computeKeyPoints)
-        const int hp = ORB_HALF_PATCH;
-        const int vmax = (int)std::floor(hp * std::sqrt(2.f) / 2 + 1), vmin = (int)std::ceil(hp * std::sqrt(2.f) / 2);
-        for (int v = 0; v <= hp + 1; ++v) um.u[v] = 0;
-        for (int v = 0; v <= vmax; ++v) um.u[v] = (int)lrint(std::sqrt((double)hp * hp - v * v));
-        for (int v = hp, v0 = 0; v >= vmin; --v) {
-            while (um.u[v0] == um.u[v0 + 1]) ++v0;
-            um.u[v] = v0;
-            ++v0;
+        OrbRows R;
+        memset(&R, 0, sizeof R);
+        unsigned rows_total = 0, words_total = 0;
+        for (int lv = 0; lv < ORB_LEVELS; ++lv) {
+            const int rows = std::max(L.lv[lv].h - 2 * ORB_EDGE, 0), cols = std::max(L.lv[lv].w - 2 * ORB_EDGE, 0);
+            R.row_ofs[lv] = rows_total;
+            R.word_ofs[lv] = words_total;
+            R.words_per_row[lv] = (cols + 31) / 32;
+            rows_total += (unsigned)rows;
+            words_total += (unsigned)rows * (unsigned)R.words_per_row[lv];
         }
-    }
-    // ---- device buffers ----
-    uint8_t *d_in, *d_pyr, *d_score, *d_blur;
-    OrbCandidate *d_cand;
-    unsigned *d_counts;
-    int rc;
-    if ((rc = scratch(ctx, S_SRC, (size_t)height * width * channels, (void **)&d_in))) return rc;
-    if ((rc = scratch(ctx, S_ORB_PYR, (size_t)bytes, (void **)&d_pyr))) return rc;
-    if ((rc = scratch(ctx, S_ORB_SCORE, (size_t)bytes, (void **)&d_score))) return rc;
-    if ((rc = scratch(ctx, S_ORB_BLUR, (size_t)bytes, (void **)&d_blur))) return rc;
-    if ((rc = scratch(ctx, S_ORB_CAND, (size_t)cand_total * sizeof(OrbCandidate), (void **)&d_cand))) return rc;
-    unsigned *d_rows, *d_masks;
-    if ((rc = scratch(ctx, S_MISC, 64 + sizeof(unsigned) * ((size_t)rows_total + words_total + 2), (void **)&d_counts))) return rc;
-    d_rows = d_counts + 16;
-    d_masks = d_rows + rows_total + 1;
-    B2G_CUDA(cudaMemcpy2DAsync(d_in, (size_t)width * channels, gray, (size_t)pitch, (size_t)width * channels, (size_t)height, cudaMemcpyHostToDevice, 0));
-    B2G_CUDA(cudaMemsetAsync(d_score, 0, (size_t)bytes, 0));
-    B2G_CUDA(cudaMemsetAsync(d_counts, 0, sizeof(unsigned) * ORB_LEVELS, 0));
-    for (int lv = 0; lv < ORB_LEVELS; ++lv) {
-        const OrbLevel &o = L.lv[lv];
-        const dim3 grid((o.w + 2 * ORB_BORDER + 255) / 256, o.h + 2 * ORB_BORDER);
-        if (lv == 0) orb_level_kernel<<<grid, 256, 0, 0>>>(d_in, (long long)width * channels, width, height, d_pyr + o.ofs, o.pitch, o.w, o.h, channels);
-        else {
-            const OrbLevel &q = L.lv[lv - 1];
-            orb_level_kernel<<<grid, 256, 0, 0>>>(d_pyr + q.ofs + (long long)ORB_BORDER * q.pitch + ORB_BORDER, (long long)q.pitch, q.w, q.h, d_pyr + o.ofs, o.pitch,
-                                                  o.w, o.h, 0);
-        }
-        B2G_CHECK_LAUNCH(ctx);
-    }
-    if (max_w > 6 && max_h > 6) {
-        orb_fast_kernel<<<dim3((max_w - 6 + 255) / 256, max_h - 6, ORB_LEVELS), 256, 0, 0>>>(d_pyr, d_score, L);
-        B2G_CHECK_LAUNCH(ctx);
-    }
-    if (max_w > 2 * ORB_EDGE && max_h > 2 * ORB_EDGE) {
-        const int max_rows = max_h - 2 * ORB_EDGE;
-        orb_rowflags_kernel<<<dim3((max_rows + 3) / 4, ORB_LEVELS), 128, 0, 0>>>(d_score, L, R, d_masks, d_rows);
-        B2G_CHECK_LAUNCH(ctx);
-        orb_rowscan_kernel<<<ORB_LEVELS, 1024, 0, 0>>>(L, R, d_rows, d_counts);
-        B2G_CHECK_LAUNCH(ctx);
-        orb_rowwrite_kernel<<<dim3((max_rows + 3) / 4, ORB_LEVELS), 128, 0, 0>>>(d_score, L, R, d_masks, d_rows, d_cand);
-        B2G_CHECK_LAUNCH(ctx);
-        orb_harris_kernel<<<dim3((L.lv[0].cand_cap + 255) / 256, ORB_LEVELS), 256, 0, 0>>>(d_pyr, L, d_counts, d_cand);
-        B2G_CHECK_LAUNCH(ctx);
-    }
-    unsigned counts[ORB_LEVELS];
-    B2G_CUDA(cudaMemcpyAsync(counts, d_counts, sizeof counts, cudaMemcpyDeviceToHost, 0));
-    orb_blur_kernel<<<dim3((max_w + 255) / 256, max_h, ORB_LEVELS), 256, 0, 0>>>(d_pyr, d_blur, L);      // runs under the host's selection below
-    B2G_CHECK_LAUNCH(ctx);
-    B2G_CUDA(cudaStreamSynchronize(0));
-    if (const char *dump = getenv("B200GEO_ORB_DUMP")) {           // debugging aid: pyramid, scores and level table to a file
-        std::vector<uint8_t> hp((size_t)bytes), hs((size_t)bytes);
-        B2G_CUDA(cudaMemcpy(hp.data(), d_pyr, (size_t)bytes, cudaMemcpyDeviceToHost));
-        B2G_CUDA(cudaMemcpy(hs.data(), d_score, (size_t)bytes, cudaMemcpyDeviceToHost));
-        if (FILE *f = fopen(dump, "wb")) {
-            fwrite(&bytes, sizeof bytes, 1, f);
-            fwrite(&L, sizeof L, 1, f);
-            fwrite(hp.data(), 1, hp.size(), f);
-            fwrite(hs.data(), 1, hs.size(), f);
-            fclose(f);
-        }
-    }
-    // ---- selection on the host, level by level, exactly as computeKeyPoints orders it ----
-    std::vector<OrbCandidate> recs;
-    std::vector<OrbKp> level_kps[ORB_LEVELS];
-    for (int lv = 0; lv < ORB_LEVELS; ++lv) {
-        const OrbLevel &o = L.lv[lv];
-        const unsigned n = std::min(counts[lv], o.cand_cap);
-        if (!n) continue;
-        recs.resize(n);
-        B2G_CUDA(cudaMemcpy(recs.data(), d_cand + o.cand_ofs, sizeof(OrbCandidate) * n, cudaMemcpyDeviceToHost));
-        // (the records arrive in FAST's row-major order)
-        std::vector<OrbKp> &kps = level_kps[lv];
-        kps.resize(n);
-        for (unsigned i = 0; i < n; ++i) kps[i] = OrbKp{(int)(recs[i].pos & 0xFFFFu), (int)(recs[i].pos >> 16), (float)recs[i].score, recs[i].harris};
-        orb_retain_best(kps, 2 * per_level[lv]);             // by FAST score (HARRIS_SCORE keeps twice the level's share first)
-        for (OrbKp &k : kps) k.response = k.harris;
-        orb_retain_best(kps, per_level[lv]);                 // by Harris response
-    }
-    std::vector<OrbPoint> pts;
-    for (int lv = 0; lv < ORB_LEVELS; ++lv)
-        for (const OrbKp &k : level_kps[lv]) pts.push_back(OrbPoint{lv, k.x, k.y, 0.f, 0.f});
-    const int n = (int)pts.size();
-    *n_out = n;
-    if (n == 0) return B200GEO_OK;
-    if (n > capacity) return fail(B200GEO_ERR_ARG, "orb: more keypoints than the output buffers hold%s%s");
-    OrbPoint *d_pts;
-    float *d_angle;
-    uint8_t *d_desc;
-    if ((rc = scratch(ctx, S_ORB_PTS, (size_t)n * (sizeof(OrbPoint) + sizeof(float) + 32), (void **)&d_pts))) return rc;
-    d_angle = reinterpret_cast<float *>(d_pts + n);
-    d_desc = reinterpret_cast<uint8_t *>(d_angle + n);
-    B2G_CUDA(cudaMemcpyAsync(d_pts, pts.data(), sizeof(OrbPoint) * n, cudaMemcpyHostToDevice, 0));
-    orb_angle_kernel<<<(n * 32 + 127) / 128, 128, 0, 0>>>(d_pyr, L, d_pts, n, um, d_angle);
-    B2G_CHECK_LAUNCH(ctx);
-    std::vector<float> angle(n);
-    B2G_CUDA(cudaMemcpyAsync(angle.data(), d_angle, sizeof(float) * n, cudaMemcpyDeviceToHost, 0));
-    B2G_CUDA(cudaStreamSynchronize(0));
-    {
-        int i = 0;
-        for (int lv = 0; lv < ORB_LEVELS; ++lv)
-            for (const OrbKp &k : level_kps[lv]) {
-                const float sf = scales[lv];
-                float *o = keypoints + 6 * (size_t)i;
-                o[0] = (float)k.x * sf; o[1] = (float)k.y * sf;          // pt *= scale
-                o[2] = ORB_PATCH * sf;                                   // size
-                o[3] = angle[i];
-                o[4] = k.response;                                       // Harris response
-                o[5] = (float)lv;                                        // octave
-                // computeOrbDescriptors: position back on the level, cos / sin of the angle in float (libm's cosf / sinf)
-                const float inv = 1.f / sf;
-                float ang = angle[i];
-                ang *= (float)(CV_PI_F64 / 180.f);
-                pts[i].x = (int)lrintf(o[0] * inv);
-                pts[i].y = (int)lrintf(o[1] * inv);
-                pts[i].a = cosf(ang);
-                pts[i].b = sinf(ang);
-                ++i;
+        int per_level[ORB_LEVELS];
+        {
+            const float factor = (float)(1.0 / scale_factor);
+            float nd = nfeatures * (1 - factor) / (1 - (float)std::pow((double)factor, (double)ORB_LEVELS));
+            int sum = 0;
+            for (int lv = 0; lv < ORB_LEVELS - 1; ++lv) {
+                per_level[lv] = (int)lrintf(nd);
+                sum += per_level[lv];
+                nd *= factor;
             }
+            per_level[ORB_LEVELS - 1] = std::max(nfeatures - sum, 0);
+        }
+        OrbUmax um;
+        {
+            // the end of each row of the circular patch (computeKeyPoints)
+            const int hp = ORB_HALF_PATCH;
+            const int vmax = (int)std::floor(hp * std::sqrt(2.f) / 2 + 1), vmin = (int)std::ceil(hp * std::sqrt(2.f) / 2);
+            for (int v = 0; v <= hp + 1; ++v) um.u[v] = 0;
+            for (int v = 0; v <= vmax; ++v) um.u[v] = (int)lrint(std::sqrt((double)hp * hp - v * v));
+            for (int v = hp, v0 = 0; v >= vmin; --v) {
+                while (um.u[v0] == um.u[v0 + 1]) ++v0;
+                um.u[v] = v0;
+                ++v0;
+            }
+        }
+        // ---- device buffers ----
+        uint8_t *d_in, *d_pyr, *d_score, *d_blur;
+        OrbCandidate *d_cand;
+        unsigned *d_counts;
+        int rc;
+        if ((rc = scratch(ctx, S_SRC, (size_t)height * width * channels, (void **)&d_in))) return rc;
+        if ((rc = scratch(ctx, S_ORB_PYR, (size_t)bytes, (void **)&d_pyr))) return rc;
+        if ((rc = scratch(ctx, S_ORB_SCORE, (size_t)bytes, (void **)&d_score))) return rc;
+        if ((rc = scratch(ctx, S_ORB_BLUR, (size_t)bytes, (void **)&d_blur))) return rc;
+        if ((rc = scratch(ctx, S_ORB_CAND, (size_t)cand_total * sizeof(OrbCandidate), (void **)&d_cand))) return rc;
+        unsigned *d_rows, *d_masks;
+        if ((rc = scratch(ctx, S_MISC, 64 + sizeof(unsigned) * ((size_t)rows_total + words_total + 2), (void **)&d_counts))) return rc;
+        d_rows = d_counts + 16;
+        d_masks = d_rows + rows_total + 1;
+        B2G_CUDA(cudaMemcpy2DAsync(d_in, (size_t)width * channels, gray, (size_t)pitch, (size_t)width * channels, (size_t)height, cudaMemcpyHostToDevice, 0));
+        B2G_CUDA(cudaMemsetAsync(d_score, 0, (size_t)bytes, 0));
+        B2G_CUDA(cudaMemsetAsync(d_counts, 0, sizeof(unsigned) * ORB_LEVELS, 0));
+        for (int lv = 0; lv < ORB_LEVELS; ++lv) {
+            const OrbLevel &o = L.lv[lv];
+            const dim3 grid((o.w + 2 * ORB_BORDER + 255) / 256, o.h + 2 * ORB_BORDER);
+            if (lv == 0) orb_level_kernel<<<grid, 256, 0, 0>>>(d_in, (long long)width * channels, width, height, d_pyr + o.ofs, o.pitch, o.w, o.h, channels);
+            else {
+                const OrbLevel &q = L.lv[lv - 1];
+                orb_level_kernel<<<grid, 256, 0, 0>>>(d_pyr + q.ofs + (long long)ORB_BORDER * q.pitch + ORB_BORDER, (long long)q.pitch, q.w, q.h, d_pyr + o.ofs, o.pitch,
+                                                      o.w, o.h, 0);
+            }
+            B2G_CHECK_LAUNCH(ctx);
+        }
+        if (max_w > 6 && max_h > 6) {
+            orb_fast_kernel<<<dim3((max_w - 6 + 255) / 256, max_h - 6, ORB_LEVELS), 256, 0, 0>>>(d_pyr, d_score, L);
+            B2G_CHECK_LAUNCH(ctx);
+        }
+        if (max_w > 2 * ORB_EDGE && max_h > 2 * ORB_EDGE) {
+            const int max_rows = max_h - 2 * ORB_EDGE;
+            orb_rowflags_kernel<<<dim3((max_rows + 3) / 4, ORB_LEVELS), 128, 0, 0>>>(d_score, L, R, d_masks, d_rows);
+            B2G_CHECK_LAUNCH(ctx);
+            orb_rowscan_kernel<<<ORB_LEVELS, 1024, 0, 0>>>(L, R, d_rows, d_counts);
+            B2G_CHECK_LAUNCH(ctx);
+            orb_rowwrite_kernel<<<dim3((max_rows + 3) / 4, ORB_LEVELS), 128, 0, 0>>>(d_score, L, R, d_masks, d_rows, d_cand);
+            B2G_CHECK_LAUNCH(ctx);
+            orb_harris_kernel<<<dim3((L.lv[0].cand_cap + 255) / 256, ORB_LEVELS), 256, 0, 0>>>(d_pyr, L, d_counts, d_cand);
+            B2G_CHECK_LAUNCH(ctx);
+        }
+        unsigned counts[ORB_LEVELS];
+        B2G_CUDA(cudaMemcpyAsync(counts, d_counts, sizeof counts, cudaMemcpyDeviceToHost, 0));
+        orb_blur_kernel<<<dim3((max_w + 255) / 256, max_h, ORB_LEVELS), 256, 0, 0>>>(d_pyr, d_blur, L);      // runs under the host's selection below
+        B2G_CHECK_LAUNCH(ctx);
+        B2G_CUDA(cudaStreamSynchronize(0));
+        if (const char *dump = getenv("B200GEO_ORB_DUMP")) {           // debugging aid: pyramid, scores and level table to a file
+            std::vector<uint8_t> hp((size_t)bytes), hs((size_t)bytes);
+            B2G_CUDA(cudaMemcpy(hp.data(), d_pyr, (size_t)bytes, cudaMemcpyDeviceToHost));
+            B2G_CUDA(cudaMemcpy(hs.data(), d_score, (size_t)bytes, cudaMemcpyDeviceToHost));
+            if (FILE *f = fopen(dump, "wb")) {
+                fwrite(&bytes, sizeof bytes, 1, f);
+                fwrite(&L, sizeof L, 1, f);
+                fwrite(hp.data(), 1, hp.size(), f);
+                fwrite(hs.data(), 1, hs.size(), f);
+                fclose(f);
+            }
+        }
+        // ---- selection on the host, level by level, exactly as computeKeyPoints orders it ----
+        std::vector<OrbCandidate> recs;
+        std::vector<OrbKp> level_kps[ORB_LEVELS];
+        for (int lv = 0; lv < ORB_LEVELS; ++lv) {
+            const OrbLevel &o = L.lv[lv];
+            const unsigned n = std::min(counts[lv], o.cand_cap);
+            if (!n) continue;
+            recs.resize(n);
+            B2G_CUDA(cudaMemcpy(recs.data(), d_cand + o.cand_ofs, sizeof(OrbCandidate) * n, cudaMemcpyDeviceToHost));
+            // (the records arrive in FAST's row-major order)
+            std::vector<OrbKp> &kps = level_kps[lv];
+            kps.resize(n);
+            for (unsigned i = 0; i < n; ++i) kps[i] = OrbKp{(int)(recs[i].pos & 0xFFFFu), (int)(recs[i].pos >> 16), (float)recs[i].score, recs[i].harris};
+            orb_retain_best(kps, 2 * per_level[lv]);             // by FAST score (HARRIS_SCORE keeps twice the level's share first)
+            for (OrbKp &k : kps) k.response = k.harris;
+            orb_retain_best(kps, per_level[lv]);                 // by Harris response
+        }
+        std::vector<OrbPoint> pts;
+        for (int lv = 0; lv < ORB_LEVELS; ++lv)
+            for (const OrbKp &k : level_kps[lv]) pts.push_back(OrbPoint{lv, k.x, k.y, 0.f, 0.f});
+        const int n = (int)pts.size();
+        *n_out = n;
+        if (n == 0) return B200GEO_OK;
+        if (n > capacity) return fail(B200GEO_ERR_ARG, "orb: more keypoints than the output buffers hold%s%s");
+        OrbPoint *d_pts;
+        float *d_angle;
+        uint8_t *d_desc;
+        if ((rc = scratch(ctx, S_ORB_PTS, (size_t)n * (sizeof(OrbPoint) + sizeof(float) + 32), (void **)&d_pts))) return rc;
+        d_angle = reinterpret_cast<float *>(d_pts + n);
+        d_desc = reinterpret_cast<uint8_t *>(d_angle + n);
+        B2G_CUDA(cudaMemcpyAsync(d_pts, pts.data(), sizeof(OrbPoint) * n, cudaMemcpyHostToDevice, 0));
+        orb_angle_kernel<<<(n * 32 + 127) / 128, 128, 0, 0>>>(d_pyr, L, d_pts, n, um, d_angle);
+        B2G_CHECK_LAUNCH(ctx);
+        std::vector<float> angle(n);
+        B2G_CUDA(cudaMemcpyAsync(angle.data(), d_angle, sizeof(float) * n, cudaMemcpyDeviceToHost, 0));
+        B2G_CUDA(cudaStreamSynchronize(0));
+        {
+            int i = 0;
+            for (int lv = 0; lv < ORB_LEVELS; ++lv)
+                for (const OrbKp &k : level_kps[lv]) {
+                    const float sf = scales[lv];
+                    float *o = keypoints + 6 * (size_t)i;
+                    o[0] = (float)k.x * sf; o[1] = (float)k.y * sf;          // pt *= scale
+                    o[2] = ORB_PATCH * sf;                                   // size
+                    o[3] = angle[i];
+                    o[4] = k.response;                                       // Harris response
+                    o[5] = (float)lv;                                        // octave
+                    // computeOrbDescriptors: position back on the level, cos / sin of the angle in float (libm's cosf / sinf)
+                    const float inv = 1.f / sf;
+                    float ang = angle[i];
+                    ang *= (float)(CV_PI_F64 / 180.f);
+                    pts[i].x = (int)lrintf(o[0] * inv);
+                    pts[i].y = (int)lrintf(o[1] * inv);
+                    pts[i].a = cosf(ang);
+                    pts[i].b = sinf(ang);
+                    ++i;
+                }
+        }
+        B2G_CUDA(cudaMemcpyAsync(d_pts, pts.data(), sizeof(OrbPoint) * n, cudaMemcpyHostToDevice, 0));
+        orb_describe_kernel<<<(n * 32 + 127) / 128, 128, 0, 0>>>(d_blur, L, d_pts, n, d_desc);
+        B2G_CHECK_LAUNCH(ctx);
+        B2G_CUDA(cudaMemcpyAsync(descriptors, d_desc, (size_t)n * 32, cudaMemcpyDeviceToHost, 0));
+        B2G_CUDA(cudaStreamSynchronize(0));
+        return B200GEO_OK;
+    
+    } catch (const std::exception &e) {
+        return fail(B200GEO_ERR_ARG, "orb: host allocation failed: %s%s", e.what());     // no C++ exception crosses the C ABI
     }
-    B2G_CUDA(cudaMemcpyAsync(d_pts, pts.data(), sizeof(OrbPoint) * n, cudaMemcpyHostToDevice, 0));
-    orb_describe_kernel<<<(n * 32 + 127) / 128, 128, 0, 0>>>(d_blur, L, d_pts, n, d_desc);
-    B2G_CHECK_LAUNCH(ctx);
-    B2G_CUDA(cudaMemcpyAsync(descriptors, d_desc, (size_t)n * 32, cudaMemcpyDeviceToHost, 0));
-    B2G_CUDA(cudaStreamSynchronize(0));
-    return B200GEO_OK;
 }
 
 int b200geo_peer_export(b200geo_ctx *ctx, int world, void *handle_out)
