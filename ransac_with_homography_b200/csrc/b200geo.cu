@@ -288,10 +288,10 @@ int launch_score(b200geo_ctx *ctx, const float *pts, int M, const float *H, cons
 
     if (method == B200GEO_REPROJ) {
         // two-sided bracket of the sum of the two errors (score_fast2_kernel), same deferred exact list
-        const int per_cta2 = FAST2_THREADS * 2;
+        const int per_cta2 = FAST2_THREADS * FAST2_T;
         int gx2 = (nk + per_cta2 - 1) / per_cta2;
         int per2 = M;
-        int splits2 = choose_splits((long long)gx2 * B, M, 2 * ctx->sm_count, FAST_CHUNK, 256, &per2);
+        int splits2 = choose_splits((long long)gx2 * B, M, FAST2_CTAS * ctx->sm_count, FAST_CHUNK, 256, &per2);
         if (splits2 > 1)
             B2G_CUDA(cudaMemset2DAsync(counts + k_begin, sizeof(int32_t) * (size_t)K_stride, 0, sizeof(int32_t) * (size_t)nk, (size_t)B, st));
         unsigned long long cap2 = (unsigned long long)nk * B * (unsigned long long)((M + FAST_CHUNK - 1) / FAST_CHUNK) / 32;

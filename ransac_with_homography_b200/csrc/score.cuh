@@ -456,7 +456,19 @@ score_fixup_kernel(const float4 *__restrict__ pts, int M, const float *__restric
 // goes to the same deferred exact work list as in score_fast_kernel, so the counts are those of
 // the reference-order chain.
 // ------------------------------------------------------------------------------------------------
-constexpr int FAST2_THREADS = 256;
+#ifndef B2G_FAST2_G
+#define B2G_FAST2_G 1        // measured on C3 (reproj, Gpairs/s): 1 pair x 256 threads x 2 CTAs 453; 2 pairs: 348 (256 x 1), 368 (256 x 2, spills), 424 (192 x 2), 449 (128 x 3)
+#endif
+#ifndef B2G_FAST2_THREADS
+#define B2G_FAST2_THREADS 256
+#endif
+#ifndef B2G_FAST2_CTAS
+#define B2G_FAST2_CTAS 2
+#endif
+constexpr int FAST2_THREADS = B2G_FAST2_THREADS;
+constexpr int FAST2_G = B2G_FAST2_G;          // packed hypothesis pairs per thread
+constexpr int FAST2_T = 2 * FAST2_G;          // hypotheses per thread
+constexpr int FAST2_CTAS = B2G_FAST2_CTAS;    // CTAs per SM the register budget is planned for
 constexpr int FAST2_TILE = 512;    // correspondences per tile: 64 bytes each -> 32 KB
 
 struct Fast2Q { float2 q1, r1, q2, r2; };
@@ -514,8 +526,12 @@ __device__ __forceinline__ int fast2_decide(float q1, float r1, float q2, float 
     return acc ? 1 : (rej ? 0 : 2);
 }
 
-// Grid: (ceil(nk / (2*FAST2_THREADS)), point_splits, B).  T > 0 and finite; H and Hinv both required.
-__global__ void __launch_bounds__(FAST2_THREADS, 2)
+// Grid: (ceil(nk / (FAST2_T*FAST2_THREADS)), point_splits, B).  T > 0 and finite; H and Hinv both required.
+// A thread owns FAST2_T = 2 FAST2_G hypotheses (FAST2_G packed pairs).  One pair per thread is the measured optimum: the kernel
+// is bound by fixed-latency dependencies of its chains and by the deferral traffic (ncu: issue slots 56 % busy, top stalls wait
+// / math throttle / barrier; 1.8 % of the chunks deferred), not by the four broadcast LDS.128 per correspondence, and two pairs per
+// thread cost occupancy (112 -> 168+ registers).
+__global__ void __launch_bounds__(FAST2_THREADS, FAST2_CTAS)
 score_fast2_kernel(const float4 *__restrict__ pts, int M, const float *__restrict__ H, const float *__restrict__ Hinv,
                    const uint8_t *__restrict__ flags, int k_begin, int k_end, int K_stride, float T, const float *__restrict__ cmax,
                    int pts_per_split, int32_t *__restrict__ counts, FastDeferred *__restrict__ wl, unsigned *__restrict__ wl_count,
@@ -535,13 +551,13 @@ score_fast2_kernel(const float4 *__restrict__ pts, int M, const float *__restric
     const float C = cmax[b];
     const float Th = 0.5f * T, invTh = 1.0f / Th;
 
-    // this thread's two hypotheses: k = base and base + FAST2_THREADS
-    const int base = k_begin + blockIdx.x * (FAST2_THREADS * 2) + threadIdx.x;
-    float2 hf[9], hb[9];
-    float ba1[2], br1[2], ba2[2], br2[2];
-    bool live[2], dead[2];
+    // this thread's hypotheses: k = base + t * FAST2_THREADS, t = 0 .. FAST2_T - 1, packed (0,1) (2,3) ...
+    const int base = k_begin + blockIdx.x * (FAST2_THREADS * FAST2_T) + threadIdx.x;
+    float2 hf[FAST2_G][9], hb[FAST2_G][9];
+    float ba1[FAST2_T], br1[FAST2_T], ba2[FAST2_T], br2[FAST2_T];
+    bool live[FAST2_T], dead[FAST2_T];
 #pragma unroll
-    for (int t = 0; t < 2; ++t) {
+    for (int t = 0; t < FAST2_T; ++t) {
         const int k = base + t * FAST2_THREADS;
         live[t] = k < k_end;
         const size_t o = (size_t)b * K_stride + (live[t] ? k : k_begin);
@@ -564,11 +580,13 @@ score_fast2_kernel(const float4 *__restrict__ pts, int M, const float *__restric
         for (int j = 6; j < 9; ++j) { f[j] = __fmul_rn(Th, f[j]); g[j] = __fmul_rn(Th, g[j]); }
 #pragma unroll
         for (int j = 0; j < 9; ++j) {
-            if (t == 0) { hf[j].x = f[j]; hb[j].x = g[j]; }
-            else { hf[j].y = f[j]; hb[j].y = g[j]; }
+            if ((t & 1) == 0) { hf[t / 2][j].x = f[j]; hb[t / 2][j].x = g[j]; }
+            else { hf[t / 2][j].y = f[j]; hb[t / 2][j].y = g[j]; }
         }
     }
-    unsigned cnt[2] = {0u, 0u};
+    unsigned cnt[FAST2_T];
+#pragma unroll
+    for (int t = 0; t < FAST2_T; ++t) cnt[t] = 0u;
     const int j_begin = blockIdx.y * pts_per_split;
     const int j_end = min(M, j_begin + pts_per_split);
     for (int t0 = j_begin; t0 < j_end; t0 += FAST2_TILE) {
@@ -587,17 +605,23 @@ score_fast2_kernel(const float4 *__restrict__ pts, int M, const float *__restric
         }
         __syncthreads();
         for (int i = 0; i < n_pad; i += FAST_CHUNK) {
-            bool und[2] = {false, false};
+            bool und[FAST2_T];
+#pragma unroll
+            for (int t = 0; t < FAST2_T; ++t) und[t] = false;
 #pragma unroll
             for (int u = 0; u < FAST_CHUNK; ++u) {
-                const Fast2Q q = fast2_q(hf, hb, tile[4 * (i + u)], tile[4 * (i + u) + 1], tile[4 * (i + u) + 2], tile[4 * (i + u) + 3]);
-                const int d0 = fast2_decide(q.q1.x, q.r1.x, q.q2.x, q.r2.x, ba1[0], br1[0], ba2[0], br2[0]);
-                const int d1 = fast2_decide(q.q1.y, q.r1.y, q.q2.y, q.r2.y, ba1[1], br1[1], ba2[1], br2[1]);
-                cnt[0] += (d0 == 1); und[0] = und[0] || (d0 == 2);
-                cnt[1] += (d1 == 1); und[1] = und[1] || (d1 == 2);
+                const float4 p0 = tile[4 * (i + u)], p1 = tile[4 * (i + u) + 1], p2 = tile[4 * (i + u) + 2], p3 = tile[4 * (i + u) + 3];
+#pragma unroll
+                for (int g = 0; g < FAST2_G; ++g) {
+                    const Fast2Q q = fast2_q(hf[g], hb[g], p0, p1, p2, p3);
+                    const int d0 = fast2_decide(q.q1.x, q.r1.x, q.q2.x, q.r2.x, ba1[2 * g], br1[2 * g], ba2[2 * g], br2[2 * g]);
+                    const int d1 = fast2_decide(q.q1.y, q.r1.y, q.q2.y, q.r2.y, ba1[2 * g + 1], br1[2 * g + 1], ba2[2 * g + 1], br2[2 * g + 1]);
+                    cnt[2 * g] += (d0 == 1); und[2 * g] = und[2 * g] || (d0 == 2);
+                    cnt[2 * g + 1] += (d1 == 1); und[2 * g + 1] = und[2 * g + 1] || (d1 == 2);
+                }
             }
 #pragma unroll
-            for (int t = 0; t < 2; ++t) {
+            for (int t = 0; t < FAST2_T; ++t) {
                 if (!und[t] || dead[t]) continue;
                 // some correspondence of this chunk is undecided: defer the chunk to score_fixup2_kernel
                 const size_t o = (size_t)b * K_stride + base + t * FAST2_THREADS;
@@ -614,9 +638,9 @@ score_fast2_kernel(const float4 *__restrict__ pts, int M, const float *__restric
                 for (int u = 0; u < FAST_CHUNK; ++u) {
                     const int jj = t0 + i + u;
                     if (jj >= j_end) break;
-                    const Fast2Q q = fast2_q(hf, hb, tile[4 * (i + u)], tile[4 * (i + u) + 1], tile[4 * (i + u) + 2], tile[4 * (i + u) + 3]);
-                    const int d = t == 0 ? fast2_decide(q.q1.x, q.r1.x, q.q2.x, q.r2.x, ba1[0], br1[0], ba2[0], br2[0])
-                                         : fast2_decide(q.q1.y, q.r1.y, q.q2.y, q.r2.y, ba1[1], br1[1], ba2[1], br2[1]);
+                    const Fast2Q q = fast2_q(hf[t / 2], hb[t / 2], tile[4 * (i + u)], tile[4 * (i + u) + 1], tile[4 * (i + u) + 2], tile[4 * (i + u) + 3]);
+                    const int d = (t & 1) == 0 ? fast2_decide(q.q1.x, q.r1.x, q.q2.x, q.r2.x, ba1[t], br1[t], ba2[t], br2[t])
+                                               : fast2_decide(q.q1.y, q.r1.y, q.q2.y, q.r2.y, ba1[t], br1[t], ba2[t], br2[t]);
                     if (d != 2) continue;
                     cnt[t] += exact_loss<B200GEO_REPROJ>(hx, hix, __ldg(pts + jj)) < T ? 1u : 0u;
                 }
@@ -624,7 +648,7 @@ score_fast2_kernel(const float4 *__restrict__ pts, int M, const float *__restric
         }
     }
 #pragma unroll
-    for (int t = 0; t < 2; ++t) {
+    for (int t = 0; t < FAST2_T; ++t) {
         if (!live[t]) continue;
         const size_t o = (size_t)b * K_stride + base + t * FAST2_THREADS;
         const int c = dead[t] ? 0 : (int)cnt[t];
